@@ -1,0 +1,273 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  C interface (ctypes) over the CPU restatement.
+// Used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+#include <chrono>
+#include <cstring>
+#include <string>
+
+#include "protocols.hpp"
+
+using namespace wo;
+
+static thread_local std::string g_err;
+#define WO_TRY try {
+#define WO_CATCH(ret)                 \
+  }                                   \
+  catch (const std::exception& e) {   \
+    g_err = e.what();                 \
+    return ret;                       \
+  }
+
+extern "C" {
+
+const char* wo_last_error() { return g_err.c_str(); }
+
+// ---- JDK primitives ---------------------------------------------------------------------
+void wo_random_next_ints(int64_t seed, int n, int32_t* out) {
+  JavaRandom r(seed);
+  for (int i = 0; i < n; ++i) out[i] = r.nextInt();
+}
+void wo_random_next_bounded(int64_t seed, int n, int32_t bound, int32_t* out) {
+  JavaRandom r(seed);
+  for (int i = 0; i < n; ++i) out[i] = r.nextInt(bound);
+}
+double wo_random_next_double(int64_t seed, int skip) {
+  JavaRandom r(seed);
+  for (int i = 0; i < skip; ++i) r.nextInt();
+  return r.nextDouble();
+}
+void wo_shuffle(int64_t seed, int n, int32_t* inout) {
+  JavaRandom r(seed);
+  javaShuffle(inout, n, r);
+}
+uint64_t wo_lcg_advance(uint64_t seed48, uint64_t n) { return lcgAdvance(seed48, n); }
+int wo_pseudo_random(int nodeId, int seed) { return Network::getPseudoRandom(nodeId, seed); }
+int32_t wo_string_hash(const char* s) { return javaStringHash(s); }
+
+// AWS builder city order (HashMap iteration order) as a ';'-joined string
+int wo_aws_city_order(char* buf, int cap) {
+  NodeBuilder nb = makeAwsCityBuilder();
+  std::string s;
+  for (auto& c : nb.citiesInfo) s += c.name + ";";
+  if (static_cast<int>(s.size()) + 1 > cap) return -1;
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return static_cast<int>(nb.citiesInfo.size());
+}
+void wo_aws_cumulative(float* out) {
+  NodeBuilder nb = makeAwsCityBuilder();
+  for (size_t i = 0; i < nb.citiesInfo.size(); ++i) out[i] = nb.citiesInfo[i].cumulativeProbability;
+}
+
+// latency table: latency(kind, param, from attrs, to attrs, delta) without building a network
+int wo_latency(const char* latencyName, int fx, int fy, int fextra, const char* fcity, int tx, int ty, int textra,
+               const char* tcity, int delta) {
+  WO_TRY
+  NetworkLatency nl = networkLatencyByName(latencyName);
+  Node f, t;
+  f.nodeId = 0;
+  t.nodeId = 1;
+  f.x = fx;
+  f.y = fy;
+  f.extraLatency = fextra;
+  f.cityName = fcity;
+  t.x = tx;
+  t.y = ty;
+  t.extraLatency = textra;
+  t.cityName = tcity;
+  return nl.getLatency(f, t, delta);
+  WO_CATCH(-1000000)
+}
+double wo_gpd_inverse(double shape, double location, double scale, double y) {
+  return GeneralizedParetoDistribution(shape, location, scale).inverseF(y);
+}
+
+// ---- PingPong ---------------------------------------------------------------------------
+void* wo_pp_create(int nodeCt, const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  PingPong::Params p;
+  p.nodeCt = nodeCt;
+  p.nodeBuilderName = nodeBuilderName ? nodeBuilderName : "";
+  p.latencyNull = networkLatencyName == nullptr;
+  p.networkLatencyName = networkLatencyName ? networkLatencyName : "";
+  return new PingPong(p);
+  WO_CATCH(nullptr)
+}
+void wo_pp_destroy(void* h) { delete static_cast<PingPong*>(h); }
+void wo_pp_set_seed(void* h, int64_t s) { static_cast<PingPong*>(h)->network.rd.setSeed(s); }
+int wo_pp_init(void* h) {
+  WO_TRY
+  static_cast<PingPong*>(h)->init();
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_pp_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<PingPong*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+int wo_pp_time(void* h) { return static_cast<PingPong*>(h)->network.time; }
+int wo_pp_msgs_size(void* h) { return static_cast<PingPong*>(h)->network.msgs.size(); }
+void wo_pp_pongs(void* h, int32_t* out) {
+  auto* p = static_cast<PingPong*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) out[i] = p->nodes[i]->pong;
+}
+static void nodeCounters(const std::vector<Node*>& nodes, int64_t* out5N) {
+  size_t n = nodes.size();
+  for (size_t i = 0; i < n; ++i) {
+    out5N[0 * n + i] = nodes[i]->msgReceived;
+    out5N[1 * n + i] = nodes[i]->msgSent;
+    out5N[2 * n + i] = nodes[i]->bytesSent;
+    out5N[3 * n + i] = nodes[i]->bytesReceived;
+    out5N[4 * n + i] = nodes[i]->doneAt;
+  }
+}
+static void nodeAttrs(const std::vector<Node*>& nodes, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed,
+                      uint8_t* down) {
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    if (x) x[i] = nodes[i]->x;
+    if (y) y[i] = nodes[i]->y;
+    if (extra) extra[i] = nodes[i]->extraLatency;
+    if (city) city[i] = nodes[i]->cityIdx < 0 ? -1 : awsRegionOf(nodes[i]->cityName);
+    if (speed) speed[i] = nodes[i]->speedRatio;
+    if (down) down[i] = nodes[i]->down ? 1 : 0;
+  }
+}
+void wo_pp_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<PingPong*>(h)->network.allNodes, out5N); }
+void wo_pp_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<PingPong*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+
+// ---- GSFSignature -----------------------------------------------------------------------
+void* wo_gsf_create(int nodeCount, int threshold, int pairingTime, int timeoutPerLevelMs, int periodDurationMs,
+                    int acceleratedCallsCount, int nodesDown, const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  GSFSignature::Params p = GSFSignature::makeParams(nodeCount, threshold, pairingTime, timeoutPerLevelMs, periodDurationMs,
+                                                    acceleratedCallsCount, nodesDown, nodeBuilderName ? nodeBuilderName : "",
+                                                    networkLatencyName ? networkLatencyName : "");
+  p.latencyNull = networkLatencyName == nullptr;
+  return new GSFSignature(p);
+  WO_CATCH(nullptr)
+}
+void wo_gsf_destroy(void* h) { delete static_cast<GSFSignature*>(h); }
+void wo_gsf_set_seed(void* h, int64_t s) { static_cast<GSFSignature*>(h)->network.rd.setSeed(s); }
+int wo_gsf_init(void* h) {
+  WO_TRY
+  static_cast<GSFSignature*>(h)->init();
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_gsf_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<GSFSignature*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+// run `steps` x runMs(ms); returns wall seconds of the runMs calls only
+double wo_gsf_run_timed(void* h, int ms, int steps) {
+  auto* p = static_cast<GSFSignature*>(h);
+  auto t0 = std::chrono::steady_clock::now();
+  try {
+    for (int i = 0; i < steps; ++i) p->network.runMs(ms);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+int wo_gsf_time(void* h) { return static_cast<GSFSignature*>(h)->network.time; }
+int wo_gsf_msgs_size(void* h) { return static_cast<GSFSignature*>(h)->network.msgs.size(); }
+int64_t wo_gsf_msgs_live(void* h) { return static_cast<GSFSignature*>(h)->network.msgs.live; }
+int wo_gsf_msgs_size_at(void* h, int t) {
+  WO_TRY
+  return static_cast<GSFSignature*>(h)->network.msgs.sizeAt(t);
+  WO_CATCH(-1)
+}
+int wo_gsf_continue_if(void* h) { return static_cast<GSFSignature*>(h)->continueIf() ? 1 : 0; }
+int wo_gsf_levels(void* h, int node) { return static_cast<int>(static_cast<GSFSignature*>(h)->node(node).levels.size()); }
+void wo_gsf_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<GSFSignature*>(h)->network.allNodes, out5N); }
+void wo_gsf_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<GSFSignature*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+// per-node protocol scalars: pairing, sigChecked, sigQueueSize, toVerify.size(), cardinality(verifiedSignatures)
+void wo_gsf_node_scalars(void* h, int32_t* pairing, int32_t* sigChecked, int32_t* sigQueueSize, int32_t* toVerifySize,
+                         int32_t* card) {
+  auto* p = static_cast<GSFSignature*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) {
+    auto& n = *p->nodes[i];
+    if (pairing) pairing[i] = n.nodePairingTime;
+    if (sigChecked) sigChecked[i] = n.sigChecked;
+    if (sigQueueSize) sigQueueSize[i] = n.sigQueueSize;
+    if (toVerifySize) toVerifySize[i] = static_cast<int>(n.toVerify.size());
+    if (card) card[i] = n.verifiedSignatures.cardinality();
+  }
+}
+// verifiedSignatures of every node as N rows of `words` uint64 (little-endian bit order: bit i of the set = bit i%64 of word i/64)
+void wo_gsf_verified(void* h, uint64_t* out, int words) {
+  auto* p = static_cast<GSFSignature*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i)
+    for (int w = 0; w < words; ++w) out[i * static_cast<size_t>(words) + static_cast<size_t>(w)] = p->nodes[i]->verifiedSignatures.rawWord(w);
+}
+// which: 0 = verifiedSignatures of the level, 1 = individualSignatures, 2 = indivVerifiedSig, 3 = waitedSigs ; OR over levels
+void wo_gsf_level_rows(void* h, int which, uint64_t* out, int words) {
+  auto* p = static_cast<GSFSignature*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) {
+    uint64_t* row = out + i * static_cast<size_t>(words);
+    for (int w = 0; w < words; ++w) row[w] = 0;
+    for (auto& l : p->nodes[i]->levels) {
+      const JBitSet& b = which == 0 ? l.verifiedSignatures : which == 1 ? l.individualSignatures : which == 2 ? l.indivVerifiedSig : l.waitedSigs;
+      for (int w = 0; w < words; ++w) row[w] |= b.rawWord(w);
+    }
+  }
+}
+// per (node, level): posInLevel, remainingCalls, cardinality(level.verifiedSignatures); arrays of N*L (row-major by node)
+void wo_gsf_level_scalars(void* h, int L, int32_t* pos, int32_t* remaining, int32_t* card) {
+  auto* p = static_cast<GSFSignature*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i)
+    for (int l = 0; l < L; ++l) {
+      size_t k = i * static_cast<size_t>(L) + static_cast<size_t>(l);
+      auto& n = *p->nodes[i];
+      bool has = l < static_cast<int>(n.levels.size());
+      if (pos) pos[k] = has ? n.levels[static_cast<size_t>(l)].posInLevel : 0;
+      if (remaining) remaining[k] = has ? n.levels[static_cast<size_t>(l)].remainingCalls : 0;
+      if (card) card[k] = has ? n.levels[static_cast<size_t>(l)].verifiedSignatures.cardinality() : 0;
+    }
+}
+int wo_gsf_peers(void* h, int node, int level, int32_t* out, int cap) {
+  auto* p = static_cast<GSFSignature*>(h);
+  auto& n = p->node(node);
+  if (level >= static_cast<int>(n.levels.size())) return 0;
+  auto& pe = n.levels[static_cast<size_t>(level)].peers;
+  int c = std::min<int>(cap, static_cast<int>(pe.size()));
+  for (int i = 0; i < c; ++i) out[i] = static_cast<int32_t>(pe[static_cast<size_t>(i)]);
+  return static_cast<int>(pe.size());
+}
+uint64_t wo_gsf_rng_state(void* h) { return static_cast<GSFSignature*>(h)->network.rd.seed; }
+// stats: [deliveries, tasks, condRuns, draws, evalEntries, evalBytes, updates, cycles, sends, multiSends, sendBytes, maxQueue]
+void wo_gsf_stats(void* h, int64_t* out12) {
+  auto* p = static_cast<GSFSignature*>(h);
+  out12[0] = p->network.statDeliveries;
+  out12[1] = p->network.statTasks;
+  out12[2] = p->network.statCondRuns;
+  out12[3] = p->network.statDraws;
+  out12[4] = p->statEvalEntries;
+  out12[5] = p->statEvalBytes;
+  out12[6] = p->statUpdates;
+  out12[7] = p->statCycles;
+  out12[8] = p->statSends;
+  out12[9] = p->statMultiSends;
+  out12[10] = p->statSendBytes;
+  out12[11] = p->statMaxQueue;
+}
+// test hook used by the restated PT/GSFSignatureTest.testGetLastFinishedLevel
+int wo_gsf_test_last_finished(void* h) {
+  auto* p = static_cast<GSFSignature*>(h);
+  auto& n0 = p->node(0);
+  int r0 = n0.getLastFinishedLevel().cardinality();
+  n0.levels[1].verifiedSignatures.or_(n0.levels[1].waitedSigs);
+  int r1 = n0.getLastFinishedLevel().cardinality();
+  n0.levels[2].verifiedSignatures.set(2);
+  int r2 = n0.getLastFinishedLevel().cardinality();
+  n0.levels[2].verifiedSignatures.set(3);
+  int r3 = n0.getLastFinishedLevel().cardinality();
+  return r0 * 1000 + r1 * 100 + r2 * 10 + r3;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the reference protocols on the hot path:
+//   protocols/PingPong.java       -> PingPong
+//   protocols/GSFSignature.java   -> GSFSignature (GSFNode, SFLevel, SendSigs)
+// Line references are to those files.  PARITY STATUS: structure / schedule / liveness are
+// pinned by the reference's own tests (PT/GSFSignatureTest.java, PT/PingPongTest.java,
+// restated in tests/test_oracle_protocols.py); the protocol END STATE (bitmaps, doneAt) is
+// "parity unpinned" — the reference's tests hold no golden end state and no JVM is available.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "core.hpp"
+#include "jbitset.hpp"
+
+namespace wo {
+
+// ----------------------------------------------------------------------------------------
+// PingPong  (protocols/PingPong.java)
+// ----------------------------------------------------------------------------------------
+struct PingPong {
+  struct Params {
+    int nodeCt = 1000;
+    std::string nodeBuilderName;  // empty == null
+    std::string networkLatencyName;
+    bool latencyNull = true;
+  };
+  struct PingPongNode : Node {
+    int pong = 0;
+    PingPong* p;
+    PingPongNode(PingPong* pp) : Node(pp->network.rd, pp->nb), p(pp) {}
+  };
+  struct Pong : Message {
+    void action(Network&, Node&, Node& to) override { static_cast<PingPongNode&>(to).pong++; }  // :77-79
+  };
+  struct Ping : Message {
+    void action(Network& network, Node& from, Node& to) override {  // :73-75
+      network.send(std::make_shared<Pong>(), to, from);
+    }
+  };
+
+  Params params;
+  Network network;
+  NodeBuilder nb;
+  std::vector<std::unique_ptr<PingPongNode>> nodes;
+
+  explicit PingPong(const Params& p) : params(p) {  // :52-57
+    nb = nodeBuilderByName(p.nodeBuilderName);
+    network.setNetworkLatency(networkLatencyByName(p.networkLatencyName, p.latencyNull));
+  }
+  void init() {  // :82-87
+    for (int i = 0; i < params.nodeCt; i++) {
+      nodes.push_back(std::make_unique<PingPongNode>(this));
+      network.addNode(nodes.back().get());
+    }
+    network.sendAll(std::make_shared<Ping>(), network.getNodeById(0));
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// GSFSignature  (protocols/GSFSignature.java)
+// ----------------------------------------------------------------------------------------
+inline int roundPow2(int n) {  // core/utils/MoreMath.java:13-19
+  int res = 1;
+  while ((res << 1) > 0 && (res << 1) <= n) res <<= 1;  // Integer.highestOneBit
+  if (res != n) res <<= 1;
+  return res;
+}
+
+struct GSFSignature {
+  struct Params {  // :27-107
+    int nodeCount = 32768 / 32;
+    int threshold = static_cast<int>((32768 / 32) * 0.99);
+    int pairingTime = 3;
+    int timeoutPerLevelMs = 50;
+    int periodDurationMs = 10;
+    int acceleratedCallsCount = 10;
+    int nodesDown = 0;
+    std::string nodeBuilderName;
+    std::string networkLatencyName;
+    bool latencyNull = false;
+  };
+  static Params makeParams(int nodeCount, int threshold, int pairingTime, int timeoutPerLevelMs, int periodDurationMs,
+                           int acceleratedCallsCount, int nodesDown, const std::string& nb, const std::string& nl) {
+    if (nodesDown >= nodeCount || nodesDown < 0 || threshold > nodeCount || (nodesDown + threshold > nodeCount))
+      throw IllegalArgument("nodeCount/threshold");  // :69-74
+    Params p;
+    p.nodeCount = nodeCount;
+    p.threshold = threshold;
+    p.pairingTime = pairingTime;
+    p.timeoutPerLevelMs = timeoutPerLevelMs;
+    p.periodDurationMs = periodDurationMs;
+    p.acceleratedCallsCount = acceleratedCallsCount;
+    p.nodesDown = nodesDown;
+    p.nodeBuilderName = nb;
+    p.networkLatencyName = nl;
+    return p;
+  }
+
+  struct GSFNode;
+  struct SFLevel;
+
+  struct SendSigs : Message, std::enable_shared_from_this<SendSigs> {  // :137-164
+    JBitSet sigs;  // mutable and shared between receivers of a multi-dest send
+    GSFNode* from;
+    int level;
+    int size_;
+    SendSigs(GSFNode* f, const JBitSet& s, const SFLevel& l);
+    int size() const override { return size_; }
+    void action(Network&, Node& from_, Node& to) override;
+  };
+  using SendSigsPtr = std::shared_ptr<SendSigs>;
+
+  struct SFLevel {  // :235-356
+    GSFNode* node;
+    int level;
+    std::vector<uint32_t> peers;  // node ids
+    JBitSet waitedSigs, verifiedSignatures, individualSignatures, indivVerifiedSig;
+    int waitedCard = 0;  // == waitedSigs.cardinality() (immutable after construction)
+    int posInLevel = 0;
+    int remainingCalls = 0;
+
+    int expectedSigs() const { return waitedCard; }  // :286-288
+    bool hasStarted(const JBitSet& toSend) const;    // :291-311
+    void doCycle(const JBitSet& toSend);             // :313-323
+    std::vector<GSFNode*> getRemainingPeers(int peersCt);  // :325-349
+  };
+
+  struct GSFNode : Node {  // :166-604
+    GSFSignature* p;
+    std::vector<SendSigsPtr> toVerify;
+    std::vector<SFLevel> levels;
+    JBitSet verifiedSignatures;
+    int nodePairingTime;
+    bool done = false;
+    int sigChecked = 0;
+    int sigQueueSize = 0;
+
+    explicit GSFNode(GSFSignature* pp)
+        : Node(pp->network.rd, pp->nb), p(pp), nodePairingTime(static_cast<int>(std::max(1.0, pp->params.pairingTime * speedRatio))) {
+      verifiedSignatures.set(nodeId);  // :176-179
+    }
+    JBitSet allSigsAtLevel(int round) const;  // :359-372
+    void initLevel();                         // :181-191
+    JBitSet getLastFinishedLevel() const;     // :193-210
+    void doCycle();                           // :212-224
+    static bool include(const JBitSet& large, const JBitSet& small) {  // :374-378
+      JBitSet a = large;
+      a.and_(small);
+      return a.equals(small);
+    }
+    void updateVerifiedSignatures(GSFNode* from, int level, JBitSet& sigs);  // :384-460
+    int evaluateSig(const SFLevel& l, const JBitSet& sig) const;             // :482-534
+    void onNewSig(GSFNode* from, const SendSigsPtr& ssigs);                  // :537-555
+    void checkSigs();                                                       // :557-583
+  };
+
+  Params params;
+  Network network;
+  NodeBuilder nb;
+  std::vector<std::unique_ptr<GSFNode>> nodes;
+  // statistics for sizing / roofline accounting (not in the reference)
+  int64_t statEvalEntries = 0, statEvalBytes = 0, statUpdates = 0, statCycles = 0, statSends = 0, statMultiSends = 0;
+  int64_t statSendBytes = 0, statMaxQueue = 0;
+
+  explicit GSFSignature(const Params& p) : params(p) {  // :109-114
+    nb = nodeBuilderByName(p.nodeBuilderName);
+    network.setNetworkLatency(networkLatencyByName(p.networkLatencyName, p.latencyNull));
+  }
+  GSFNode& node(int i) { return *nodes[static_cast<size_t>(i)]; }
+
+  void init() {  // :611-635
+    for (int i = 0; i < params.nodeCount; i++) {
+      nodes.push_back(std::make_unique<GSFNode>(this));
+      network.addNode(nodes.back().get());
+    }
+    for (int setDown = 0; setDown < params.nodesDown;) {
+      int down = network.rd.nextInt(params.nodeCount);
+      Node& n = *network.allNodes[static_cast<size_t>(down)];
+      if (!n.isDown() && down != 1) {
+        n.stop();
+        setDown++;
+      }
+    }
+    for (auto& up : nodes) {
+      GSFNode* n = up.get();
+      if (!n->isDown()) {
+        n->initLevel();
+        network.registerPeriodicTask([n] { n->doCycle(); }, 1, params.periodDurationMs, *n);
+        network.registerConditionalTask([n] { n->checkSigs(); }, 1, n->nodePairingTime, *n,
+                                        [n] { return !n->toVerify.empty(); }, [n] { return !n->done; });
+      }
+    }
+  }
+  // newConfIf :670-682 — true while some live node is below the threshold
+  bool continueIf() const {
+    for (auto& n : nodes)
+      if (!n->isDown() && n->verifiedSignatures.cardinality() < params.threshold) return true;
+    return false;
+  }
+};
+
+inline GSFSignature::SendSigs::SendSigs(GSFNode* f, const JBitSet& s, const SFLevel& l)
+    : sigs(s), from(f), level(l.level), size_(1 + l.expectedSigs() / 8 + 96) {}  // :145-153 (clone; size)
+
+inline void GSFSignature::SendSigs::action(Network&, Node& from_, Node& to) {  // :161-163
+  GSFNode& t = static_cast<GSFNode&>(to);
+  t.onNewSig(static_cast<GSFNode*>(&from_), shared_from_this());
+}
+
+inline JBitSet GSFSignature::GSFNode::allSigsAtLevel(int round) const {  // :359-372
+  if (round < 1) throw IllegalArgument("round");
+  JBitSet res;
+  int cMask = (1 << round) - 1;
+  int start = (cMask | nodeId) ^ cMask;
+  int end = nodeId | cMask;
+  end = std::min(end, p->params.nodeCount - 1);
+  res.setRange(start, end + 1);
+  res.set(nodeId, false);
+  return res;
+}
+
+inline void GSFSignature::GSFNode::initLevel() {  // :181-191, SFLevel ctors :260-280, randomSubset :462-476
+  int roundedPow2NodeCount = roundPow2(p->params.nodeCount);
+  JBitSet allPreviousNodes;
+  levels.emplace_back();
+  {
+    SFLevel& l0 = levels.back();  // level 0: only our own signature, no peer (:260-267)
+    l0.node = this;
+    l0.level = 0;
+    l0.waitedSigs.set(nodeId);
+    l0.waitedCard = 1;
+    l0.verifiedSignatures.set(nodeId);
+    l0.remainingCalls = 0;
+  }
+  for (int l = 1; (1LL << l) <= roundedPow2NodeCount; l++) {
+    allPreviousNodes.or_(levels.back().waitedSigs);
+    SFLevel nl;
+    nl.node = this;
+    nl.level = levels.back().level + 1;
+    nl.waitedSigs = allSigsAtLevel(nl.level);
+    nl.waitedSigs.andNot(allPreviousNodes);
+    nl.waitedCard = nl.waitedSigs.cardinality();
+    // randomSubset(waitedSigs, MAX_VALUE): ids in increasing order, then Collections.shuffle(res, network.rd)
+    nl.peers.reserve(static_cast<size_t>(nl.waitedCard));
+    for (int cur = nl.waitedSigs.nextSetBit(0); cur >= 0; cur = nl.waitedSigs.nextSetBit(cur + 1))
+      nl.peers.push_back(static_cast<uint32_t>(cur));
+    javaShuffle(nl.peers, p->network.rd);
+    nl.remainingCalls = static_cast<int>(nl.peers.size());
+    levels.push_back(std::move(nl));
+  }
+}
+
+inline JBitSet GSFSignature::GSFNode::getLastFinishedLevel() const {  // :193-210
+  JBitSet res;
+  const SFLevel* sfl = &levels[0];
+  bool done_ = false;
+  while (!done_) {
+    if (sfl->waitedSigs.equals(sfl->verifiedSignatures)) {
+      res.or_(sfl->waitedSigs);
+      if (sfl->level < static_cast<int>(levels.size()) - 1)
+        sfl = &levels[static_cast<size_t>(sfl->level + 1)];
+      else
+        done_ = true;
+    } else {
+      done_ = true;
+    }
+  }
+  return res;
+}
+
+inline void GSFSignature::GSFNode::doCycle() {  // :212-224
+  ++p->statCycles;
+  JBitSet toSend = getLastFinishedLevel();
+  for (SFLevel& sfl : levels) {
+    sfl.doCycle(toSend);
+    toSend.or_(sfl.verifiedSignatures);
+  }
+}
+
+inline bool GSFSignature::SFLevel::hasStarted(const JBitSet& toSend) const {  // :291-311
+  if (node->p->network.time >= level * node->p->params.timeoutPerLevelMs) return true;
+  if (toSend.cardinality() >= expectedSigs()) return true;
+  return false;
+}
+
+inline void GSFSignature::SFLevel::doCycle(const JBitSet& toSend) {  // :313-323
+  if (remainingCalls == 0 || !hasStarted(toSend)) return;
+  std::vector<GSFNode*> dest = getRemainingPeers(1);
+  if (!dest.empty()) {
+    auto ss = std::make_shared<SendSigs>(node, toSend, *this);
+    ++node->p->statSends;
+    node->p->statSendBytes += static_cast<int64_t>(toSend.storedBytes());
+    node->p->network.send(ss, *node, *dest[0]);
+  }
+}
+
+inline std::vector<GSFSignature::GSFNode*> GSFSignature::SFLevel::getRemainingPeers(int peersCt) {  // :325-349
+  std::vector<GSFNode*> res;
+  while (peersCt > 0 && remainingCalls > 0) {
+    remainingCalls--;
+    GSFNode* pn = &node->p->node(static_cast<int>(peers[static_cast<size_t>(posInLevel++)]));
+    if (posInLevel >= static_cast<int>(peers.size())) posInLevel = 0;
+    // `count == null || true` (:338): the "skip finished peers" branch is dead code
+    res.push_back(pn);
+    peersCt--;
+  }
+  return res;
+}
+
+inline void GSFSignature::GSFNode::updateVerifiedSignatures(GSFNode* from, int level, JBitSet& sigsRef) {  // :384-460
+  ++p->statUpdates;
+  SFLevel* sfl = &levels[static_cast<size_t>(level)];
+  JBitSet* sigs = &sigsRef;  // aliases the (possibly shared) message payload, like the reference
+  JBitSet local;
+
+  if (sigs->cardinality() == 1) sfl->indivVerifiedSig.set(from->nodeId);
+  sigs->or_(sfl->indivVerifiedSig);
+
+  bool resetRemaining = false;
+  if (sigs->cardinality() > sfl->expectedSigs()) {
+    for (size_t i = 1; i < levels.size() && include(*sigs, levels[i].waitedSigs); i++) {
+      SFLevel& l = levels[i];
+      if (!l.verifiedSignatures.equals(l.waitedSigs)) {
+        l.verifiedSignatures.or_(l.waitedSigs);
+        verifiedSignatures.or_(l.waitedSigs);
+        resetRemaining = true;
+      }
+      if (resetRemaining) l.remainingCalls = static_cast<int>(l.peers.size());
+    }
+    local = sfl->waitedSigs;  // sigs = (BitSet) sfl.waitedSigs.clone();
+    sigs = &local;
+  }
+
+  if (sfl->verifiedSignatures.cardinality() > 0 && !sigs->intersects(sfl->verifiedSignatures)) {
+    sigs->or_(sfl->verifiedSignatures);
+  }
+
+  if (sigs->cardinality() > sfl->verifiedSignatures.cardinality() || resetRemaining) {
+    for (size_t i = static_cast<size_t>(sfl->level); i < levels.size(); i++)
+      levels[i].remainingCalls = static_cast<int>(levels[i].peers.size());
+
+    sfl->verifiedSignatures.andNot(sfl->waitedSigs);
+    sfl->verifiedSignatures.or_(*sigs);
+
+    verifiedSignatures.andNot(sfl->waitedSigs);
+    verifiedSignatures.or_(*sigs);
+
+    if (p->params.acceleratedCallsCount > 0) {
+      JBitSet bestToSend = getLastFinishedLevel();
+      while (include(bestToSend, sfl->waitedSigs) && sfl->level < static_cast<int>(levels.size()) - 1) {
+        sfl = &levels[static_cast<size_t>(sfl->level + 1)];
+        auto sendSigs = std::make_shared<SendSigs>(this, bestToSend, *sfl);
+        std::vector<GSFNode*> peers = sfl->getRemainingPeers(p->params.acceleratedCallsCount);
+        if (!peers.empty()) {
+          ++p->statMultiSends;
+          std::vector<Node*> dests(peers.begin(), peers.end());
+          p->network.send(sendSigs, *this, dests);
+        }
+      }
+    }
+    if (doneAt == 0 && verifiedSignatures.cardinality() >= p->params.threshold) doneAt = p->network.time;
+  }
+}
+
+inline int GSFSignature::GSFNode::evaluateSig(const SFLevel& l, const JBitSet& sig) const {  // :482-534
+  int newTotal = 0, addedSigs = 0;
+  if (l.verifiedSignatures.cardinality() >= l.expectedSigs()) return 0;
+  JBitSet withIndiv = l.indivVerifiedSig;
+  withIndiv.or_(sig);
+  if (l.verifiedSignatures.cardinality() == 0) {
+    newTotal = sig.cardinality();
+    addedSigs = newTotal;
+  } else {
+    if (sig.intersects(l.verifiedSignatures)) {
+      newTotal = withIndiv.cardinality();
+      addedSigs = newTotal - l.verifiedSignatures.cardinality();
+    } else {
+      withIndiv.or_(l.verifiedSignatures);
+      newTotal = withIndiv.cardinality();
+      addedSigs = newTotal - l.verifiedSignatures.cardinality();
+    }
+  }
+  if (addedSigs <= 0) {
+    if (sig.cardinality() == 1 && !sig.intersects(l.indivVerifiedSig)) return 1;
+    return 0;
+  }
+  if (newTotal == l.expectedSigs()) return 1000000 - l.level * 10;
+  return 100000 - l.level * 100 + addedSigs;
+}
+
+inline void GSFSignature::GSFNode::onNewSig(GSFNode* from, const SendSigsPtr& ssigs) {  // :537-555
+  SFLevel& l = levels[static_cast<size_t>(ssigs->level)];
+  // l.received.put(from, 1) feeds only the dead branch of getRemainingPeers (:337-345)
+  toVerify.push_back(ssigs);
+  if (!l.individualSignatures.get(from->nodeId)) {
+    JBitSet indiv;
+    indiv.set(from->nodeId);
+    toVerify.push_back(std::make_shared<SendSigs>(from, indiv, l));
+    l.individualSignatures.set(from->nodeId);
+  }
+  sigQueueSize = static_cast<int>(toVerify.size());
+  if (sigQueueSize > p->statMaxQueue) p->statMaxQueue = sigQueueSize;
+}
+
+inline void GSFSignature::GSFNode::checkSigs() {  // :557-583
+  SendSigsPtr best;
+  int score = 0;
+  size_t w = 0;
+  for (size_t i = 0; i < toVerify.size(); ++i) {
+    SendSigsPtr& cur = toVerify[i];
+    const SFLevel& l = levels[static_cast<size_t>(cur->level)];
+    ++p->statEvalEntries;
+    p->statEvalBytes += static_cast<int64_t>(cur->sigs.storedBytes());
+    int ns = evaluateSig(l, cur->sigs);
+    bool remove = false;
+    if (ns > score) {
+      score = ns;
+      best = cur;
+    } else if (ns == 0) {
+      remove = true;  // it.remove()
+    }
+    if (!remove) {
+      if (w != i) toVerify[w] = std::move(toVerify[i]);
+      ++w;
+    }
+  }
+  toVerify.resize(w);
+
+  if (best) {
+    // toVerify.remove(best): first element equal (identity) to best
+    for (size_t i = 0; i < toVerify.size(); ++i)
+      if (toVerify[i] == best) {
+        toVerify.erase(toVerify.begin() + static_cast<long>(i));
+        break;
+      }
+    sigChecked++;
+    sigQueueSize = static_cast<int>(toVerify.size());
+    SendSigsPtr tBest = best;
+    GSFNode* self = this;
+    p->network.registerTask([self, tBest] { self->updateVerifiedSignatures(tBest->from, tBest->level, tBest->sigs); },
+                            p->network.time + nodePairingTime, *this);
+  }
+}
+
+}  // namespace wo

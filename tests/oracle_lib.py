@@ -1,0 +1,207 @@
+"""ctypes binding of the CPU oracle (oracle/libwtg_oracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (wittgenstein_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "all"])
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = os.path.join(ORACLE_DIR, "libwtg_oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".hpp", ".cpp"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        build()
+    lib = C.CDLL(so)
+    lib.wo_last_error.restype = C.c_char_p
+    lib.wo_lcg_advance.restype = C.c_uint64
+    lib.wo_lcg_advance.argtypes = [C.c_uint64, C.c_uint64]
+    lib.wo_random_next_double.restype = C.c_double
+    lib.wo_random_next_double.argtypes = [C.c_int64, C.c_int]
+    lib.wo_gpd_inverse.restype = C.c_double
+    lib.wo_gpd_inverse.argtypes = [C.c_double] * 4
+    lib.wo_latency.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    for name in ("wo_pp_create", "wo_gsf_create"):
+        getattr(lib, name).restype = C.c_void_p
+    lib.wo_pp_create.argtypes = [C.c_int, C.c_char_p, C.c_char_p]
+    lib.wo_gsf_create.argtypes = [C.c_int] * 7 + [C.c_char_p, C.c_char_p]
+    lib.wo_gsf_run_timed.restype = C.c_double
+    lib.wo_gsf_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.wo_gsf_rng_state.restype = C.c_uint64
+    lib.wo_gsf_msgs_live.restype = C.c_int64
+    for name in dir(lib):
+        pass
+    _lib = lib
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _b(s):
+    return None if s is None else s.encode()
+
+
+class OraclePingPong:
+    """protocols/PingPong.java through the oracle."""
+
+    def __init__(self, node_ct=1000, node_builder=None, latency=None, seed=None):
+        self.lib = load()
+        self.n = node_ct
+        self.h = C.c_void_p(self.lib.wo_pp_create(node_ct, _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+        if seed is not None:
+            self.lib.wo_pp_set_seed(self.h, C.c_int64(seed))
+
+    def init(self):
+        if self.lib.wo_pp_init(self.h) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def run_ms(self, ms):
+        r = self.lib.wo_pp_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    @property
+    def time(self):
+        return self.lib.wo_pp_time(self.h)
+
+    def msgs_size(self):
+        return self.lib.wo_pp_msgs_size(self.h)
+
+    def pongs(self):
+        out = np.zeros(self.n, np.int32)
+        self.lib.wo_pp_pongs(self.h, _p(out, C.c_int32))
+        return out
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_pp_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_pp_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.wo_pp_destroy(self.h)
+            self.h = None
+
+
+class OracleGSF:
+    """protocols/GSFSignature.java through the oracle."""
+
+    def __init__(self, node_count, threshold, pairing_time, timeout_per_level_ms, period_ms, accelerated_calls, nodes_down,
+                 node_builder, latency, seed=None):
+        self.lib = load()
+        self.n = node_count
+        self.params = (node_count, threshold, pairing_time, timeout_per_level_ms, period_ms, accelerated_calls, nodes_down)
+        self.h = C.c_void_p(self.lib.wo_gsf_create(*self.params, _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+        if seed is not None:
+            self.lib.wo_gsf_set_seed(self.h, C.c_int64(seed))
+        self.words = (node_count + 63) // 64
+
+    def init(self):
+        if self.lib.wo_gsf_init(self.h) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        self.L = self.lib.wo_gsf_levels(self.h, 1)
+
+    def run_ms(self, ms):
+        r = self.lib.wo_gsf_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    def run_timed(self, ms, steps):
+        t = self.lib.wo_gsf_run_timed(self.h, ms, steps)
+        if t < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return t
+
+    @property
+    def time(self):
+        return self.lib.wo_gsf_time(self.h)
+
+    def msgs_size(self):
+        return self.lib.wo_gsf_msgs_size(self.h)
+
+    def msgs_live(self):
+        return self.lib.wo_gsf_msgs_live(self.h)
+
+    def continue_if(self):
+        return bool(self.lib.wo_gsf_continue_if(self.h))
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_gsf_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_gsf_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def scalars(self):
+        a = [np.zeros(self.n, np.int32) for _ in range(5)]
+        self.lib.wo_gsf_node_scalars(self.h, *[_p(v, C.c_int32) for v in a])
+        return dict(pairing=a[0], sig_checked=a[1], sig_queue_size=a[2], to_verify=a[3], card=a[4])
+
+    def verified(self):
+        out = np.zeros((self.n, self.words), np.uint64)
+        self.lib.wo_gsf_verified(self.h, _p(out, C.c_uint64), self.words)
+        return out
+
+    def level_rows(self, which):
+        out = np.zeros((self.n, self.words), np.uint64)
+        self.lib.wo_gsf_level_rows(self.h, which, _p(out, C.c_uint64), self.words)
+        return out
+
+    def level_scalars(self):
+        L = self.L
+        a = [np.zeros((self.n, L), np.int32) for _ in range(3)]
+        self.lib.wo_gsf_level_scalars(self.h, L, *[_p(v, C.c_int32) for v in a])
+        return dict(pos=a[0], remaining=a[1], card=a[2])
+
+    def peers(self, node, level):
+        cap = max(1, self.n)
+        out = np.zeros(cap, np.int32)
+        k = self.lib.wo_gsf_peers(self.h, node, level, _p(out, C.c_int32), cap)
+        return out[:k].copy()
+
+    def rng_state(self):
+        return int(self.lib.wo_gsf_rng_state(self.h))
+
+    def stats(self):
+        out = np.zeros(12, np.int64)
+        self.lib.wo_gsf_stats(self.h, _p(out, C.c_int64))
+        keys = ["deliveries", "tasks", "cond_runs", "draws", "eval_entries", "eval_bytes", "updates", "cycles", "sends",
+                "multi_sends", "send_bytes", "max_queue"]
+        return dict(zip(keys, out.tolist()))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.wo_gsf_destroy(self.h)
+            self.h = None
