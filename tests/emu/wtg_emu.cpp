@@ -1,0 +1,102 @@
+// TEST INFRASTRUCTURE — host-compiled instantiation of the device state-transition bodies
+// (wittgenstein_b200/csrc/wtg_logic.cuh) with a 1-lane coop, driven by the same Engine
+// orchestration.  Purpose: debug the exact-order logic of the tick pipeline against the oracle
+// on a machine without a GPU.  It is NOT part of the product: the package never loads it, and it
+// exports wtgemu_* symbols only.  Scans and the multisplit are plain sequential loops here; the
+// CUDA kernels that implement them are validated on the GPU by tests/ -m gpu.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../wittgenstein_b200/csrc/wtg_engine.hpp"
+
+namespace wtg {
+
+class HostBackend : public Backend {
+ public:
+  long long launches = 0;
+  void* alloc(size_t bytes) override { return std::calloc(1, bytes); }
+  void release(void* p) override { std::free(p); }
+  void upload(void* dst, const void* src, size_t bytes) override { std::memcpy(dst, src, bytes); }
+  void download(void* dst, const void* src, size_t bytes) override { std::memcpy(dst, src, bytes); }
+  void sync() override {}
+
+  void pairScan(const Dev& d, int which) {
+    int M = scanCount(d, which);
+    Pair run{0, 0};
+    for (int j = 0; j < M; ++j) {
+      Pair v = scanLoad(d, which, j);
+      scanStore(d, which, j, run);
+      run.a += v.a;
+      run.b += v.b;
+    }
+    scanTotals(d, which, run);
+  }
+  void tick(const Dev& d, int mode) override {
+    CoopSerial c;
+    std::vector<uint32_t> keep((size_t)std::max(1, d.qcap));
+    tickBegin(d, mode);
+    if (d.ctl->error) return;
+    if (d.proto == PROTO_GSF)
+      for (int n = 0; n < d.N; ++n) gsfCond(d, c, n, keep.data());
+    if (mode != 2) {
+      int nEv = d.ctl->nEv;
+      for (int i = 0; i < nEv; ++i) dispatchCount(d, i);
+      pairScan(d, 0);
+      if (d.ctl->error) return;
+      for (int i = 0; i < nEv; ++i) dispatchScatter(d, i);
+      for (int n = 0; n < d.N; ++n) nodeProcess(d, c, n);
+    }
+    pairScan(d, 1);
+    if (d.ctl->error) return;
+    for (int n = 0; n < d.N; ++n) emitCond(d, n);
+    for (int i = 0; i < d.ctl->nDesc; ++i) emitDesc(d, i);
+    // multisplit: stable append into the ring in creation order
+    int G = d.ctl->totalSlots;
+    for (int g = 0; g < G; ++g) {
+      int t = d.newTarget[g];
+      if (t < 0) continue;
+      int slot = t & (d.ring - 1);
+      int pos = d.bucketCount[slot];
+      if (pos >= d.bcap) {
+        setError(d, ERR_BUCKET_OVERFLOW, t);
+        continue;
+      }
+      d.buckets[(size_t)slot * d.bcap + pos] = d.newEv[g];
+      d.bucketCount[slot] = pos + 1;
+    }
+    int nf = std::min(d.ctl->freeTop, d.freeCap);
+    for (int i = 0; i < nf; ++i) freeApply(d, i);
+    tickEnd(d, mode);
+    launches += 1;
+  }
+  void gsfInitNodes(const Dev& d) override {
+    for (int n = 0; n < d.N; ++n) gsfInitNodeBody(d, n);
+  }
+  void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
+                     std::vector<unsigned long long>& out) override {
+    int cap = (int)(count / 256 + 65536);
+    std::vector<u64> buf((size_t)cap);
+    int cnt = 0;
+    rngCandidateChunk(d, s0, 0, count, maxBound, buf.data(), &cnt, cap);
+    if (cnt > cap) throw std::runtime_error("rng candidate list overflow");
+    out.assign(buf.begin(), buf.begin() + cnt);
+  }
+  void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) override {
+    for (int l = d.L - 1; l >= 1; --l)
+      for (int n = 0; n < d.N; ++n) {
+        if (d.peerBits == 16)
+          gsfShuffleLevel<uint16_t>(d, n, l, s0, liveRank, rejOrd, nRej);
+        else
+          gsfShuffleLevel<uint32_t>(d, n, l, s0, liveRank, rejOrd, nRej);
+      }
+  }
+};
+
+Backend* makeBackend() { return new HostBackend(); }
+long long backendLaunches(Backend* b) { return static_cast<HostBackend*>(b)->launches; }
+
+}  // namespace wtg
+
+#define WTG_API(name) wtgemu_##name
+#include "../../wittgenstein_b200/csrc/wtg_capi.inl"

@@ -1,0 +1,5 @@
+"""wittgenstein_b200 — B200-native discrete-event engine behind the Wittgenstein
+Protocol / Network / Node / Message surface (hot path only: see DESIGN.md)."""
+from ._lib import WtgError  # noqa: F401
+from .network import Network  # noqa: F401
+from .protocols import GSFSignature, GSFSignatureParameters, PingPong, PingPongParameters  # noqa: F401

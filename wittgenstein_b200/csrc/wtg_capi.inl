@@ -1,0 +1,277 @@
+// wittgenstein_b200 — C ABI implementation (see include/wtg.h for the contract and the reference
+// interface each entry point replaces).  Included by the CUDA backend translation unit with
+// WTG_API(name) = wtg_##name; the tests/emu debugging build includes it with another prefix.
+#include <cstring>
+#include <string>
+
+namespace wtg {
+Backend* makeBackend();
+long long backendLaunches(Backend* b);
+}  // namespace wtg
+
+namespace {
+thread_local std::string g_lastError;
+struct NetHandle {
+  wtg::Engine eng;
+  NetHandle() : eng(wtg::makeBackend()) {}
+};
+template <class F>
+int guard(F f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return -1;
+  } catch (...) {
+    g_lastError = "unknown error";
+    return -1;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* WTG_API(last_error)(void) { return g_lastError.c_str(); }
+
+void* WTG_API(create)(void) {
+  try {
+    return new NetHandle();
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return nullptr;
+  }
+}
+void WTG_API(destroy)(void* h) { delete static_cast<NetHandle*>(h); }
+
+#define ENG (static_cast<NetHandle*>(h)->eng)
+
+int WTG_API(set_seed)(void* h, long long seed) {
+  return guard([&] {
+    ENG.setSeed(seed);
+    return 0;
+  });
+}
+int WTG_API(set_network_latency)(void* h, const char* name) {
+  return guard([&] {
+    ENG.requireNotInited();
+    ENG.hm.setLatencyByName(name);
+    return 0;
+  });
+}
+int WTG_API(set_network_latency_measured)(void* h, const int* proportions, const int* values, int n) {
+  return guard([&] {
+    ENG.requireNotInited();
+    ENG.hm.setLatencyMeasured(proportions, values, n);
+    return 0;
+  });
+}
+int WTG_API(set_node_builder)(void* h, const char* name) {
+  return guard([&] {
+    ENG.requireNotInited();
+    ENG.hm.setBuilderByName(name);
+    return 0;
+  });
+}
+int WTG_API(set_msg_discard_time)(void* h, int ms) {
+  return guard([&] {
+    ENG.requireNotInited();
+    ENG.msgDiscardTime = ms;
+    return 0;
+  });
+}
+// capacities: key in {"bcap","qcap","pool_slots_per_node","desc_cap","rec_cap","ring"}
+int WTG_API(set_tunable)(void* h, const char* key, long long v) {
+  return guard([&] {
+    ENG.requireNotInited();
+    std::string k = key;
+    if (k == "bcap") ENG.tun.bcap = v;
+    else if (k == "qcap") ENG.tun.qcap = v;
+    else if (k == "pool_slots_per_node") ENG.tun.poolSlotsPerNode = v;
+    else if (k == "desc_cap") ENG.tun.descCap = v;
+    else if (k == "rec_cap") ENG.tun.recCap = v;
+    else if (k == "ring") ENG.tun.ring = v;
+    else throw std::invalid_argument("unknown tunable " + k);
+    return 0;
+  });
+}
+int WTG_API(pingpong_init)(void* h, int nodeCt) {
+  return guard([&] {
+    ENG.pingpongInit(nodeCt);
+    return 0;
+  });
+}
+int WTG_API(gsf_init)(void* h, const int* params7) {
+  return guard([&] {
+    wtg::GsfParams p{params7[0], params7[1], params7[2], params7[3], params7[4], params7[5], params7[6]};
+    ENG.gsfInit(p);
+    return 0;
+  });
+}
+int WTG_API(run_ms)(void* h, int ms) {
+  return guard([&] { return ENG.runMs(ms); });
+}
+int WTG_API(time)(void* h) { return ENG.time; }
+int WTG_API(node_count)(void* h) { return ENG.d.N; }
+int WTG_API(msgs_size)(void* h) {
+  return guard([&] { return ENG.msgsSize(); });
+}
+int WTG_API(msgs_size_at)(void* h, int t) {
+  return guard([&] { return ENG.msgsSizeAt(t); });
+}
+int WTG_API(stop_node)(void* h, int id) {
+  return guard([&] {
+    ENG.setDown(id, true);
+    return 0;
+  });
+}
+int WTG_API(start_node)(void* h, int id) {
+  return guard([&] {
+    ENG.setDown(id, false);
+    return 0;
+  });
+}
+int WTG_API(partition)(void* h, float part) {
+  return guard([&] {
+    ENG.partition(part);
+    return 0;
+  });
+}
+int WTG_API(end_partition)(void* h) {
+  return guard([&] {
+    ENG.endPartition();
+    return 0;
+  });
+}
+unsigned long long WTG_API(rng_state)(void* h) {
+  unsigned long long r = 0;
+  guard([&] {
+    r = ENG.inited ? ENG.readCtl().rng : ENG.hm.rd.seed;
+    return 0;
+  });
+  return r;
+}
+
+// ---- read-back -------------------------------------------------------------------------------
+// out5N: msgReceived[N], msgSent[N], bytesSent[N], bytesReceived[N], doneAt[N]
+int WTG_API(node_counters)(void* h, long long* out5N) {
+  return guard([&] {
+    ENG.requireInited();
+    size_t n = (size_t)ENG.d.N;
+    ENG.fetch(out5N + 0 * n, ENG.d.msgReceived, n);
+    ENG.fetch(out5N + 1 * n, ENG.d.msgSent, n);
+    ENG.fetch(out5N + 2 * n, ENG.d.bytesSent, n);
+    ENG.fetch(out5N + 3 * n, ENG.d.bytesReceived, n);
+    ENG.fetch(out5N + 4 * n, ENG.d.doneAt, n);
+    return 0;
+  });
+}
+int WTG_API(node_attrs)(void* h, int* x, int* y, int* extra, int* city, double* speed, unsigned char* down) {
+  return guard([&] {
+    ENG.requireInited();
+    for (int i = 0; i < ENG.d.N; ++i) {
+      const wtg::HostNode& n = ENG.hm.nodes[(size_t)i];
+      if (x) x[i] = n.x;
+      if (y) y[i] = n.y;
+      if (extra) extra[i] = n.extra;
+      if (city) city[i] = ENG.hm.builder == wtg::HostModel::B_AWS ? n.city : -1;
+      if (speed) speed[i] = n.speed;
+      if (down) down[i] = n.down ? 1 : 0;
+    }
+    return 0;
+  });
+}
+int WTG_API(pingpong_pongs)(void* h, int* out) {
+  return guard([&] {
+    ENG.requireInited();
+    if (ENG.d.proto != wtg::PROTO_PINGPONG) throw std::logic_error("not a PingPong network");
+    ENG.fetch(out, ENG.d.pong, (size_t)ENG.d.N);
+    return 0;
+  });
+}
+static void requireGsf(wtg::Engine& e) {
+  e.requireInited();
+  if (e.d.proto != wtg::PROTO_GSF) throw std::logic_error("not a GSFSignature network");
+}
+int WTG_API(gsf_levels)(void* h) { return ENG.d.L; }
+int WTG_API(gsf_verified)(void* h, unsigned long long* outNW) {
+  return guard([&] {
+    requireGsf(ENG);
+    ENG.fetch(outNW, ENG.d.verified, (size_t)ENG.d.N * ENG.d.W64);
+    return 0;
+  });
+}
+// which: 0 verified, 1 individualSignatures (seen), 2 indivVerifiedSig
+int WTG_API(gsf_rows)(void* h, int which, unsigned long long* outNW) {
+  return guard([&] {
+    requireGsf(ENG);
+    const unsigned long long* src = which == 0 ? ENG.d.verified : which == 1 ? ENG.d.indivSeen : ENG.d.indivVer;
+    ENG.fetch(outNW, src, (size_t)ENG.d.N * ENG.d.W64);
+    return 0;
+  });
+}
+int WTG_API(gsf_node_scalars)(void* h, int* pairing, int* sigChecked, int* sigQueueSize, int* toVerifySize, int* card) {
+  return guard([&] {
+    requireGsf(ENG);
+    size_t n = (size_t)ENG.d.N;
+    if (pairing) ENG.fetch(pairing, ENG.d.pairing, n);
+    if (sigChecked) ENG.fetch(sigChecked, ENG.d.sigChecked, n);
+    if (sigQueueSize) ENG.fetch(sigQueueSize, ENG.d.sigQueueSize, n);
+    if (toVerifySize) ENG.fetch(toVerifySize, ENG.d.qLen, n);
+    if (card) ENG.fetch(card, ENG.d.totalCard, n);
+    return 0;
+  });
+}
+// arrays of N*L, row-major by node
+int WTG_API(gsf_level_scalars)(void* h, int* pos, int* remaining, int* card) {
+  return guard([&] {
+    requireGsf(ENG);
+    size_t n = (size_t)ENG.d.N * ENG.d.L;
+    if (pos) ENG.fetch(pos, ENG.d.pos, n);
+    if (remaining) ENG.fetch(remaining, ENG.d.remaining, n);
+    if (card) ENG.fetch(card, ENG.d.cntVer, n);
+    return 0;
+  });
+}
+int WTG_API(gsf_peers)(void* h, int node, int level, int* out, int cap) {
+  return guard([&] {
+    requireGsf(ENG);
+    if (node < 0 || node >= ENG.d.N || level < 0 || level >= ENG.d.L) throw std::invalid_argument("node/level");
+    if (level == 0 || ENG.hm.nodes[(size_t)node].down) return 0;
+    int size = 1 << (level - 1);
+    size_t off = (size_t)node * (size_t)(ENG.d.N - 1) + (size_t)(size - 1);
+    int cnt = size < cap ? size : cap;
+    if (ENG.d.peerBits == 16) {
+      std::vector<unsigned short> tmp((size_t)cnt);
+      ENG.fetch(tmp.data(), (const unsigned short*)ENG.d.peers + off, (size_t)cnt);
+      int sib = wtg::levelBlock(node ^ (1 << (level - 1)), level).base;
+      for (int i = 0; i < cnt; ++i) out[i] = sib + tmp[(size_t)i];
+    } else {
+      std::vector<unsigned> tmp((size_t)cnt);
+      ENG.fetch(tmp.data(), (const unsigned*)ENG.d.peers + off, (size_t)cnt);
+      for (int i = 0; i < cnt; ++i) out[i] = (int)tmp[(size_t)i];
+    }
+    return size;
+  });
+}
+// stats (int64 x 24): deliveries, tasks, condRuns, draws, evalEntries, evalWords, updates, cycles, sends,
+// multiSends, sendWords, events, maxQueue, maxBucket, maxInbox, recTop, recDestTop, kernelLaunches,
+// minPoolFree (over levels), initDraws, ring, bcap, qcap, peerBits
+int WTG_API(stats)(void* h, long long* out24) {
+  return guard([&] {
+    ENG.requireInited();
+    wtg::Ctl c = ENG.readCtl();
+    long long minFree = -1;
+    for (int l = wtg::INLINE_MAX_LEVEL + 1; l < ENG.d.L; ++l)
+      if (minFree < 0 || c.poolMinFree[l] < minFree) minFree = c.poolMinFree[l];
+    long long v[24] = {(long long)c.statDeliveries, (long long)c.statTasks, (long long)c.statCondRuns, (long long)c.statDraws,
+                       (long long)c.statEvalEntries, (long long)c.statEvalWords, (long long)c.statUpdates, (long long)c.statCycles,
+                       (long long)c.statSends, (long long)c.statMultiSends, (long long)c.statSendWords, (long long)c.statEvents,
+                       c.maxQueue, c.maxBucket, c.maxInbox, c.recTop, c.recDestTop, wtg::backendLaunches(ENG.be.get()),
+                       minFree, (long long)ENG.initDraws, ENG.d.ring, ENG.d.bcap, ENG.d.qcap, ENG.d.peerBits};
+    std::memcpy(out24, v, sizeof(v));
+    return 0;
+  });
+}
+
+#undef ENG
+}  // extern "C"

@@ -1,0 +1,478 @@
+// wittgenstein_b200 — CUDA backend (sm_100a): the kernels of the tick pipeline and the C ABI.
+//
+// One simulated millisecond = one pass of this kernel sequence over SoA state resident in HBM:
+//   k_begin -> k_cond (conditional tasks, warp per node) -> k_dispatch_count -> pair scan A ->
+//   k_dispatch_scatter -> k_node (handlers, warp per node) -> pair scan B -> k_emit (seed / latency /
+//   arrival) -> multisplit (count, column scan, stable scatter into the time ring) -> k_free -> k_end
+// All sizes are read from the device control block, so a whole runMs window is enqueued without
+// a host round trip.  See DESIGN.md §4 for why this reproduces the reference's sequential order.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "wtg_engine.hpp"
+
+namespace wtg {
+
+#define CUDA_OK(x)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
+  } while (0)
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int NODE_BLOCK = WARPS_PER_BLOCK * 32;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void k_begin(Dev d, int mode) { tickBegin(d, mode); }
+__global__ void k_end(Dev d, int mode) { tickEnd(d, mode); }
+
+// ---- conditional tasks: warp per node ------------------------------------------------------
+__global__ void __launch_bounds__(NODE_BLOCK) k_cond(Dev d) {
+  extern __shared__ uint32_t keepAll[];
+  if (d.ctl->error) return;
+  int warp = threadIdx.x >> 5;
+  int n = blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (n >= d.N) return;
+  CoopWarp c;
+  gsfCond(d, c, n, keepAll + (size_t)warp * (size_t)(d.qcap / 32));
+}
+
+// ---- dispatch -----------------------------------------------------------------------------
+__global__ void k_dispatch_count(Dev d) {
+  if (d.ctl->error) return;
+  int nEv = d.ctl->nEv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEv; i += gridDim.x * blockDim.x) dispatchCount(d, i);
+}
+__global__ void k_dispatch_scatter(Dev d) {
+  if (d.ctl->error) return;
+  int nEv = d.ctl->nEv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEv; i += gridDim.x * blockDim.x) dispatchScatter(d, i);
+}
+
+// ---- handlers: warp per node ----------------------------------------------------------------
+__global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
+  if (d.ctl->error) return;
+  int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (n >= d.N) return;
+  CoopWarp c;
+  nodeProcess(d, c, n);
+}
+
+// ---- pair scans ---------------------------------------------------------------------------
+__device__ __forceinline__ Pair pairAdd(Pair x, Pair y) {
+  Pair r;
+  r.a = x.a + y.a;
+  r.b = x.b + y.b;
+  return r;
+}
+// exclusive scan of one value per thread across the block; returns the block total in `total`
+__device__ __forceinline__ Pair blockExclusive(Pair v, Pair& total) {
+  __shared__ Pair warpSums[33];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  Pair inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int ta = __shfl_up_sync(0xffffffffu, inc.a, o), tb = __shfl_up_sync(0xffffffffu, inc.b, o);
+    if (lane >= o) {
+      inc.a += ta;
+      inc.b += tb;
+    }
+  }
+  __syncthreads();  // warpSums may still be read by a previous call
+  if (lane == 31) warpSums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    Pair w;
+    w.a = lane < nw ? warpSums[lane].a : 0;
+    w.b = lane < nw ? warpSums[lane].b : 0;
+    Pair wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int ta = __shfl_up_sync(0xffffffffu, wi.a, o), tb = __shfl_up_sync(0xffffffffu, wi.b, o);
+      if (lane >= o) {
+        wi.a += ta;
+        wi.b += tb;
+      }
+    }
+    Pair ex;
+    ex.a = wi.a - w.a;
+    ex.b = wi.b - w.b;
+    warpSums[lane] = ex;
+    if (lane == 31) warpSums[32] = wi;
+  }
+  __syncthreads();
+  total = warpSums[32];
+  Pair base = warpSums[warp];
+  Pair r;
+  r.a = base.a + inc.a - v.a;
+  r.b = base.b + inc.b - v.b;
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(Dev d, int which) {
+  if (d.ctl->error) return;
+  int M = scanCount(d, which);
+  int nTiles = (M + SCAN_TILE - 1) / SCAN_TILE;
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    int j0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    Pair s;
+    s.a = 0;
+    s.b = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+      if (j0 + k < M) s = pairAdd(s, scanLoad(d, which, j0 + k));
+    Pair total;
+    blockExclusive(s, total);
+    if (threadIdx.x == 0) {
+      d.scanPartial[2 * tile] = total.a;
+      d.scanPartial[2 * tile + 1] = total.b;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(1024) k_scan_tiles(Dev d, int which) {
+  if (d.ctl->error) return;
+  int M = scanCount(d, which);
+  int nTiles = (M + SCAN_TILE - 1) / SCAN_TILE;
+  int per = (nTiles + 1023) / 1024;
+  int t0 = threadIdx.x * per;
+  Pair s;
+  s.a = 0;
+  s.b = 0;
+  for (int k = 0; k < per; ++k)
+    if (t0 + k < nTiles) {
+      s.a += d.scanPartial[2 * (t0 + k)];
+      s.b += d.scanPartial[2 * (t0 + k) + 1];
+    }
+  Pair total;
+  Pair ex = blockExclusive(s, total);
+  for (int k = 0; k < per; ++k)
+    if (t0 + k < nTiles) {
+      int a = d.scanPartial[2 * (t0 + k)], b = d.scanPartial[2 * (t0 + k) + 1];
+      d.scanPartial[2 * (t0 + k)] = ex.a;
+      d.scanPartial[2 * (t0 + k) + 1] = ex.b;
+      ex.a += a;
+      ex.b += b;
+    }
+  if (threadIdx.x == 0) scanTotals(d, which, total);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
+  if (d.ctl->error) return;
+  int M = scanCount(d, which);
+  int nTiles = (M + SCAN_TILE - 1) / SCAN_TILE;
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    int j0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    Pair v[SCAN_ITEMS];
+    Pair s;
+    s.a = 0;
+    s.b = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      if (j0 + k < M)
+        v[k] = scanLoad(d, which, j0 + k);
+      else {
+        v[k].a = 0;
+        v[k].b = 0;
+      }
+      s = pairAdd(s, v[k]);
+    }
+    Pair total;
+    Pair ex = blockExclusive(s, total);
+    ex.a += d.scanPartial[2 * tile];
+    ex.b += d.scanPartial[2 * tile + 1];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      if (j0 + k < M) scanStore(d, which, j0 + k, ex);
+      ex = pairAdd(ex, v[k]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- emit ------------------------------------------------------------------------------------
+__global__ void k_emit(Dev d) {
+  if (d.ctl->error) return;
+  int nDesc = d.ctl->nDesc;
+  int total = d.N + nDesc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < d.N)
+      emitCond(d, i);
+    else
+      emitDesc(d, i - d.N);
+  }
+}
+
+// ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
+// chunk = MS_CHUNK consecutive envelopes in creation order, one warp per chunk
+__global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) {
+  extern __shared__ int msHist[];  // [WARPS_PER_BLOCK][ring]
+  if (d.ctl->error) return;
+  int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
+  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* hist = msHist + warp * ring;
+  for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
+    for (int b = lane; b < ring; b += 32) hist[b] = 0;
+    __syncwarp();
+    int g0 = ch * MS_CHUNK;
+    for (int k = lane; k < MS_CHUNK; k += 32) {
+      int g = g0 + k;
+      if (g < G) {
+        int t = d.newTarget[g];
+        if (t >= 0) atomicAdd(&hist[t - tick], 1);
+      }
+    }
+    __syncwarp();
+    int* row = d.msCount + (size_t)ch * ring;
+    for (int b = lane; b < ring; b += 32) row[b] = hist[b];
+    __syncwarp();
+  }
+}
+// per ring bin: running offset over chunks, starting at the bucket's current fill
+__global__ void k_ms_scan(Dev d) {
+  if (d.ctl->error) return;
+  int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
+  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
+  if (nChunks == 0) return;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < ring; b += gridDim.x * blockDim.x) {
+    int slot = (tick + b) & (ring - 1);
+    int run = d.bucketCount[slot];
+    for (int ch = 0; ch < nChunks; ++ch) {
+      int* p = d.msCount + (size_t)ch * ring + b;
+      int v = *p;
+      *p = run;
+      run += v;
+    }
+    if (run > d.bcap) {
+      setError(d, ERR_BUCKET_OVERFLOW, tick + b);
+      run = d.bcap;
+    }
+    d.bucketCount[slot] = run;
+  }
+}
+__global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
+  extern __shared__ int msHist[];
+  if (d.ctl->error) return;
+  int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
+  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* base = msHist + warp * ring;
+  for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
+    const int* row = d.msCount + (size_t)ch * ring;
+    for (int b = lane; b < ring; b += 32) base[b] = row[b];
+    __syncwarp();
+    int g0 = ch * MS_CHUNK;
+    for (int k0 = 0; k0 < MS_CHUNK; k0 += 32) {
+      int g = g0 + k0 + lane;
+      int t = -1;
+      if (g < G) t = d.newTarget[g];
+      int bin = t >= 0 ? t - tick : -1 - lane;  // unique negative key for lanes without an envelope
+      unsigned peers = __match_any_sync(0xffffffffu, bin);
+      int rank = __popc(peers & ((1u << lane) - 1u));
+      int leader = __ffs(peers) - 1;
+      int b0 = 0;
+      if (t >= 0 && lane == leader) {
+        b0 = base[bin];
+        base[bin] = b0 + __popc(peers);
+      }
+      b0 = __shfl_sync(0xffffffffu, b0, leader);
+      if (t >= 0) {
+        int pos = b0 + rank;
+        if (pos < d.bcap) d.buckets[(size_t)(t & (ring - 1)) * (size_t)d.bcap + pos] = d.newEv[g];
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void k_free(Dev d) {
+  if (d.ctl->error) return;
+  int n = d.ctl->freeTop;
+  if (n > d.freeCap) n = d.freeCap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) freeApply(d, i);
+}
+
+// ---- init kernels ---------------------------------------------------------------------------
+__global__ void k_gsf_init_nodes(Dev d) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < d.N) gsfInitNodeBody(d, n);
+}
+__global__ void k_rng_candidates(Dev d, u64 s0, u64 count, u64 chunk, int maxBound, u64* out, int* outCount, int cap) {
+  u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 start = t * chunk;
+  if (start >= count) return;
+  u64 len = start + chunk <= count ? chunk : count - start;
+  rngCandidateChunk(d, s0, start, len, maxBound, out, outCount, cap);
+}
+template <class PeerT>
+__global__ void k_gsf_shuffle(Dev d, int l, u64 s0, const int* liveRank, const u64* rejOrd, int nRej) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < d.N) gsfShuffleLevel<PeerT>(d, n, l, s0, liveRank, rejOrd, nRej);
+}
+
+// ------------------------------------------------------------------------------------------------
+class CudaBackend : public Backend {
+ public:
+  cudaStream_t st = nullptr;
+  int sms = 148;
+  cudaGraphExec_t tickGraph = nullptr;
+  const void* graphFor = nullptr;
+  bool useGraph = true;
+  long long launches = 0;
+
+  CudaBackend() {
+    int dev = 0;
+    const char* e = std::getenv("LOCAL_RANK");
+    int cnt = 0;
+    CUDA_OK(cudaGetDeviceCount(&cnt));
+    if (cnt == 0) throw std::runtime_error("no CUDA device");
+    if (e) dev = std::atoi(e) % cnt;
+    const char* e2 = std::getenv("WTG_DEVICE");
+    if (e2) dev = std::atoi(e2) % cnt;
+    CUDA_OK(cudaSetDevice(dev));
+    cudaDeviceProp p;
+    CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    sms = p.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const char* g = std::getenv("WTG_NO_GRAPH");
+    if (g && g[0] == '1') useGraph = false;
+  }
+  ~CudaBackend() override {
+    if (tickGraph) cudaGraphExecDestroy(tickGraph);
+    if (st) cudaStreamDestroy(st);
+  }
+  void* alloc(size_t bytes) override {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) throw std::runtime_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    CUDA_OK(cudaMemsetAsync(p, 0, bytes, st));
+    return p;
+  }
+  void release(void* p) override { cudaFree(p); }
+  void upload(void* dst, const void* src, size_t bytes) override {
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  void download(void* dst, const void* src, size_t bytes) override {
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  void sync() override { CUDA_OK(cudaStreamSynchronize(st)); }
+
+  void enqueueTick(const Dev& d, int mode) {
+    const int nodeBlocks = (d.N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int wide = sms * 8;
+    const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    k_begin<<<1, 1, 0, st>>>(d, mode);
+    if (d.proto == PROTO_GSF) {
+      size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
+      k_cond<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
+      launches += 1;
+    }
+    if (mode != 2) {
+      k_dispatch_count<<<wide, 256, 0, st>>>(d);
+      k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
+      k_scan_tiles<<<1, 1024, 0, st>>>(d, 0);
+      k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
+      k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
+      k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      launches += 6;
+    }
+    k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
+    k_scan_tiles<<<1, 1024, 0, st>>>(d, 1);
+    k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
+    k_emit<<<wide, 256, 0, st>>>(d);
+    k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    k_ms_scan<<<(d.ring + 127) / 128, 128, 0, st>>>(d);
+    k_ms_scatter<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    k_free<<<sms, 256, 0, st>>>(d);
+    k_end<<<1, 1, 0, st>>>(d, mode);
+    launches += 10;
+  }
+  void configure(const Dev& d) {
+    size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    CUDA_OK(cudaFuncSetAttribute(k_ms_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
+    CUDA_OK(cudaFuncSetAttribute(k_ms_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
+  }
+  void tick(const Dev& d, int mode) override {
+    configure(d);
+    enqueueTick(d, mode);
+    CUDA_OK(cudaGetLastError());
+  }
+  void ticks(const Dev& d, int count) override {
+    configure(d);
+    if (!useGraph || count < 4) {
+      for (int i = 0; i < count; ++i) enqueueTick(d, 1);
+      CUDA_OK(cudaGetLastError());
+      return;
+    }
+    if (!tickGraph || graphFor != (const void*)d.ctl) {
+      if (tickGraph) cudaGraphExecDestroy(tickGraph);
+      cudaGraph_t g;
+      CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      enqueueTick(d, 1);
+      CUDA_OK(cudaStreamEndCapture(st, &g));
+      CUDA_OK(cudaGraphInstantiate(&tickGraph, g, 0));
+      cudaGraphDestroy(g);
+      graphFor = (const void*)d.ctl;
+    }
+    for (int i = 0; i < count; ++i) CUDA_OK(cudaGraphLaunch(tickGraph, st));
+  }
+  void gsfInitNodes(const Dev& d) override {
+    k_gsf_init_nodes<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+    CUDA_OK(cudaGetLastError());
+  }
+  void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
+                     std::vector<unsigned long long>& out) override {
+    const u64 chunk = 16384;
+    u64 threads = (count + chunk - 1) / chunk;
+    int cap = (int)std::min<u64>((u64)1 << 26, count / 1024 + (1 << 16));
+    u64* dOut = nullptr;
+    int* dCnt = nullptr;
+    CUDA_OK(cudaMalloc(&dOut, (size_t)cap * sizeof(u64)));
+    CUDA_OK(cudaMalloc(&dCnt, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(dCnt, 0, sizeof(int), st));
+    u64 blocks = (threads + 127) / 128;
+    k_rng_candidates<<<(unsigned)blocks, 128, 0, st>>>(d, s0, count, chunk, maxBound, dOut, dCnt, cap);
+    CUDA_OK(cudaGetLastError());
+    int n = 0;
+    CUDA_OK(cudaMemcpyAsync(&n, dCnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (n > cap) {
+      cudaFree(dOut);
+      cudaFree(dCnt);
+      throw std::runtime_error("rng candidate list overflow");
+    }
+    out.resize((size_t)n);
+    if (n) CUDA_OK(cudaMemcpyAsync(out.data(), dOut, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(dOut);
+    cudaFree(dCnt);
+  }
+  void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) override {
+    for (int l = d.L - 1; l >= 1; --l) {
+      if (d.peerBits == 16)
+        k_gsf_shuffle<uint16_t><<<(d.N + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
+      else
+        k_gsf_shuffle<uint32_t><<<(d.N + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+};
+
+Backend* makeBackend() { return new CudaBackend(); }
+long long backendLaunches(Backend* b) { return static_cast<CudaBackend*>(b)->launches; }
+
+}  // namespace wtg
+
+#define WTG_API(name) wtg_##name
+#include "wtg_capi.inl"

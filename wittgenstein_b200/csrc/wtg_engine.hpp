@@ -1,0 +1,533 @@
+// wittgenstein_b200 — engine orchestration: owns the device state, runs protocol init and the
+// runMs tick loop through a Backend (the CUDA backend in wtg_cuda.cu; a host backend exists only
+// under tests/emu for debugging the exact-order logic).
+//
+// Reference surface mirrored here (core/Network.java): runMs :318-338, setNetworkLatency
+// :665-677, partition :693-707, msgs.size() :204-210, time :49, rd :32; Protocol.init() of
+// protocols/PingPong.java:82-87 and protocols/GSFSignature.java:611-635.
+#pragma once
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "wtg_host.hpp"
+#include "wtg_logic.cuh"
+#include "wtg_types.h"
+
+namespace wtg {
+
+struct GsfParams {
+  int nodeCount, threshold, pairingTime, timeoutPerLevelMs, periodDurationMs, acceleratedCallsCount, nodesDown;
+};
+
+struct Tunables {  // capacities; 0 = derive from N
+  long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
+};
+
+struct Backend {
+  virtual ~Backend() {}
+  virtual void* alloc(size_t bytes) = 0;  // zero-initialised device memory
+  virtual void release(void* p) = 0;
+  virtual void upload(void* dst, const void* src, size_t bytes) = 0;
+  virtual void download(void* dst, const void* src, size_t bytes) = 0;
+  virtual void sync() = 0;
+  // one tick of the pipeline; mode 0 = messages of the current time only, 1 = clock tick + conditional
+  // tasks + messages, 2 = end-of-window conditional pass
+  virtual void tick(const Dev& d, int mode) = 0;
+  // `count` consecutive mode-1 ticks (lets the CUDA backend replay a captured graph)
+  virtual void ticks(const Dev& d, int count) {
+    for (int i = 0; i < count; ++i) tick(d, 1);
+  }
+  virtual void gsfInitNodes(const Dev& d) = 0;
+  // scan `count` stream positions after state s0 for values that nextInt(bound<=maxBound) could reject
+  virtual void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
+                             std::vector<unsigned long long>& out) = 0;
+  // Fisher-Yates of every (live node, level) peer list; rejOrd = sorted ordinals of rejected draws
+  virtual void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) = 0;
+};
+
+class Engine {
+ public:
+  std::unique_ptr<Backend> be;
+  HostModel hm;
+  Dev d;
+  Tunables tun;
+  std::vector<void*> allocs;
+  bool inited = false;
+  int time = 0;
+  int ringMask = 0;
+  bool pendingAtNow = false;  // host inserted an event arriving at the current time
+  std::vector<int> partitionsInX;
+  int msgDiscardTime = 0x7fffffff;
+  std::string err;
+  std::vector<int> liveRank;  // GSF: rank among live nodes, -1 when down
+  unsigned long long initDraws = 0;
+
+  explicit Engine(Backend* b) : be(b) { std::memset(&d, 0, sizeof(d)); }
+  ~Engine() { freeAll(); }
+
+  void freeAll() {
+    for (void* p : allocs) be->release(p);
+    allocs.clear();
+  }
+  template <class T>
+  T* dalloc(size_t n) {
+    void* p = be->alloc(std::max<size_t>(n, 1) * sizeof(T));
+    allocs.push_back(p);
+    return (T*)p;
+  }
+  template <class T>
+  T* dupload(const std::vector<T>& v) {
+    T* p = dalloc<T>(v.size());
+    if (!v.empty()) be->upload(p, v.data(), v.size() * sizeof(T));
+    return p;
+  }
+  void requireNotInited() const {
+    if (inited) throw std::logic_error("network already initialised");
+  }
+  void requireInited() const {
+    if (!inited) throw std::logic_error("protocol not initialised");
+  }
+
+  // ---- configuration (before init) ----
+  void setSeed(long long s) {
+    requireNotInited();
+    hm.rd.setSeed(s);
+  }
+
+  // ---- common device state ----
+  void allocCommon(int N, int proto) {
+    d.N = N;
+    d.proto = proto;
+    d.msgDiscardTime = msgDiscardTime;
+    int ring = 2048;
+    int need = hm.latMax + 64;
+    while (ring < need) ring <<= 1;
+    if (tun.ring) ring = (int)tun.ring;
+    d.ring = ring;
+    ringMask = ring - 1;
+    long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 4LL * N);
+    d.bcap = (int)bcap;
+    d.itemCap = (int)(2 * bcap + 1024);
+    d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 24LL * N));
+    d.destScratchCap = d.descCap;
+    d.newEvCap = d.descCap + N;
+    d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * N));
+    d.recDestCap = d.recCap * 4 + N + 1024;
+    d.freeCap = d.descCap;
+    d.latKind = hm.latKind;
+    d.latParam = hm.latParam;
+
+    d.ctl = dalloc<Ctl>(1);
+    std::vector<int16_t> x(N), y(N), ex(N);
+    std::vector<uint8_t> city(N), down(N), part(N, 0);
+    for (int i = 0; i < N; ++i) {
+      x[i] = (int16_t)hm.nodes[i].x;
+      y[i] = (int16_t)hm.nodes[i].y;
+      ex[i] = (int16_t)hm.nodes[i].extra;
+      city[i] = (uint8_t)hm.nodes[i].city;
+      down[i] = hm.nodes[i].down ? 1 : 0;
+    }
+    d.nx = dupload(x);
+    d.ny = dupload(y);
+    d.nextra = dupload(ex);
+    d.ncity = dupload(city);
+    d.ndown = dupload(down);
+    d.npart = dupload(part);
+    d.msgReceived = dalloc<long long>(N);
+    d.msgSent = dalloc<long long>(N);
+    d.bytesSent = dalloc<long long>(N);
+    d.bytesReceived = dalloc<long long>(N);
+    d.doneAt = dalloc<long long>(N);
+    d.latTab = dupload(hm.latTab);
+    d.latBase = dupload(hm.latBase);
+    d.latJit = dupload(hm.latJit);
+    std::vector<unsigned long long> ja(48), jc(48);
+    lcgJumpTables((uint64_t*)ja.data(), (uint64_t*)jc.data());
+    d.jumpA = dupload(ja);
+    d.jumpC = dupload(jc);
+    d.buckets = dalloc<Ev>((size_t)ring * (size_t)d.bcap);
+    d.bucketCount = dalloc<int>(ring);
+    d.inboxCnt = dalloc<int>(N);
+    d.inboxOff = dalloc<int>(N);
+    d.inboxFill = dalloc<int>(N);
+    d.inbox = dalloc<unsigned long long>((size_t)d.itemCap);
+    d.subCount = dalloc<int>(d.bcap);
+    d.itemBase = dalloc<int>(d.bcap);
+    d.evSlots = dalloc<int>(d.itemCap);
+    d.evDraws = dalloc<int>(d.itemCap);
+    d.condFired = dalloc<int>(N);
+    d.condEv = dalloc<Ev>(N);
+    d.condTarget = dalloc<int>(N);
+    d.slotBase = dalloc<int>((size_t)N + d.itemCap);
+    d.drawBase = dalloc<int>((size_t)N + d.itemCap);
+    d.scanPartial = dalloc<int>(2 * 8192);
+    d.desc = dalloc<Desc>(d.descCap);
+    d.destScratch = dalloc<uint32_t>(d.destScratchCap);
+    d.newEv = dalloc<Ev>(d.newEvCap);
+    d.newTarget = dalloc<int>(d.newEvCap);
+    d.msChunks = (d.newEvCap + MS_CHUNK - 1) / MS_CHUNK;
+    d.msCount = dalloc<int>((size_t)d.msChunks * (size_t)ring);
+    d.rec = dalloc<MultiRec>(d.recCap);
+    d.recDest = dalloc<uint32_t>(d.recDestCap);
+    d.recArrival = dalloc<int>(d.recDestCap);
+    d.freeList = dalloc<uint32_t>(d.freeCap);
+  }
+
+  Ctl readCtl() {
+    Ctl c;
+    be->sync();
+    be->download(&c, d.ctl, sizeof(Ctl));
+    return c;
+  }
+  void writeCtl(const Ctl& c) { be->upload(d.ctl, &c, sizeof(Ctl)); }
+
+  void checkLatencyBuilder() const {
+    if (hm.latKind == LAT_CITY && hm.builder != HostModel::B_AWS)
+      throw std::invalid_argument("AwsRegionNetworkLatency needs nodes built by an AWS_* node builder");  // NetworkLatency.java:146-148
+  }
+
+  // ---- PingPong.init()  (protocols/PingPong.java:82-87) ----
+  void pingpongInit(int nodeCt) {
+    requireNotInited();
+    if (nodeCt <= 0) throw std::invalid_argument("nodeCt");
+    checkLatencyBuilder();
+    hm.buildNodes(nodeCt);
+    allocCommon(nodeCt, PROTO_PINGPONG);
+    d.pong = dalloc<int>(nodeCt);
+    // network.sendAll(new Ping(), node0): one draw, per-destination arrival, stable sort (Network.java:420-467)
+    int32_t seed = hm.rd.nextInt();
+    Dev hd = hostView();
+    struct Arr {
+      int arrival;
+      uint32_t dest;
+    };
+    std::vector<Arr> da;
+    for (int to = 0; to < nodeCt; ++to) {
+      int nt = latency(hd, 0, to, pseudoRandom(to, seed));
+      if (nt < msgDiscardTime) da.push_back({1 + nt, (uint32_t)to});
+    }
+    std::stable_sort(da.begin(), da.end(), [](const Arr& a, const Arr& b) { return a.arrival < b.arrival; });
+    std::vector<long long> sent(nodeCt, 0);
+    sent[0] = nodeCt;  // msgSent++ / bytesSent += 1 per destination (Network.java:476-477)
+    be->upload(d.msgSent, sent.data(), sizeof(long long) * nodeCt);
+    be->upload(d.bytesSent, sent.data(), sizeof(long long) * nodeCt);
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    c.callId = 1;
+    if (!da.empty()) {
+      if ((int)da.size() > d.recDestCap) throw std::runtime_error("record arena too small");
+      Ev ev;
+      std::memset(&ev, 0, sizeof(ev));
+      ev.from = 0;
+      ev.meta = PP_PING;
+      ev.to = da[0].dest;
+      if (da.size() == 1) {
+        ev.kind = EV_MSG;
+      } else {
+        ev.kind = EV_MULTI;
+        ev.aux = 0;
+        MultiRec rc;
+        std::memset(&rc, 0, sizeof(rc));
+        rc.from = 0;
+        rc.meta = PP_PING;
+        rc.n = (uint32_t)da.size();
+        rc.cur = 0;
+        rc.off = 0;
+        be->upload(d.rec, &rc, sizeof(rc));
+        std::vector<uint32_t> dst(da.size());
+        std::vector<int> arr(da.size());
+        for (size_t i = 0; i < da.size(); ++i) {
+          dst[i] = da[i].dest;
+          arr[i] = da[i].arrival;
+        }
+        be->upload(d.recDest, dst.data(), dst.size() * 4);
+        be->upload(d.recArrival, arr.data(), arr.size() * 4);
+        c.recTop = 1;
+        c.recDestTop = (int)da.size();
+      }
+      int tgt = da[0].arrival;
+      if (tgt >= d.ring) throw std::runtime_error("latency exceeds the time ring");
+      be->upload(d.buckets + (size_t)(tgt & ringMask) * d.bcap, &ev, sizeof(ev));
+      int one = 1;
+      be->upload(d.bucketCount + (tgt & ringMask), &one, sizeof(int));
+    }
+    c.rng = hm.rd.seed;
+    writeCtl(c);
+    inited = true;
+  }
+
+  // host-side view of node attributes for the few latency evaluations done at init
+  std::vector<int16_t> hx_, hy_, hex_;
+  std::vector<uint8_t> hcity_;
+  Dev hostView() {
+    int N = (int)hm.nodes.size();
+    hx_.resize(N);
+    hy_.resize(N);
+    hex_.resize(N);
+    hcity_.resize(N);
+    for (int i = 0; i < N; ++i) {
+      hx_[i] = (int16_t)hm.nodes[i].x;
+      hy_[i] = (int16_t)hm.nodes[i].y;
+      hex_[i] = (int16_t)hm.nodes[i].extra;
+      hcity_[i] = (uint8_t)hm.nodes[i].city;
+    }
+    Dev h;
+    std::memset(&h, 0, sizeof(h));
+    h.N = N;
+    h.nx = hx_.data();
+    h.ny = hy_.data();
+    h.nextra = hex_.data();
+    h.ncity = hcity_.data();
+    h.latKind = hm.latKind;
+    h.latParam = hm.latParam;
+    h.latTab = hm.latTab.data();
+    h.latBase = hm.latBase.data();
+    h.latJit = hm.latJit.data();
+    return h;
+  }
+
+  // ---- GSFSignature.init()  (protocols/GSFSignature.java:611-635) ----
+  GsfParams gp{};
+  void gsfInit(const GsfParams& p) {
+    requireNotInited();
+    const int N = p.nodeCount;
+    if (p.nodesDown >= N || p.nodesDown < 0 || p.threshold > N || (p.nodesDown + p.threshold > N))  // :69-74
+      throw std::invalid_argument("nodeCount=" + std::to_string(N) + ", threshold=" + std::to_string(p.threshold));
+    if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("the B200 engine needs a power-of-two nodeCount >= 2 for GSFSignature");
+    if (p.acceleratedCallsCount > MAX_ACC || p.acceleratedCallsCount < 0) throw std::invalid_argument("acceleratedCallsCount must be in [0,16]");
+    if (p.periodDurationMs <= 0 || p.pairingTime < 0) throw std::invalid_argument("period/pairing");
+    checkLatencyBuilder();
+    gp = p;
+    hm.buildNodes(N);
+    // dead nodes: nextInt(nodeCount) until nodesDown distinct ids != 1 are chosen (:617-625)
+    for (int setDown = 0; setDown < p.nodesDown;) {
+      int down = hm.rd.nextInt(N);
+      if (!hm.nodes[down].down && down != 1) {
+        hm.nodes[down].down = true;
+        setDown++;
+      }
+    }
+    int L = 1;
+    while ((1 << L) <= N) ++L;  // levels 0..log2(N)   (:186)
+    allocCommon(N, PROTO_GSF);
+    d.L = L;
+    d.W64 = std::max(1, N / 64);
+    d.threshold = p.threshold;
+    d.timeoutPerLevel = p.timeoutPerLevelMs;
+    d.period = p.periodDurationMs;
+    d.accel = p.acceleratedCallsCount;
+    d.qcap = (int)(tun.qcap ? tun.qcap : std::min<long long>(4096, std::max<long long>(64, 2LL * N)));
+    d.qcap = (d.qcap + 31) / 32 * 32;
+    d.verified = dalloc<unsigned long long>((size_t)N * d.W64);
+    d.indivSeen = dalloc<unsigned long long>((size_t)N * d.W64);
+    d.indivVer = dalloc<unsigned long long>((size_t)N * d.W64);
+    d.pos = dalloc<int>((size_t)N * L);
+    d.remaining = dalloc<int>((size_t)N * L);
+    d.cntVer = dalloc<int>((size_t)N * L);
+    d.cntIndiv = dalloc<int>((size_t)N * L);
+    d.cntUnion = dalloc<int>((size_t)N * L);
+    d.totalCard = dalloc<int>(N);
+    d.minStart = dalloc<int>(N);
+    d.stamp = dalloc<uint32_t>(N);
+    d.qLen = dalloc<int>(N);
+    d.sigChecked = dalloc<int>(N);
+    d.sigQueueSize = dalloc<int>(N);
+    d.queue = dalloc<QEntry>((size_t)N * d.qcap);
+    std::vector<int> pairing(N);
+    for (int i = 0; i < N; ++i) pairing[i] = (int)std::max(1.0, p.pairingTime * hm.nodes[i].speed);  // :170
+    d.pairing = dupload(pairing);
+    d.peerBits = (N / 2 <= 65536) ? 16 : 32;
+    d.peers = be->alloc((size_t)N * (size_t)(N - 1) * (size_t)(d.peerBits / 8));
+    allocs.push_back(d.peers);
+    // payload pools for levels whose block is wider than one word
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
+    for (int l = INLINE_MAX_LEVEL + 1; l < L; ++l) {
+      long long slots = std::max<long long>(1024, perNode * N);
+      d.poolCap[l] = (int)slots;
+      d.pool[l] = dalloc<unsigned long long>((size_t)slots * (size_t)poolWords(l));
+      std::vector<uint32_t> fl((size_t)slots);
+      for (long long i = 0; i < slots; ++i) fl[(size_t)i] = (uint32_t)(slots - 1 - i);
+      d.poolFree[l] = dupload(fl);
+      c.poolFreeCnt[l] = (int)slots;
+      c.poolMinFree[l] = (int)slots;
+    }
+    c.callId = 1;
+    writeCtl(c);
+    be->gsfInitNodes(d);
+
+    // peer lists: Collections.shuffle of every level of every live node on the network RNG (:462-476)
+    liveRank.assign(N, -1);
+    int live = 0;
+    for (int i = 0; i < N; ++i)
+      if (!hm.nodes[i].down) liveRank[i] = live++;
+    const unsigned long long D = (unsigned long long)(N - L);  // draws per node without rejections
+    unsigned long long s0 = hm.rd.seed;
+    std::vector<unsigned long long> rejOrd;
+    if (N > 2) {
+      std::vector<unsigned long long> cand;
+      unsigned long long nominal = (unsigned long long)live * D;
+      be->rngCandidates(d, s0, nominal + nominal / 16384 + 4096, N / 2, cand);
+      std::sort(cand.begin(), cand.end());
+      // serial fix-up: which candidates are real rejections, and how far they shift the stream
+      unsigned long long shift = 0;
+      for (unsigned long long pos : cand) {
+        unsigned long long o = pos - shift;
+        if (o >= nominal) break;
+        unsigned long long rem = o % D;
+        int l = 1;
+        while (true) {  // level whose draw range contains rem: cum(l) = 2^(l-1) - l
+          unsigned long long nxt = (1ULL << l) - (unsigned long long)(l + 1);
+          if (rem < nxt) break;
+          ++l;
+        }
+        unsigned long long cum = (1ULL << (l - 1)) - (unsigned long long)l;
+        int bound = (1 << (l - 1)) - (int)(rem - cum);
+        if ((bound & (bound - 1)) == 0) continue;
+        uint64_t st = lcgAdvance((const u64*)hostJumpA(), (const u64*)hostJumpC(), s0, pos + 1);
+        int32_t u = (int32_t)(uint32_t)(st >> 17);  // next(31)
+        int32_t r = u % bound;
+        if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)(bound - 1)) < 0) {
+          rejOrd.push_back(o);
+          ++shift;
+        }
+      }
+      unsigned long long total = nominal + shift;
+      hm.rd.seed = lcgAdvance((const u64*)hostJumpA(), (const u64*)hostJumpC(), s0, total);
+      initDraws = total;
+    }
+    int* dRank = dupload(liveRank);
+    unsigned long long* dRej = dupload(rejOrd);
+    be->gsfShufflePeers(d, s0, dRank, dRej, (int)rejOrd.size());
+
+    // registerPeriodicTask(doCycle, 1, period) for live nodes in id order (:630) -> bucket of ms 1
+    std::vector<Ev> per;
+    for (int i = 0; i < N; ++i)
+      if (!hm.nodes[i].down) {
+        Ev ev;
+        std::memset(&ev, 0, sizeof(ev));
+        ev.kind = EV_PERIODIC;
+        ev.to = (uint32_t)i;
+        ev.from = (uint32_t)i;
+        per.push_back(ev);
+      }
+    if ((int)per.size() > d.bcap) throw std::runtime_error("bucket capacity too small");
+    be->upload(d.buckets + (size_t)1 * d.bcap, per.data(), per.size() * sizeof(Ev));
+    int cnt = (int)per.size();
+    be->upload(d.bucketCount + 1, &cnt, sizeof(int));
+    c = readCtl();
+    c.rng = hm.rd.seed;
+    writeCtl(c);
+    inited = true;
+  }
+  uint64_t hja_[48], hjc_[48];
+  bool hjInit_ = false;
+  const uint64_t* hostJumpA() {
+    if (!hjInit_) {
+      lcgJumpTables(hja_, hjc_);
+      hjInit_ = true;
+    }
+    return hja_;
+  }
+  const uint64_t* hostJumpC() {
+    hostJumpA();
+    return hjc_;
+  }
+
+  // ---- runMs  (Network.java:318-338) ----
+  int runMs(int ms) {
+    requireInited();
+    if (ms <= 0) throw std::invalid_argument("Should be greater than 0. ms=" + std::to_string(ms));
+    long long endAt = (long long)time + ms;
+    if (endAt > 0x7fffffffLL) throw std::runtime_error("Maximum time reached!");
+    Ctl c = readCtl();
+    if (c.error) throwDeviceError(c);
+    c.until = (int)endAt;
+    c.callId += 1;  // a new nextMessage() call starts with the window
+    c.didSomething = 0;
+    writeCtl(c);
+    if (pendingAtNow) {
+      be->tick(d, 0);
+      pendingAtNow = false;
+    }
+    be->ticks(d, ms);
+    be->tick(d, 2);
+    c = readCtl();
+    if (c.error) throwDeviceError(c);
+    time = (int)endAt;
+    if (c.time != time) throw std::runtime_error("internal: device clock out of step");
+    return c.didSomething ? 1 : 0;
+  }
+  void throwDeviceError(const Ctl& c) {
+    static const char* names[] = {"ok", "time-bucket capacity exceeded", "toVerify queue capacity exceeded", "payload pool exhausted",
+                                  "arrival beyond the time ring", "descriptor arena exceeded", "multi-destination record arena exceeded",
+                                  "deferred-free list exceeded", "internal error", "inbox overflow"};
+    throw std::runtime_error(std::string("device engine error: ") + names[c.error < 10 ? c.error : 8] + " (detail " + std::to_string(c.errorDetail) + ")");
+  }
+
+  int msgsSize() {
+    requireInited();
+    std::vector<int> bc(d.ring);
+    be->sync();
+    be->download(bc.data(), d.bucketCount, sizeof(int) * d.ring);
+    long long s = 0;
+    for (int v : bc) s += v;
+    return (int)s;
+  }
+  int msgsSizeAt(int t) {
+    requireInited();
+    if (t < time || t >= time + d.ring) return 0;
+    int v;
+    be->sync();
+    be->download(&v, d.bucketCount + (t & ringMask), sizeof(int));
+    return v;
+  }
+
+  void setDown(int id, bool down) {
+    requireInited();
+    if (id < 0 || id >= d.N) throw std::invalid_argument("node id");
+    hm.nodes[id].down = down;
+    uint8_t v = down ? 1 : 0;
+    be->sync();
+    be->upload(d.ndown + id, &v, 1);
+  }
+  void uploadPartitions() {
+    std::vector<uint8_t> part(d.N);
+    for (int i = 0; i < d.N; ++i) {
+      int pId = 0;  // Network.java:639-649
+      for (int x : partitionsInX) {
+        if (x > hm.nodes[i].x) break;
+        pId++;
+      }
+      part[i] = (uint8_t)pId;
+    }
+    be->sync();
+    be->upload(d.npart, part.data(), part.size());
+  }
+  void partition(float part) {  // Network.java:693-703
+    requireInited();
+    if (part <= 0 || part >= 1) throw std::invalid_argument("part needs to be a percentage between 0 & 100 excluded");
+    int xPoint = (int)(2000 * part);
+    if (std::find(partitionsInX.begin(), partitionsInX.end(), xPoint) != partitionsInX.end())
+      throw std::invalid_argument("this partition exists already");
+    partitionsInX.push_back(xPoint);
+    std::sort(partitionsInX.begin(), partitionsInX.end());
+    uploadPartitions();
+  }
+  void endPartition() {
+    requireInited();
+    partitionsInX.clear();
+    uploadPartitions();
+  }
+
+  template <class T>
+  void fetch(T* out, const T* dev, size_t n) {
+    be->sync();
+    be->download(out, dev, n * sizeof(T));
+  }
+};
+
+}  // namespace wtg

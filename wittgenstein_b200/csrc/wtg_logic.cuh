@@ -1,0 +1,1323 @@
+// wittgenstein_b200 — state-transition bodies of the tick engine.
+//
+// Every function here is the body of one CUDA kernel work item.  Work items that touch
+// bitmaps are executed by one warp ("coop" = 32 lanes: lane-strided 64-bit loads over the
+// level block + warp reductions); scalar control flow is warp-uniform.  The same bodies are
+// instantiated with a 1-lane coop by the host-side unit tests (tests/emu) to debug the
+// exact-order logic without a GPU; the product library only ever runs the CUDA instantiation.
+//
+// Reference semantics restated here (file:line are under /root/reference):
+//   core/Network.java:493-503   getPseudoRandom / hash                  -> pseudoRandom
+//   core/NetworkLatency.java:27-34 getLatency                            -> latency
+//   core/Network.java:533-570   conditional-task polling                 -> gsfCond
+//   protocols/GSFSignature.java:482-534 evaluateSig                      -> gsfScore*
+//   protocols/GSFSignature.java:557-583 checkSigs                        -> gsfCheckSigs
+//   protocols/GSFSignature.java:537-555 onNewSig                         -> gsfOnNewSig
+//   protocols/GSFSignature.java:384-460 updateVerifiedSignatures         -> gsfUpdate
+//   protocols/GSFSignature.java:212-224, 313-349 doCycle/getRemainingPeers -> gsfCycle
+//   protocols/PingPong.java:60-87                                        -> ppDeliver
+#pragma once
+#include "wtg_types.h"
+
+// host stand-ins (single-threaded debugging build / nvcc host pass of __host__ __device__ bodies)
+template <class T, class U>
+static inline T wtg_host_fetch_add(T* p, U v) {
+  T o = *p;
+  *p = (T)(o + (T)v);
+  return o;
+}
+template <class T>
+static inline T wtg_host_fetch_max(T* p, T v) {
+  T o = *p;
+  if (v > o) *p = v;
+  return o;
+}
+template <class T>
+static inline T wtg_host_fetch_min(T* p, T v) {
+  T o = *p;
+  if (v < o) *p = v;
+  return o;
+}
+template <class T>
+static inline T wtg_host_cas(T* p, T a, T b) {
+  T o = *p;
+  if (o == a) *p = b;
+  return o;
+}
+#if defined(__CUDA_ARCH__)
+#define WTG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define WTG_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define WTG_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define WTG_ATOMIC_CAS(p, a, b) atomicCAS((p), (a), (b))
+#define WTG_POPC64(x) __popcll(x)
+#else
+#define WTG_ATOMIC_ADD(p, v) wtg_host_fetch_add((p), (v))
+#define WTG_ATOMIC_MAX(p, v) wtg_host_fetch_max((p), (v))
+#define WTG_ATOMIC_MIN(p, v) wtg_host_fetch_min((p), (v))
+#define WTG_ATOMIC_CAS(p, a, b) wtg_host_cas((p), (a), (b))
+#define WTG_POPC64(x) __builtin_popcountll(x)
+#endif
+
+namespace wtg {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------
+// coop: the group of lanes that executes one work item
+// ------------------------------------------------------------------------------------------
+struct CoopSerial {
+  static constexpr int LANES = 1;
+  WTG_HD int lane() const { return 0; }
+  WTG_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+  WTG_HD int sum(int v) const { return v; }
+  WTG_HD int maxv(int v) const { return v; }
+  WTG_HD int minv(int v) const { return v; }
+  WTG_HD bool any(bool p) const { return p; }
+  WTG_HD int bcast(int v, int) const { return v; }
+  WTG_HD u64 bcast64(u64 v, int) const { return v; }
+  WTG_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+struct CoopWarp {
+  static constexpr int LANES = 32;
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+  __device__ __forceinline__ int maxv(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+  __device__ __forceinline__ int minv(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+  __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ u64 bcast64(u64 v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+#endif
+
+WTG_HD void setError(const Dev& d, int code, int detail) {
+  if (WTG_ATOMIC_CAS(&d.ctl->error, 0, code) == 0) d.ctl->errorDetail = detail;
+}
+
+// ------------------------------------------------------------------------------------------
+// java.util.Random stream addressing: state after n steps, from 48 (a,c) power tables
+// ------------------------------------------------------------------------------------------
+constexpr u64 LCG_MASK = (1ULL << 48) - 1;
+WTG_HD u64 lcgAdvance(const u64* jumpA, const u64* jumpC, u64 s, u64 n) {
+  for (int i = 0; n != 0; ++i, n >>= 1)
+    if (n & 1) s = (s * jumpA[i] + jumpC[i]) & LCG_MASK;
+  return s;
+}
+// value of the (k+1)-th rd.nextInt() after state s (k = 0 -> next draw)
+WTG_HD int32_t lcgNextIntAt(const Dev& d, u64 s, u64 k) {
+  u64 st = lcgAdvance(d.jumpA, d.jumpC, s, k + 1);
+  return (int32_t)(uint32_t)(st >> 16);
+}
+
+// core/Network.java:493-503
+WTG_HD int32_t javaHash(int32_t a0) {
+  uint32_t a = (uint32_t)a0;
+  a ^= (a << 13);
+  a ^= (a >> 17);
+  a ^= (a << 5);
+  return (int32_t)a;
+}
+WTG_HD int pseudoRandom(int nodeId, int32_t seed) {
+  int32_t x = javaHash(nodeId) ^ seed;
+  int32_t r = x % 100;
+  return r < 0 ? -r : r;
+}
+
+// core/Node.java:278-282 — (int) Math.sqrt(dx*dx + dy*dy), toroidal
+WTG_HD int nodeDist(const Dev& d, int a, int b) {
+  int ax = d.nx[a], ay = d.ny[a], bx = d.nx[b], by = d.ny[b];
+  int ddx = ax > bx ? ax - bx : bx - ax;
+  int ddy = ay > by ? ay - by : by - ay;
+  int dx = ddx < 2000 - ddx ? ddx : 2000 - ddx;
+  int dy = ddy < 1112 - ddy ? ddy : 1112 - ddy;
+  int v = dx * dx + dy * dy;
+  int r = (int)sqrt((double)v);
+  while (r * r > v) --r;  // exact integer floor, independent of the sqrt implementation
+  while ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+
+// core/NetworkLatency.java:27-34 with the samplers folded into integer tables
+WTG_HD int latency(const Dev& d, int from, int to, int delta) {
+  if (from == to) return 1;
+  int extra = (int)d.nextra[from] + (int)d.nextra[to];
+  int ext;
+  switch (d.latKind) {
+    case LAT_DIST_DELTA:
+      ext = d.latTab[nodeDist(d, from, to) * 100 + delta];
+      break;
+    case LAT_CITY: {
+      int cf = d.ncity[from], ct = d.ncity[to];
+      if (cf == ct)
+        ext = 1;
+      else {
+        ext = (int)d.latBase[cf * 11 + ct] + (int)d.latJit[delta];
+        if (ext < 1) ext = 1;
+      }
+      break;
+    }
+    case LAT_CONST:
+      ext = d.latParam;
+      break;
+    case LAT_DELTA:
+      ext = d.latTab[delta];
+      break;
+    case LAT_DELTA_2X: {
+      int inner = extra + (int)d.latTab[delta];
+      ext = inner < 1 ? 1 : inner;
+      break;
+    }
+    default:  // LAT_DIST
+      ext = d.latTab[nodeDist(d, from, to)];
+      break;
+  }
+  int base = extra + ext;
+  return base < 1 ? 1 : base;
+}
+
+// ------------------------------------------------------------------------------------------
+// level geometry: level l of a node = the aligned block of 2^(l-1) ids that contains `id`
+// ------------------------------------------------------------------------------------------
+struct Blk {
+  int base;  // first id
+  int size;  // ids in the block
+  int w0;    // first 64-bit word of the row
+  int nw;    // words
+  u64 mask;  // valid bits of the (single) word when size < 64
+};
+WTG_HD Blk levelBlock(int id, int l) {
+  Blk b;
+  int sh = l - 1;
+  b.size = 1 << sh;
+  b.base = (id >> sh) << sh;
+  b.w0 = b.base >> 6;
+  if (b.size >= 64) {
+    b.nw = b.size >> 6;
+    b.mask = ~0ULL;
+  } else {
+    b.nw = 1;
+    b.mask = ((1ULL << b.size) - 1ULL) << (b.base & 63);
+  }
+  return b;
+}
+WTG_HD int poolWords(int l) { return 1 << (l - 1 - 6); }  // l > INLINE_MAX_LEVEL
+
+WTG_HD int msgSize(int l) { return 1 + ((1 << (l - 1)) / 8) + 96; }  // GSFSignature.java:150
+
+WTG_HD uint32_t peerAt(const Dev& d, int n, int l, int idx) {
+  size_t off = (size_t)n * (size_t)(d.N - 1) + (size_t)((1 << (l - 1)) - 1) + (size_t)idx;
+  if (d.peerBits == 16) {
+    int sib = levelBlock(n ^ (1 << (l - 1)), l).base;
+    return (uint32_t)sib + (uint32_t)((const uint16_t*)d.peers)[off];
+  }
+  return ((const uint32_t*)d.peers)[off];
+}
+
+WTG_HD void freePush(const Dev& d, int level, uint32_t slot) {
+  int i = WTG_ATOMIC_ADD(&d.ctl->freeTop, 1);
+  if (i < d.freeCap)
+    d.freeList[i] = ((uint32_t)level << 27) | slot;
+  else
+    setError(d, ERR_FREE_OVERFLOW, i);
+}
+WTG_HD bool poolAlloc(const Dev& d, int level, uint32_t& slot) {
+  int i = WTG_ATOMIC_ADD(&d.ctl->poolFreeCnt[level], -1) - 1;
+  if (i < 0) {
+    setError(d, ERR_POOL_EXHAUSTED, level);
+    slot = 0;
+    return false;
+  }
+  slot = d.poolFree[level][i];
+  WTG_ATOMIC_MIN(&d.ctl->poolMinFree[level], i);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluateSig  (GSFSignature.java:482-534) on range-compressed operands
+// ------------------------------------------------------------------------------------------
+WTG_HD int gsfScoreFrom(int l, int size, int cV, int cSig, bool inter, int cWI, int cWIV, bool interIndiv) {
+  int newTotal, added;
+  if (cV == 0) {
+    newTotal = cSig;
+    added = cSig;
+  } else if (inter) {
+    newTotal = cWI;
+    added = cWI - cV;
+  } else {
+    newTotal = cWIV;
+    added = cWIV - cV;
+  }
+  if (added <= 0) return (cSig == 1 && !interIndiv) ? 1 : 0;
+  if (newTotal == size) return 1000000 - l * 10;
+  return 100000 - l * 100 + added;
+}
+
+// O(1) kinds: evaluated by a single lane
+WTG_HD int gsfScoreScalar(const Dev& d, int n, const QEntry& e) {
+  int l = (int)metaLevel(e.meta);
+  int kind = (int)metaKind(e.meta);
+  int size = 1 << (l - 1);
+  int cV = d.cntVer[n * d.L + l];
+  if (cV >= size) return 0;
+  const u64* rowV = d.verified + (size_t)n * d.W64;
+  const u64* rowI = d.indivVer + (size_t)n * d.W64;
+  if (kind == PK_FULL) {
+    int k = (int)metaK(e.meta);
+    int c = 1 << k;
+    bool interIndiv = d.cntIndiv[n * d.L + l] > 0;
+    return gsfScoreFrom(l, size, cV, c, cV > 0, c, c, interIndiv);
+  }
+  if (kind == PK_INDIV) {
+    int f = (int)e.from;
+    bool inV = (rowV[f >> 6] >> (f & 63)) & 1ULL;
+    bool inI = (rowI[f >> 6] >> (f & 63)) & 1ULL;
+    int cI = d.cntIndiv[n * d.L + l], cU = d.cntUnion[n * d.L + l];
+    return gsfScoreFrom(l, size, cV, 1, inV, cI + (inI ? 0 : 1), cU + ((inI || inV) ? 0 : 1), inI);
+  }
+  // PK_INLINE
+  Blk b = levelBlock((int)e.from, l);
+  u64 s = e.pl, v = rowV[b.w0] & b.mask, i = rowI[b.w0] & b.mask;
+  return gsfScoreFrom(l, size, cV, WTG_POPC64(s), (s & v) != 0, WTG_POPC64(i | s), WTG_POPC64(i | s | v), (s & i) != 0);
+}
+
+// PK_POOL: the whole coop scans the level block
+template <class C>
+WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u64 pl) {
+  int l = (int)metaLevel(meta);
+  int size = 1 << (l - 1);
+  int cV = d.cntVer[n * d.L + l];
+  if (cV >= size) return 0;
+  Blk b = levelBlock((int)from, l);
+  const u64* rowV = d.verified + (size_t)n * d.W64 + b.w0;
+  const u64* rowI = d.indivVer + (size_t)n * d.W64 + b.w0;
+  const u64* sig = d.pool[l] + (size_t)(uint32_t)pl * (size_t)b.nw;
+  int cWI = 0, cWIV = 0, inter = 0, interI = 0;
+  for (int w = c.lane(); w < b.nw; w += C::LANES) {
+    u64 s = sig[w], v = rowV[w], i = rowI[w];
+    cWI += WTG_POPC64(i | s);
+    cWIV += WTG_POPC64(i | s | v);
+    inter |= (s & v) != 0;
+    interI |= (s & i) != 0;
+  }
+  cWI = c.sum(cWI);
+  cWIV = c.sum(cWIV);
+  bool bi = c.any(inter != 0), bii = c.any(interI != 0);
+  return gsfScoreFrom(l, size, cV, (int)(pl >> 32), bi, cWI, cWIV, bii);
+}
+
+// ------------------------------------------------------------------------------------------
+// checkSigs  (GSFSignature.java:557-583): scan toVerify, evict score-0 entries, take the first
+// max-score entry, schedule updateVerifiedSignatures at time + nodePairingTime.
+// keepBits: scratch of qcap/32 words private to this coop.
+// Returns true and fills `task` when a best entry was found.
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& best) {
+  int len = d.qLen[n];
+  QEntry* q = d.queue + (size_t)n * d.qcap;
+  int bestScore = 0, bestIdx = 0x7fffffff;
+  unsigned long long words = 0;
+  for (int base = 0; base < len; base += C::LANES) {
+    int i = base + c.lane();
+    QEntry e;
+    e.from = 0;
+    e.meta = 0;
+    e.pl = 0;
+    int s = 0;
+    bool isPool = false;
+    if (i < len) {
+      e = q[i];
+      if (metaKind(e.meta) == PK_POOL)
+        isPool = true;
+      else
+        s = gsfScoreScalar(d, n, e);
+    }
+    uint32_t pm = c.ballot(isPool);
+    while (pm) {
+#if defined(__CUDA_ARCH__)
+      int src = __ffs(pm) - 1;
+#else
+      int src = __builtin_ctz(pm);
+#endif
+      pm &= pm - 1;
+      uint32_t f = (uint32_t)c.bcast((int)e.from, src);
+      uint32_t m = (uint32_t)c.bcast((int)e.meta, src);
+      u64 p = c.bcast64(e.pl, src);
+      int sc = gsfScorePool(d, c, n, f, m, p);
+      words += (unsigned long long)(3 * poolWords((int)metaLevel(m)));
+      if (c.lane() == src) s = sc;
+    }
+    uint32_t km = c.ballot(s > 0);
+    if (c.lane() == 0) keepBits[base / C::LANES] = km;
+    if (s > bestScore) {  // strict >: keeps this lane's earliest max
+      bestScore = s;
+      bestIdx = i;
+    }
+  }
+  int mx = c.maxv(bestScore);
+  int bi = c.minv(bestScore == mx ? bestIdx : 0x7fffffff);
+  bool found = mx > 0;
+  c.sync();
+  // order-preserving compaction: drop score-0 entries and the best one
+  int w = 0;
+  for (int base = 0; base < len; base += C::LANES) {
+    int i = base + c.lane();
+    QEntry e;
+    e.from = 0;
+    e.meta = 0;
+    e.pl = 0;
+    bool keep = false, evict = false;
+    if (i < len) {
+      e = q[i];
+      bool k0 = (keepBits[base / C::LANES] >> (C::LANES == 1 ? 0 : c.lane())) & 1u;
+      keep = k0 && !(found && i == bi);
+      evict = !k0;
+    }
+    uint32_t km = c.ballot(keep);
+    c.sync();  // all lanes have loaded their entry before anyone overwrites the chunk
+#if defined(__CUDA_ARCH__)
+    int off = __popc(km & ((1u << c.lane()) - 1u));
+    int tot = __popc(km);
+#else
+    int off = 0;
+    int tot = (int)(km & 1u);
+#endif
+    if (keep) q[w + off] = e;
+    if (evict && metaKind(e.meta) == PK_POOL) freePush(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
+    if (found && i == bi) best = e;
+    w += tot;
+  }
+  if (found) {
+    int srcLane = (C::LANES == 1) ? 0 : (bi % C::LANES);
+    best.from = (uint32_t)c.bcast((int)best.from, srcLane);
+    best.meta = (uint32_t)c.bcast((int)best.meta, srcLane);
+    best.pl = c.bcast64(best.pl, srcLane);
+  }
+  if (c.lane() == 0) {
+    d.qLen[n] = w;
+    WTG_ATOMIC_ADD(&d.ctl->statEvalEntries, (unsigned long long)len);
+    WTG_ATOMIC_ADD(&d.ctl->statEvalWords, words);
+    if (found) {
+      d.sigChecked[n] += 1;
+      d.sigQueueSize[n] = w;
+    }
+  }
+  return found;
+}
+
+// ------------------------------------------------------------------------------------------
+// conditional-task pass for node n  (Network.java:543-565 restated per node)
+//   mode 1: clock has just ticked to `tick` inside a runMs window ending at `until`
+//   mode 2: the reference's extra time++ past `until` at the end of the window
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD void gsfCond(const Dev& d, C& c, int n, uint32_t* keepBits) {
+  const Ctl& ctl = *d.ctl;
+  int fired = 0;
+  if (ctl.condMode != 0 && !d.ndown[n]) {
+    int ms = d.minStart[n];
+    bool due = ctl.condMode == 1 ? (ms <= ctl.tick) : (ms <= ctl.until);
+    if (due && d.stamp[n] != ctl.callId) {
+      c.sync();
+      if (c.lane() == 0) d.stamp[n] = ctl.callId;
+      if (d.qLen[n] > 0) {  // startIf: !toVerify.isEmpty()
+        QEntry best;
+        best.from = 0;
+        best.meta = 0;
+        best.pl = 0;
+        bool found = gsfCheckSigs(d, c, n, keepBits, best);
+        if (c.lane() == 0) {
+          d.minStart[n] = ctl.tick + d.pairing[n];
+          WTG_ATOMIC_ADD(&d.ctl->statCondRuns, 1ULL);
+          if (found) {  // registerTask(updateVerifiedSignatures, time + nodePairingTime, this)
+            Ev ev;
+            ev.kind = EV_TASK;
+            ev.to = (uint32_t)n;
+            ev.from = best.from;
+            ev.meta = best.meta;
+            ev.pl = best.pl;
+            ev.aux = 0;
+            ev.pad = 0;
+            d.condEv[n] = ev;
+            d.condTarget[n] = ctl.tick + d.pairing[n];
+          }
+        }
+        fired = found ? 1 : 0;
+      }
+    }
+  }
+  if (c.lane() == 0) d.condFired[n] = fired;
+}
+
+// ------------------------------------------------------------------------------------------
+// descriptor helpers
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD int descAlloc(const Dev& d, C& c, int cnt) {
+  int base = 0;
+  if (c.lane() == 0) {
+    base = WTG_ATOMIC_ADD(&d.ctl->nDesc, cnt);
+    if (base + cnt > d.descCap) {
+      setError(d, ERR_DESC_OVERFLOW, base + cnt);
+      base = -1;
+    }
+  }
+  return c.bcast(base, 0);
+}
+
+WTG_HD void gsfLevelCounters(const Dev& d, int n, int l, int& cV, int& cI, int& cU) {
+  cV = d.cntVer[n * d.L + l];
+  cI = d.cntIndiv[n * d.L + l];
+  cU = d.cntUnion[n * d.L + l];
+}
+
+// number of consecutive complete levels: levels 0..k complete (getLastFinishedLevel :193-210)
+WTG_HD int gsfLastFinished(const Dev& d, int n) {
+  int k = 0;
+  for (int j = 1; j < d.L; ++j) {
+    if (d.cntVer[n * d.L + j] == (1 << (j - 1)))
+      k = j;
+    else
+      break;
+  }
+  return k;
+}
+
+// onNewSig (GSFSignature.java:537-555) — executed by lane 0 only
+WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 pl) {
+  int l = (int)metaLevel(meta);
+  int len = d.qLen[n];
+  QEntry* q = d.queue + (size_t)n * d.qcap;
+  if (len + 2 > d.qcap) {
+    setError(d, ERR_QUEUE_OVERFLOW, n);
+    if (metaKind(meta) == PK_POOL) freePush(d, l, (uint32_t)pl);
+    return;
+  }
+  QEntry e;
+  e.from = from;
+  e.meta = meta;
+  e.pl = pl;
+  q[len++] = e;
+  u64* rowS = d.indivSeen + (size_t)n * d.W64;
+  u64 bit = 1ULL << (from & 63);
+  if (!(rowS[from >> 6] & bit)) {
+    rowS[from >> 6] |= bit;
+    QEntry ie;
+    ie.from = from;
+    ie.meta = metaMake(PK_INDIV, (uint32_t)l, 0);
+    ie.pl = 0;
+    q[len++] = ie;
+  }
+  d.qLen[n] = len;
+  d.sigQueueSize[n] = len;
+  WTG_ATOMIC_MAX(&d.ctl->maxQueue, len);
+}
+
+// take up to `want` peers of level l (getRemainingPeers :325-349); returns the count, writes ids
+template <class C>
+WTG_HD int gsfTakePeers(const Dev& d, C& c, int n, int l, int want, uint32_t* out) {
+  int rem = d.remaining[n * d.L + l];
+  int p = d.pos[n * d.L + l];
+  int sz = 1 << (l - 1);
+  int cnt = want < rem ? want : rem;
+  for (int i = 0; i < cnt; ++i) {
+    out[i] = peerAt(d, n, l, p);
+    if (++p >= sz) p = 0;
+  }
+  c.sync();
+  if (c.lane() == 0) {
+    d.remaining[n * d.L + l] = rem - cnt;
+    d.pos[n * d.L + l] = p;
+  }
+  c.sync();
+  return cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// updateVerifiedSignatures  (GSFSignature.java:384-460)
+// item: scan item of this event; returns via evSlots/evDraws/desc
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u64 pl, int item, int& outSlots, int& outDraws) {
+  const int L = d.L;
+  const int tick = d.ctl->tick;
+  int l = (int)metaLevel(meta);
+  int kind = (int)metaKind(meta);
+  int k = (int)metaK(meta);
+  int size = 1 << (l - 1);
+  Blk b = levelBlock((int)from, l);
+  u64* rowV = d.verified + (size_t)n * d.W64;
+  u64* rowI = d.indivVer + (size_t)n * d.W64;
+  int cV, cI, cU;
+  gsfLevelCounters(d, n, l, cV, cI, cU);
+  int total = d.totalCard[n];
+  int cSig = kind == PK_INDIV ? 1 : kind == PK_FULL ? (1 << k) : kind == PK_INLINE ? WTG_POPC64(pl) : (int)(pl >> 32);
+  if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statUpdates, 1ULL);
+
+  // :387-389  if (sigs.cardinality() == 1) sfl.indivVerifiedSig.set(from.nodeId);
+  if (cSig == 1) {
+    u64 bit = 1ULL << (from & 63);
+    u64 wI = rowI[from >> 6], wV = rowV[from >> 6];
+    c.sync();
+    if (!(wI & bit)) {
+      if (c.lane() == 0) rowI[from >> 6] = wI | bit;
+      cI += 1;
+      if (!(wV & bit)) cU += 1;
+    }
+    c.sync();
+  }
+
+  bool changed = false;  // the `if (sigs.cardinality() > sfl.verified.cardinality() || resetRemaining)` branch
+  bool superset = (kind == PK_FULL && k >= l);  // :397  sigs.cardinality() > sfl.expectedSigs()
+  if (superset) {
+    bool resetRemaining = false;
+    for (int i = 1; i < L && i <= k; ++i) {  // :401  include(sigs, levels[i].waitedSigs)  <=>  i <= k
+      int ci = d.cntVer[n * L + i];
+      int si = 1 << (i - 1);
+      if (ci != si) {  // :403-407
+        Blk wb = levelBlock(n ^ (1 << (i - 1)), i);
+        for (int w = c.lane(); w < wb.nw; w += C::LANES) rowV[wb.w0 + w] |= wb.mask;
+        total += si - ci;
+        if (c.lane() == 0) {
+          d.cntVer[n * L + i] = si;
+          d.cntUnion[n * L + i] = si;
+        }
+        if (i == l) {
+          cV = si;
+          cU = si;
+        }
+        resetRemaining = true;
+      }
+      if (resetRemaining && c.lane() == 0) d.remaining[n * L + i] = si;  // :408-410
+    }
+    c.sync();
+    // sigs = clone(waitedSigs): full block; level l is complete (l <= k) so no merge and |sigs| == |verified|
+    changed = resetRemaining;
+  } else {
+    // sig' = sigs | indivVerifiedSig (both inside the level block); count and test against verified
+    int cA = 0;
+    bool inter = false;
+    if (kind == PK_FULL) {  // k == l-1: the whole block
+      cA = size;
+      inter = cV > 0;
+    } else if (kind == PK_INDIV) {  // {from} | indiv == indiv (from was just added)
+      cA = cI;
+      inter = (cI + cV - cU) > 0;
+    } else if (kind == PK_INLINE) {
+      u64 a = pl | (rowI[b.w0] & b.mask);
+      cA = WTG_POPC64(a);
+      inter = (a & rowV[b.w0] & b.mask) != 0;
+    } else {
+      const u64* sig = d.pool[l] + (size_t)(uint32_t)pl * (size_t)b.nw;
+      int ca = 0, it = 0;
+      for (int w = c.lane(); w < b.nw; w += C::LANES) {
+        u64 a = sig[w] | rowI[b.w0 + w];
+        ca += WTG_POPC64(a);
+        it |= (a & rowV[b.w0 + w]) != 0;
+      }
+      cA = c.sum(ca);
+      inter = c.any(it != 0);
+    }
+    bool merge = (cV > 0 && !inter);  // :415-420
+    int cM = merge ? cA + cV : cA;
+    if (cM > cV) {  // :422
+      changed = true;
+      // :432-436 replace the level block (and the same bits of the node-wide set) by sig' [| verified]
+      c.sync();
+      if (kind == PK_FULL) {
+        for (int w = c.lane(); w < b.nw; w += C::LANES) rowV[b.w0 + w] |= b.mask;
+      } else if (kind == PK_INDIV) {
+        for (int w = c.lane(); w < b.nw; w += C::LANES) {
+          u64 cur = rowV[b.w0 + w];
+          u64 nv = (rowI[b.w0 + w] & b.mask) | (merge ? (cur & b.mask) : 0ULL);
+          rowV[b.w0 + w] = (cur & ~b.mask) | nv;
+        }
+      } else if (kind == PK_INLINE) {
+        if (c.lane() == 0) {
+          u64 cur = rowV[b.w0];
+          u64 nv = pl | (rowI[b.w0] & b.mask) | (merge ? (cur & b.mask) : 0ULL);
+          rowV[b.w0] = (cur & ~b.mask) | nv;
+        }
+      } else {
+        const u64* sig = d.pool[l] + (size_t)(uint32_t)pl * (size_t)b.nw;
+        for (int w = c.lane(); w < b.nw; w += C::LANES) {
+          u64 nv = sig[w] | rowI[b.w0 + w];
+          if (merge) nv |= rowV[b.w0 + w];
+          rowV[b.w0 + w] = nv;
+        }
+      }
+      total += cM - cV;
+      cV = cM;
+      cU = cM;  // the new verified set contains indivVerifiedSig
+      if (c.lane() == 0) d.cntVer[n * L + l] = cV;
+      c.sync();
+    }
+  }
+  if (c.lane() == 0) {
+    d.cntIndiv[n * L + l] = cI;
+    d.cntUnion[n * L + l] = cU;
+    d.totalCard[n] = total;
+  }
+  if (kind == PK_POOL && c.lane() == 0) freePush(d, l, (uint32_t)pl);
+  c.sync();
+
+  outSlots = 0;
+  outDraws = 0;
+  if (!changed) return;
+
+  // :424-428 new signatures: reset remainingCalls of this level and all levels above
+  for (int i = l + c.lane(); i < L; i += C::LANES) d.remaining[n * L + i] = 1 << (i - 1);
+  c.sync();
+
+  if (d.accel > 0) {  // :438-451
+    int kf = gsfLastFinished(d, n);
+    // count the sends first so the descriptor block can be allocated in one go
+    int nSend = 0;
+    for (int cur = l; cur <= kf && cur < L - 1;) {
+      ++cur;
+      if (d.remaining[n * L + cur] > 0) ++nSend;
+    }
+    if (nSend > 0) {
+      int base = descAlloc(d, c, nSend);
+      int sub = 0;
+      long long sentMsgs = 0, sentBytes = 0;
+      for (int cur = l; cur <= kf && cur < L - 1;) {
+        ++cur;
+        uint32_t dests[MAX_ACC];
+        int cnt = gsfTakePeers(d, c, n, cur, d.accel, dests);
+        if (cnt == 0) continue;
+        sentMsgs += cnt;
+        sentBytes += (long long)cnt * msgSize(cur);
+        if (base >= 0 && c.lane() == 0) {
+          Desc ds;
+          ds.item = (uint32_t)(d.N + item);
+          ds.sub = (uint32_t)sub;
+          ds.from = (uint32_t)n;
+          ds.evKind = EV_MSG;
+          ds.meta = metaMake(PK_FULL, (uint32_t)cur, (uint32_t)kf);
+          ds.pl = 0;
+          ds.target = 0;
+          ds.aux = 0;
+          if (cnt == 1) {  // Network.send(m, from, dests) with one dest -> single-destination path (:357-358)
+            ds.dkind = DK_SEND_SINGLE;
+            ds.to = dests[0];
+            ds.nDest = 1;
+          } else {
+            int off = WTG_ATOMIC_ADD(&d.ctl->nDestScratch, cnt);
+            if (off + cnt > d.destScratchCap) {
+              setError(d, ERR_DESC_OVERFLOW, off);
+              off = 0;
+            } else {
+              for (int i = 0; i < cnt; ++i) d.destScratch[off + i] = dests[i];
+            }
+            ds.dkind = DK_SEND_MULTI;
+            ds.to = (uint32_t)off;
+            ds.nDest = (uint32_t)cnt;
+          }
+          d.desc[base + sub] = ds;
+        }
+        ++sub;
+      }
+      if (c.lane() == 0) {
+        d.msgSent[n] += sentMsgs;
+        d.bytesSent[n] += sentBytes;
+        WTG_ATOMIC_ADD(&d.ctl->statMultiSends, (unsigned long long)sub);
+      }
+      outSlots = sub;
+      outDraws = sub;
+    }
+  }
+  // :452-453
+  if (c.lane() == 0 && d.doneAt[n] == 0 && total >= d.threshold) d.doneAt[n] = tick;
+  c.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// doCycle  (GSFSignature.java:212-224 + SFLevel.doCycle :313-323) and the periodic re-arm
+// (messages/PeriodicTask.java:40-47)
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& outDraws) {
+  const int L = d.L;
+  const int tick = d.ctl->tick;
+  const u64* rowV = d.verified + (size_t)n * d.W64;
+  int kf = gsfLastFinished(d, n);
+  // pass 1: which levels send
+  uint32_t sendMask = 0;
+  {
+    int prefix = 1;
+    for (int l = 1; l < L; ++l) {
+      int card = (kf >= l - 1) ? (1 << kf) : prefix;
+      bool started = tick >= l * d.timeoutPerLevel || card >= (1 << (l - 1));  // hasStarted :291-311
+      if (d.remaining[n * L + l] > 0 && started) sendMask |= 1u << l;
+      prefix += d.cntVer[n * L + l];
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  int nSend = __popc(sendMask);
+#else
+  int nSend = __builtin_popcount(sendMask);
+#endif
+  int base = descAlloc(d, c, nSend + 1);
+  int sub = 0;
+  long long sentBytes = 0;
+  unsigned long long words = 0;
+  int prefix = 1;
+  for (int l = 1; l < L; ++l) {
+    int cvl = d.cntVer[n * L + l];
+    if (sendMask & (1u << l)) {
+      uint32_t dest = 0;
+      gsfTakePeers(d, c, n, l, 1, &dest);
+      uint32_t meta;
+      u64 pl = 0;
+      if (kf >= l - 1) {
+        meta = metaMake(PK_FULL, (uint32_t)l, (uint32_t)kf);
+      } else {
+        Blk ob = levelBlock(n, l);  // our own half: what the receiver waits for at its level l
+        if (l <= INLINE_MAX_LEVEL) {
+          meta = metaMake(PK_INLINE, (uint32_t)l, 0);
+          pl = rowV[ob.w0] & ob.mask;
+        } else {
+          meta = metaMake(PK_POOL, (uint32_t)l, 0);
+          uint32_t slot = 0;
+          int ok = 1;
+          if (c.lane() == 0) ok = poolAlloc(d, l, slot) ? 1 : 0;
+          slot = (uint32_t)c.bcast((int)slot, 0);
+          ok = c.bcast(ok, 0);
+          if (ok) {
+            u64* dst = d.pool[l] + (size_t)slot * (size_t)ob.nw;
+            for (int w = c.lane(); w < ob.nw; w += C::LANES) dst[w] = rowV[ob.w0 + w];
+            words += (unsigned long long)(2 * ob.nw);
+          }
+          pl = (u64)slot | ((u64)(uint32_t)prefix << 32);
+        }
+      }
+      sentBytes += msgSize(l);
+      if (base >= 0 && c.lane() == 0) {
+        Desc ds;
+        ds.dkind = DK_SEND_SINGLE;
+        ds.item = (uint32_t)(d.N + item);
+        ds.sub = (uint32_t)sub;
+        ds.from = (uint32_t)n;
+        ds.to = dest;
+        ds.nDest = 1;
+        ds.evKind = EV_MSG;
+        ds.meta = meta;
+        ds.pl = pl;
+        ds.target = 0;
+        ds.aux = 0;
+        d.desc[base + sub] = ds;
+      }
+      ++sub;
+    }
+    prefix += cvl;
+  }
+  if (c.lane() == 0) {
+    if (base >= 0) {  // re-arm: network.sendArriveAt(this, time + period, sender, sender)
+      Desc ds;
+      ds.dkind = DK_INSERT_AT;
+      ds.item = (uint32_t)(d.N + item);
+      ds.sub = (uint32_t)sub;
+      ds.from = (uint32_t)n;
+      ds.to = (uint32_t)n;
+      ds.nDest = 0;
+      ds.evKind = EV_PERIODIC;
+      ds.meta = 0;
+      ds.pl = 0;
+      ds.target = tick + d.period;
+      ds.aux = 0;
+      d.desc[base + sub] = ds;
+    }
+    d.msgSent[n] += nSend;
+    d.bytesSent[n] += sentBytes;
+    WTG_ATOMIC_ADD(&d.ctl->statCycles, 1ULL);
+    WTG_ATOMIC_ADD(&d.ctl->statSends, (unsigned long long)nSend);
+    WTG_ATOMIC_ADD(&d.ctl->statSendWords, words);
+  }
+  c.sync();
+  outSlots = nSend + 1;
+  outDraws = nSend;
+}
+
+// ------------------------------------------------------------------------------------------
+// one delivery at node n (Network.receiveUntil :603-627 + the protocol's Message.action)
+// `ev` is the envelope, item its scan item.  Writes evSlots/evDraws[item].
+// ------------------------------------------------------------------------------------------
+template <class C>
+WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint32_t meta, u64 pl, int item) {
+  int slots = 0, draws = 0;
+  bool isTask = (ev.kind == EV_TASK || ev.kind == EV_PERIODIC);
+  uint32_t envFrom = isTask ? (uint32_t)n : from;  // tasks are self-addressed envelopes (Network.java:505-519)
+  bool ok = !d.ndown[n] && d.npart[envFrom] == d.npart[n];  // :606
+  if (!ok) {
+    // dropped: a pooled payload dies with the envelope
+    if (d.proto == PROTO_GSF && (ev.kind == EV_MSG || ev.kind == EV_TASK) && metaKind(meta) == PK_POOL && c.lane() == 0)
+      freePush(d, (int)metaLevel(meta), (uint32_t)pl);
+  } else if (d.proto == PROTO_GSF) {
+    if (ev.kind == EV_MSG || ev.kind == EV_MULTI) {
+      if (c.lane() == 0) {
+        d.msgReceived[n] += 1;
+        d.bytesReceived[n] += msgSize((int)metaLevel(meta));
+        WTG_ATOMIC_ADD(&d.ctl->statDeliveries, 1ULL);
+        gsfOnNewSig(d, n, from, meta, pl);
+      }
+      c.sync();
+    } else if (ev.kind == EV_TASK) {
+      if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statTasks, 1ULL);
+      gsfUpdate(d, c, n, from, meta, pl, item, slots, draws);
+    } else {
+      if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statTasks, 1ULL);
+      gsfCycle(d, c, n, item, slots, draws);
+    }
+  } else if (d.proto == PROTO_PINGPONG) {
+    if (c.lane() == 0) {
+      d.msgReceived[n] += 1;
+      d.bytesReceived[n] += 1;  // Message.size() default (messages/Message.java:27-29)
+      WTG_ATOMIC_ADD(&d.ctl->statDeliveries, 1ULL);
+    }
+    if (meta == PP_PING) {  // PingPong.java:73-75  onPing: network.send(new Pong(), this, from)
+      int base = descAlloc(d, c, 1);
+      if (c.lane() == 0) {
+        if (base >= 0) {
+          Desc ds;
+          ds.dkind = DK_SEND_SINGLE;
+          ds.item = (uint32_t)(d.N + item);
+          ds.sub = 0;
+          ds.from = (uint32_t)n;
+          ds.to = from;
+          ds.nDest = 1;
+          ds.evKind = EV_MSG;
+          ds.meta = PP_PONG;
+          ds.pl = 0;
+          ds.target = 0;
+          ds.aux = 0;
+          d.desc[base] = ds;
+        }
+        d.msgSent[n] += 1;
+        d.bytesSent[n] += 1;
+      }
+      slots = 1;
+      draws = 1;
+    } else {  // :77-79 onPong
+      if (c.lane() == 0) d.pong[n] += 1;
+    }
+    c.sync();
+  }
+  if (c.lane() == 0) {
+    d.evSlots[item] = slots;
+    d.evDraws[item] = draws;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// node work item: process this tick's inbox of node n in reference order
+// inbox word: (item << 32) | (entry index << 8 ... see below)
+// ------------------------------------------------------------------------------------------
+WTG_HD u64 inboxMake(int item, int entry) { return ((u64)(uint32_t)item << 32) | (u64)(uint32_t)entry; }
+WTG_HD int inboxItem(u64 w) { return (int)(w >> 32); }
+WTG_HD int inboxEntry(u64 w) { return (int)(w & 0xFFFFFFFFULL); }
+
+template <class C>
+WTG_HD void nodeProcess(const Dev& d, C& c, int n) {
+  int cnt = d.inboxFill[n];
+  if (cnt == 0) return;
+  const u64* in = d.inbox + d.inboxOff[n];
+  const Ev* bucket = d.buckets + (size_t)(d.ctl->tick & (d.ring - 1)) * (size_t)d.bcap;
+  int lastItem = -1;
+  for (int r = 0; r < cnt; ++r) {
+    // next delivery in reference order = smallest item index not yet processed (inboxes are tiny)
+    int bestItem = 0x7fffffff;
+    u64 bestW = 0;
+    for (int i = c.lane(); i < cnt; i += C::LANES) {
+      u64 w = in[i];
+      int it = inboxItem(w);
+      if (it > lastItem && it < bestItem) {
+        bestItem = it;
+        bestW = w;
+      }
+    }
+    int mn = c.minv(bestItem);
+    uint32_t who = c.ballot(bestItem == mn);
+#if defined(__CUDA_ARCH__)
+    int src = __ffs(who) - 1;
+#else
+    int src = __builtin_ctz(who);
+#endif
+    u64 w = c.bcast64(bestW, src);
+    lastItem = mn;
+    int item = inboxItem(w), entry = inboxEntry(w);
+    Ev ev = bucket[entry];
+    uint32_t from = ev.from, meta = ev.meta;
+    u64 pl = ev.pl;
+    if (ev.kind == EV_MULTI) {
+      const MultiRec& rc = d.rec[ev.aux];
+      from = rc.from;
+      meta = rc.meta;
+      pl = rc.pl;
+    }
+    deliver(d, c, n, ev, from, meta, pl, item);
+  }
+  if (c.lane() == 0) {
+    WTG_ATOMIC_MAX(&d.ctl->maxInbox, cnt);
+    d.inboxFill[n] = 0;  // ready for the next tick
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch: expand the bucket of this tick into per-node deliveries (thread per event)
+// pass 0 counts (subCount, inboxCnt); pass 1 scatters (after itemBase / inboxOff scans)
+// ------------------------------------------------------------------------------------------
+WTG_HD void dispatchCount(const Dev& d, int i) {
+  const Ctl& ctl = *d.ctl;
+  int p = ctl.nEv - 1 - i;  // LIFO: processing position (Network.java:145-147)
+  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  int m = 1, rep = 0;
+  if (ev.kind == EV_MULTI) {
+    const MultiRec& rc = d.rec[ev.aux];
+    int j = (int)rc.cur;
+    m = 0;
+    while (j < (int)rc.n && d.recArrival[rc.off + j] == ctl.tick) {
+      WTG_ATOMIC_ADD(&d.inboxCnt[d.recDest[rc.off + j]], 1);
+      ++j;
+      ++m;
+    }
+    rep = j < (int)rc.n ? 1 : 0;
+  } else {
+    WTG_ATOMIC_ADD(&d.inboxCnt[ev.to], 1);
+  }
+  d.subCount[p] = m + rep;
+}
+
+// itemBase[p] = exclusive scan of subCount over processing positions
+WTG_HD void dispatchScatter(const Dev& d, int i) {
+  const Ctl& ctl = *d.ctl;
+  int p = ctl.nEv - 1 - i;
+  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  int item0 = d.itemBase[p];
+  if (ev.kind == EV_MULTI) {
+    MultiRec& rc = d.rec[ev.aux];
+    int j = (int)rc.cur, m = 0;
+    while (j < (int)rc.n && d.recArrival[rc.off + j] == ctl.tick) {
+      int to = (int)d.recDest[rc.off + j];
+      int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+      d.inbox[s] = inboxMake(item0 + m, i);
+      ++j;
+      ++m;
+    }
+    if (j < (int)rc.n) {  // Network.java:629-632: re-push for the next destination, after the handler ran
+      int di = WTG_ATOMIC_ADD(&d.ctl->nDesc, 1);
+      if (di < d.descCap) {
+        Desc ds;
+        ds.dkind = DK_INSERT_AT;
+        ds.item = (uint32_t)(d.N + item0 + m);
+        ds.sub = 0;
+        ds.from = rc.from;
+        ds.to = d.recDest[rc.off + j];
+        ds.nDest = 0;
+        ds.evKind = EV_MULTI;
+        ds.meta = 0;
+        ds.pl = 0;
+        ds.target = d.recArrival[rc.off + j];
+        ds.aux = ev.aux;
+        d.desc[di] = ds;
+      } else {
+        setError(d, ERR_DESC_OVERFLOW, di);
+      }
+      d.evSlots[item0 + m] = 1;
+      d.evDraws[item0 + m] = 0;
+    }
+    rc.cur = (uint32_t)j;
+  } else {
+    int to = (int)ev.to;
+    int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+    d.inbox[s] = inboxMake(item0, i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// emit: turn one descriptor into a new envelope (seed -> latency -> arrival), in creation order
+// ------------------------------------------------------------------------------------------
+WTG_HD void emitDesc(const Dev& d, int di) {
+  const Ctl& ctl = *d.ctl;
+  const Desc& ds = d.desc[di];
+  int g = d.slotBase[ds.item] + (int)ds.sub;
+  if (g >= d.newEvCap) {
+    setError(d, ERR_DESC_OVERFLOW, g);
+    return;
+  }
+  Ev ev;
+  ev.kind = ds.evKind;
+  ev.to = ds.to;
+  ev.from = ds.from;
+  ev.meta = ds.meta;
+  ev.pl = ds.pl;
+  ev.aux = ds.aux;
+  ev.pad = 0;
+  int target = -1;
+  int sendTime = ctl.tick + 1;  // send(m, from, to) == send(m, time + 1, from, to)   Network.java:364-366
+  if (ds.dkind == DK_INSERT_AT) {
+    target = ds.target;
+  } else {
+    int32_t seed = lcgNextIntAt(d, ctl.rng, (u64)(d.drawBase[ds.item] + (int)ds.sub));
+    int from = (int)ds.from;
+    if (ds.dkind == DK_SEND_SINGLE) {
+      int to = (int)ds.to;
+      // createMessageArrival :478-484
+      if (d.npart[from] == d.npart[to] && !d.ndown[from] && !d.ndown[to]) {
+        int nt = latency(d, from, to, pseudoRandom(to, seed));
+        if (nt < d.msgDiscardTime) target = sendTime + nt;
+      }
+    } else {
+      // createMessageArrivals :449-467 + envelope choice :435-446
+      uint32_t dst[MAX_ACC];
+      int arr[MAX_ACC];
+      int cnt = 0;
+      for (int i = 0; i < (int)ds.nDest; ++i) {
+        int to = (int)d.destScratch[ds.to + i];
+        if (d.npart[from] == d.npart[to] && !d.ndown[from] && !d.ndown[to]) {
+          int nt = latency(d, from, to, pseudoRandom(to, seed));
+          if (nt < d.msgDiscardTime) {
+            int a = sendTime + nt;
+            int j = cnt++;  // stable insertion sort by arrival (Collections.sort is stable)
+            while (j > 0 && arr[j - 1] > a) {
+              arr[j] = arr[j - 1];
+              dst[j] = dst[j - 1];
+              --j;
+            }
+            arr[j] = a;
+            dst[j] = (uint32_t)to;
+          }
+        }
+      }
+      if (cnt == 1) {
+        ev.to = dst[0];
+        target = arr[0];
+      } else if (cnt > 1) {
+        int ri = WTG_ATOMIC_ADD(&d.ctl->recTop, 1);
+        int off = WTG_ATOMIC_ADD(&d.ctl->recDestTop, cnt);
+        if (ri >= d.recCap || off + cnt > d.recDestCap) {
+          setError(d, ERR_REC_OVERFLOW, ri);
+        } else {
+          MultiRec rc;
+          rc.from = ds.from;
+          rc.meta = ds.meta;
+          rc.pl = ds.pl;
+          rc.n = (uint32_t)cnt;
+          rc.cur = 0;
+          rc.off = (uint32_t)off;
+          rc.pad = 0;
+          d.rec[ri] = rc;
+          for (int i = 0; i < cnt; ++i) {
+            d.recDest[off + i] = dst[i];
+            d.recArrival[off + i] = arr[i];
+          }
+          ev.kind = EV_MULTI;
+          ev.to = dst[0];
+          ev.aux = (uint32_t)ri;
+          target = arr[0];
+        }
+      }
+    }
+    if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL) freePush(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
+  }
+  if (target >= 0 && target - ctl.tick >= d.ring) {
+    setError(d, ERR_FAR_FUTURE, target);
+    target = -1;
+  }
+  d.newEv[g] = ev;
+  d.newTarget[g] = target;
+}
+
+// conditional-task inserts come first in creation order (slot = scan over nodes)
+WTG_HD void emitCond(const Dev& d, int n) {
+  if (!d.condFired[n]) return;
+  int g = d.slotBase[n];
+  if (g >= d.newEvCap) {
+    setError(d, ERR_DESC_OVERFLOW, g);
+    return;
+  }
+  int target = d.condTarget[n];
+  if (target - d.ctl->tick >= d.ring) {
+    setError(d, ERR_FAR_FUTURE, target);
+    target = -1;
+  }
+  d.newEv[g] = d.condEv[n];
+  d.newTarget[g] = target;
+}
+
+// ------------------------------------------------------------------------------------------
+// tick bookkeeping (single thread)
+// ------------------------------------------------------------------------------------------
+WTG_HD void tickBegin(const Dev& d, int mode) {
+  Ctl& c = *d.ctl;
+  if (mode == 1) {
+    c.time += 1;  // nextMessage(): time++   (Network.java:541)
+    c.tick = c.time;
+    c.condMode = 1;
+    c.nEv = d.bucketCount[c.tick & (d.ring - 1)];
+  } else if (mode == 0) {
+    c.tick = c.time;
+    c.condMode = 0;
+    c.nEv = d.bucketCount[c.tick & (d.ring - 1)];
+  } else {  // the extra time++ past `until`; runMs then forces time = endAt (Network.java:336)
+    c.tick = c.time + 1;
+    c.condMode = 2;
+    c.nEv = 0;
+  }
+  c.nDesc = 0;
+  c.nDestScratch = 0;
+  c.nItems = 0;
+  c.totalSlots = 0;
+  c.totalDraws = 0;
+  if (c.nEv > c.maxBucket) c.maxBucket = c.nEv;
+}
+WTG_HD void tickEnd(const Dev& d, int mode) {
+  Ctl& c = *d.ctl;
+  c.rng = lcgAdvance(d.jumpA, d.jumpC, c.rng, (u64)c.totalDraws);
+  c.statDraws += (unsigned long long)c.totalDraws;
+  c.statEvents += (unsigned long long)c.nItems;
+  if (c.nEv > 0) {
+    c.callId += 1;  // every processed message starts a new nextMessage() call
+    c.didSomething = 1;
+  }
+  if (mode != 2) d.bucketCount[c.tick & (d.ring - 1)] = 0;
+  c.freeTop = 0;
+}
+// deferred frees -> pool free stacks (no allocation runs concurrently)
+WTG_HD void freeApply(const Dev& d, int i) {
+  uint32_t w = d.freeList[i];
+  int level = (int)(w >> 27);
+  uint32_t slot = w & 0x7FFFFFFu;
+  int k = WTG_ATOMIC_ADD(&d.ctl->poolFreeCnt[level], 1);
+  d.poolFree[level][k] = slot;
+}
+
+// ------------------------------------------------------------------------------------------
+// GSF init bodies
+// ------------------------------------------------------------------------------------------
+WTG_HD void gsfInitNodeBody(const Dev& d, int n) {  // GSFNode ctor :176-179, SFLevel ctors :260-280
+  d.verified[(size_t)n * d.W64 + (n >> 6)] = 1ULL << (n & 63);
+  d.totalCard[n] = 1;
+  d.minStart[n] = 1;  // registerConditionalTask(checkSigs, 1, nodePairingTime, ...) :631-632
+  if (!d.ndown[n]) {  // initLevel() runs for live nodes only (:627-629)
+    d.cntVer[n * d.L] = 1;
+    d.cntUnion[n * d.L] = 1;
+    for (int l = 1; l < d.L; ++l) d.remaining[n * d.L + l] = 1 << (l - 1);
+  }
+}
+
+// positions in [start, start+len) of the stream after s0 whose next(31) value could be rejected by
+// nextInt(bound) for some bound <= maxBound (u >= 2^31 - maxBound)
+WTG_HD void rngCandidateChunk(const Dev& d, u64 s0, u64 start, u64 len, int maxBound, u64* out, int* outCount, int cap) {
+  u64 s = lcgAdvance(d.jumpA, d.jumpC, s0, start);
+  const uint32_t thr = 0x80000000u - (uint32_t)maxBound;
+  for (u64 i = 0; i < len; ++i) {
+    s = (s * 0x5DEECE66DULL + 0xBULL) & LCG_MASK;
+    uint32_t u = (uint32_t)(s >> 17);
+    if (u >= thr) {
+      int k = WTG_ATOMIC_ADD(outCount, 1);
+      if (k < cap) out[k] = start + i;
+    }
+  }
+}
+
+// Collections.shuffle(peers_l, network.rd) for one (node, level)  (GSFSignature.java:462-476)
+template <class PeerT>
+WTG_HD void gsfShuffleLevel(const Dev& d, int n, int l, u64 s0, const int* liveRank, const u64* rejOrd, int nRej) {
+  int r = liveRank[n];
+  if (r < 0) return;
+  const int size = 1 << (l - 1);
+  const int sib = levelBlock(n ^ (1 << (l - 1)), l).base;
+  PeerT* arr = (PeerT*)d.peers + (size_t)n * (size_t)(d.N - 1) + (size_t)(size - 1);
+  const PeerT add = sizeof(PeerT) == 2 ? (PeerT)0 : (PeerT)sib;
+  for (int i = 0; i < size; ++i) arr[i] = (PeerT)(add + (PeerT)i);  // ids in increasing order (nextSetBit walk)
+  if (size < 2) return;
+  const u64 D = (u64)(d.N - d.L);
+  u64 q = (u64)r * D + ((1ULL << (l - 1)) - (u64)l);
+  int lo = 0, hi = nRej;  // rejections before ordinal q shift the stream position
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (rejOrd[mid] < q)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  u64 s = lcgAdvance(d.jumpA, d.jumpC, s0, q + (u64)lo);
+  for (int i = size; i > 1; --i) {
+    int j;
+    s = (s * 0x5DEECE66DULL + 0xBULL) & LCG_MASK;
+    int32_t rr = (int32_t)(uint32_t)(s >> 17);
+    if ((i & (i - 1)) == 0) {
+      j = (int)(((long long)i * (long long)rr) >> 31);
+    } else {
+      int32_t u = rr;
+      for (;;) {
+        j = u % i;
+        if ((int32_t)((uint32_t)u - (uint32_t)j + (uint32_t)(i - 1)) >= 0) break;
+        s = (s * 0x5DEECE66DULL + 0xBULL) & LCG_MASK;
+        u = (int32_t)(uint32_t)(s >> 17);
+      }
+    }
+    PeerT t = arr[i - 1];
+    arr[i - 1] = arr[j];
+    arr[j] = t;
+  }
+}
+
+// scan item accessors (pair scans)
+//   scan A: [0,nEv) -> (subCount, 0);  [nEv, nEv+N) -> (0, inboxCnt)
+//   scan B: [0,N)   -> (condFired, 0); [N, N+nItems) -> (evSlots, evDraws)
+struct Pair {
+  int a, b;
+};
+WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
+  Pair p;
+  if (which == 0) {
+    int nEv = d.ctl->nEv;
+    if (j < nEv) {
+      p.a = d.subCount[j];
+      p.b = 0;
+    } else {
+      p.a = 0;
+      p.b = d.inboxCnt[j - nEv];
+    }
+  } else {
+    if (j < d.N) {
+      p.a = d.condFired[j];
+      p.b = 0;
+    } else {
+      p.a = d.evSlots[j - d.N];
+      p.b = d.evDraws[j - d.N];
+    }
+  }
+  return p;
+}
+WTG_HD int scanCount(const Dev& d, int which) { return which == 0 ? d.ctl->nEv + d.N : d.N + d.ctl->nItems; }
+WTG_HD void scanStore(const Dev& d, int which, int j, Pair ex) {
+  if (which == 0) {
+    int nEv = d.ctl->nEv;
+    if (j < nEv)
+      d.itemBase[j] = ex.a;
+    else {
+      d.inboxOff[j - nEv] = ex.b;
+      d.inboxCnt[j - nEv] = 0;
+    }
+  } else {
+    d.slotBase[j] = ex.a;
+    d.drawBase[j] = ex.b;
+  }
+}
+WTG_HD void scanTotals(const Dev& d, int which, Pair tot) {
+  if (which == 0) {
+    d.ctl->nItems = tot.a;
+    if (tot.a > d.itemCap || tot.b > d.itemCap) setError(d, ERR_INBOX_OVERFLOW, tot.a);
+  } else {
+    d.ctl->totalSlots = tot.a;
+    d.ctl->totalDraws = tot.b;
+    if (tot.a > d.newEvCap) setError(d, ERR_DESC_OVERFLOW, tot.a);
+  }
+}
+
+}  // namespace wtg

@@ -1,0 +1,232 @@
+// wittgenstein_b200 — B200-native discrete-event engine behind the reference's
+// Protocol / Network / Node / Message surface.  Shared POD types (host + device).
+//
+// Data layout in HBM:
+//   * node attributes / counters: SoA arrays indexed by node id
+//   * time ring: RING buckets of fixed capacity, each an append-only array of 32-byte Ev
+//     records kept in *insertion order* (the reference's per-ms list is LIFO by insertion:
+//     core/Network.java:145-147, so processing position = count-1-index)
+//   * GSF: three N-bit rows per node (verified / individual-seen / individual-verified);
+//     level l of a node is the aligned sub-range (block) of the row, so no per-level bitsets
+//   * payload pools: per-level slabs of 2^(l-1) bits for in-flight / queued aggregates
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WTG_HD __host__ __device__ __forceinline__
+#else
+#define WTG_HD inline
+#endif
+
+namespace wtg {
+
+constexpr int MS_CHUNK = 1024;       // new envelopes per multisplit chunk (one warp)
+constexpr int MAX_LEVELS = 24;
+constexpr int MAX_ACC = 16;          // max destinations of a protocol multi-send handled on device
+constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bits for l <= 7
+constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
+
+// protocols
+enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2 };
+
+// event kinds (Ev.kind)
+enum : uint32_t {
+  EV_MSG = 0,       // single-destination message      (Envelope.SingleDestEnvelope)
+  EV_MULTI = 1,     // multi-destination message, aux = record index (Envelope.MultipleDest*Envelope)
+  EV_TASK = 2,      // one-shot task on node `to`       (messages/Task.java)
+  EV_PERIODIC = 3   // periodic task on node `to`       (messages/PeriodicTask.java)
+};
+
+// message / payload kinds, low 2 bits of Ev.meta / QEntry.meta for GSF
+enum : uint32_t {
+  PK_INLINE = 0,  // bits of the level block stored in `pl` (block <= 64 bits, bits in row position)
+  PK_POOL = 1,    // bits stored in a pool slab; pl = slot | (cardinality << 32)
+  PK_FULL = 2,    // the aligned 2^k block around `from` (k in meta)
+  PK_INDIV = 3    // the single signature of `from`
+};
+WTG_HD uint32_t metaMake(uint32_t kind, uint32_t level, uint32_t k) { return kind | (level << 2) | (k << 7); }
+WTG_HD uint32_t metaKind(uint32_t m) { return m & 3u; }
+WTG_HD uint32_t metaLevel(uint32_t m) { return (m >> 2) & 31u; }
+WTG_HD uint32_t metaK(uint32_t m) { return (m >> 7) & 31u; }
+// PingPong message types (Ev.meta)
+enum : uint32_t { PP_PING = 1, PP_PONG = 2 };
+
+struct Ev {  // 32 bytes: one in-flight envelope / task
+  uint32_t kind;
+  uint32_t to;
+  uint32_t from;
+  uint32_t meta;
+  uint64_t pl;
+  uint32_t aux;
+  uint32_t pad;
+};
+
+struct QEntry {  // 16 bytes: one entry of a GSF node's toVerify list
+  uint32_t from;
+  uint32_t meta;
+  uint64_t pl;
+};
+
+struct MultiRec {  // multi-destination envelope: sorted destinations + explicit arrivals
+  uint32_t from;
+  uint32_t meta;
+  uint64_t pl;
+  uint32_t n;
+  uint32_t cur;
+  uint32_t off;  // offset into recDest / recArrival
+  uint32_t pad;
+};
+
+// descriptor kinds: what a handler asks the engine to do (in program order)
+enum : uint32_t {
+  DK_SEND_SINGLE = 0,  // network.send(msg, from, to): one rd.nextInt()
+  DK_SEND_MULTI = 1,   // network.send(msg, from, dests): one rd.nextInt()
+  DK_INSERT_AT = 2     // sendArriveAt / registerTask / multi-dest re-push: no draw
+};
+struct Desc {  // 48 bytes
+  uint32_t dkind;
+  uint32_t item;  // scan item (N + pos for events)
+  uint32_t sub;   // program-order index inside the event
+  uint32_t from;
+  uint32_t to;      // SINGLE: dest; MULTI: offset into destScratch; INSERT_AT: dest node
+  uint32_t nDest;   // MULTI
+  uint32_t evKind;  // kind of the Ev to create
+  uint32_t meta;
+  uint64_t pl;
+  int32_t target;  // INSERT_AT: arrival tick
+  uint32_t aux;
+};
+
+// latency model kinds (device form: integer tables built on the host)
+enum : int {
+  LAT_DIST_DELTA = 0,  // tab[dist*100+delta]           NetworkLatencyByDistanceWJitter
+  LAT_CITY = 1,        // same city -> 1 else max(1, base[cf*11+ct] + jit[delta])   AwsRegionNetworkLatency
+  LAT_CONST = 2,       // param                          NetworkFixedLatency / NetworkNoLatency
+  LAT_DELTA = 3,       // tab[delta]                     NetworkUniformLatency / MeasuredNetworkLatency
+  LAT_DELTA_2X = 4,    // max(1, extra+extra+tab[delta]) then extras again (EthScanNetworkLatency quirk)
+  LAT_DIST = 5         // tab[dist]                      IC3NetworkLatency
+};
+
+struct Ctl {  // device-resident control block (one per engine)
+  int time;       // network.time
+  int until;      // end of the current runMs window (inclusive)
+  int tick;       // tick being processed
+  int condMode;   // 0 = no conditional-task pass, 1 = normal, 2 = end-of-window overshoot pass
+  int nEv;        // events in this tick's bucket
+  int nDesc;      // descriptors allocated this tick
+  int nDestScratch;
+  int nItems;     // scan items this tick (N + nEv)
+  int totalSlots, totalDraws;
+  uint32_t callId;  // identity of the reference's current nextMessage() call (conditional-task snapshot)
+  int didSomething;
+  unsigned long long rng;  // java.util.Random state
+  int error;               // first error code (0 = ok)
+  int errorDetail;
+  int recTop, recDestTop;  // multi-destination record arenas
+  int freeTop;             // deferred payload frees
+  int maxQueue, maxBucket, maxInbox;
+  unsigned long long statDeliveries, statTasks, statCondRuns, statDraws, statEvalEntries, statEvalWords;
+  unsigned long long statUpdates, statCycles, statSends, statMultiSends, statSendWords, statEvents;
+  int poolFreeCnt[MAX_LEVELS];
+  int poolMinFree[MAX_LEVELS];
+};
+
+enum : int {
+  ERR_NONE = 0,
+  ERR_BUCKET_OVERFLOW = 1,
+  ERR_QUEUE_OVERFLOW = 2,
+  ERR_POOL_EXHAUSTED = 3,
+  ERR_FAR_FUTURE = 4,
+  ERR_DESC_OVERFLOW = 5,
+  ERR_REC_OVERFLOW = 6,
+  ERR_FREE_OVERFLOW = 7,
+  ERR_INTERNAL = 8,
+  ERR_INBOX_OVERFLOW = 9
+};
+
+// All device pointers + sizes; passed by value to kernels.
+struct Dev {
+  // ---- sizes / parameters ----
+  int N, L, W64;
+  int ring;      // buckets in the time ring (power of two > largest latency + period)
+  int msChunks;  // rows of msCount
+  int proto;
+  int threshold, timeoutPerLevel, period, accel;
+  int qcap, bcap;
+  int msgDiscardTime;
+  int descCap, destScratchCap, recCap, recDestCap, freeCap, newEvCap, itemCap;
+  int latKind, latParam;
+  int peerBits;  // 16 or 32
+  // ---- control ----
+  Ctl* ctl;
+  // ---- nodes ----
+  int16_t* nx;
+  int16_t* ny;
+  int16_t* nextra;
+  uint8_t* ncity;
+  uint8_t* ndown;
+  uint8_t* npart;
+  long long* msgReceived;
+  long long* msgSent;
+  long long* bytesSent;
+  long long* bytesReceived;
+  long long* doneAt;
+  // ---- latency tables ----
+  const int16_t* latTab;   // LAT_DIST_DELTA: [1145*100]; LAT_DELTA*: [100]; LAT_DIST: [1145]
+  const int16_t* latBase;  // LAT_CITY: [11*11]
+  const int16_t* latJit;   // LAT_CITY: [100]
+  const unsigned long long* jumpA;  // LCG jump tables: a^(2^i), c(2^i), 48 entries
+  const unsigned long long* jumpC;
+  // ---- time ring ----
+  Ev* buckets;        // [ring][bcap]
+  int* bucketCount;   // [ring]
+  // ---- per-tick scratch ----
+  int* inboxCnt;      // [N]  events addressed to the node this tick
+  int* inboxOff;      // [N]
+  int* inboxFill;     // [N]
+  unsigned long long* inbox;  // [bcap*? ] (key<<32 | entry index)
+  int* subCount;      // [bcap] deliveries (+ re-push) of the event at processing position p
+  int* itemBase;      // [bcap] exclusive scan of subCount
+  int* evSlots;       // [itemCap] descriptors emitted by scan item
+  int* evDraws;       // [itemCap] rd.nextInt() draws consumed by scan item
+  int* condFired;     // [N]
+  Ev* condEv;         // [N] task created by the conditional task of node n
+  int* condTarget;    // [N]
+  int* slotBase;      // [N + itemCap]
+  int* drawBase;      // [N + itemCap]
+  int* scanPartial;   // [2 * tiles]
+  Desc* desc;         // [descCap]
+  uint32_t* destScratch;  // [destScratchCap]
+  Ev* newEv;          // [newEvCap] in creation order
+  int* newTarget;     // [newEvCap]
+  int* msCount;       // [msChunks][ring]
+  MultiRec* rec;      // [recCap]
+  uint32_t* recDest;  // [recDestCap]
+  int* recArrival;    // [recDestCap]
+  uint32_t* freeList; // [freeCap] level<<27 | slot
+  // ---- PingPong ----
+  int* pong;  // [N]
+  // ---- GSF ----
+  unsigned long long* verified;   // [N][W64]
+  unsigned long long* indivSeen;  // [N][W64]
+  unsigned long long* indivVer;   // [N][W64]
+  int* pos;        // [N][L]
+  int* remaining;  // [N][L]
+  int* cntVer;     // [N][L]
+  int* cntIndiv;   // [N][L]
+  int* cntUnion;   // [N][L]
+  int* totalCard;  // [N]
+  int* minStart;   // [N]
+  uint32_t* stamp; // [N]
+  int* pairing;    // [N]
+  int* qLen;       // [N]
+  int* sigChecked; // [N]
+  int* sigQueueSize;  // [N]
+  QEntry* queue;   // [N][qcap]
+  void* peers;     // [N][N-1] uint16 (block-relative) or uint32 (absolute ids)
+  unsigned long long* pool[MAX_LEVELS];  // slabs
+  uint32_t* poolFree[MAX_LEVELS];        // free stacks
+  int poolCap[MAX_LEVELS];
+};
+
+}  // namespace wtg

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's `Network` surface for the accelerated path.
+
+Reference: core/src/main/java/net/consensys/wittgenstein/core/Network.java — `rd.setSeed` (:32),
+`setNetworkLatency` (:665-677), `runMs` / `run` (:306-338), `time` (:49), `msgs.size()` /
+`msgs.sizeAt` (:204-220), `partition` / `endPartition` (:693-707), `Node.stop/start`
+(core/Node.java:120-127), per-node counters (core/Node.java:72-79).
+Every method is a thin call through the C ABI declared in include/wtg.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import WtgError
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Network:
+    def __init__(self, _api=None):
+        self.api = _api or _lib.api()
+        self.h = C.c_void_p(self.api.create())
+        if not self.h:
+            raise WtgError(self.api.last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----
+    def set_seed(self, seed):
+        """network.rd.setSeed(seed) — before Protocol.init() (RunMultipleTimes.java:47)."""
+        self.api.check(self.api.set_seed(self.h, int(seed)))
+
+    def set_network_latency(self, name):
+        """RegistryNetworkLatencies.getByName(name); None -> NetworkLatencyByDistanceWJitter."""
+        self.api.check(self.api.set_network_latency(self.h, None if name is None else name.encode()))
+
+    def set_network_latency_measured(self, proportions, values):
+        p = np.asarray(proportions, np.int32)
+        v = np.asarray(values, np.int32)
+        self.api.check(self.api.set_network_latency_measured(self.h, _p(p, C.c_int), _p(v, C.c_int), len(p)))
+
+    def set_node_builder(self, name):
+        self.api.check(self.api.set_node_builder(self.h, None if name is None else name.encode()))
+
+    def set_msg_discard_time(self, ms):
+        self.api.check(self.api.set_msg_discard_time(self.h, int(ms)))
+
+    def set_tunable(self, key, value):
+        self.api.check(self.api.set_tunable(self.h, key.encode(), int(value)))
+
+    # ---- run ----
+    def run_ms(self, ms):
+        return bool(self.api.check(self.api.run_ms(self.h, int(ms))))
+
+    def run(self, seconds):
+        return self.run_ms(seconds * 1000)
+
+    @property
+    def time(self):
+        return self.api.time(self.h)
+
+    @property
+    def node_count(self):
+        return self.api.node_count(self.h)
+
+    def msgs_size(self):
+        return self.api.check(self.api.msgs_size(self.h))
+
+    def msgs_size_at(self, t):
+        return self.api.check(self.api.msgs_size_at(self.h, int(t)))
+
+    def stop_node(self, node_id):
+        self.api.check(self.api.stop_node(self.h, int(node_id)))
+
+    def start_node(self, node_id):
+        self.api.check(self.api.start_node(self.h, int(node_id)))
+
+    def partition(self, part):
+        self.api.check(self.api.partition(self.h, float(part)))
+
+    def end_partition(self):
+        self.api.check(self.api.end_partition(self.h))
+
+    def rng_state(self):
+        return int(self.api.rng_state(self.h))
+
+    # ---- read-back ----
+    def counters(self):
+        """rows: msgReceived, msgSent, bytesSent, bytesReceived, doneAt (int64, [5, N])."""
+        out = np.zeros((5, self.node_count), np.int64)
+        self.api.check(self.api.node_counters(self.h, _p(out, C.c_longlong)))
+        return out
+
+    def attrs(self):
+        n = self.node_count
+        x = np.zeros(n, np.int32); y = np.zeros(n, np.int32); e = np.zeros(n, np.int32); c = np.zeros(n, np.int32)
+        s = np.zeros(n, np.float64); d = np.zeros(n, np.uint8)
+        self.api.check(self.api.node_attrs(self.h, _p(x, C.c_int), _p(y, C.c_int), _p(e, C.c_int), _p(c, C.c_int),
+                                           _p(s, C.c_double), _p(d, C.c_ubyte)))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def stats(self):
+        out = np.zeros(24, np.int64)
+        self.api.check(self.api.stats(self.h, _p(out, C.c_longlong)))
+        keys = ["deliveries", "tasks", "cond_runs", "draws", "eval_entries", "eval_words", "updates", "cycles", "sends",
+                "multi_sends", "send_words", "events", "max_queue", "max_bucket", "max_inbox", "rec_top", "rec_dest_top",
+                "kernel_launches", "min_pool_free", "init_draws", "ring", "bcap", "qcap", "peer_bits"]
+        return dict(zip(keys, out.tolist()))

@@ -1,0 +1,132 @@
+"""Host-side mirrors of the reference protocols whose `Message.action` bodies run as device
+state-transition kernels: same constructor parameters, `init()`, `network()`, `copy()`.
+
+Reference: protocols/src/main/java/net/consensys/wittgenstein/protocols/PingPong.java and
+GSFSignature.java; core/Protocol.java:7-22.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import WtgError
+from .network import Network, _p
+
+
+class PingPongParameters:
+    """PingPong.PingPongParameters (PingPong.java:34-50)."""
+
+    def __init__(self, node_ct=1000, node_builder_name=None, network_latency_name=None):
+        self.node_ct = node_ct
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+
+
+class PingPong:
+    def __init__(self, params=None, _api=None):
+        self.params = params or PingPongParameters()
+        self._api = _api
+        self._net = Network(_api)
+        self._net.set_node_builder(self.params.node_builder_name)  # RegistryNodeBuilders.getByName (PingPong.java:54)
+        self._net.set_network_latency(self.params.network_latency_name)  # :55-56
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return PingPong(self.params, self._api)
+
+    def init(self):
+        self._net.api.check(self._net.api.pingpong_init(self._net.h, int(self.params.node_ct)))
+
+    def pongs(self):
+        out = np.zeros(self._net.node_count, np.int32)
+        self._net.api.check(self._net.api.pingpong_pongs(self._net.h, _p(out, C.c_int)))
+        return out
+
+
+class GSFSignatureParameters:
+    """GSFSignature.GSFSignatureParameters (GSFSignature.java:27-107); ratios are accepted like the
+    second constructor (:86-106) when threshold / nodes_down are floats."""
+
+    def __init__(self, node_count=32768 // 32, threshold=None, pairing_time=3, timeout_per_level_ms=50, period_duration_ms=10,
+                 accelerated_calls_count=10, nodes_down=0, node_builder_name=None, network_latency_name=None):
+        if threshold is None:
+            threshold = int(node_count * 0.99)
+        if isinstance(threshold, float):
+            threshold = int(threshold * node_count)
+        if isinstance(nodes_down, float):
+            nodes_down = int(nodes_down * node_count)
+        if nodes_down >= node_count or nodes_down < 0 or threshold > node_count or nodes_down + threshold > node_count:
+            raise WtgError(f"nodeCount={node_count}, threshold={threshold}")  # :69-74
+        self.node_count = node_count
+        self.threshold = threshold
+        self.pairing_time = pairing_time
+        self.timeout_per_level_ms = timeout_per_level_ms
+        self.period_duration_ms = period_duration_ms
+        self.accelerated_calls_count = accelerated_calls_count
+        self.nodes_down = nodes_down
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+
+
+class GSFSignature:
+    def __init__(self, params, _api=None, tunables=None):
+        self.params = params
+        self._api = _api
+        self._tunables = dict(tunables or {})
+        self._net = Network(_api)
+        self._net.set_node_builder(params.node_builder_name)  # GSFSignature.java:111
+        self._net.set_network_latency(params.network_latency_name)  # :112-113
+        for k, v in self._tunables.items():
+            self._net.set_tunable(k, v)
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return GSFSignature(self.params, self._api, self._tunables)
+
+    def init(self):
+        p = self.params
+        arr = np.array([p.node_count, p.threshold, p.pairing_time, p.timeout_per_level_ms, p.period_duration_ms,
+                        p.accelerated_calls_count, p.nodes_down], np.int32)
+        self._net.api.check(self._net.api.gsf_init(self._net.h, _p(arr, C.c_int)))
+        self.levels = self._net.api.gsf_levels(self._net.h)
+        self.words = max(1, p.node_count // 64)
+
+    # ---- read-back of node state (GSFNode fields) ----
+    def verified(self):
+        """verifiedSignatures of every node: uint64 [N, N/64]; bit i of the set = bit i%64 of word i//64."""
+        out = np.zeros((self.params.node_count, self.words), np.uint64)
+        self._net.api.check(self._net.api.gsf_verified(self._net.h, _p(out, C.c_ulonglong)))
+        return out
+
+    def rows(self, which):
+        """0 verified, 1 individualSignatures (union over levels), 2 indivVerifiedSig (union over levels)."""
+        out = np.zeros((self.params.node_count, self.words), np.uint64)
+        self._net.api.check(self._net.api.gsf_rows(self._net.h, int(which), _p(out, C.c_ulonglong)))
+        return out
+
+    def scalars(self):
+        n = self.params.node_count
+        a = [np.zeros(n, np.int32) for _ in range(5)]
+        self._net.api.check(self._net.api.gsf_node_scalars(self._net.h, *[_p(v, C.c_int) for v in a]))
+        return dict(pairing=a[0], sig_checked=a[1], sig_queue_size=a[2], to_verify=a[3], card=a[4])
+
+    def level_scalars(self):
+        n, L = self.params.node_count, self.levels
+        a = [np.zeros((n, L), np.int32) for _ in range(3)]
+        self._net.api.check(self._net.api.gsf_level_scalars(self._net.h, *[_p(v, C.c_int) for v in a]))
+        return dict(pos=a[0], remaining=a[1], card=a[2])
+
+    def peers(self, node, level):
+        cap = max(1, self.params.node_count)
+        out = np.zeros(cap, np.int32)
+        k = self._net.api.check(self._net.api.gsf_peers(self._net.h, node, level, _p(out, C.c_int), cap))
+        return out[:k].copy()
+
+    def continue_if(self):
+        """GSFSignature.newConfIf (:670-682): some live node is still below the threshold."""
+        card = self.scalars()["card"]
+        down = self._net.attrs()["down"]
+        return bool(((card < self.params.threshold) & (down == 0)).any())
