@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: simulated-ms/sec (and msgs/sec) of
+GSFSignature, 131 072 nodes (BASELINE.json), through the C ABI of wittgenstein_b200.
+
+A "step" is one `network.runMs(STEP_MS)` window of one continuing simulation (the reference drives
+its runs the same way: ProgressPerTime.java:79-95 calls runMs in a loop).  W warm-up steps, then
+exactly K timed steps:
+  value  = K*STEP_MS / device time (CUDA events on the engine's stream; max over ranks)
+  e2e    = same metric through the public API with host buffers: every step also reads back what the
+           reference's callers read after each runMs (per-node signature count + the 5 node counters)
+           and writes/reads the control block — a fresh, identically seeded network, wall clock.
+  roofline: dominant kernel of the timed region (per-kernel CUDA-event timing in a third identical
+           pass), algorithmic bytes / its time, against MEASURED_PEAKS.json.
+  cpu_baseline: the CPU oracle (C++ restatement of the reference engine, 1 thread like the reference)
+           on a bounded sample of the same workload.
+--impl reference times the reference's CPU path (the oracle port; the Java reference cannot run here:
+no JVM) on the host cores with the same step definition.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
+
+
+def gsf_params(n):
+    # GSFSignature.newProtocol() ratios (GSFSignature.java:684-697): threshold .85, dead .10, pairing 4,
+    # level timeout 50, period 20, 10 accelerated calls, AWS regions + uniform speed + 33 % Tor
+    return dict(node_count=n, threshold=int(0.85 * n), pairing_time=4, timeout_per_level_ms=50, period_duration_ms=20,
+                accelerated_calls_count=10, nodes_down=int(0.10 * n), node_builder_name=AWS_NB, network_latency_name=AWS_NL)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        import statistics
+
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_gsf(n, seed):
+    from wittgenstein_b200 import GSFSignature, GSFSignatureParameters
+
+    p = GSFSignature(GSFSignatureParameters(**gsf_params(n)))
+    p.network().set_seed(seed)
+    t0 = time.time()
+    p.init()
+    p.network().msgs_size()  # sync
+    return p, time.time() - t0
+
+
+def event_counts(st0, st1):
+    return {k: st1[k] - st0[k] for k in ("deliveries", "tasks", "cond_runs", "draws", "eval_entries", "eval_words", "updates",
+                                         "cycles", "sends", "multi_sends", "send_words", "events")}
+
+
+def algorithmic_bytes(ev):
+    """minimal traffic per event type of this engine's layout (bytes)."""
+    b = {}
+    b["k_cond"] = 16 * ev["eval_entries"] + 8 * ev["eval_words"] + 16 * ev["eval_entries"] + 64 * ev["cond_runs"]
+    b["k_node"] = 96 * ev["deliveries"] + 8 * ev["send_words"] + 48 * (ev["sends"] + ev["multi_sends"]) + 128 * ev["updates"] + 64 * ev["cycles"]
+    b["k_emit"] = (48 + 32 + 4) * (ev["sends"] + ev["multi_sends"] + ev["cycles"] + ev["cond_runs"])
+    b["k_ms_scatter"] = (32 + 32 + 4) * (ev["sends"] + ev["multi_sends"] + ev["cycles"] + ev["cond_runs"])
+    return b
+
+
+def cpu_baseline(n_cpu, step_ms, budget_s, threads=1):
+    """Oracle (C++ port of the reference engine, single thread like the reference) on a bounded sample:
+    the first runMs windows of the same GSF workload at n_cpu nodes, until ~budget_s of CPU time."""
+    from tests.oracle_lib import OracleGSF
+
+    g = gsf_params(n_cpu)
+    o = OracleGSF(n_cpu, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
+    t0 = time.time()
+    o.init()
+    init_s = time.time() - t0
+    sim = 0
+    wall = 0.0
+    st0 = o.stats()
+    while wall < budget_s and sim < 4000:
+        wall += o.run_timed(step_ms, 1)
+        sim += step_ms
+    st1 = o.stats()
+    msgs = (st1["deliveries"] - st0["deliveries"]) + (st1["tasks"] - st0["tasks"]) + (st1["cond_runs"] - st0["cond_runs"])
+    return {"value": sim / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
+            "sample": f"oracle (C++ restatement, 1 thread), GSFSignature {n_cpu} nodes, first {sim} simulated ms in {wall:.1f} s "
+                      f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Java engine cannot run here (no JVM/gradle/jars:
+    SURVEY.md §8c), so this times the oracle port with the same step definition on a bounded sample."""
+    import psutil
+
+    n = args.nodes
+    need = n * n * 4 * 1.4
+    while n > 1024 and (need > psutil.virtual_memory().available * 0.8 or n > args.cpu_max_nodes):
+        n //= 2
+        need = n * n * 4 * 1.4
+    from tests.oracle_lib import OracleGSF
+
+    g = gsf_params(n)
+    o = OracleGSF(n, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
+    o.init()
+    step_ms = args.ref_step_ms
+    for _ in range(args.warmup):
+        o.run_timed(step_ms, 1)
+    wall = o.run_timed(step_ms, args.steps)
+    val = args.steps * step_ms / wall
+    line = {"impl": "reference", "metric": "simulated-ms/sec, GSFSignature", "value": val, "unit": "simulated-ms/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitmaps / int32", "data": "synthetic",
+            "config": {"workload": f"GSFSignature {n} nodes (target {args.nodes}), AWS regions, 33% Tor, 10% dead; step = runMs({step_ms})",
+                       "note": "reference = C++ oracle port, 1 thread (the reference engine is single-threaded: Network.java:10); "
+                               "Java reference not runnable here (no JVM)"},
+            "cpu_baseline": {"value": val, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
+                             "sample": f"{args.steps} x runMs({step_ms}) after {args.warmup} warm-up steps at {n} nodes"},
+            "e2e": {"value": val, "unit": "simulated-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nodes", type=int, default=131072)
+    ap.add_argument("--step-ms", type=int, default=100)
+    ap.add_argument("--ref-step-ms", type=int, default=10)
+    ap.add_argument("--cpu-nodes", type=int, default=16384)
+    ap.add_argument("--cpu-max-nodes", type=int, default=16384)
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+
+    import __graft_entry__ as g
+
+    if rank == 0:
+        g.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    os.environ["WTG_DEVICE"] = str(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n, K, W, S = args.nodes, args.steps, args.warmup, args.step_ms
+    seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)
+
+    # ---- pass 1: device-timed (value) ----
+    p, init_s = make_gsf(n, seed)
+    net = p.network()
+    for _ in range(W):
+        net.run_ms(S)
+    st0 = net.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    net.timer_start()
+    for _ in range(K):
+        net.run_ms(S)
+    dev_ms = net.timer_stop_ms()
+    torch.cuda.synchronize()
+    barrier()
+    sampler.stop_flag = True
+    st1 = net.stats()
+    ev = event_counts(st0, st1)
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    card_end = p.scalars()["card"]
+    done = not p.continue_if()
+    dev_ms = max_over_ranks(dev_ms)
+    del p, net
+
+    # ---- pass 2: end to end through the public API with host read-backs every step ----
+    p, _ = make_gsf(n, seed)
+    net = p.network()
+    for _ in range(W):
+        net.run_ms(S)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(K):
+        net.run_ms(S)
+        card = p.scalars()["card"]          # StatsGetter: verifiedSignatures.cardinality() of every node
+        cnt = net.counters()                # msgReceived / msgSent / bytesSent / bytesReceived / doneAt
+        d2h = card.nbytes * 5 + cnt.nbytes
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert (card == card_end).all(), "e2e pass diverged from the device-timed pass"
+    ctl_bytes = 384
+
+    # ---- pass 3: per-kernel CUDA-event timing of the same window (roofline of the dominant kernel) ----
+    prof = {}
+    if not args.no_profile:
+        net.profile_enable(False)
+        del p, net
+        p, _ = make_gsf(n, seed)
+        net = p.network()
+        for _ in range(W):
+            net.run_ms(S)
+        net.profile_enable(True)
+        for _ in range(K):
+            net.run_ms(S)
+        prof = net.profile_read()
+        net.profile_enable(False)
+    del p, net
+
+    value = sum_over_ranks(K * S) / (dev_ms / 1000.0)
+    e2e = sum_over_ranks(K * S) / e2e_s
+    msgs = ev["deliveries"] + ev["tasks"] + ev["cond_runs"]
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roof = None
+    if prof:
+        ab = algorithmic_bytes(ev)
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        kname, (kms, kcnt) = top
+        total_ms = sum(v[0] for v in prof.values())
+        if kname in ab and kcnt:
+            achieved = ab[kname] / (kms / 1000.0) / 1e9
+            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                    "avg_launch_us": 1000.0 * kms / kcnt, "algorithmic_bytes_per_launch": ab[kname] / kcnt,
+                    "share_of_step": kms / total_ms,
+                    "kernel_ms": {k: round(v[0], 3) for k, v in prof.items()}}
+
+    line = {"metric": "simulated-ms/sec, GSFSignature 131,072 nodes", "value": value, "unit": "simulated-ms/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bitmaps / int32", "data": "synthetic",
+            "config": {"workload": f"GSFSignature {n} nodes, threshold {int(.85*n)}, {int(.1*n)} dead, pairing 4, level timeout 50, period 20, "
+                                   f"10 accelerated calls, {AWS_NB}, {AWS_NL}; step = runMs({S}) of one continuing run, timed window "
+                                   f"[{W*S},{(W+K)*S}] ms",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas (no data-path collective)",
+                       "l2": "per-step working set (node rows + queues + ring) exceeds L2 at this size",
+                       "all_nodes_done_at_end": bool(done)},
+            "msgs_per_s": sum_over_ranks(msgs) / (dev_ms / 1000.0),
+            "e2e": {"value": e2e, "unit": "simulated-ms/s", "h2d_bytes_per_step": ctl_bytes, "d2h_bytes_per_step": int(d2h + ctl_bytes * 3)},
+            "gpu_launches": int(launches), "init_s": init_s, "events": ev, "clocks": sampler.summary()}
+    if roof:
+        line["roofline"] = roof
+    if rank == 0 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_baseline(min(args.cpu_nodes, n), 10, args.cpu_budget_s)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+/* wittgenstein_b200 — C ABI of the B200-native simulation engine.
+ *
+ * The reference (ConsenSys/wittgenstein, Java) has no FFI of its own: the seam is the Java API
+ * `Protocol { network(); copy(); init(); }` (core/Protocol.java:7-22) and the public members of
+ * `core.Network`.  Each entry point below names the reference member it stands in for; a JNI
+ * (or ctypes) binding maps them 1:1 — see INTEGRATION.md.  All paths are relative to
+ * core/src/main/java/net/consensys/wittgenstein/core/ unless they start with protocols/.
+ *
+ * Conventions:
+ *   - single caller thread per network, like the reference (Network.java:10);
+ *   - functions returning int return >= 0 on success and -1 on failure; the message of the
+ *     IllegalArgumentException / IllegalStateException the reference would have thrown is then
+ *     available from wtg_last_error() (thread-local);
+ *   - the engine owns all node/message state (device memory); read-back functions copy out;
+ *   - same seed => identical results, bit for bit, as the reference engine.
+ *   - there is no CPU fallback: wtg_create() fails when no CUDA device is present.
+ */
+#ifndef WTG_H
+#define WTG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void wtg_net; /* opaque: one core.Network + the protocol state living on it */
+
+const char* wtg_last_error(void);
+
+/* new Network<>()  — Network.java:13-49: rd = new Random(0), time = 0, IC3NetworkLatency */
+wtg_net* wtg_create(void);
+void wtg_destroy(wtg_net* net);
+
+/* network.rd.setSeed(seed) before Protocol.init() — RunMultipleTimes.java:47, ProgressPerTime.java:71 */
+int wtg_set_seed(wtg_net* net, long long seed);
+
+/* network.setNetworkLatency(RegistryNetworkLatencies.singleton.getByName(name)) —
+ * Network.java:669-677, RegistryNetworkLatencies.java:28-58.  name == NULL selects
+ * NetworkLatencyByDistanceWJitter like the registry does.  Supported: NetworkLatencyByDistanceWJitter,
+ * AwsRegionNetworkLatency, NetworkNoLatency, EthScanNetworkLatency, IC3NetworkLatency,
+ * "NetworkFixedLatency(f)" / "NetworkUniformLatency(f)" for the registry's f values. */
+int wtg_set_network_latency(wtg_net* net, const char* name);
+/* network.setNetworkLatency(int[] distribProp, int[] distribVal) — Network.java:665-667 */
+int wtg_set_network_latency_measured(wtg_net* net, const int* proportions, const int* values, int n);
+
+/* nb = RegistryNodeBuilders.singleton.getByName(name) — RegistryNodeBuilders.java:71-81
+ * ("<AWS|RANDOM>_SPEED=<CONSTANT|GAUSSIAN>_TOR=<d.dd>"; NULL/blank = RANDOM, constant speed, no Tor) */
+int wtg_set_node_builder(wtg_net* net, const char* name);
+
+/* network.setMsgDiscardTime(ms) — Network.java:103-106 */
+int wtg_set_msg_discard_time(wtg_net* net, int ms);
+
+/* device capacities (no reference counterpart): "bcap", "qcap", "pool_slots_per_node", "desc_cap",
+ * "rec_cap", "ring".  Exceeding a capacity makes wtg_run_ms fail loudly; it never drops events. */
+int wtg_set_tunable(wtg_net* net, const char* key, long long value);
+
+/* new PingPong(params).init() — protocols/PingPong.java:52-57, 82-87 */
+int wtg_pingpong_init(wtg_net* net, int node_ct);
+
+/* new GSFSignature(params).init() — protocols/GSFSignature.java:59-84, 611-635.
+ * params7 = { nodeCount, threshold, pairingTime, timeoutPerLevelMs, periodDurationMs,
+ *             acceleratedCallsCount, nodesDown }  (the fields of GSFSignatureParameters) */
+int wtg_gsf_init(wtg_net* net, const int* params7);
+
+/* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
+int wtg_run_ms(wtg_net* net, int ms);
+/* network.time — Network.java:49 */
+int wtg_time(wtg_net* net);
+/* network.allNodes.size() — Network.java:29 */
+int wtg_node_count(wtg_net* net);
+/* network.msgs.size() / network.msgs.sizeAt(t) — Network.java:204-220 */
+int wtg_msgs_size(wtg_net* net);
+int wtg_msgs_size_at(wtg_net* net, int t);
+
+/* node.stop() / node.start() — Node.java:120-127 */
+int wtg_stop_node(wtg_net* net, int node_id);
+int wtg_start_node(wtg_net* net, int node_id);
+/* network.partition(part) / network.endPartition() — Network.java:693-707 */
+int wtg_partition(wtg_net* net, float part);
+int wtg_end_partition(wtg_net* net);
+
+/* the 48-bit state of network.rd (for parity checks of the consumed stream position) */
+unsigned long long wtg_rng_state(wtg_net* net);
+
+/* Node.msgReceived / msgSent / bytesSent / bytesReceived / doneAt — Node.java:72-79.
+ * out5N = 5 arrays of N int64, in that order. */
+int wtg_node_counters(wtg_net* net, long long* out5N);
+/* Node.x / y / extraLatency / city (AWS region index, -1 otherwise) / speedRatio / isDown() — Node.java:36-69.
+ * Any pointer may be NULL. */
+int wtg_node_attrs(wtg_net* net, int* x, int* y, int* extra, int* city, double* speed, unsigned char* down);
+
+/* PingPongNode.pong — protocols/PingPong.java:61 */
+int wtg_pingpong_pongs(wtg_net* net, int* out);
+
+/* GSFNode.levels.size() — protocols/GSFSignature.java:168 */
+int wtg_gsf_levels(wtg_net* net);
+/* GSFNode.verifiedSignatures of every node as N rows of N/64 uint64 (bit i = word i/64, bit i%64) — :169 */
+int wtg_gsf_verified(wtg_net* net, unsigned long long* outNW);
+/* which: 0 verifiedSignatures, 1 union over levels of SFLevel.individualSignatures, 2 of SFLevel.indivVerifiedSig — :242-244 */
+int wtg_gsf_rows(wtg_net* net, int which, unsigned long long* outNW);
+/* nodePairingTime, sigChecked, sigQueueSize, toVerify.size(), verifiedSignatures.cardinality() — :167-174 */
+int wtg_gsf_node_scalars(wtg_net* net, int* pairing, int* sig_checked, int* sig_queue_size, int* to_verify_size, int* card);
+/* SFLevel.posInLevel, remainingCalls, verifiedSignatures.cardinality() as N*L arrays — :251-254 */
+int wtg_gsf_level_scalars(wtg_net* net, int* pos, int* remaining, int* card);
+/* SFLevel.peers of one node / level — :239 ; returns the list length */
+int wtg_gsf_peers(wtg_net* net, int node, int level, int* out, int cap);
+
+/* engine statistics (24 int64), see wittgenstein_b200/network.py:Network.stats for the keys */
+int wtg_stats(wtg_net* net, long long* out24);
+
+/* measurement hooks (no reference counterpart): a CUDA-event stopwatch on the engine's stream, and
+ * per-kernel event timing of the tick pipeline (names[i] are static strings) */
+int wtg_timer_start(wtg_net* net);
+double wtg_timer_stop_ms(wtg_net* net);
+int wtg_profile_enable(wtg_net* net, int on);
+int wtg_profile_read(wtg_net* net, double* ms, long long* launches, const char** names, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTG_H */

@@ -1,0 +1,154 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on the same
+seeded inputs — bit-exact (integer / bitmap work).  Sizes are chosen so the oracle finishes in seconds;
+full-size properties live in test_gpu_properties.py."""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import OracleGSF, OraclePingPong
+from tests.parity import compare_gsf, compare_init, run_lockstep
+
+pytestmark = pytest.mark.gpu
+
+NL = "NetworkLatencyByDistanceWJitter"
+NB = "RANDOM_SPEED=CONSTANT_TOR=0.00"
+AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
+
+
+def mk(n, thr, pairing, timeout, period, acc, dead, nb, nl, seed=None):
+    from wittgenstein_b200 import GSFSignature, GSFSignatureParameters
+
+    prm = GSFSignatureParameters(n, thr, pairing, timeout, period, acc, dead, nb, nl)
+    p = GSFSignature(prm)
+    o = OracleGSF(n, prm.threshold, pairing, timeout, period, acc, prm.nodes_down, nb, nl)
+    if seed is not None:
+        p.network().set_seed(seed)
+        o.lib.wo_gsf_set_seed(o.h, seed)
+    p.init()
+    o.init()
+    bad = compare_init(p, o) + compare_gsf(p, o, "init")
+    assert not bad, bad
+    return p, o
+
+
+@pytest.mark.parametrize("latency", [None, "NetworkNoLatency", "IC3NetworkLatency", "NetworkFixedLatency(100)",
+                                     "NetworkUniformLatency(200)"])
+def test_pingpong_config1(latency):
+    """BASELINE config #1: PingPong 1000 nodes, 1000 ms, 10 x runMs(100)."""
+    from wittgenstein_b200 import PingPong, PingPongParameters
+
+    p = PingPong(PingPongParameters(1000, None, latency))
+    o = OraclePingPong(1000, None, latency)
+    p.init(); o.init()
+    a, b = p.network().attrs(), o.attrs()
+    for k in ("x", "y", "extra", "down"):
+        assert (a[k] == b[k]).all()
+    for _ in range(10):
+        assert p.network().run_ms(100) == o.run_ms(100)
+        assert (p.pongs() == o.pongs()).all()
+        assert (p.network().counters() == o.counters()).all()
+        assert p.network().msgs_size() == o.msgs_size()
+    assert p.pongs()[0] == 1000 and p.network().msgs_size() == 0
+    assert p.network().stats()["kernel_launches"] > 0
+
+
+def test_pingpong_aws_tor_and_seeds():
+    from wittgenstein_b200 import PingPong, PingPongParameters
+
+    for seed in (0, 1, 2, -7):
+        p = PingPong(PingPongParameters(777, AWS_NB, AWS_NL))
+        o = OraclePingPong(777, AWS_NB, AWS_NL, seed=seed)
+        p.network().set_seed(seed)
+        p.init(); o.init()
+        for ms in (1, 2, 7, 90, 400, 1500, 3000):
+            assert p.network().run_ms(ms) == o.run_ms(ms)
+            assert (p.pongs() == o.pongs()).all() and (p.network().counters() == o.counters()).all()
+            assert p.network().msgs_size() == o.msgs_size()
+        assert p.pongs()[0] == 777
+
+
+def test_gsf_32_every_ms():
+    """Reference test size (PT/GSFSignatureTest): 32 nodes, compared after every single ms."""
+    p, o = mk(32, 1.0, 3, 20, 10, 10, 0, NB, NL)
+    assert p.network().run_ms(1) == o.run_ms(1)
+    assert p.network().msgs_size() == 64  # GSFSignatureTest.testSend
+    run_lockstep(p, o, 1, 500)
+    assert (p.scalars()["card"] == 32).all()
+
+
+def test_gsf_128_copy_params_dead_nodes():
+    """GSFSignatureTest.testCopy parameters: 128 nodes, 20 % dead, pairing 6, timeout 10, period 5."""
+    p, o = mk(128, .75, 6, 10, 5, 10, .2, NB, NL)
+    run_lockstep(p, o, 1, 300)
+    run_lockstep(p, o, 13, 2000, full_every=4)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_gsf_256_aws_tor_slicing(seed):
+    """AWS regions + Tor + uniform speed; odd runMs slicing exercises the end-of-window conditional pass."""
+    p, o = mk(256, 0.8, 4, 50, 20, 10, 0.1, AWS_NB, AWS_NL, seed=seed)
+    for step in (1, 2, 3, 5, 7, 11, 1, 1, 29):
+        run_lockstep(p, o, step, p.network().time + step)
+    run_lockstep(p, o, 7, 2100, full_every=8)
+    assert not p.continue_if() and not o.continue_if()
+
+
+def test_gsf_accel_off_and_small_accel():
+    for acc in (0, 1, 3):
+        p, o = mk(64, 1.0, 2, 30, 10, acc, 0, NB, "NetworkFixedLatency(100)")
+        run_lockstep(p, o, 10, 1500, full_every=5)
+
+
+def test_gsf_4096_config2():
+    """BASELINE config #2: GSFSignature 4096 nodes = GSFSignature.newProtocol() (GSFSignature.java:684-697),
+    runMs(10) until every live node reached the threshold; full state compared every 100 ms."""
+    p, o = mk(4096, 0.85, 4, 50, 20, 10, 0.10, AWS_NB, AWS_NL)
+    steps = 0
+    while o.continue_if() and steps < 400:
+        assert p.network().run_ms(10) == o.run_ms(10)
+        steps += 1
+        bad = compare_gsf(p, o, f"t={o.time}", full=(steps % 10 == 0))
+        assert not bad, bad
+    assert not p.continue_if()
+    bad = compare_gsf(p, o, "end", full=True)
+    assert not bad, bad
+    st = p.network().stats()
+    assert st["kernel_launches"] > 1000 and st["min_pool_free"] > 0
+
+
+def test_gsf_4096_random_positions_no_tor():
+    p, o = mk(4096, 0.99, 3, 50, 10, 10, 0, NB, NL)
+    for _ in range(12):
+        assert p.network().run_ms(50) == o.run_ms(50)
+    bad = compare_gsf(p, o, "t=600", full=True)
+    assert not bad, bad
+
+
+def test_error_paths():
+    from wittgenstein_b200 import GSFSignature, GSFSignatureParameters, Network, PingPong, PingPongParameters, WtgError
+
+    with pytest.raises(WtgError):
+        GSFSignatureParameters(32, 33, 3, 20, 10, 10, 0, NB, NL)
+    with pytest.raises(WtgError):
+        GSFSignature(GSFSignatureParameters(32, 30, 3, 20, 10, 10, 0, "NOPE_SPEED=CONSTANT_TOR=0.00", NL))
+    with pytest.raises(WtgError):
+        PingPong(PingPongParameters(10, None, "NoSuchLatency"))
+    p = PingPong(PingPongParameters(10, None, None))
+    with pytest.raises(WtgError):
+        p.network().run_ms(5)  # not initialised
+    p.init()
+    with pytest.raises(WtgError):
+        p.network().run_ms(0)  # Network.java:319-321
+    with pytest.raises(WtgError):
+        p.network().set_seed(1)  # after init
+    g = GSFSignature(GSFSignatureParameters(48, 40, 3, 20, 10, 10, 0, NB, NL))
+    with pytest.raises(WtgError):
+        g.init()  # power-of-two node counts only on the device engine
+    g = GSFSignature(GSFSignatureParameters(64, 60, 3, 20, 10, 10, 0, NB, AWS_NL))
+    with pytest.raises(WtgError):
+        g.init()  # AWS latency with non-AWS builder (NetworkLatency.java:146-148)
+    # a capacity that is too small fails loudly instead of dropping events
+    g = GSFSignature(GSFSignatureParameters(256, 250, 3, 20, 10, 10, 0, NB, NL), tunables={"qcap": 32})
+    g.init()
+    with pytest.raises(WtgError):
+        for _ in range(100):
+            g.network().run_ms(10)

@@ -1,0 +1,46 @@
+"""Size-independent properties of the GPU engine at sizes the oracle cannot reach in seconds."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
+
+
+def popcount_rows(a):
+    return np.unpackbits(a.view(np.uint8), axis=1).sum(axis=1)
+
+
+def make(n, tun=None):
+    from wittgenstein_b200 import GSFSignature, GSFSignatureParameters
+
+    p = GSFSignature(GSFSignatureParameters(n, 0.85, 4, 50, 20, 10, 0.10, AWS_NB, AWS_NL), tunables=tun)
+    p.init()
+    return p
+
+
+@pytest.mark.parametrize("n", [16384])
+def test_gsf_invariants_and_determinism(n):
+    a, b = make(n), make(n)
+    prev = np.ones(n, np.int64)
+    for i in range(12):
+        a.network().run_ms(100)
+        card = popcount_rows(a.verified()).astype(np.int64)
+        assert (card == a.scalars()["card"]).all()          # cached cardinality == popcount of the row
+        assert (card >= prev).all()                           # verified sets never shrink
+        prev = card
+        c = a.network().counters()
+        assert c[1].sum() >= c[0].sum()                       # every received message was sent
+        lv = a.level_scalars()
+        assert (lv["card"].sum(axis=1)[a.network().attrs()["down"] == 0] == card[a.network().attrs()["down"] == 0]).all()
+        # own signature always present
+        ids = np.arange(n)
+        assert ((a.verified()[ids, ids // 64] >> (ids % 64).astype(np.uint64)) & np.uint64(1)).all()
+    # same seed, different runMs slicing in busy ticks -> same state (determinism across two engines)
+    for i in range(24):
+        b.network().run_ms(50)
+    assert (a.verified() == b.verified()).all()
+    assert (a.network().counters() == b.network().counters()).all()
+    assert a.network().rng_state() == b.network().rng_state()
+    down = a.network().attrs()["down"] == 1
+    assert (prev[down] == 1).all()

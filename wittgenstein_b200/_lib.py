@@ -52,6 +52,10 @@ class Api:
         "gsf_level_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),
         "gsf_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
         "stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+        "timer_start": (C.c_int, [C.c_void_p]),
+        "timer_stop_ms": (C.c_double, [C.c_void_p]),
+        "profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+        "profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_char_p), C.c_int]),
     }
 
     def __init__(self, path=LIB_PATH, prefix="wtg_"):

@@ -273,5 +273,32 @@ int WTG_API(stats)(void* h, long long* out24) {
   });
 }
 
+// device-side stopwatch around whatever is enqueued between the two calls (CUDA events on the engine stream)
+int WTG_API(timer_start)(void* h) {
+  return guard([&] {
+    ENG.be->timerStart();
+    return 0;
+  });
+}
+double WTG_API(timer_stop_ms)(void* h) {
+  double r = -1.0;
+  guard([&] {
+    r = ENG.be->timerStopMs();
+    return 0;
+  });
+  return r;
+}
+// per-kernel event timing (adds a cudaEvent pair around every launch; disables graph replay while on)
+int WTG_API(profile_enable)(void* h, int on) {
+  return guard([&] {
+    ENG.be->profileEnable(on != 0);
+    return 0;
+  });
+}
+// returns the number of kernels; ms[i], launches[i] accumulated since enable; names[i] static strings
+int WTG_API(profile_read)(void* h, double* ms, long long* launches, const char** names, int cap) {
+  return guard([&] { return ENG.be->profileRead(ms, launches, names, cap); });
+}
+
 #undef ENG
 }  // extern "C"

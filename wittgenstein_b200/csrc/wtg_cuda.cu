@@ -327,6 +327,18 @@ class CudaBackend : public Backend {
   const void* graphFor = nullptr;
   bool useGraph = true;
   long long launches = 0;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  // per-kernel profiling
+  static constexpr int NK = 16;
+  bool profiling = false;
+  std::vector<cudaEvent_t> evPool;
+  std::vector<int> evKernel;  // kernel id of each event pair
+  size_t evUsed = 0;
+  double profMs[NK] = {};
+  long long profCnt[NK] = {};
+  const char* profNames[NK] = {"k_begin", "k_cond", "k_dispatch_count", "k_scan_partial", "k_scan_tiles", "k_scan_final",
+                               "k_dispatch_scatter", "k_node", "k_emit", "k_ms_count", "k_ms_scan", "k_ms_scatter", "k_free",
+                               "k_end", "", ""};
 
   CudaBackend() {
     int dev = 0;
@@ -365,36 +377,139 @@ class CudaBackend : public Backend {
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
   }
-  void sync() override { CUDA_OK(cudaStreamSynchronize(st)); }
+  void sync() override {
+    CUDA_OK(cudaStreamSynchronize(st));
+    drainProfile();
+  }
+  void timerStart() override {
+    if (!tm0) {
+      CUDA_OK(cudaEventCreate(&tm0));
+      CUDA_OK(cudaEventCreate(&tm1));
+    }
+    CUDA_OK(cudaEventRecord(tm0, st));
+  }
+  double timerStopMs() override {
+    CUDA_OK(cudaEventRecord(tm1, st));
+    CUDA_OK(cudaEventSynchronize(tm1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, tm0, tm1));
+    return (double)ms;
+  }
+  void profileEnable(bool on) override {
+    sync();
+    profiling = on;
+    if (on) {
+      for (int i = 0; i < NK; ++i) {
+        profMs[i] = 0;
+        profCnt[i] = 0;
+      }
+    }
+  }
+  int profileRead(double* ms, long long* cnt, const char** names, int cap) override {
+    sync();
+    int k = 0;
+    for (int i = 0; i < 14 && k < cap; ++i, ++k) {
+      ms[k] = profMs[i];
+      cnt[k] = profCnt[i];
+      names[k] = profNames[i];
+    }
+    return k;
+  }
+  void drainProfile() {
+    for (size_t i = 0; i < evUsed; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evPool[2 * i], evPool[2 * i + 1]);
+      profMs[evKernel[i]] += ms;
+      profCnt[evKernel[i]] += 1;
+    }
+    evUsed = 0;
+  }
+  void profBegin(int kid) {
+    if (!profiling) return;
+    if (evUsed * 2 + 2 > evPool.size()) {
+      if (evUsed >= 8192) {  // bound the pool: drain what has completed so far
+        CUDA_OK(cudaStreamSynchronize(st));
+        drainProfile();
+      } else {
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreate(&a));
+        CUDA_OK(cudaEventCreate(&b));
+        evPool.push_back(a);
+        evPool.push_back(b);
+        evKernel.push_back(0);
+      }
+    }
+    evKernel[evUsed] = kid;
+    CUDA_OK(cudaEventRecord(evPool[2 * evUsed], st));
+  }
+  void profEnd() {
+    if (!profiling) return;
+    CUDA_OK(cudaEventRecord(evPool[2 * evUsed + 1], st));
+    ++evUsed;
+  }
 
   void enqueueTick(const Dev& d, int mode) {
     const int nodeBlocks = (d.N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    profBegin(0);
     k_begin<<<1, 1, 0, st>>>(d, mode);
+    profEnd();
     if (d.proto == PROTO_GSF) {
       size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
-      k_cond<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
+      profBegin(1);
+    k_cond<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
+    profEnd();
       launches += 1;
     }
     if (mode != 2) {
-      k_dispatch_count<<<wide, 256, 0, st>>>(d);
-      k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
-      k_scan_tiles<<<1, 1024, 0, st>>>(d, 0);
-      k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
-      k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
-      k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      profBegin(2);
+    k_dispatch_count<<<wide, 256, 0, st>>>(d);
+    profEnd();
+      profBegin(3);
+    k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
+    profEnd();
+      profBegin(4);
+    k_scan_tiles<<<1, 1024, 0, st>>>(d, 0);
+    profEnd();
+      profBegin(5);
+    k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
+    profEnd();
+      profBegin(6);
+    k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
+    profEnd();
+      profBegin(7);
+    k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+    profEnd();
       launches += 6;
     }
+    profBegin(3);
     k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
+    profEnd();
+    profBegin(4);
     k_scan_tiles<<<1, 1024, 0, st>>>(d, 1);
+    profEnd();
+    profBegin(5);
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
+    profEnd();
+    profBegin(8);
     k_emit<<<wide, 256, 0, st>>>(d);
+    profEnd();
+    profBegin(9);
     k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    profEnd();
+    profBegin(10);
     k_ms_scan<<<(d.ring + 127) / 128, 128, 0, st>>>(d);
+    profEnd();
+    profBegin(11);
     k_ms_scatter<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    profEnd();
+    profBegin(12);
     k_free<<<sms, 256, 0, st>>>(d);
+    profEnd();
+    profBegin(13);
     k_end<<<1, 1, 0, st>>>(d, mode);
+    profEnd();
     launches += 10;
   }
   void configure(const Dev& d) {
@@ -409,7 +524,7 @@ class CudaBackend : public Backend {
   }
   void ticks(const Dev& d, int count) override {
     configure(d);
-    if (!useGraph || count < 4) {
+    if (!useGraph || profiling || count < 4) {
       for (int i = 0; i < count; ++i) enqueueTick(d, 1);
       CUDA_OK(cudaGetLastError());
       return;

@@ -39,6 +39,11 @@ struct Backend {
   virtual void ticks(const Dev& d, int count) {
     for (int i = 0; i < count; ++i) tick(d, 1);
   }
+  // device-side timing (CUDA events on the engine's stream); no-ops on backends without a device
+  virtual void timerStart() {}
+  virtual double timerStopMs() { return 0.0; }
+  virtual void profileEnable(bool) {}
+  virtual int profileRead(double* ms, long long* launches, const char** names, int cap) { (void)ms; (void)launches; (void)names; (void)cap; return 0; }
   virtual void gsfInitNodes(const Dev& d) = 0;
   // scan `count` stream positions after state s0 for values that nextInt(bound<=maxBound) could reject
   virtual void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
@@ -107,7 +112,7 @@ class Engine {
     if (tun.ring) ring = (int)tun.ring;
     d.ring = ring;
     ringMask = ring - 1;
-    long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 4LL * N);
+    long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 3LL * N);
     d.bcap = (int)bcap;
     d.itemCap = (int)(2 * bcap + 1024);
     d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 24LL * N));

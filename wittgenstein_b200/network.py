@@ -117,3 +117,21 @@ class Network:
                 "multi_sends", "send_words", "events", "max_queue", "max_bucket", "max_inbox", "rec_top", "rec_dest_top",
                 "kernel_launches", "min_pool_free", "init_draws", "ring", "bcap", "qcap", "peer_bits"]
         return dict(zip(keys, out.tolist()))
+
+    # ---- measurement hooks ----
+    def timer_start(self):
+        self.api.check(self.api.timer_start(self.h))
+
+    def timer_stop_ms(self):
+        return float(self.api.timer_stop_ms(self.h))
+
+    def profile_enable(self, on=True):
+        self.api.check(self.api.profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        cap = 64
+        ms = (C.c_double * cap)()
+        cnt = (C.c_longlong * cap)()
+        names = (C.c_char_p * cap)()
+        k = self.api.check(self.api.profile_read(self.h, ms, cnt, names, cap))
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
