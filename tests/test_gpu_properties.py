@@ -36,9 +36,10 @@ def test_gsf_invariants_and_determinism(n):
         # own signature always present
         ids = np.arange(n)
         assert ((a.verified()[ids, ids // 64] >> (ids % 64).astype(np.uint64)) & np.uint64(1)).all()
-    # same seed, different runMs slicing in busy ticks -> same state (determinism across two engines)
-    for i in range(24):
-        b.network().run_ms(50)
+    # same seed + same runMs slicing -> identical state on a second engine (the reference's testCopy property;
+    # a different slicing may legitimately differ: SURVEY.md A.1 rule 2)
+    for i in range(12):
+        b.network().run_ms(100)
     assert (a.verified() == b.verified()).all()
     assert (a.network().counters() == b.network().counters()).all()
     assert a.network().rng_state() == b.network().rng_state()
