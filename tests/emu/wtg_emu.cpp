@@ -50,7 +50,10 @@ class HostBackend : public Backend {
     pairScan(d, 1);
     if (d.ctl->error) return;
     for (int n = 0; n < d.N; ++n) emitCond(d, n);
-    for (int i = 0; i < d.ctl->nDesc; ++i) emitDesc(d, i);
+    {
+      int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
+      for (int t = 0; t < tot; ++t) emitDesc(d, stripedIndex(d.ctl->descCnt, per, t));
+    }
     // multisplit: stable append into the ring in creation order
     int G = d.ctl->totalSlots;
     for (int g = 0; g < G; ++g) {
@@ -65,8 +68,10 @@ class HostBackend : public Backend {
       d.buckets[(size_t)slot * d.bcap + pos] = d.newEv[g];
       d.bucketCount[slot] = pos + 1;
     }
-    int nf = std::min(d.ctl->freeTop, d.freeCap);
-    for (int i = 0; i < nf; ++i) freeApply(d, i);
+    {
+      int per = d.freeCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->freeCnt, per);
+      for (int t = 0; t < tot; ++t) freeApply(d, stripedIndex(d.ctl->freeCnt, per, t));
+    }
     tickEnd(d, mode);
     launches += 1;
   }

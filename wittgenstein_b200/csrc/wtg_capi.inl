@@ -263,10 +263,12 @@ int WTG_API(stats)(void* h, long long* out24) {
     long long minFree = -1;
     for (int l = wtg::INLINE_MAX_LEVEL + 1; l < ENG.d.L; ++l)
       if (minFree < 0 || c.poolMinFree[l] < minFree) minFree = c.poolMinFree[l];
-    long long v[24] = {(long long)c.statDeliveries, (long long)c.statTasks, (long long)c.statCondRuns, (long long)c.statDraws,
-                       (long long)c.statEvalEntries, (long long)c.statEvalWords, (long long)c.statUpdates, (long long)c.statCycles,
-                       (long long)c.statSends, (long long)c.statMultiSends, (long long)c.statSendWords, (long long)c.statEvents,
-                       c.maxQueue, c.maxBucket, c.maxInbox, c.recTop, c.recDestTop, wtg::backendLaunches(ENG.be.get()),
+    std::vector<unsigned long long> st = ENG.readStats();
+    long long v[24] = {(long long)st[wtg::ST_DELIVERIES], (long long)st[wtg::ST_TASKS], (long long)st[wtg::ST_CONDRUNS], (long long)c.statDraws,
+                       (long long)st[wtg::ST_EVALENTRIES], (long long)st[wtg::ST_EVALWORDS], (long long)st[wtg::ST_UPDATES],
+                       (long long)st[wtg::ST_CYCLES], (long long)st[wtg::ST_SENDS], (long long)st[wtg::ST_MULTISENDS],
+                       (long long)st[wtg::ST_SENDWORDS], (long long)c.statEvents, (long long)st[wtg::ST_MAXQUEUE], c.maxBucket,
+                       (long long)st[wtg::ST_MAXINBOX], c.recTop, c.recDestTop, wtg::backendLaunches(ENG.be.get()),
                        minFree, (long long)ENG.initDraws, ENG.d.ring, ENG.d.bcap, ENG.d.qcap, ENG.d.peerBits};
     std::memcpy(out24, v, sizeof(v));
     return 0;

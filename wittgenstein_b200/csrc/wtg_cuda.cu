@@ -199,13 +199,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
 // ---- emit ------------------------------------------------------------------------------------
 __global__ void k_emit(Dev d) {
   if (d.ctl->error) return;
-  int nDesc = d.ctl->nDesc;
-  int total = d.N + nDesc;
+  const int per = d.descCap / ARENA_STRIPES;
+  int total = d.N + stripedTotal(d.ctl->descCnt, per);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     if (i < d.N)
       emitCond(d, i);
     else
-      emitDesc(d, i - d.N);
+      emitDesc(d, stripedIndex(d.ctl->descCnt, per, i - d.N));
   }
 }
 
@@ -295,9 +295,9 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
 
 __global__ void k_free(Dev d) {
   if (d.ctl->error) return;
-  int n = d.ctl->freeTop;
-  if (n > d.freeCap) n = d.freeCap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) freeApply(d, i);
+  const int per = d.freeCap / ARENA_STRIPES;
+  int n = stripedTotal(d.ctl->freeCnt, per);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) freeApply(d, stripedIndex(d.ctl->freeCnt, per, i));
 }
 
 // ---- init kernels ---------------------------------------------------------------------------

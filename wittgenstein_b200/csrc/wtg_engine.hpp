@@ -115,7 +115,8 @@ class Engine {
     long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 3LL * N);
     d.bcap = (int)bcap;
     d.itemCap = (int)(2 * bcap + 1024);
-    d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 24LL * N));
+    d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 32LL * N));
+    d.descCap = (d.descCap + ARENA_STRIPES - 1) / ARENA_STRIPES * ARENA_STRIPES;
     d.destScratchCap = d.descCap;
     d.newEvCap = d.descCap + N;
     d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * N));
@@ -125,6 +126,7 @@ class Engine {
     d.latParam = hm.latParam;
 
     d.ctl = dalloc<Ctl>(1);
+    d.stats = dalloc<unsigned long long>((size_t)STAT_SLOTS * ST_COUNT);
     std::vector<int16_t> x(N), y(N), ex(N);
     std::vector<uint8_t> city(N), down(N), part(N, 0);
     for (int i = 0; i < N; ++i) {
@@ -352,12 +354,16 @@ class Engine {
     long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
     for (int l = INLINE_MAX_LEVEL + 1; l < L; ++l) {
       long long slots = std::max<long long>(1024, perNode * N);
+      slots = (slots + POOL_STRIPES - 1) / POOL_STRIPES * POOL_STRIPES;
       d.poolCap[l] = (int)slots;
       d.pool[l] = dalloc<unsigned long long>((size_t)slots * (size_t)poolWords(l));
       std::vector<uint32_t> fl((size_t)slots);
-      for (long long i = 0; i < slots; ++i) fl[(size_t)i] = (uint32_t)(slots - 1 - i);
+      long long per = slots / POOL_STRIPES;
+      for (int sidx = 0; sidx < POOL_STRIPES; ++sidx) {
+        for (long long i = 0; i < per; ++i) fl[(size_t)(sidx * per + i)] = (uint32_t)(sidx * per + (per - 1 - i));
+        c.poolFreeCnt[l][sidx] = (int)per;
+      }
       d.poolFree[l] = dupload(fl);
-      c.poolFreeCnt[l] = (int)slots;
       c.poolMinFree[l] = (int)slots;
     }
     c.callId = 1;
@@ -528,6 +534,21 @@ class Engine {
     uploadPartitions();
   }
 
+  // striped statistics summed (or max-ed) over the slots
+  std::vector<unsigned long long> readStats() {
+    std::vector<unsigned long long> raw((size_t)STAT_SLOTS * ST_COUNT), out(ST_COUNT, 0);
+    be->sync();
+    be->download(raw.data(), d.stats, raw.size() * sizeof(unsigned long long));
+    for (int sl = 0; sl < STAT_SLOTS; ++sl)
+      for (int k = 0; k < ST_COUNT; ++k) {
+        unsigned long long v = raw[(size_t)sl * ST_COUNT + k];
+        if (k == ST_MAXQUEUE || k == ST_MAXINBOX)
+          out[k] = std::max(out[k], v);
+        else
+          out[k] += v;
+      }
+    return out;
+  }
   template <class T>
   void fetch(T* out, const T* dev, size_t n) {
     be->sync();

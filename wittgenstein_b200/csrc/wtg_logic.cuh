@@ -92,6 +92,13 @@ struct CoopWarp {
 };
 #endif
 
+WTG_HD void statAdd(const Dev& d, int n, int idx, unsigned long long v) {
+  WTG_ATOMIC_ADD(&d.stats[(size_t)(n & (STAT_SLOTS - 1)) * ST_COUNT + idx], v);
+}
+WTG_HD void statMax(const Dev& d, int n, int idx, unsigned long long v) {
+  unsigned long long* p = &d.stats[(size_t)(n & (STAT_SLOTS - 1)) * ST_COUNT + idx];
+  if (*p < v) WTG_ATOMIC_MAX(p, v);
+}
 WTG_HD void setError(const Dev& d, int code, int detail) {
   if (WTG_ATOMIC_CAS(&d.ctl->error, 0, code) == 0) d.ctl->errorDetail = detail;
 }
@@ -215,23 +222,41 @@ WTG_HD uint32_t peerAt(const Dev& d, int n, int l, int idx) {
   return ((const uint32_t*)d.peers)[off];
 }
 
-WTG_HD void freePush(const Dev& d, int level, uint32_t slot) {
-  int i = WTG_ATOMIC_ADD(&d.ctl->freeTop, 1);
-  if (i < d.freeCap)
-    d.freeList[i] = ((uint32_t)level << 27) | slot;
+// return a payload slab to its pool.  Kernels that never allocate (k_cond, k_emit) push straight onto the
+// stripe's free stack; the handler kernel (which allocates) defers the push to k_free.
+WTG_HD void freeDirect(const Dev& d, int level, uint32_t slot) {
+  const int per = d.poolCap[level] / POOL_STRIPES;
+  int sidx = (int)(slot / (uint32_t)per);
+  int k = WTG_ATOMIC_ADD(&d.ctl->poolFreeCnt[level][sidx], 1);
+  d.poolFree[level][(size_t)sidx * per + k] = slot;
+}
+WTG_HD void freeDeferred(const Dev& d, int n, int level, uint32_t slot) {
+  int st = n & (ARENA_STRIPES - 1);
+  int per = d.freeCap / ARENA_STRIPES;
+  int i = WTG_ATOMIC_ADD(&d.ctl->freeCnt[st], 1);
+  if (i < per)
+    d.freeList[(size_t)st * per + i] = ((uint32_t)level << 27) | slot;
   else
     setError(d, ERR_FREE_OVERFLOW, i);
 }
-WTG_HD bool poolAlloc(const Dev& d, int level, uint32_t& slot) {
-  int i = WTG_ATOMIC_ADD(&d.ctl->poolFreeCnt[level], -1) - 1;
-  if (i < 0) {
-    setError(d, ERR_POOL_EXHAUSTED, level);
-    slot = 0;
-    return false;
+// striped free stacks: stripe s of level l owns slots [s*cap/S, (s+1)*cap/S); a node allocates from the
+// stripe of its id and falls over to the next stripes when it is empty
+WTG_HD bool poolAlloc(const Dev& d, int level, int n, uint32_t& slot) {
+  const int per = d.poolCap[level] / POOL_STRIPES;
+  for (int t = 0; t < POOL_STRIPES; ++t) {
+    int sidx = (n + t) & (POOL_STRIPES - 1);
+    int* cnt = &d.ctl->poolFreeCnt[level][sidx];
+    if (*cnt <= 0) continue;
+    int i = WTG_ATOMIC_ADD(cnt, -1) - 1;
+    if (i >= 0) {
+      slot = d.poolFree[level][(size_t)sidx * per + i];
+      return true;
+    }
+    WTG_ATOMIC_ADD(cnt, 1);  // lost the race for the last slot of this stripe
   }
-  slot = d.poolFree[level][i];
-  WTG_ATOMIC_MIN(&d.ctl->poolMinFree[level], i);
-  return true;
+  setError(d, ERR_POOL_EXHAUSTED, level);
+  slot = 0;
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -385,7 +410,7 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
     int tot = (int)(km & 1u);
 #endif
     if (keep) q[w + off] = e;
-    if (evict && metaKind(e.meta) == PK_POOL) freePush(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
+    if (evict && metaKind(e.meta) == PK_POOL) freeDirect(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
     if (found && i == bi) best = e;
     w += tot;
   }
@@ -397,8 +422,8 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
   }
   if (c.lane() == 0) {
     d.qLen[n] = w;
-    WTG_ATOMIC_ADD(&d.ctl->statEvalEntries, (unsigned long long)len);
-    WTG_ATOMIC_ADD(&d.ctl->statEvalWords, words);
+    statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
+    if (words) statAdd(d, n, ST_EVALWORDS, words);
     if (found) {
       d.sigChecked[n] += 1;
       d.sigQueueSize[n] = w;
@@ -430,7 +455,7 @@ WTG_HD void gsfCond(const Dev& d, C& c, int n, uint32_t* keepBits) {
         bool found = gsfCheckSigs(d, c, n, keepBits, best);
         if (c.lane() == 0) {
           d.minStart[n] = ctl.tick + d.pairing[n];
-          WTG_ATOMIC_ADD(&d.ctl->statCondRuns, 1ULL);
+          statAdd(d, n, ST_CONDRUNS, 1ULL);
           if (found) {  // registerTask(updateVerifiedSignatures, time + nodePairingTime, this)
             Ev ev;
             ev.kind = EV_TASK;
@@ -455,16 +480,31 @@ WTG_HD void gsfCond(const Dev& d, C& c, int n, uint32_t* keepBits) {
 // descriptor helpers
 // ------------------------------------------------------------------------------------------
 template <class C>
-WTG_HD int descAlloc(const Dev& d, C& c, int cnt) {
+WTG_HD int descAlloc(const Dev& d, C& c, int n, int cnt) {
   int base = 0;
   if (c.lane() == 0) {
-    base = WTG_ATOMIC_ADD(&d.ctl->nDesc, cnt);
-    if (base + cnt > d.descCap) {
-      setError(d, ERR_DESC_OVERFLOW, base + cnt);
+    int st = n & (ARENA_STRIPES - 1);
+    int per = d.descCap / ARENA_STRIPES;
+    int i = WTG_ATOMIC_ADD(&d.ctl->descCnt[st], cnt);
+    if (i + cnt > per) {
+      setError(d, ERR_DESC_OVERFLOW, i + cnt);
       base = -1;
+    } else {
+      base = st * per + i;
     }
   }
   return c.bcast(base, 0);
+}
+// scratch for the destination list of a multi-send (same striping)
+WTG_HD int destAlloc(const Dev& d, int n, int cnt) {
+  int st = n & (ARENA_STRIPES - 1);
+  int per = d.destScratchCap / ARENA_STRIPES;
+  int i = WTG_ATOMIC_ADD(&d.ctl->destCnt[st], cnt);
+  if (i + cnt > per) {
+    setError(d, ERR_DESC_OVERFLOW, i + cnt);
+    return -1;
+  }
+  return st * per + i;
 }
 
 WTG_HD void gsfLevelCounters(const Dev& d, int n, int l, int& cV, int& cI, int& cU) {
@@ -492,7 +532,7 @@ WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 p
   QEntry* q = d.queue + (size_t)n * d.qcap;
   if (len + 2 > d.qcap) {
     setError(d, ERR_QUEUE_OVERFLOW, n);
-    if (metaKind(meta) == PK_POOL) freePush(d, l, (uint32_t)pl);
+    if (metaKind(meta) == PK_POOL) freeDeferred(d, n, l, (uint32_t)pl);
     return;
   }
   QEntry e;
@@ -512,7 +552,7 @@ WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 p
   }
   d.qLen[n] = len;
   d.sigQueueSize[n] = len;
-  WTG_ATOMIC_MAX(&d.ctl->maxQueue, len);
+  statMax(d, n, ST_MAXQUEUE, (unsigned long long)len);
 }
 
 // take up to `want` peers of level l (getRemainingPeers :325-349); returns the count, writes ids
@@ -554,7 +594,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
   gsfLevelCounters(d, n, l, cV, cI, cU);
   int total = d.totalCard[n];
   int cSig = kind == PK_INDIV ? 1 : kind == PK_FULL ? (1 << k) : kind == PK_INLINE ? WTG_POPC64(pl) : (int)(pl >> 32);
-  if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statUpdates, 1ULL);
+  if (c.lane() == 0) statAdd(d, n, ST_UPDATES, 1ULL);
 
   // :387-389  if (sigs.cardinality() == 1) sfl.indivVerifiedSig.set(from.nodeId);
   if (cSig == 1) {
@@ -660,7 +700,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
     d.cntUnion[n * L + l] = cU;
     d.totalCard[n] = total;
   }
-  if (kind == PK_POOL && c.lane() == 0) freePush(d, l, (uint32_t)pl);
+  if (kind == PK_POOL && c.lane() == 0) freeDeferred(d, n, l, (uint32_t)pl);
   c.sync();
 
   outSlots = 0;
@@ -680,7 +720,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
       if (d.remaining[n * L + cur] > 0) ++nSend;
     }
     if (nSend > 0) {
-      int base = descAlloc(d, c, nSend);
+      int base = descAlloc(d, c, n, nSend);
       int sub = 0;
       long long sentMsgs = 0, sentBytes = 0;
       for (int cur = l; cur <= kf && cur < L - 1;) {
@@ -705,16 +745,12 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
             ds.to = dests[0];
             ds.nDest = 1;
           } else {
-            int off = WTG_ATOMIC_ADD(&d.ctl->nDestScratch, cnt);
-            if (off + cnt > d.destScratchCap) {
-              setError(d, ERR_DESC_OVERFLOW, off);
-              off = 0;
-            } else {
+            int off = destAlloc(d, n, cnt);
+            if (off >= 0)
               for (int i = 0; i < cnt; ++i) d.destScratch[off + i] = dests[i];
-            }
             ds.dkind = DK_SEND_MULTI;
-            ds.to = (uint32_t)off;
-            ds.nDest = (uint32_t)cnt;
+            ds.to = (uint32_t)(off < 0 ? 0 : off);
+            ds.nDest = (uint32_t)(off < 0 ? 0 : cnt);
           }
           d.desc[base + sub] = ds;
         }
@@ -723,7 +759,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
       if (c.lane() == 0) {
         d.msgSent[n] += sentMsgs;
         d.bytesSent[n] += sentBytes;
-        WTG_ATOMIC_ADD(&d.ctl->statMultiSends, (unsigned long long)sub);
+        statAdd(d, n, ST_MULTISENDS, (unsigned long long)sub);
       }
       outSlots = sub;
       outDraws = sub;
@@ -760,7 +796,7 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
 #else
   int nSend = __builtin_popcount(sendMask);
 #endif
-  int base = descAlloc(d, c, nSend + 1);
+  int base = descAlloc(d, c, n, nSend + 1);
   int sub = 0;
   long long sentBytes = 0;
   unsigned long long words = 0;
@@ -783,7 +819,7 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
           meta = metaMake(PK_POOL, (uint32_t)l, 0);
           uint32_t slot = 0;
           int ok = 1;
-          if (c.lane() == 0) ok = poolAlloc(d, l, slot) ? 1 : 0;
+          if (c.lane() == 0) ok = poolAlloc(d, l, n, slot) ? 1 : 0;
           slot = (uint32_t)c.bcast((int)slot, 0);
           ok = c.bcast(ok, 0);
           if (ok) {
@@ -832,9 +868,9 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
     }
     d.msgSent[n] += nSend;
     d.bytesSent[n] += sentBytes;
-    WTG_ATOMIC_ADD(&d.ctl->statCycles, 1ULL);
-    WTG_ATOMIC_ADD(&d.ctl->statSends, (unsigned long long)nSend);
-    WTG_ATOMIC_ADD(&d.ctl->statSendWords, words);
+    statAdd(d, n, ST_CYCLES, 1ULL);
+    statAdd(d, n, ST_SENDS, (unsigned long long)nSend);
+    if (words) statAdd(d, n, ST_SENDWORDS, words);
   }
   c.sync();
   outSlots = nSend + 1;
@@ -854,31 +890,31 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
   if (!ok) {
     // dropped: a pooled payload dies with the envelope
     if (d.proto == PROTO_GSF && (ev.kind == EV_MSG || ev.kind == EV_TASK) && metaKind(meta) == PK_POOL && c.lane() == 0)
-      freePush(d, (int)metaLevel(meta), (uint32_t)pl);
+      freeDeferred(d, n, (int)metaLevel(meta), (uint32_t)pl);
   } else if (d.proto == PROTO_GSF) {
     if (ev.kind == EV_MSG || ev.kind == EV_MULTI) {
       if (c.lane() == 0) {
         d.msgReceived[n] += 1;
         d.bytesReceived[n] += msgSize((int)metaLevel(meta));
-        WTG_ATOMIC_ADD(&d.ctl->statDeliveries, 1ULL);
+        statAdd(d, n, ST_DELIVERIES, 1ULL);
         gsfOnNewSig(d, n, from, meta, pl);
       }
       c.sync();
     } else if (ev.kind == EV_TASK) {
-      if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statTasks, 1ULL);
+      if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
       gsfUpdate(d, c, n, from, meta, pl, item, slots, draws);
     } else {
-      if (c.lane() == 0) WTG_ATOMIC_ADD(&d.ctl->statTasks, 1ULL);
+      if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
       gsfCycle(d, c, n, item, slots, draws);
     }
   } else if (d.proto == PROTO_PINGPONG) {
     if (c.lane() == 0) {
       d.msgReceived[n] += 1;
       d.bytesReceived[n] += 1;  // Message.size() default (messages/Message.java:27-29)
-      WTG_ATOMIC_ADD(&d.ctl->statDeliveries, 1ULL);
+      statAdd(d, n, ST_DELIVERIES, 1ULL);
     }
     if (meta == PP_PING) {  // PingPong.java:73-75  onPing: network.send(new Pong(), this, from)
-      int base = descAlloc(d, c, 1);
+      int base = descAlloc(d, c, n, 1);
       if (c.lane() == 0) {
         if (base >= 0) {
           Desc ds;
@@ -960,7 +996,7 @@ WTG_HD void nodeProcess(const Dev& d, C& c, int n) {
     deliver(d, c, n, ev, from, meta, pl, item);
   }
   if (c.lane() == 0) {
-    WTG_ATOMIC_MAX(&d.ctl->maxInbox, cnt);
+    statMax(d, n, ST_MAXINBOX, (unsigned long long)cnt);
     d.inboxFill[n] = 0;  // ready for the next tick
   }
 }
@@ -1007,8 +1043,11 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
       ++m;
     }
     if (j < (int)rc.n) {  // Network.java:629-632: re-push for the next destination, after the handler ran
-      int di = WTG_ATOMIC_ADD(&d.ctl->nDesc, 1);
-      if (di < d.descCap) {
+      int dst_ = i & (ARENA_STRIPES - 1), dper_ = d.descCap / ARENA_STRIPES;
+      int di = WTG_ATOMIC_ADD(&d.ctl->descCnt[dst_], 1);
+      bool dok_ = di < dper_;
+      di += dst_ * dper_;
+      if (dok_) {
         Desc ds;
         ds.dkind = DK_INSERT_AT;
         ds.item = (uint32_t)(d.N + item0 + m);
@@ -1120,7 +1159,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
         }
       }
     }
-    if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL) freePush(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
+    if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL) freeDirect(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
   }
   if (target >= 0 && target - ctl.tick >= d.ring) {
     setError(d, ERR_FAR_FUTURE, target);
@@ -1166,8 +1205,10 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
     c.condMode = 2;
     c.nEv = 0;
   }
-  c.nDesc = 0;
-  c.nDestScratch = 0;
+  for (int t = 0; t < ARENA_STRIPES; ++t) {
+    c.descCnt[t] = 0;
+    c.destCnt[t] = 0;
+  }
   c.nItems = 0;
   c.totalSlots = 0;
   c.totalDraws = 0;
@@ -1183,15 +1224,33 @@ WTG_HD void tickEnd(const Dev& d, int mode) {
     c.didSomething = 1;
   }
   if (mode != 2) d.bucketCount[c.tick & (d.ring - 1)] = 0;
-  c.freeTop = 0;
+  for (int t = 0; t < ARENA_STRIPES; ++t) c.freeCnt[t] = 0;
+  if (d.proto == PROTO_GSF && (c.tick & 15) == 0)
+    for (int l = INLINE_MAX_LEVEL + 1; l < d.L; ++l) {
+      int f = 0;
+      for (int t = 0; t < POOL_STRIPES; ++t) f += c.poolFreeCnt[l][t];
+      if (f < c.poolMinFree[l]) c.poolMinFree[l] = f;
+    }
 }
-// deferred frees -> pool free stacks (no allocation runs concurrently)
+// deferred frees -> pool free stacks (no allocation runs concurrently).  i indexes the striped list.
 WTG_HD void freeApply(const Dev& d, int i) {
   uint32_t w = d.freeList[i];
-  int level = (int)(w >> 27);
-  uint32_t slot = w & 0x7FFFFFFu;
-  int k = WTG_ATOMIC_ADD(&d.ctl->poolFreeCnt[level], 1);
-  d.poolFree[level][k] = slot;
+  freeDirect(d, (int)(w >> 27), w & 0x7FFFFFFu);
+}
+// map a dense work index onto the striped arena: returns the arena index or -1
+WTG_HD int stripedIndex(const int* cnt, int per, int t) {
+  for (int s = 0; s < ARENA_STRIPES; ++s) {
+    int c = cnt[s];
+    if (c > per) c = per;
+    if (t < c) return s * per + t;
+    t -= c;
+  }
+  return -1;
+}
+WTG_HD int stripedTotal(const int* cnt, int per) {
+  int tot = 0;
+  for (int s = 0; s < ARENA_STRIPES; ++s) tot += cnt[s] > per ? per : cnt[s];
+  return tot;
 }
 
 // ------------------------------------------------------------------------------------------

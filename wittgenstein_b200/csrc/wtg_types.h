@@ -20,6 +20,8 @@
 
 namespace wtg {
 
+constexpr int POOL_STRIPES = 64;     // independent free stacks per pool level (allocation contention / 64)
+constexpr int ARENA_STRIPES = 64;    // per-tick arenas are striped by node id for the same reason
 constexpr int MS_CHUNK = 1024;       // new envelopes per multisplit chunk (one warp)
 constexpr int MAX_LEVELS = 24;
 constexpr int MAX_ACC = 16;          // max destinations of a protocol multi-send handled on device
@@ -113,7 +115,7 @@ struct Ctl {  // device-resident control block (one per engine)
   int tick;       // tick being processed
   int condMode;   // 0 = no conditional-task pass, 1 = normal, 2 = end-of-window overshoot pass
   int nEv;        // events in this tick's bucket
-  int nDesc;      // descriptors allocated this tick
+  int nDesc;      // (unused) total descriptors; per-stripe counts below
   int nDestScratch;
   int nItems;     // scan items this tick (N + nEv)
   int totalSlots, totalDraws;
@@ -123,13 +125,21 @@ struct Ctl {  // device-resident control block (one per engine)
   int error;               // first error code (0 = ok)
   int errorDetail;
   int recTop, recDestTop;  // multi-destination record arenas
-  int freeTop;             // deferred payload frees
-  int maxQueue, maxBucket, maxInbox;
-  unsigned long long statDeliveries, statTasks, statCondRuns, statDraws, statEvalEntries, statEvalWords;
-  unsigned long long statUpdates, statCycles, statSends, statMultiSends, statSendWords, statEvents;
-  int poolFreeCnt[MAX_LEVELS];
-  int poolMinFree[MAX_LEVELS];
+  int maxBucket;
+  unsigned long long statDraws, statEvents;
+  int descCnt[ARENA_STRIPES];   // descriptors allocated this tick, per stripe (stripe = node id & 63)
+  int destCnt[ARENA_STRIPES];   // multi-send destination scratch, per stripe
+  int freeCnt[ARENA_STRIPES];   // deferred payload frees, per stripe
+  int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
+  int poolFreeCnt[MAX_LEVELS][POOL_STRIPES];   // free slots per (level, stripe)
 };
+
+// striped statistics (node-id striping keeps hot-path counters off a single L2 address)
+enum : int {
+  ST_DELIVERIES = 0, ST_TASKS, ST_CONDRUNS, ST_EVALENTRIES, ST_EVALWORDS, ST_UPDATES, ST_CYCLES, ST_SENDS, ST_MULTISENDS,
+  ST_SENDWORDS, ST_EVALPOOL, ST_UPDATEWORDS, ST_MAXQUEUE, ST_MAXINBOX, ST_COUNT = 16
+};
+constexpr int STAT_SLOTS = 1024;
 
 enum : int {
   ERR_NONE = 0,
@@ -159,6 +169,7 @@ struct Dev {
   int peerBits;  // 16 or 32
   // ---- control ----
   Ctl* ctl;
+  unsigned long long* stats;  // [STAT_SLOTS][ST_COUNT]
   // ---- nodes ----
   int16_t* nx;
   int16_t* ny;
