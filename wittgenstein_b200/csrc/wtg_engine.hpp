@@ -342,6 +342,9 @@ class Engine {
     d.sigChecked = dalloc<int>(N);
     d.sigQueueSize = dalloc<int>(N);
     d.queue = dalloc<QEntry>((size_t)N * d.qcap);
+    d.qScore = dalloc<int>((size_t)N * d.qcap);
+    d.qStamp = dalloc<uint32_t>((size_t)N * d.qcap);
+    d.lvVer = dalloc<uint32_t>((size_t)N * L);
     std::vector<int> pairing(N);
     for (int i = 0; i < N; ++i) pairing[i] = (int)std::max(1.0, p.pairingTime * hm.nodes[i].speed);  // :170
     d.pairing = dupload(pairing);

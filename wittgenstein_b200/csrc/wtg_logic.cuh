@@ -342,8 +342,12 @@ template <class C>
 WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& best) {
   int len = d.qLen[n];
   QEntry* q = d.queue + (size_t)n * d.qcap;
+  int* qsc = d.qScore + (size_t)n * d.qcap;
+  uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
+  const uint32_t* ver = d.lvVer + (size_t)n * d.L;
   int bestScore = 0, bestIdx = 0x7fffffff;
   unsigned long long words = 0;
+  int reeval = 0;
   for (int base = 0; base < len; base += C::LANES) {
     int i = base + c.lane();
     QEntry e;
@@ -352,12 +356,20 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
     e.pl = 0;
     int s = 0;
     bool isPool = false;
+    uint32_t v = 0;
+    bool fresh = false;
     if (i < len) {
       e = q[i];
-      if (metaKind(e.meta) == PK_POOL)
-        isPool = true;
-      else
-        s = gsfScoreScalar(d, n, e);
+      v = ver[metaLevel(e.meta)];
+      if (qst[i] == v) {
+        s = qsc[i];  // the level has not changed since this entry was scored
+      } else {
+        fresh = true;
+        if (metaKind(e.meta) == PK_POOL)
+          isPool = true;
+        else
+          s = gsfScoreScalar(d, n, e);
+      }
     }
     uint32_t pm = c.ballot(isPool);
     while (pm) {
@@ -374,6 +386,11 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
       words += (unsigned long long)(3 * poolWords((int)metaLevel(m)));
       if (c.lane() == src) s = sc;
     }
+    if (fresh) {
+      qsc[i] = s;
+      qst[i] = v;
+      ++reeval;
+    }
     uint32_t km = c.ballot(s > 0);
     if (c.lane() == 0) keepBits[base / C::LANES] = km;
     if (s > bestScore) {  // strict >: keeps this lane's earliest max
@@ -384,6 +401,7 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
   int mx = c.maxv(bestScore);
   int bi = c.minv(bestScore == mx ? bestIdx : 0x7fffffff);
   bool found = mx > 0;
+  reeval = c.sum(reeval);
   c.sync();
   // order-preserving compaction: drop score-0 entries and the best one
   int w = 0;
@@ -393,15 +411,16 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
     e.from = 0;
     e.meta = 0;
     e.pl = 0;
+    int es = 0;
+    uint32_t et = 0;
     bool keep = false, evict = false;
+    uint32_t kw = keepBits[base / C::LANES];
     if (i < len) {
-      e = q[i];
-      bool k0 = (keepBits[base / C::LANES] >> (C::LANES == 1 ? 0 : c.lane())) & 1u;
+      bool k0 = (kw >> (C::LANES == 1 ? 0 : c.lane())) & 1u;
       keep = k0 && !(found && i == bi);
       evict = !k0;
     }
     uint32_t km = c.ballot(keep);
-    c.sync();  // all lanes have loaded their entry before anyone overwrites the chunk
 #if defined(__CUDA_ARCH__)
     int off = __popc(km & ((1u << c.lane()) - 1u));
     int tot = __popc(km);
@@ -409,9 +428,22 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
     int off = 0;
     int tot = (int)(km & 1u);
 #endif
-    if (keep) q[w + off] = e;
-    if (evict && metaKind(e.meta) == PK_POOL) freeDirect(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
-    if (found && i == bi) best = e;
+    bool chunkStatic = (w == base) && (tot == (len - base < C::LANES ? len - base : C::LANES));  // nothing removed so far, nor here
+    if (!chunkStatic) {
+      if (i < len) {
+        e = q[i];
+        es = qsc[i];
+        et = qst[i];
+      }
+      c.sync();  // all lanes have loaded their entry before anyone overwrites the chunk
+      if (keep && w + off != i) {
+        q[w + off] = e;
+        qsc[w + off] = es;
+        qst[w + off] = et;
+      }
+      if (evict && metaKind(e.meta) == PK_POOL) freeDirect(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
+      if (found && i == bi) best = e;
+    }
     w += tot;
   }
   if (found) {
@@ -423,6 +455,7 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
   if (c.lane() == 0) {
     d.qLen[n] = w;
     statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
+    statAdd(d, n, ST_EVALPOOL, (unsigned long long)reeval);
     if (words) statAdd(d, n, ST_EVALWORDS, words);
     if (found) {
       d.sigChecked[n] += 1;
@@ -539,6 +572,8 @@ WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 p
   e.from = from;
   e.meta = meta;
   e.pl = pl;
+  uint32_t* qs = d.qStamp + (size_t)n * d.qcap;
+  qs[len] = 0;  // score not evaluated yet
   q[len++] = e;
   u64* rowS = d.indivSeen + (size_t)n * d.W64;
   u64 bit = 1ULL << (from & 63);
@@ -548,6 +583,7 @@ WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 p
     ie.from = from;
     ie.meta = metaMake(PK_INDIV, (uint32_t)l, 0);
     ie.pl = 0;
+    qs[len] = 0;
     q[len++] = ie;
   }
   d.qLen[n] = len;
@@ -594,7 +630,10 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
   gsfLevelCounters(d, n, l, cV, cI, cU);
   int total = d.totalCard[n];
   int cSig = kind == PK_INDIV ? 1 : kind == PK_FULL ? (1 << k) : kind == PK_INLINE ? WTG_POPC64(pl) : (int)(pl >> 32);
-  if (c.lane() == 0) statAdd(d, n, ST_UPDATES, 1ULL);
+  if (c.lane() == 0) {
+    statAdd(d, n, ST_UPDATES, 1ULL);
+    d.lvVer[n * L + l] += 1;  // cached scores of this level's queue entries are stale from here on
+  }
 
   // :387-389  if (sigs.cardinality() == 1) sfl.indivVerifiedSig.set(from.nodeId);
   if (cSig == 1) {
@@ -623,6 +662,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
         if (c.lane() == 0) {
           d.cntVer[n * L + i] = si;
           d.cntUnion[n * L + i] = si;
+          d.lvVer[n * L + i] += 1;
         }
         if (i == l) {
           cV = si;
@@ -1265,6 +1305,7 @@ WTG_HD void gsfInitNodeBody(const Dev& d, int n) {  // GSFNode ctor :176-179, SF
     d.cntUnion[n * d.L] = 1;
     for (int l = 1; l < d.L; ++l) d.remaining[n * d.L + l] = 1 << (l - 1);
   }
+  for (int l = 0; l < d.L; ++l) d.lvVer[n * d.L + l] = 1;
 }
 
 // positions in [start, start+len) of the stream after s0 whose next(31) value could be rejected by

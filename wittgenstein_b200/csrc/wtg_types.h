@@ -234,6 +234,9 @@ struct Dev {
   int* sigChecked; // [N]
   int* sigQueueSize;  // [N]
   QEntry* queue;   // [N][qcap]
+  int* qScore;     // [N][qcap] cached evaluateSig score of the entry ...
+  uint32_t* qStamp;  // [N][qcap] ... valid while it equals lvVer of the entry's level (0 = never evaluated)
+  uint32_t* lvVer;   // [N][L] bumped whenever the level's verified / individual sets change
   void* peers;     // [N][N-1] uint16 (block-relative) or uint32 (absolute ids)
   unsigned long long* pool[MAX_LEVELS];  // slabs
   uint32_t* poolFree[MAX_LEVELS];        // free stacks
