@@ -104,7 +104,7 @@ def cpu_baseline(n_cpu, step_ms, budget_s, threads=1):
     g = gsf_params(n_cpu)
     o = OracleGSF(n_cpu, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
     t0 = time.time()
-    o.init()
+    o.init_fast(min(64, os.cpu_count() or 1))  # init is threaded (and untimed); runMs below is single-threaded
     init_s = time.time() - t0
     sim = 0
     wall = 0.0
@@ -119,34 +119,44 @@ def cpu_baseline(n_cpu, step_ms, budget_s, threads=1):
                       f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim}
 
 
+def feasible_cpu_nodes(n, cap):
+    """largest power-of-two node count <= n whose oracle state (peer tables: 4 N^2 bytes) fits in host RAM"""
+    import psutil
+
+    avail = psutil.virtual_memory().available
+    while n > 1024 and (n * n * 4 * 1.5 > avail * 0.7 or n > cap):
+        n //= 2
+    return n
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The Java engine cannot run here (no JVM/gradle/jars:
     SURVEY.md §8c), so this times the oracle port with the same step definition on a bounded sample."""
-    import psutil
-
     n = args.nodes
-    need = n * n * 4 * 1.4
-    while n > 1024 and (need > psutil.virtual_memory().available * 0.8 or n > args.cpu_max_nodes):
-        n //= 2
-        need = n * n * 4 * 1.4
+    n = feasible_cpu_nodes(n, args.cpu_max_nodes)
     from tests.oracle_lib import OracleGSF
 
     g = gsf_params(n)
     o = OracleGSF(n, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
-    o.init()
+    o.init_fast(min(64, os.cpu_count() or 1))
     step_ms = args.ref_step_ms
+    w = OracleGSF(1024, 870, 4, 50, 20, 10, 102, AWS_NB, AWS_NL)  # warm-up steps on a throw-away small network
+    w.init()
     for _ in range(args.warmup):
-        o.run_timed(step_ms, 1)
+        w.run_timed(step_ms, 1)
+    del w
     wall = o.run_timed(step_ms, args.steps)
     val = args.steps * step_ms / wall
     line = {"impl": "reference", "metric": "simulated-ms/sec, GSFSignature", "value": val, "unit": "simulated-ms/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitmaps / int32", "data": "synthetic",
-            "config": {"workload": f"GSFSignature {n} nodes (target {args.nodes}), AWS regions, 33% Tor, 10% dead; step = runMs({step_ms})",
+            "config": {"workload": f"GSFSignature {n} nodes (target {args.nodes}), AWS regions, 33% Tor, 10% dead; step = runMs({step_ms}) "
+                                   f"of one run, timed window [0,{args.steps*step_ms}] ms "
+                                   "(the cheapest part of the run for the CPU engine: its cost per tick grows with the queues)",
                        "note": "reference = C++ oracle port, 1 thread (the reference engine is single-threaded: Network.java:10); "
                                "Java reference not runnable here (no JVM)"},
             "cpu_baseline": {"value": val, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
-                             "sample": f"{args.steps} x runMs({step_ms}) after {args.warmup} warm-up steps at {n} nodes"},
+                             "sample": f"{args.steps} x runMs({step_ms}) from t=0 at {n} nodes (init threaded and untimed)"},
             "e2e": {"value": val, "unit": "simulated-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -154,14 +164,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=19)
+    ap.add_argument("--steps", type=int, default=22)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nodes", type=int, default=131072)
     ap.add_argument("--step-ms", type=int, default=100)
-    ap.add_argument("--ref-step-ms", type=int, default=10)
-    ap.add_argument("--cpu-nodes", type=int, default=16384)
-    ap.add_argument("--cpu-max-nodes", type=int, default=16384)
+    ap.add_argument("--ref-step-ms", type=int, default=20)
+    ap.add_argument("--cpu-nodes", type=int, default=131072)
+    ap.add_argument("--cpu-max-nodes", type=int, default=131072)
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -212,11 +222,18 @@ def main():
     n, K, W, S = args.nodes, args.steps, args.warmup, args.step_ms
     seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)
 
+    # ---- warm-up: W untimed steps on a throw-away network of the same configuration (module load, graph
+    #      instantiation, clocks); the timed passes below each start a fresh, identically seeded network at t=0 so
+    #      that the timed window is the whole run [0, K*S] ----
+    p, _ = make_gsf(n, seed)
+    for _ in range(W):
+        p.network().run_ms(S)
+    p.network().msgs_size()
+    del p
+
     # ---- pass 1: device-timed (value) ----
     p, init_s = make_gsf(n, seed)
     net = p.network()
-    for _ in range(W):
-        net.run_ms(S)
     st0 = net.stats()
     sampler = ClockSampler(local)
     barrier()
@@ -240,8 +257,6 @@ def main():
     # ---- pass 2: end to end through the public API with host read-backs every step ----
     p, _ = make_gsf(n, seed)
     net = p.network()
-    for _ in range(W):
-        net.run_ms(S)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -254,23 +269,38 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     assert (card == card_end).all(), "e2e pass diverged from the device-timed pass"
-    ctl_bytes = 384
+    ctl_bytes = 6000
+    del p, net
 
     # ---- pass 3: per-kernel CUDA-event timing of the same window (roofline of the dominant kernel) ----
     prof = {}
     if not args.no_profile:
-        net.profile_enable(False)
-        del p, net
         p, _ = make_gsf(n, seed)
         net = p.network()
-        for _ in range(W):
-            net.run_ms(S)
         net.profile_enable(True)
         for _ in range(K):
             net.run_ms(S)
         prof = net.profile_read()
         net.profile_enable(False)
-    del p, net
+        del p, net
+
+    # ---- CPU baseline on a bounded sample (prefix of the same run), and the GPU over the same prefix ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline(feasible_cpu_nodes(min(args.cpu_nodes, n), args.cpu_max_nodes), 10, args.cpu_budget_s)
+            if cpu["nodes"] == n:
+                p, _ = make_gsf(n, seed)
+                net = p.network()
+                net.timer_start()
+                for _ in range(cpu["sim_ms"] // 10):
+                    net.run_ms(10)
+                pm = net.timer_stop_ms()
+                cpu["gpu_same_window"] = {"value": cpu["sim_ms"] / (pm / 1000.0), "unit": "simulated-ms/s",
+                                          "window": f"[0,{cpu['sim_ms']}] ms, runMs(10) slicing, device-timed"}
+                del p, net
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": str(e)}
 
     value = sum_over_ranks(K * S) / (dev_ms / 1000.0)
     e2e = sum_over_ranks(K * S) / e2e_s
@@ -300,8 +330,8 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bitmaps / int32", "data": "synthetic",
             "config": {"workload": f"GSFSignature {n} nodes, threshold {int(.85*n)}, {int(.1*n)} dead, pairing 4, level timeout 50, period 20, "
-                                   f"10 accelerated calls, {AWS_NB}, {AWS_NL}; step = runMs({S}) of one continuing run, timed window "
-                                   f"[{W*S},{(W+K)*S}] ms",
+                                   f"10 accelerated calls, {AWS_NB}, {AWS_NL}; step = runMs({S}) of one run, timed window "
+                                   f"[0,{K*S}] ms (fresh network; {W} warm-up steps ran on a throw-away network of the same config)",
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas (no data-path collective)",
                        "l2": "per-step working set (node rows + queues + ring) exceeds L2 at this size",
                        "all_nodes_done_at_end": bool(done)},
@@ -310,11 +340,8 @@ def main():
             "gpu_launches": int(launches), "init_s": init_s, "events": ev, "clocks": sampler.summary()}
     if roof:
         line["roofline"] = roof
-    if rank == 0 and not args.no_cpu:
-        try:
-            line["cpu_baseline"] = cpu_baseline(min(args.cpu_nodes, n), 10, args.cpu_budget_s)
-        except Exception as e:  # noqa: BLE001
-            line["cpu_baseline"] = {"error": str(e)}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -155,6 +155,12 @@ int wo_gsf_init(void* h) {
   return 0;
   WO_CATCH(-1)
 }
+int wo_gsf_init_fast(void* h, int threads) {
+  WO_TRY
+  static_cast<GSFSignature*>(h)->initFast(threads);
+  return 0;
+  WO_CATCH(-1)
+}
 int wo_gsf_run_ms(void* h, int ms) {
   WO_TRY
   return static_cast<GSFSignature*>(h)->network.runMs(ms) ? 1 : 0;

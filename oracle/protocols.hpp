@@ -8,8 +8,10 @@
 // restated in tests/test_oracle_protocols.py); the protocol END STATE (bitmaps, doneAt) is
 // "parity unpinned" — the reference's tests hold no golden end state and no JVM is available.
 #pragma once
+#include <atomic>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "core.hpp"
@@ -143,7 +145,7 @@ struct GSFSignature {
       verifiedSignatures.set(nodeId);  // :176-179
     }
     JBitSet allSigsAtLevel(int round) const;  // :359-372
-    void initLevel();                         // :181-191
+    void initLevel(JavaRandom& rd);           // :181-191 (rd == network.rd in the reference)
     JBitSet getLastFinishedLevel() const;     // :193-210
     void doCycle();                           // :212-224
     static bool include(const JBitSet& large, const JBitSet& small) {  // :374-378
@@ -187,13 +189,19 @@ struct GSFSignature {
     for (auto& up : nodes) {
       GSFNode* n = up.get();
       if (!n->isDown()) {
-        n->initLevel();
+        n->initLevel(network.rd);
         network.registerPeriodicTask([n] { n->doCycle(); }, 1, params.periodDurationMs, *n);
         network.registerConditionalTask([n] { n->checkSigs(); }, 1, n->nodePairingTime, *n,
                                         [n] { return !n->toVerify.empty(); }, [n] { return !n->done; });
       }
     }
   }
+  // Same result as init(), built for large N (test infrastructure convenience, not a reference code path):
+  // a sequential pre-pass steps network.rd through every shuffle draw (no swaps) to record the RNG state at
+  // the start of each node, then the per-node initLevel() calls run on `threads` threads from those states.
+  // tests/test_oracle_protocols.py checks initFast() == init() state for state.
+  void initFast(int threads);
+
   // newConfIf :670-682 — true while some live node is below the threshold
   bool continueIf() const {
     for (auto& n : nodes)
@@ -222,7 +230,7 @@ inline JBitSet GSFSignature::GSFNode::allSigsAtLevel(int round) const {  // :359
   return res;
 }
 
-inline void GSFSignature::GSFNode::initLevel() {  // :181-191, SFLevel ctors :260-280, randomSubset :462-476
+inline void GSFSignature::GSFNode::initLevel(JavaRandom& rd) {  // :181-191, SFLevel ctors :260-280, randomSubset :462-476
   int roundedPow2NodeCount = roundPow2(p->params.nodeCount);
   JBitSet allPreviousNodes;
   levels.emplace_back();
@@ -247,7 +255,7 @@ inline void GSFSignature::GSFNode::initLevel() {  // :181-191, SFLevel ctors :26
     nl.peers.reserve(static_cast<size_t>(nl.waitedCard));
     for (int cur = nl.waitedSigs.nextSetBit(0); cur >= 0; cur = nl.waitedSigs.nextSetBit(cur + 1))
       nl.peers.push_back(static_cast<uint32_t>(cur));
-    javaShuffle(nl.peers, p->network.rd);
+    javaShuffle(nl.peers, rd);
     nl.remainingCalls = static_cast<int>(nl.peers.size());
     levels.push_back(std::move(nl));
   }
@@ -442,6 +450,74 @@ inline void GSFSignature::GSFNode::checkSigs() {  // :557-583
     GSFNode* self = this;
     p->network.registerTask([self, tBest] { self->updateVerifiedSignatures(tBest->from, tBest->level, tBest->sigs); },
                             p->network.time + nodePairingTime, *this);
+  }
+}
+
+inline void GSFSignature::initFast(int threads) {
+  for (int i = 0; i < params.nodeCount; i++) {
+    nodes.push_back(std::make_unique<GSFNode>(this));
+    network.addNode(nodes.back().get());
+  }
+  for (int setDown = 0; setDown < params.nodesDown;) {
+    int down = network.rd.nextInt(params.nodeCount);
+    Node& n = *network.allNodes[static_cast<size_t>(down)];
+    if (!n.isDown() && down != 1) {
+      n.stop();
+      setDown++;
+    }
+  }
+  const int N = params.nodeCount;
+  const int rounded = roundPow2(N);
+  std::vector<uint64_t> startSeed(static_cast<size_t>(N), 0);
+  JavaRandom r = network.rd;
+  for (int id = 0; id < N; ++id) {
+    if (nodes[static_cast<size_t>(id)]->isDown()) continue;
+    startSeed[static_cast<size_t>(id)] = r.seed;
+    for (int l = 1; (1LL << l) <= rounded; l++) {
+      // |waitedSigs| of level l: the sibling half of the 2^l block, clipped to [0, N)
+      int mask = (1 << l) - 1, half = 1 << (l - 1);
+      int start = (id | mask) ^ mask;
+      int sibLo = (id & half) ? start : start + half;
+      int sibHi = std::min(sibLo + half, N);
+      int size = std::max(0, sibHi - sibLo);
+      // the draws of Collections.shuffle without the swaps.  nextInt(i) can only loop when
+      // u >= 2^31 - i (java.util.Random.nextInt rejection test), so the exact test runs on those draws only.
+      for (int i = size; i > 1; i--) {
+        int32_t u = r.next(31);
+        if ((i & (i - 1)) != 0 && static_cast<uint32_t>(u) >= 0x80000000u - static_cast<uint32_t>(i)) {
+          for (;;) {
+            int32_t rem = u % i;
+            if (static_cast<int32_t>(static_cast<uint32_t>(u) - static_cast<uint32_t>(rem) + static_cast<uint32_t>(i - 1)) >= 0) break;
+            u = r.next(31);
+          }
+        }
+      }
+    }
+  }
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (;;) {
+      int id = next.fetch_add(1);
+      if (id >= N) break;
+      GSFNode* n = nodes[static_cast<size_t>(id)].get();
+      if (n->isDown()) continue;
+      JavaRandom rr(0);
+      rr.seed = startSeed[static_cast<size_t>(id)];
+      n->initLevel(rr);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::max(1, threads); ++t) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  network.rd.draws += r.draws - network.rd.draws;
+  network.rd.seed = r.seed;
+  for (auto& up : nodes) {
+    GSFNode* n = up.get();
+    if (!n->isDown()) {
+      network.registerPeriodicTask([n] { n->doCycle(); }, 1, params.periodDurationMs, *n);
+      network.registerConditionalTask([n] { n->checkSigs(); }, 1, n->nodePairingTime, *n,
+                                      [n] { return !n->toVerify.empty(); }, [n] { return !n->done; });
+    }
   }
 }
 

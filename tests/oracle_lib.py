@@ -128,6 +128,11 @@ class OracleGSF:
             raise RuntimeError(self.lib.wo_last_error().decode())
         self.L = self.lib.wo_gsf_levels(self.h, 1)
 
+    def init_fast(self, threads):
+        if self.lib.wo_gsf_init_fast(self.h, int(threads)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        self.L = self.lib.wo_gsf_levels(self.h, 1)
+
     def run_ms(self, ms):
         r = self.lib.wo_gsf_run_ms(self.h, ms)
         if r < 0:

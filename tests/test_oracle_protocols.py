@@ -159,3 +159,17 @@ def test_pingpong_trajectory_is_monotone_and_soft_matches_readme():
     assert int(p.pongs()[0]) == 1000
     # one-way latency <= (1144 pts * 10.87 mi * 0.022 + 4.862)/2 ~ 139 ms + jitter: ping+pong done by ~300 ms
     assert 0 < traj[1] < traj[2] < 1000 and traj[4] == 1000
+
+
+def test_gsf_init_fast_equals_init():
+    """initFast (threaded, used by the bench's CPU legs at large N) must reproduce init() exactly."""
+    for n, dead in ((256, 25), (1024, 100), (4096, 409)):
+        a = OracleGSF(n, int(.8 * n), 4, 50, 20, 10, dead, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"); a.init()
+        b = OracleGSF(n, int(.8 * n), 4, 50, 20, 10, dead, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"); b.init_fast(4)
+        assert a.rng_state() == b.rng_state()
+        for node in (0, 1, n // 2 + 1, n - 1):
+            for l in range(a.L):
+                assert (a.peers(node, l) == b.peers(node, l)).all()
+        for _ in range(20):
+            a.run_ms(10); b.run_ms(10)
+        assert (a.verified() == b.verified()).all() and (a.counters() == b.counters()).all() and a.rng_state() == b.rng_state()
