@@ -37,8 +37,12 @@ class HostBackend : public Backend {
     std::vector<uint32_t> keep((size_t)std::max(1, d.qcap));
     tickBegin(d, mode);
     if (d.ctl->error) return;
-    if (d.proto == PROTO_GSF)
-      for (int n = 0; n < d.N; ++n) gsfCond(d, c, n, keep.data());
+    if (d.proto == PROTO_GSF) {
+      for (int n = 0; n < d.N; ++n) gsfCondScan(d, c, n);
+      int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
+      for (int t = 0; t < tot; ++t) gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
+      for (int n = 0; n < d.N; ++n) gsfCondSelect(d, c, n, keep.data());
+    }
     if (mode != 2) {
       int nEv = d.ctl->nEv;
       for (int i = 0; i < nEv; ++i) dispatchCount(d, i);

@@ -33,15 +33,31 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 __global__ void k_begin(Dev d, int mode) { tickBegin(d, mode); }
 __global__ void k_end(Dev d, int mode) { tickEnd(d, mode); }
 
-// ---- conditional tasks: warp per node ------------------------------------------------------
-__global__ void __launch_bounds__(NODE_BLOCK) k_cond(Dev d) {
+// ---- conditional tasks (checkSigs): scan -> score -> select ---------------------------------------
+__global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
+  if (d.ctl->error) return;
+  int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (n >= d.N) return;
+  CoopWarp c;
+  gsfCondScan(d, c, n);
+}
+__global__ void __launch_bounds__(256) k_cond_score(Dev d) {
+  if (d.ctl->error) return;
+  const int per = d.workCap / ARENA_STRIPES;
+  const int total = stripedTotal(d.ctl->workCnt, per);
+  CoopWarp c;
+  const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warpsPerGrid)
+    gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
+}
+__global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
   extern __shared__ uint32_t keepAll[];
   if (d.ctl->error) return;
   int warp = threadIdx.x >> 5;
   int n = blockIdx.x * WARPS_PER_BLOCK + warp;
   if (n >= d.N) return;
   CoopWarp c;
-  gsfCond(d, c, n, keepAll + (size_t)warp * (size_t)(d.qcap / 32));
+  gsfCondSelect(d, c, n, keepAll + (size_t)warp * (size_t)(d.qcap / 32));
 }
 
 // ---- dispatch -----------------------------------------------------------------------------
@@ -336,9 +352,9 @@ class CudaBackend : public Backend {
   size_t evUsed = 0;
   double profMs[NK] = {};
   long long profCnt[NK] = {};
-  const char* profNames[NK] = {"k_begin", "k_cond", "k_dispatch_count", "k_scan_partial", "k_scan_tiles", "k_scan_final",
+  const char* profNames[NK] = {"k_begin", "k_cond_scan", "k_dispatch_count", "k_scan_partial", "k_scan_tiles", "k_scan_final",
                                "k_dispatch_scatter", "k_node", "k_emit", "k_ms_count", "k_ms_scan", "k_ms_scatter", "k_free",
-                               "k_end", "", ""};
+                               "k_end", "k_cond_score", "k_cond_select"};
 
   CudaBackend() {
     int dev = 0;
@@ -408,7 +424,7 @@ class CudaBackend : public Backend {
   int profileRead(double* ms, long long* cnt, const char** names, int cap) override {
     sync();
     int k = 0;
-    for (int i = 0; i < 14 && k < cap; ++i, ++k) {
+    for (int i = 0; i < NK && k < cap; ++i, ++k) {
       ms[k] = profMs[i];
       cnt[k] = profCnt[i];
       names[k] = profNames[i];
@@ -458,9 +474,15 @@ class CudaBackend : public Backend {
     if (d.proto == PROTO_GSF) {
       size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);
-    k_cond<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
-    profEnd();
-      launches += 1;
+      k_cond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      profEnd();
+      profBegin(14);
+      k_cond_score<<<sms * 8, 256, 0, st>>>(d);
+      profEnd();
+      profBegin(15);
+      k_cond_select<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
+      profEnd();
+      launches += 3;
     }
     if (mode != 2) {
       profBegin(2);

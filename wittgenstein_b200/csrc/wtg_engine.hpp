@@ -165,6 +165,9 @@ class Engine {
     d.evSlots = dalloc<int>(d.itemCap);
     d.evDraws = dalloc<int>(d.itemCap);
     d.condFired = dalloc<int>(N);
+    d.condDue = dalloc<int>(N);
+    d.workCap = (int)std::max<long long>(1 << 16, 64LL * N) / ARENA_STRIPES * ARENA_STRIPES;
+    d.workList = dalloc<uint32_t>(d.workCap);
     d.condEv = dalloc<Ev>(N);
     d.condTarget = dalloc<int>(N);
     d.slotBase = dalloc<int>((size_t)N + d.itemCap);

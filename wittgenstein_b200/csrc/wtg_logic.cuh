@@ -319,6 +319,27 @@ WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta,
   const u64* rowI = d.indivVer + (size_t)n * d.W64 + b.w0;
   const u64* sig = d.pool[l] + (size_t)(uint32_t)pl * (size_t)b.nw;
   int cWI = 0, cWIV = 0, inter = 0, interI = 0;
+#if defined(__CUDA_ARCH__)
+  {  // 128-bit loads, two independent triples in flight per lane (nw is even for pooled levels)
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(sig);
+    const ulonglong2* v2 = reinterpret_cast<const ulonglong2*>(rowV);
+    const ulonglong2* i2 = reinterpret_cast<const ulonglong2*>(rowI);
+    const int n2 = b.nw >> 1;
+    for (int w = c.lane(); w < n2; w += 64) {
+      ulonglong2 sa = s2[w], va = v2[w], ia = i2[w];
+      ulonglong2 sb = make_ulonglong2(0, 0), vb = sb, ib = sb;
+      if (w + 32 < n2) {
+        sb = s2[w + 32];
+        vb = v2[w + 32];
+        ib = i2[w + 32];
+      }
+      cWI += __popcll(ia.x | sa.x) + __popcll(ia.y | sa.y) + __popcll(ib.x | sb.x) + __popcll(ib.y | sb.y);
+      cWIV += __popcll(ia.x | sa.x | va.x) + __popcll(ia.y | sa.y | va.y) + __popcll(ib.x | sb.x | vb.x) + __popcll(ib.y | sb.y | vb.y);
+      inter |= ((sa.x & va.x) | (sa.y & va.y) | (sb.x & vb.x) | (sb.y & vb.y)) != 0;
+      interI |= ((sa.x & ia.x) | (sa.y & ia.y) | (sb.x & ib.x) | (sb.y & ib.y)) != 0;
+    }
+  }
+#else
   for (int w = c.lane(); w < b.nw; w += C::LANES) {
     u64 s = sig[w], v = rowV[w], i = rowI[w];
     cWI += WTG_POPC64(i | s);
@@ -326,6 +347,7 @@ WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta,
     inter |= (s & v) != 0;
     interI |= (s & i) != 0;
   }
+#endif
   cWI = c.sum(cWI);
   cWIV = c.sum(cWIV);
   bool bi = c.any(inter != 0), bii = c.any(interI != 0);
@@ -333,67 +355,114 @@ WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta,
 }
 
 // ------------------------------------------------------------------------------------------
-// checkSigs  (GSFSignature.java:557-583): scan toVerify, evict score-0 entries, take the first
-// max-score entry, schedule updateVerifiedSignatures at time + nodePairingTime.
-// keepBits: scratch of qcap/32 words private to this coop.
-// Returns true and fills `task` when a best entry was found.
+// checkSigs  (GSFSignature.java:557-583) in three device phases:
+//   A  gsfCondScan   (warp / node)   conditional-task bookkeeping (Network.java:543-565 restated per node, see
+//                                    DESIGN.md §2.3); re-scores stale O(1) entries in place and lists the stale
+//                                    pooled entries (those whose level changed since they were last scored)
+//   B  gsfScoreItem  (warp / entry)  evaluateSig of one listed pooled entry: all lanes stream the level block
+//   C  gsfCondSelect (warp / node)   first max score, evict score 0, order-preserving compaction, schedule
+//                                    updateVerifiedSignatures at time + nodePairingTime
+//   condMode 1: the clock has just ticked to `tick` inside a runMs window ending at `until`
+//   condMode 2: the reference's extra time++ past `until` at the end of the window
 // ------------------------------------------------------------------------------------------
 template <class C>
-WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& best) {
+WTG_HD void gsfCondScan(const Dev& d, C& c, int n) {
+  const Ctl& ctl = *d.ctl;
+  int dueNow = 0;
+  if (ctl.condMode != 0 && !d.ndown[n]) {
+    int ms = d.minStart[n];
+    bool due = ctl.condMode == 1 ? (ms <= ctl.tick) : (ms <= ctl.until);
+    if (due && d.stamp[n] != ctl.callId) {
+      c.sync();
+      if (c.lane() == 0) d.stamp[n] = ctl.callId;
+      int len = d.qLen[n];
+      if (len > 0) {  // startIf: !toVerify.isEmpty()
+        dueNow = 1;
+        QEntry* q = d.queue + (size_t)n * d.qcap;
+        int* qsc = d.qScore + (size_t)n * d.qcap;
+        uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
+        const uint32_t* ver = d.lvVer + (size_t)n * d.L;
+        const int st = n & (ARENA_STRIPES - 1);
+        const int per = d.workCap / ARENA_STRIPES;
+        int reeval = 0;
+        for (int base = 0; base < len; base += C::LANES) {
+          int i = base + c.lane();
+          bool stalePool = false;
+          if (i < len) {
+            QEntry e = q[i];
+            uint32_t v = ver[metaLevel(e.meta)];
+            if (qst[i] != v) {
+              ++reeval;
+              if (metaKind(e.meta) == PK_POOL) {
+                stalePool = true;
+              } else {
+                qsc[i] = gsfScoreScalar(d, n, e);
+                qst[i] = v;
+              }
+            }
+          }
+          uint32_t pm = c.ballot(stalePool);
+          if (pm) {
+#if defined(__CUDA_ARCH__)
+            int cnt = __popc(pm), off = __popc(pm & ((1u << c.lane()) - 1u));
+#else
+            int cnt = (int)(pm & 1u), off = 0;
+#endif
+            int b0 = 0;
+            if (c.lane() == 0) b0 = WTG_ATOMIC_ADD(&d.ctl->workCnt[st], cnt);
+            b0 = c.bcast(b0, 0);
+            if (stalePool) {
+              if (b0 + off < per)
+                d.workList[(size_t)st * per + b0 + off] = (uint32_t)((size_t)n * d.qcap + i);
+              else
+                setError(d, ERR_DESC_OVERFLOW, -n);
+            }
+          }
+        }
+        reeval = c.sum(reeval);
+        if (c.lane() == 0) {
+          d.minStart[n] = ctl.tick + d.pairing[n];
+          statAdd(d, n, ST_CONDRUNS, 1ULL);
+          statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
+          statAdd(d, n, ST_EVALPOOL, (unsigned long long)reeval);
+        }
+      }
+    }
+  }
+  if (c.lane() == 0) {
+    d.condDue[n] = dueNow;
+    if (!dueNow) d.condFired[n] = 0;
+  }
+}
+
+template <class C>
+WTG_HD void gsfScoreItem(const Dev& d, C& c, uint32_t item) {
+  int n = (int)(item / (uint32_t)d.qcap);
+  QEntry e = d.queue[item];
+  int s = gsfScorePool(d, c, n, e.from, e.meta, e.pl);
+  if (c.lane() == 0) {
+    d.qScore[item] = s;
+    d.qStamp[item] = d.lvVer[(size_t)n * d.L + metaLevel(e.meta)];
+    statAdd(d, n, ST_EVALWORDS, (unsigned long long)(3 * poolWords((int)metaLevel(e.meta))));
+  }
+}
+
+// keepBits: scratch of qcap/LANES words private to this coop
+template <class C>
+WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {
+  if (!d.condDue[n]) return;
+  const Ctl& ctl = *d.ctl;
   int len = d.qLen[n];
   QEntry* q = d.queue + (size_t)n * d.qcap;
   int* qsc = d.qScore + (size_t)n * d.qcap;
   uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
-  const uint32_t* ver = d.lvVer + (size_t)n * d.L;
   int bestScore = 0, bestIdx = 0x7fffffff;
-  unsigned long long words = 0;
-  int reeval = 0;
   for (int base = 0; base < len; base += C::LANES) {
     int i = base + c.lane();
-    QEntry e;
-    e.from = 0;
-    e.meta = 0;
-    e.pl = 0;
-    int s = 0;
-    bool isPool = false;
-    uint32_t v = 0;
-    bool fresh = false;
-    if (i < len) {
-      e = q[i];
-      v = ver[metaLevel(e.meta)];
-      if (qst[i] == v) {
-        s = qsc[i];  // the level has not changed since this entry was scored
-      } else {
-        fresh = true;
-        if (metaKind(e.meta) == PK_POOL)
-          isPool = true;
-        else
-          s = gsfScoreScalar(d, n, e);
-      }
-    }
-    uint32_t pm = c.ballot(isPool);
-    while (pm) {
-#if defined(__CUDA_ARCH__)
-      int src = __ffs(pm) - 1;
-#else
-      int src = __builtin_ctz(pm);
-#endif
-      pm &= pm - 1;
-      uint32_t f = (uint32_t)c.bcast((int)e.from, src);
-      uint32_t m = (uint32_t)c.bcast((int)e.meta, src);
-      u64 p = c.bcast64(e.pl, src);
-      int sc = gsfScorePool(d, c, n, f, m, p);
-      words += (unsigned long long)(3 * poolWords((int)metaLevel(m)));
-      if (c.lane() == src) s = sc;
-    }
-    if (fresh) {
-      qsc[i] = s;
-      qst[i] = v;
-      ++reeval;
-    }
+    int s = i < len ? qsc[i] : 0;
     uint32_t km = c.ballot(s > 0);
     if (c.lane() == 0) keepBits[base / C::LANES] = km;
-    if (s > bestScore) {  // strict >: keeps this lane's earliest max
+    if (s > bestScore) {  // strict >: keeps this lane's earliest max (checkSigs :565-567)
       bestScore = s;
       bestIdx = i;
     }
@@ -401,18 +470,15 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
   int mx = c.maxv(bestScore);
   int bi = c.minv(bestScore == mx ? bestIdx : 0x7fffffff);
   bool found = mx > 0;
-  reeval = c.sum(reeval);
   c.sync();
-  // order-preserving compaction: drop score-0 entries and the best one
+  // order-preserving compaction: drop score-0 entries (it.remove() :568-570) and the best one (:574)
+  QEntry best;
+  best.from = 0;
+  best.meta = 0;
+  best.pl = 0;
   int w = 0;
   for (int base = 0; base < len; base += C::LANES) {
     int i = base + c.lane();
-    QEntry e;
-    e.from = 0;
-    e.meta = 0;
-    e.pl = 0;
-    int es = 0;
-    uint32_t et = 0;
     bool keep = false, evict = false;
     uint32_t kw = keepBits[base / C::LANES];
     if (i < len) {
@@ -428,14 +494,21 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
     int off = 0;
     int tot = (int)(km & 1u);
 #endif
-    bool chunkStatic = (w == base) && (tot == (len - base < C::LANES ? len - base : C::LANES));  // nothing removed so far, nor here
+    int inChunk = len - base < C::LANES ? len - base : C::LANES;
+    bool chunkStatic = (w == base) && (tot == inChunk);  // nothing removed before or inside this chunk
     if (!chunkStatic) {
+      QEntry e;
+      e.from = 0;
+      e.meta = 0;
+      e.pl = 0;
+      int es = 0;
+      uint32_t et = 0;
       if (i < len) {
         e = q[i];
         es = qsc[i];
         et = qst[i];
       }
-      c.sync();  // all lanes have loaded their entry before anyone overwrites the chunk
+      c.sync();  // every lane has loaded its entry before anyone overwrites the chunk
       if (keep && w + off != i) {
         q[w + off] = e;
         qsc[w + off] = es;
@@ -454,59 +527,22 @@ WTG_HD bool gsfCheckSigs(const Dev& d, C& c, int n, uint32_t* keepBits, QEntry& 
   }
   if (c.lane() == 0) {
     d.qLen[n] = w;
-    statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
-    statAdd(d, n, ST_EVALPOOL, (unsigned long long)reeval);
-    if (words) statAdd(d, n, ST_EVALWORDS, words);
-    if (found) {
+    if (found) {  // registerTask(updateVerifiedSignatures, time + nodePairingTime, this)  :575-581
       d.sigChecked[n] += 1;
       d.sigQueueSize[n] = w;
+      Ev ev;
+      ev.kind = EV_TASK;
+      ev.to = (uint32_t)n;
+      ev.from = best.from;
+      ev.meta = best.meta;
+      ev.pl = best.pl;
+      ev.aux = 0;
+      ev.pad = 0;
+      d.condEv[n] = ev;
+      d.condTarget[n] = ctl.tick + d.pairing[n];
     }
+    d.condFired[n] = found ? 1 : 0;
   }
-  return found;
-}
-
-// ------------------------------------------------------------------------------------------
-// conditional-task pass for node n  (Network.java:543-565 restated per node)
-//   mode 1: clock has just ticked to `tick` inside a runMs window ending at `until`
-//   mode 2: the reference's extra time++ past `until` at the end of the window
-// ------------------------------------------------------------------------------------------
-template <class C>
-WTG_HD void gsfCond(const Dev& d, C& c, int n, uint32_t* keepBits) {
-  const Ctl& ctl = *d.ctl;
-  int fired = 0;
-  if (ctl.condMode != 0 && !d.ndown[n]) {
-    int ms = d.minStart[n];
-    bool due = ctl.condMode == 1 ? (ms <= ctl.tick) : (ms <= ctl.until);
-    if (due && d.stamp[n] != ctl.callId) {
-      c.sync();
-      if (c.lane() == 0) d.stamp[n] = ctl.callId;
-      if (d.qLen[n] > 0) {  // startIf: !toVerify.isEmpty()
-        QEntry best;
-        best.from = 0;
-        best.meta = 0;
-        best.pl = 0;
-        bool found = gsfCheckSigs(d, c, n, keepBits, best);
-        if (c.lane() == 0) {
-          d.minStart[n] = ctl.tick + d.pairing[n];
-          statAdd(d, n, ST_CONDRUNS, 1ULL);
-          if (found) {  // registerTask(updateVerifiedSignatures, time + nodePairingTime, this)
-            Ev ev;
-            ev.kind = EV_TASK;
-            ev.to = (uint32_t)n;
-            ev.from = best.from;
-            ev.meta = best.meta;
-            ev.pl = best.pl;
-            ev.aux = 0;
-            ev.pad = 0;
-            d.condEv[n] = ev;
-            d.condTarget[n] = ctl.tick + d.pairing[n];
-          }
-        }
-        fired = found ? 1 : 0;
-      }
-    }
-  }
-  if (c.lane() == 0) d.condFired[n] = fired;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -917,6 +953,139 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
   outDraws = nSend;
 }
 
+#if defined(__CUDACC__)
+// 128-bit lane-strided copy of `nw` 64-bit words (nw even, both sides 16-byte aligned)
+__device__ __forceinline__ void warpCopyWords(u64* __restrict__ dst, const u64* __restrict__ src, int nw, int lane) {
+  const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+  ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+  const int n2 = nw >> 1;
+  int w = lane;
+  for (; w + 96 < n2; w += 128) {  // 4 independent 16-byte loads in flight per lane
+    ulonglong2 a = s2[w], b = s2[w + 32], c = s2[w + 64], e = s2[w + 96];
+    d2[w] = a;
+    d2[w + 32] = b;
+    d2[w + 64] = c;
+    d2[w + 96] = e;
+  }
+  for (; w < n2; w += 32) d2[w] = s2[w];
+}
+
+// doCycle with one lane per level: all per-level scalars (cardinalities, remainingCalls, cursor, next peer) are
+// loaded and decided in parallel; only the payload snapshots are copied cooperatively.  Same results as gsfCycle.
+__device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int& outSlots, int& outDraws) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int L = d.L;
+  const int tick = d.ctl->tick;
+  const int l = lane;
+  const bool valid = l >= 1 && l < L;
+  const u64* rowV = d.verified + (size_t)n * d.W64;
+  int cv = l < L ? d.cntVer[n * L + l] : 0;
+  int rem = valid ? d.remaining[n * L + l] : 0;
+  int p = valid ? d.pos[n * L + l] : 0;
+  const int size = valid ? (1 << (l - 1)) : 0;
+  unsigned comp = __ballot_sync(FULLM, valid && cv == size);
+  int kf = __ffs(~(comp >> 1)) - 1;  // levels 1..kf complete (getLastFinishedLevel)
+  int inc = cv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULLM, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int prefix = inc - cv;  // sum of the cardinalities of levels 0..l-1
+  const int card = (kf >= l - 1) ? (1 << kf) : prefix;
+  const bool started = tick >= l * d.timeoutPerLevel || card >= size;  // hasStarted :291-311
+  const bool snd = valid && rem > 0 && started;
+  const unsigned sendMask = __ballot_sync(FULLM, snd);
+  const int nSend = __popc(sendMask);
+  int base = 0;
+  if (lane == 0) {
+    int st = n & (ARENA_STRIPES - 1), per = d.descCap / ARENA_STRIPES;
+    int i = atomicAdd(&d.ctl->descCnt[st], nSend + 1);
+    if (i + nSend + 1 > per) {
+      setError(d, ERR_DESC_OVERFLOW, i);
+      base = -1;
+    } else {
+      base = st * per + i;
+    }
+  }
+  base = __shfl_sync(FULLM, base, 0);
+  const int sub = __popc(sendMask & ((1u << lane) - 1u));
+  uint32_t dest = 0, meta = 0, slot = 0;
+  u64 pl = 0;
+  bool pooled = false;
+  if (snd) {
+    dest = peerAt(d, n, l, p);  // getRemainingPeers(1) :325-349
+    int p2 = p + 1 >= size ? 0 : p + 1;
+    d.pos[n * L + l] = p2;
+    d.remaining[n * L + l] = rem - 1;
+    if (kf >= l - 1) {
+      meta = metaMake(PK_FULL, (uint32_t)l, (uint32_t)kf);
+    } else if (l <= INLINE_MAX_LEVEL) {
+      Blk ob = levelBlock(n, l);
+      meta = metaMake(PK_INLINE, (uint32_t)l, 0);
+      pl = rowV[ob.w0] & ob.mask;
+    } else {
+      meta = metaMake(PK_POOL, (uint32_t)l, 0);
+      pooled = poolAlloc(d, l, n, slot);
+      pl = (u64)slot | ((u64)(uint32_t)prefix << 32);
+    }
+  }
+  unsigned pm = __ballot_sync(FULLM, pooled);
+  unsigned long long words = 0;
+  while (pm) {
+    int src = __ffs(pm) - 1;
+    pm &= pm - 1;
+    uint32_t sl = __shfl_sync(FULLM, slot, src);
+    Blk ob = levelBlock(n, src);  // our own half of level `src`: what the receiver waits for at its level
+    warpCopyWords(d.pool[src] + (size_t)sl * (size_t)ob.nw, rowV + ob.w0, ob.nw, lane);
+    words += (unsigned long long)(2 * ob.nw);
+  }
+  if (snd && base >= 0) {
+    Desc ds;
+    ds.dkind = DK_SEND_SINGLE;
+    ds.item = (uint32_t)(d.N + item);
+    ds.sub = (uint32_t)sub;
+    ds.from = (uint32_t)n;
+    ds.to = dest;
+    ds.nDest = 1;
+    ds.evKind = EV_MSG;
+    ds.meta = meta;
+    ds.pl = pl;
+    ds.target = 0;
+    ds.aux = 0;
+    d.desc[base + sub] = ds;
+  }
+  int bytes = snd ? msgSize(l) : 0;
+  bytes = __reduce_add_sync(FULLM, bytes);
+  if (lane == 0) {
+    if (base >= 0) {  // re-arm: network.sendArriveAt(this, time + period, sender, sender)
+      Desc ds;
+      ds.dkind = DK_INSERT_AT;
+      ds.item = (uint32_t)(d.N + item);
+      ds.sub = (uint32_t)nSend;
+      ds.from = (uint32_t)n;
+      ds.to = (uint32_t)n;
+      ds.nDest = 0;
+      ds.evKind = EV_PERIODIC;
+      ds.meta = 0;
+      ds.pl = 0;
+      ds.target = tick + d.period;
+      ds.aux = 0;
+      d.desc[base + nSend] = ds;
+    }
+    d.msgSent[n] += nSend;
+    d.bytesSent[n] += bytes;
+    statAdd(d, n, ST_CYCLES, 1ULL);
+    statAdd(d, n, ST_SENDS, (unsigned long long)nSend);
+    if (words) statAdd(d, n, ST_SENDWORDS, words);
+  }
+  __syncwarp();
+  outSlots = nSend + 1;
+  outDraws = nSend;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // one delivery at node n (Network.receiveUntil :603-627 + the protocol's Message.action)
 // `ev` is the envelope, item its scan item.  Writes evSlots/evDraws[item].
@@ -945,7 +1114,11 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
       gsfUpdate(d, c, n, from, meta, pl, item, slots, draws);
     } else {
       if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
+#if defined(__CUDA_ARCH__)
+      gsfCycleWarp(d, n, item, slots, draws);
+#else
       gsfCycle(d, c, n, item, slots, draws);
+#endif
     }
   } else if (d.proto == PROTO_PINGPONG) {
     if (c.lane() == 0) {
@@ -1248,6 +1421,7 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
   for (int t = 0; t < ARENA_STRIPES; ++t) {
     c.descCnt[t] = 0;
     c.destCnt[t] = 0;
+    c.workCnt[t] = 0;
   }
   c.nItems = 0;
   c.totalSlots = 0;

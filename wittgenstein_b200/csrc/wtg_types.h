@@ -130,6 +130,7 @@ struct Ctl {  // device-resident control block (one per engine)
   int descCnt[ARENA_STRIPES];   // descriptors allocated this tick, per stripe (stripe = node id & 63)
   int destCnt[ARENA_STRIPES];   // multi-send destination scratch, per stripe
   int freeCnt[ARENA_STRIPES];   // deferred payload frees, per stripe
+  int workCnt[ARENA_STRIPES];   // stale pooled queue entries to re-score this tick, per stripe
   int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
   int poolFreeCnt[MAX_LEVELS][POOL_STRIPES];   // free slots per (level, stripe)
 };
@@ -164,7 +165,7 @@ struct Dev {
   int threshold, timeoutPerLevel, period, accel;
   int qcap, bcap;
   int msgDiscardTime;
-  int descCap, destScratchCap, recCap, recDestCap, freeCap, newEvCap, itemCap;
+  int descCap, destScratchCap, recCap, recDestCap, freeCap, newEvCap, itemCap, workCap;
   int latKind, latParam;
   int peerBits;  // 16 or 32
   // ---- control ----
@@ -200,6 +201,8 @@ struct Dev {
   int* itemBase;      // [bcap] exclusive scan of subCount
   int* evSlots;       // [itemCap] descriptors emitted by scan item
   int* evDraws;       // [itemCap] rd.nextInt() draws consumed by scan item
+  int* condDue;       // [N] conditional task of node n is examined this tick and its queue is not empty
+  uint32_t* workList; // [workCap] global queue-entry index (n*qcap+i) of stale pooled entries, striped
   int* condFired;     // [N]
   Ev* condEv;         // [N] task created by the conditional task of node n
   int* condTarget;    // [N]
