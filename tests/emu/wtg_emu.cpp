@@ -38,7 +38,8 @@ class HostBackend : public Backend {
     tickBegin(d, mode);
     if (d.ctl->error) return;
     if (d.proto == PROTO_GSF) {
-      for (int n = 0; n < d.N; ++n) gsfCondScan(d, c, n);
+      for (int n = 0; n < d.N; ++n)
+        if (gsfCondMark(d, n)) gsfCondScanQueue(d, c, n);
       int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
       for (int t = 0; t < tot; ++t) gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
       for (int n = 0; n < d.N; ++n) gsfCondSelect(d, c, n, keep.data());

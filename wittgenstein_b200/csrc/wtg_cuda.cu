@@ -34,12 +34,31 @@ __global__ void k_begin(Dev d, int mode) { tickBegin(d, mode); }
 __global__ void k_end(Dev d, int mode) { tickEnd(d, mode); }
 
 // ---- conditional tasks (checkSigs): scan -> score -> select ---------------------------------------
+// A block covers NODE_BLOCK consecutive nodes: one thread per node decides whether the node has work, the
+// block compacts those nodes into shared memory, then its warps take them one by one.  (Launching a warp for
+// every node cost ~60 us per tick in block dispatch alone at 131 072 nodes: profiles/r01.)
+__device__ __forceinline__ int blockCompact(bool active, int n, int* list, int* cnt) {
+  if (threadIdx.x == 0) *cnt = 0;
+  __syncthreads();
+  unsigned m = __ballot_sync(0xffffffffu, active);
+  if (m) {
+    int lane = threadIdx.x & 31, base = 0;
+    if (lane == 0) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) list[base + __popc(m & ((1u << lane) - 1u))] = n;
+  }
+  __syncthreads();
+  return *cnt;
+}
 __global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
+  __shared__ int list[NODE_BLOCK];
+  __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (n >= d.N) return;
+  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  bool due = n < d.N && gsfCondMark(d, n);
+  int total = blockCompact(due, n, list, &cnt);
   CoopWarp c;
-  gsfCondScan(d, c, n);
+  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) gsfCondScanQueue(d, c, list[k]);
 }
 __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
   if (d.ctl->error) return;
@@ -52,12 +71,15 @@ __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
 }
 __global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
   extern __shared__ uint32_t keepAll[];
+  __shared__ int list[NODE_BLOCK];
+  __shared__ int cnt;
   if (d.ctl->error) return;
-  int warp = threadIdx.x >> 5;
-  int n = blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (n >= d.N) return;
+  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  bool due = n < d.N && d.condDue[n] != 0;
+  int total = blockCompact(due, n, list, &cnt);
   CoopWarp c;
-  gsfCondSelect(d, c, n, keepAll + (size_t)warp * (size_t)(d.qcap / 32));
+  int warp = threadIdx.x >> 5;
+  for (int k = warp; k < total; k += WARPS_PER_BLOCK) gsfCondSelect(d, c, list[k], keepAll + (size_t)warp * (size_t)(d.qcap / 32));
 }
 
 // ---- dispatch -----------------------------------------------------------------------------
@@ -74,11 +96,14 @@ __global__ void k_dispatch_scatter(Dev d) {
 
 // ---- handlers: warp per node ----------------------------------------------------------------
 __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
+  __shared__ int list[NODE_BLOCK];
+  __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (n >= d.N) return;
+  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  bool active = n < d.N && d.inboxFill[n] > 0;
+  int total = blockCompact(active, n, list, &cnt);
   CoopWarp c;
-  nodeProcess(d, c, n);
+  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k]);
 }
 
 // ---- pair scans ---------------------------------------------------------------------------
@@ -465,7 +490,7 @@ class CudaBackend : public Backend {
   }
 
   void enqueueTick(const Dev& d, int mode) {
-    const int nodeBlocks = (d.N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int nodeBlocks = (d.N + NODE_BLOCK - 1) / NODE_BLOCK;
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
     profBegin(0);

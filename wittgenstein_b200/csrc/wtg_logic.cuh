@@ -365,73 +365,76 @@ WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta,
 //   condMode 1: the clock has just ticked to `tick` inside a runMs window ending at `until`
 //   condMode 2: the reference's extra time++ past `until` at the end of the window
 // ------------------------------------------------------------------------------------------
-template <class C>
-WTG_HD void gsfCondScan(const Dev& d, C& c, int n) {
+// phase A, scalar part (one thread per node): is the conditional task examined now and is startIf true?
+WTG_HD bool gsfCondMark(const Dev& d, int n) {
   const Ctl& ctl = *d.ctl;
-  int dueNow = 0;
+  bool dueNow = false;
   if (ctl.condMode != 0 && !d.ndown[n]) {
     int ms = d.minStart[n];
     bool due = ctl.condMode == 1 ? (ms <= ctl.tick) : (ms <= ctl.until);
     if (due && d.stamp[n] != ctl.callId) {
-      c.sync();
-      if (c.lane() == 0) d.stamp[n] = ctl.callId;
-      int len = d.qLen[n];
-      if (len > 0) {  // startIf: !toVerify.isEmpty()
-        dueNow = 1;
-        QEntry* q = d.queue + (size_t)n * d.qcap;
-        int* qsc = d.qScore + (size_t)n * d.qcap;
-        uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
-        const uint32_t* ver = d.lvVer + (size_t)n * d.L;
-        const int st = n & (ARENA_STRIPES - 1);
-        const int per = d.workCap / ARENA_STRIPES;
-        int reeval = 0;
-        for (int base = 0; base < len; base += C::LANES) {
-          int i = base + c.lane();
-          bool stalePool = false;
-          if (i < len) {
-            QEntry e = q[i];
-            uint32_t v = ver[metaLevel(e.meta)];
-            if (qst[i] != v) {
-              ++reeval;
-              if (metaKind(e.meta) == PK_POOL) {
-                stalePool = true;
-              } else {
-                qsc[i] = gsfScoreScalar(d, n, e);
-                qst[i] = v;
-              }
-            }
-          }
-          uint32_t pm = c.ballot(stalePool);
-          if (pm) {
-#if defined(__CUDA_ARCH__)
-            int cnt = __popc(pm), off = __popc(pm & ((1u << c.lane()) - 1u));
-#else
-            int cnt = (int)(pm & 1u), off = 0;
-#endif
-            int b0 = 0;
-            if (c.lane() == 0) b0 = WTG_ATOMIC_ADD(&d.ctl->workCnt[st], cnt);
-            b0 = c.bcast(b0, 0);
-            if (stalePool) {
-              if (b0 + off < per)
-                d.workList[(size_t)st * per + b0 + off] = (uint32_t)((size_t)n * d.qcap + i);
-              else
-                setError(d, ERR_DESC_OVERFLOW, -n);
-            }
-          }
-        }
-        reeval = c.sum(reeval);
-        if (c.lane() == 0) {
-          d.minStart[n] = ctl.tick + d.pairing[n];
-          statAdd(d, n, ST_CONDRUNS, 1ULL);
-          statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
-          statAdd(d, n, ST_EVALPOOL, (unsigned long long)reeval);
-        }
+      d.stamp[n] = ctl.callId;
+      if (d.qLen[n] > 0) {  // startIf: !toVerify.isEmpty()
+        dueNow = true;
+        d.minStart[n] = ctl.tick + d.pairing[n];
+        statAdd(d, n, ST_CONDRUNS, 1ULL);
       }
     }
   }
+  d.condDue[n] = dueNow ? 1 : 0;
+  if (!dueNow) d.condFired[n] = 0;
+  return dueNow;
+}
+
+// phase A, queue part (one coop per due node)
+template <class C>
+WTG_HD void gsfCondScanQueue(const Dev& d, C& c, int n) {
+  int len = d.qLen[n];
+  QEntry* q = d.queue + (size_t)n * d.qcap;
+  int* qsc = d.qScore + (size_t)n * d.qcap;
+  uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
+  const uint32_t* ver = d.lvVer + (size_t)n * d.L;
+  const int st = n & (ARENA_STRIPES - 1);
+  const int per = d.workCap / ARENA_STRIPES;
+  int reeval = 0;
+  for (int base = 0; base < len; base += C::LANES) {
+    int i = base + c.lane();
+    bool stalePool = false;
+    if (i < len) {
+      QEntry e = q[i];
+      uint32_t v = ver[metaLevel(e.meta)];
+      if (qst[i] != v) {
+        ++reeval;
+        if (metaKind(e.meta) == PK_POOL) {
+          stalePool = true;
+        } else {
+          qsc[i] = gsfScoreScalar(d, n, e);
+          qst[i] = v;
+        }
+      }
+    }
+    uint32_t pm = c.ballot(stalePool);
+    if (pm) {
+#if defined(__CUDA_ARCH__)
+      int cnt = __popc(pm), off = __popc(pm & ((1u << c.lane()) - 1u));
+#else
+      int cnt = (int)(pm & 1u), off = 0;
+#endif
+      int b0 = 0;
+      if (c.lane() == 0) b0 = WTG_ATOMIC_ADD(&d.ctl->workCnt[st], cnt);
+      b0 = c.bcast(b0, 0);
+      if (stalePool) {
+        if (b0 + off < per)
+          d.workList[(size_t)st * per + b0 + off] = (uint32_t)((size_t)n * d.qcap + i);
+        else
+          setError(d, ERR_DESC_OVERFLOW, -n);
+      }
+    }
+  }
+  reeval = c.sum(reeval);
   if (c.lane() == 0) {
-    d.condDue[n] = dueNow;
-    if (!dueNow) d.condFired[n] = 0;
+    statAdd(d, n, ST_EVALENTRIES, (unsigned long long)len);
+    statAdd(d, n, ST_EVALPOOL, (unsigned long long)reeval);
   }
 }
 
