@@ -26,6 +26,7 @@ namespace wtg {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int NODE_BLOCK = WARPS_PER_BLOCK * 32;
+constexpr int NODE_SPAN = 32;  // nodes covered by one block of the handler kernels
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -54,8 +55,8 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
-  bool due = n < d.N && gsfCondMark(d, n);
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
+  bool due = threadIdx.x < NODE_SPAN && n < d.N && gsfCondMark(d, n);
   int total = blockCompact(due, n, list, &cnt);
   CoopWarp c;
   for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) gsfCondScanQueue(d, c, list[k]);
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
-  bool due = n < d.N && d.condDue[n] != 0;
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
+  bool due = threadIdx.x < NODE_SPAN && n < d.N && d.condDue[n] != 0;
   int total = blockCompact(due, n, list, &cnt);
   CoopWarp c;
   int warp = threadIdx.x >> 5;
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
-  bool active = n < d.N && d.inboxFill[n] > 0;
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
+  bool active = threadIdx.x < NODE_SPAN && n < d.N && d.inboxFill[n] > 0;
   int total = blockCompact(active, n, list, &cnt);
   CoopWarp c;
   for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k]);
@@ -490,7 +491,7 @@ class CudaBackend : public Backend {
   }
 
   void enqueueTick(const Dev& d, int mode) {
-    const int nodeBlocks = (d.N + NODE_BLOCK - 1) / NODE_BLOCK;
+    const int nodeBlocks = (d.N + NODE_SPAN - 1) / NODE_SPAN;
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
     profBegin(0);

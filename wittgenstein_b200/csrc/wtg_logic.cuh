@@ -386,7 +386,9 @@ WTG_HD bool gsfCondMark(const Dev& d, int n) {
   return dueNow;
 }
 
-// phase A, queue part (one coop per due node)
+// phase A, queue part (one coop per due node).  COND_UNROLL chunks of LANES entries are loaded before any is
+// used so that a lane keeps several independent 16-byte loads in flight (the scan is latency-bound otherwise).
+constexpr int COND_UNROLL = 4;
 template <class C>
 WTG_HD void gsfCondScanQueue(const Dev& d, C& c, int n) {
   int len = d.qLen[n];
@@ -397,37 +399,54 @@ WTG_HD void gsfCondScanQueue(const Dev& d, C& c, int n) {
   const int st = n & (ARENA_STRIPES - 1);
   const int per = d.workCap / ARENA_STRIPES;
   int reeval = 0;
-  for (int base = 0; base < len; base += C::LANES) {
-    int i = base + c.lane();
-    bool stalePool = false;
-    if (i < len) {
-      QEntry e = q[i];
-      uint32_t v = ver[metaLevel(e.meta)];
-      if (qst[i] != v) {
-        ++reeval;
-        if (metaKind(e.meta) == PK_POOL) {
-          stalePool = true;
-        } else {
-          qsc[i] = gsfScoreScalar(d, n, e);
-          qst[i] = v;
-        }
+  for (int base0 = 0; base0 < len; base0 += C::LANES * COND_UNROLL) {
+    QEntry e[COND_UNROLL];
+    uint32_t es[COND_UNROLL];
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int i = base0 + u * C::LANES + c.lane();
+      if (i < len) {
+        e[u] = q[i];
+        es[u] = qst[i];
+      } else {
+        e[u].from = 0;
+        e[u].meta = 0;
+        e[u].pl = 0;
+        es[u] = 0;
       }
     }
-    uint32_t pm = c.ballot(stalePool);
-    if (pm) {
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int i = base0 + u * C::LANES + c.lane();
+      bool stalePool = false;
+      if (i < len) {
+        uint32_t v = ver[metaLevel(e[u].meta)];
+        if (es[u] != v) {
+          ++reeval;
+          if (metaKind(e[u].meta) == PK_POOL) {
+            stalePool = true;
+          } else {
+            qsc[i] = gsfScoreScalar(d, n, e[u]);
+            qst[i] = v;
+          }
+        }
+      }
+      uint32_t pm = c.ballot(stalePool);
+      if (pm) {
 #if defined(__CUDA_ARCH__)
-      int cnt = __popc(pm), off = __popc(pm & ((1u << c.lane()) - 1u));
+        int cnt = __popc(pm), off = __popc(pm & ((1u << c.lane()) - 1u));
 #else
-      int cnt = (int)(pm & 1u), off = 0;
+        int cnt = (int)(pm & 1u), off = 0;
 #endif
-      int b0 = 0;
-      if (c.lane() == 0) b0 = WTG_ATOMIC_ADD(&d.ctl->workCnt[st], cnt);
-      b0 = c.bcast(b0, 0);
-      if (stalePool) {
-        if (b0 + off < per)
-          d.workList[(size_t)st * per + b0 + off] = (uint32_t)((size_t)n * d.qcap + i);
-        else
-          setError(d, ERR_DESC_OVERFLOW, -n);
+        int b0 = 0;
+        if (c.lane() == 0) b0 = WTG_ATOMIC_ADD(&d.ctl->workCnt[st], cnt);
+        b0 = c.bcast(b0, 0);
+        if (stalePool) {
+          if (b0 + off < per)
+            d.workList[(size_t)st * per + b0 + off] = (uint32_t)((size_t)n * d.qcap + i);
+          else
+            setError(d, ERR_DESC_OVERFLOW, -n);
+        }
       }
     }
   }
@@ -460,67 +479,100 @@ WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {
   int* qsc = d.qScore + (size_t)n * d.qcap;
   uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
   int bestScore = 0, bestIdx = 0x7fffffff;
-  for (int base = 0; base < len; base += C::LANES) {
-    int i = base + c.lane();
-    int s = i < len ? qsc[i] : 0;
-    uint32_t km = c.ballot(s > 0);
-    if (c.lane() == 0) keepBits[base / C::LANES] = km;
-    if (s > bestScore) {  // strict >: keeps this lane's earliest max (checkSigs :565-567)
-      bestScore = s;
-      bestIdx = i;
+  for (int base0 = 0; base0 < len; base0 += C::LANES * COND_UNROLL) {
+    int sc[COND_UNROLL];
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int i = base0 + u * C::LANES + c.lane();
+      sc[u] = i < len ? qsc[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int base = base0 + u * C::LANES;
+      if (base >= len) break;
+      int i = base + c.lane();
+      uint32_t km = c.ballot(sc[u] > 0);
+      if (c.lane() == 0) keepBits[base / C::LANES] = km;
+      if (sc[u] > bestScore) {  // strict >: keeps this lane's earliest max (checkSigs :565-567)
+        bestScore = sc[u];
+        bestIdx = i;
+      }
     }
   }
   int mx = c.maxv(bestScore);
   int bi = c.minv(bestScore == mx ? bestIdx : 0x7fffffff);
   bool found = mx > 0;
   c.sync();
-  // order-preserving compaction: drop score-0 entries (it.remove() :568-570) and the best one (:574)
+  // order-preserving compaction: drop score-0 entries (it.remove() :568-570) and the best one (:574).
+  // Chunks before the first removal do not move; from there on COND_UNROLL chunks are loaded, then stored.
   QEntry best;
   best.from = 0;
   best.meta = 0;
   best.pl = 0;
   int w = 0;
-  for (int base = 0; base < len; base += C::LANES) {
-    int i = base + c.lane();
-    bool keep = false, evict = false;
-    uint32_t kw = keepBits[base / C::LANES];
-    if (i < len) {
-      bool k0 = (kw >> (C::LANES == 1 ? 0 : c.lane())) & 1u;
-      keep = k0 && !(found && i == bi);
-      evict = !k0;
-    }
-    uint32_t km = c.ballot(keep);
+  int base0 = 0;
+  for (; base0 < len; base0 += C::LANES) {  // skip the static prefix
+    uint32_t kw = keepBits[base0 / C::LANES];
+    int inChunk = len - base0 < C::LANES ? len - base0 : C::LANES;
 #if defined(__CUDA_ARCH__)
-    int off = __popc(km & ((1u << c.lane()) - 1u));
-    int tot = __popc(km);
+    int tot = __popc(kw);
 #else
-    int off = 0;
-    int tot = (int)(km & 1u);
+    int tot = (int)(kw & 1u);
 #endif
-    int inChunk = len - base < C::LANES ? len - base : C::LANES;
-    bool chunkStatic = (w == base) && (tot == inChunk);  // nothing removed before or inside this chunk
-    if (!chunkStatic) {
-      QEntry e;
-      e.from = 0;
-      e.meta = 0;
-      e.pl = 0;
-      int es = 0;
-      uint32_t et = 0;
-      if (i < len) {
-        e = q[i];
-        es = qsc[i];
-        et = qst[i];
-      }
-      c.sync();  // every lane has loaded its entry before anyone overwrites the chunk
-      if (keep && w + off != i) {
-        q[w + off] = e;
-        qsc[w + off] = es;
-        qst[w + off] = et;
-      }
-      if (evict && metaKind(e.meta) == PK_POOL) freeDirect(d, (int)metaLevel(e.meta), (uint32_t)e.pl);
-      if (found && i == bi) best = e;
-    }
+    bool hasBest = found && bi >= base0 && bi < base0 + C::LANES;
+    if (tot != inChunk || hasBest) break;
     w += tot;
+  }
+  for (; base0 < len; base0 += C::LANES * COND_UNROLL) {
+    QEntry e[COND_UNROLL];
+    int es[COND_UNROLL];
+    uint32_t et[COND_UNROLL];
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int i = base0 + u * C::LANES + c.lane();
+      if (i < len) {
+        e[u] = q[i];
+        es[u] = qsc[i];
+        et[u] = qst[i];
+      } else {
+        e[u].from = 0;
+        e[u].meta = 0;
+        e[u].pl = 0;
+        es[u] = 0;
+        et[u] = 0;
+      }
+    }
+    c.sync();  // every lane has loaded its entries before anyone overwrites these chunks
+#pragma unroll
+    for (int u = 0; u < COND_UNROLL; ++u) {
+      int base = base0 + u * C::LANES;
+      if (base >= len) break;
+      int i = base + c.lane();
+      bool keep = false, evict = false;
+      uint32_t kw = keepBits[base / C::LANES];
+      if (i < len) {
+        bool k0 = (kw >> (C::LANES == 1 ? 0 : c.lane())) & 1u;
+        keep = k0 && !(found && i == bi);
+        evict = !k0;
+      }
+      uint32_t km = c.ballot(keep);
+#if defined(__CUDA_ARCH__)
+      int off = __popc(km & ((1u << c.lane()) - 1u));
+      int tot = __popc(km);
+#else
+      int off = 0;
+      int tot = (int)(km & 1u);
+#endif
+      if (keep && w + off != i) {
+        q[w + off] = e[u];
+        qsc[w + off] = es[u];
+        qst[w + off] = et[u];
+      }
+      if (evict && metaKind(e[u].meta) == PK_POOL) freeDirect(d, (int)metaLevel(e[u].meta), (uint32_t)e[u].pl);
+      if (found && i == bi) best = e[u];
+      w += tot;
+    }
+    c.sync();
   }
   if (found) {
     int srcLane = (C::LANES == 1) ? 0 : (bi % C::LANES);
