@@ -50,7 +50,7 @@ class HostBackend : public Backend {
       pairScan(d, 0);
       if (d.ctl->error) return;
       for (int i = 0; i < nEv; ++i) dispatchScatter(d, i);
-      for (int n = 0; n < d.N; ++n) nodeProcess(d, c, n);
+      for (int n = 0; n < d.N; ++n) nodeProcess(d, c, n, 0);
     }
     pairScan(d, 1);
     if (d.ctl->error) return;

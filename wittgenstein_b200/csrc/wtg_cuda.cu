@@ -100,11 +100,20 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
   if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool active = threadIdx.x < NODE_SPAN && n < d.N && d.inboxFill[n] > 0;
-  int total = blockCompact(active, n, list, &cnt);
-  CoopWarp c;
-  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k]);
+  const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
+  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  bool coop = false;
+  if (n < d.N && d.inboxFill[n] > 0) {
+    if (split) {
+      CoopSerial cs;  // message deliveries: one thread per node
+      coop = nodeProcess(d, cs, n, 1) > 0;
+    } else {
+      coop = true;
+    }
+  }
+  int total = blockCompact(coop, n, list, &cnt);
+  CoopWarp c;  // tasks (updateVerifiedSignatures / doCycle): one warp per node
+  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k], split ? 2 : 0);
 }
 
 // ---- pair scans ---------------------------------------------------------------------------
@@ -179,37 +188,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(Dev d, int which)
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(1024) k_scan_tiles(Dev d, int which) {
-  if (d.ctl->error) return;
-  int M = scanCount(d, which);
-  int nTiles = (M + SCAN_TILE - 1) / SCAN_TILE;
-  int per = (nTiles + 1023) / 1024;
-  int t0 = threadIdx.x * per;
-  Pair s;
-  s.a = 0;
-  s.b = 0;
-  for (int k = 0; k < per; ++k)
-    if (t0 + k < nTiles) {
-      s.a += d.scanPartial[2 * (t0 + k)];
-      s.b += d.scanPartial[2 * (t0 + k) + 1];
-    }
-  Pair total;
-  Pair ex = blockExclusive(s, total);
-  for (int k = 0; k < per; ++k)
-    if (t0 + k < nTiles) {
-      int a = d.scanPartial[2 * (t0 + k)], b = d.scanPartial[2 * (t0 + k) + 1];
-      d.scanPartial[2 * (t0 + k)] = ex.a;
-      d.scanPartial[2 * (t0 + k) + 1] = ex.b;
-      ex.a += a;
-      ex.b += b;
-    }
-  if (threadIdx.x == 0) scanTotals(d, which, total);
-}
+// second (last) scan kernel: every block first sums the partials of the tiles before its own (a few hundred
+// pairs at most), then scans its tile; the block of the last tile also publishes the totals.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
   if (d.ctl->error) return;
   int M = scanCount(d, which);
   int nTiles = (M + SCAN_TILE - 1) / SCAN_TILE;
+  if (nTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    Pair z;
+    z.a = 0;
+    z.b = 0;
+    scanTotals(d, which, z);
+  }
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    Pair pre;
+    pre.a = 0;
+    pre.b = 0;
+    for (int t = threadIdx.x; t < tile; t += SCAN_THREADS) {
+      pre.a += d.scanPartial[2 * t];
+      pre.b += d.scanPartial[2 * t + 1];
+    }
+    Pair tileBase;
+    blockExclusive(pre, tileBase);  // tileBase = sum over all threads
     int j0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     Pair v[SCAN_ITEMS];
     Pair s;
@@ -227,13 +227,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
     }
     Pair total;
     Pair ex = blockExclusive(s, total);
-    ex.a += d.scanPartial[2 * tile];
-    ex.b += d.scanPartial[2 * tile + 1];
+    ex = pairAdd(ex, tileBase);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
       if (j0 + k < M) scanStore(d, which, j0 + k, ex);
       ex = pairAdd(ex, v[k]);
     }
+    if (tile == nTiles - 1 && threadIdx.x == 0) scanTotals(d, which, pairAdd(tileBase, total));
     __syncthreads();
   }
 }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* hist = msHist + warp * ring;
   for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
-    for (int b = lane; b < ring; b += 32) hist[b] = 0;
+    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(hist + b) = make_int4(0, 0, 0, 0);
     __syncwarp();
     int g0 = ch * MS_CHUNK;
     for (int k = lane; k < MS_CHUNK; k += 32) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) {
     }
     __syncwarp();
     int* row = d.msCount + (size_t)ch * ring;
-    for (int b = lane; b < ring; b += 32) row[b] = hist[b];
+    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(row + b) = *reinterpret_cast<const int4*>(hist + b);
     __syncwarp();
   }
 }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
   int* base = msHist + warp * ring;
   for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
     const int* row = d.msCount + (size_t)ch * ring;
-    for (int b = lane; b < ring; b += 32) base[b] = row[b];
+    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(base + b) = *reinterpret_cast<const int4*>(row + b);
     __syncwarp();
     int g0 = ch * MS_CHUNK;
     for (int k0 = 0; k0 < MS_CHUNK; k0 += 32) {
@@ -517,9 +517,6 @@ class CudaBackend : public Backend {
       profBegin(3);
     k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
     profEnd();
-      profBegin(4);
-    k_scan_tiles<<<1, 1024, 0, st>>>(d, 0);
-    profEnd();
       profBegin(5);
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 0);
     profEnd();
@@ -527,15 +524,12 @@ class CudaBackend : public Backend {
     k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
     profEnd();
       profBegin(7);
-    k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+    k_node<<<(d.N + NODE_BLOCK - 1) / NODE_BLOCK, NODE_BLOCK, 0, st>>>(d);
     profEnd();
-      launches += 6;
+      launches += 5;
     }
     profBegin(3);
     k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
-    profEnd();
-    profBegin(4);
-    k_scan_tiles<<<1, 1024, 0, st>>>(d, 1);
     profEnd();
     profBegin(5);
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
@@ -558,7 +552,7 @@ class CudaBackend : public Backend {
     profBegin(13);
     k_end<<<1, 1, 0, st>>>(d, mode);
     profEnd();
-    launches += 10;
+    launches += 9;
   }
   void configure(const Dev& d) {
     size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);

@@ -1170,7 +1170,10 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
     } else {
       if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
 #if defined(__CUDA_ARCH__)
-      gsfCycleWarp(d, n, item, slots, draws);
+      if (C::LANES == 32)
+        gsfCycleWarp(d, n, item, slots, draws);
+      else
+        gsfCycle(d, c, n, item, slots, draws);
 #else
       gsfCycle(d, c, n, item, slots, draws);
 #endif
@@ -1223,13 +1226,19 @@ WTG_HD u64 inboxMake(int item, int entry) { return ((u64)(uint32_t)item << 32) |
 WTG_HD int inboxItem(u64 w) { return (int)(w >> 32); }
 WTG_HD int inboxEntry(u64 w) { return (int)(w & 0xFFFFFFFFULL); }
 
+// filter 0: every item in reference order (generic).  filter 1: messages only; filter 2: tasks only — used by the
+// CUDA handler kernel for GSF / PingPong, where a message delivery (onNewSig: queue, individual-seen row, receive
+// counters) and a task (updateVerifiedSignatures / doCycle: verified rows, level scalars, send counters) touch
+// disjoint state of the node, so deliveries can run one thread per node and only tasks need a whole warp.
+// Returns the number of items skipped by the filter.
 template <class C>
-WTG_HD void nodeProcess(const Dev& d, C& c, int n) {
+WTG_HD int nodeProcess(const Dev& d, C& c, int n, int filter) {
   int cnt = d.inboxFill[n];
-  if (cnt == 0) return;
+  if (cnt == 0) return 0;
   const u64* in = d.inbox + d.inboxOff[n];
   const Ev* bucket = d.buckets + (size_t)(d.ctl->tick & (d.ring - 1)) * (size_t)d.bcap;
   int lastItem = -1;
+  int skipped = 0;
   for (int r = 0; r < cnt; ++r) {
     // next delivery in reference order = smallest item index not yet processed (inboxes are tiny)
     int bestItem = 0x7fffffff;
@@ -1253,6 +1262,11 @@ WTG_HD void nodeProcess(const Dev& d, C& c, int n) {
     lastItem = mn;
     int item = inboxItem(w), entry = inboxEntry(w);
     Ev ev = bucket[entry];
+    bool isTask = ev.kind == EV_TASK || ev.kind == EV_PERIODIC;
+    if ((filter == 1 && isTask) || (filter == 2 && !isTask)) {
+      ++skipped;
+      continue;
+    }
     uint32_t from = ev.from, meta = ev.meta;
     u64 pl = ev.pl;
     if (ev.kind == EV_MULTI) {
@@ -1263,10 +1277,11 @@ WTG_HD void nodeProcess(const Dev& d, C& c, int n) {
     }
     deliver(d, c, n, ev, from, meta, pl, item);
   }
-  if (c.lane() == 0) {
+  if (c.lane() == 0 && (filter == 0 || filter == 2 || skipped == 0)) {
     statMax(d, n, ST_MAXINBOX, (unsigned long long)cnt);
     d.inboxFill[n] = 0;  // ready for the next tick
   }
+  return skipped;
 }
 
 // ------------------------------------------------------------------------------------------
