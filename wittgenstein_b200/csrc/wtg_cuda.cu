@@ -253,6 +253,7 @@ __global__ void k_emit(Dev d) {
 
 // ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
 // chunk = MS_CHUNK consecutive envelopes in creation order, one warp per chunk
+constexpr int MS_ROUNDS = MS_CHUNK / 32;
 __global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) {
   extern __shared__ int msHist[];  // [WARPS_PER_BLOCK][ring]
   if (d.ctl->error) return;
@@ -261,16 +262,18 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* hist = msHist + warp * ring;
   for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
+    int g0 = ch * MS_CHUNK;
+    int tg[MS_ROUNDS];  // all targets of the chunk are in flight before the first one is used
+#pragma unroll
+    for (int r = 0; r < MS_ROUNDS; ++r) {
+      int g = g0 + r * 32 + lane;
+      tg[r] = g < G ? d.newTarget[g] : -1;
+    }
     for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(hist + b) = make_int4(0, 0, 0, 0);
     __syncwarp();
-    int g0 = ch * MS_CHUNK;
-    for (int k = lane; k < MS_CHUNK; k += 32) {
-      int g = g0 + k;
-      if (g < G) {
-        int t = d.newTarget[g];
-        if (t >= 0) atomicAdd(&hist[t - tick], 1);
-      }
-    }
+#pragma unroll
+    for (int r = 0; r < MS_ROUNDS; ++r)
+      if (tg[r] >= 0) atomicAdd(&hist[tg[r] - tick], 1);
     __syncwarp();
     int* row = d.msCount + (size_t)ch * ring;
     for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(row + b) = *reinterpret_cast<const int4*>(hist + b);
@@ -286,11 +289,16 @@ __global__ void k_ms_scan(Dev d) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < ring; b += gridDim.x * blockDim.x) {
     int slot = (tick + b) & (ring - 1);
     int run = d.bucketCount[slot];
-    for (int ch = 0; ch < nChunks; ++ch) {
-      int* p = d.msCount + (size_t)ch * ring + b;
-      int v = *p;
-      *p = run;
-      run += v;
+    for (int ch0 = 0; ch0 < nChunks; ch0 += 8) {
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ch0 + k < nChunks ? d.msCount[(size_t)(ch0 + k) * ring + b] : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (ch0 + k < nChunks) {
+          d.msCount[(size_t)(ch0 + k) * ring + b] = run;
+          run += v[k];
+        }
     }
     if (run > d.bcap) {
       setError(d, ERR_BUCKET_OVERFLOW, tick + b);
@@ -307,14 +315,20 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* base = msHist + warp * ring;
   for (int ch = blockIdx.x * WARPS_PER_BLOCK + warp; ch < nChunks; ch += gridDim.x * WARPS_PER_BLOCK) {
+    int g0 = ch * MS_CHUNK;
+    int tg[MS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < MS_ROUNDS; ++r) {
+      int g = g0 + r * 32 + lane;
+      tg[r] = g < G ? d.newTarget[g] : -1;
+    }
     const int* row = d.msCount + (size_t)ch * ring;
     for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(base + b) = *reinterpret_cast<const int4*>(row + b);
     __syncwarp();
-    int g0 = ch * MS_CHUNK;
-    for (int k0 = 0; k0 < MS_CHUNK; k0 += 32) {
-      int g = g0 + k0 + lane;
-      int t = -1;
-      if (g < G) t = d.newTarget[g];
+#pragma unroll
+    for (int r = 0; r < MS_ROUNDS; ++r) {
+      int g = g0 + r * 32 + lane;
+      int t = tg[r];
       int bin = t >= 0 ? t - tick : -1 - lane;  // unique negative key for lanes without an envelope
       unsigned peers = __match_any_sync(0xffffffffu, bin);
       int rank = __popc(peers & ((1u << lane) - 1u));
@@ -327,11 +341,16 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
       b0 = __shfl_sync(0xffffffffu, b0, leader);
       if (t >= 0) {
         int pos = b0 + rank;
-        if (pos < d.bcap) d.buckets[(size_t)(t & (ring - 1)) * (size_t)d.bcap + pos] = d.newEv[g];
+        if (pos < d.bcap) {
+          const int4* src = reinterpret_cast<const int4*>(d.newEv + g);
+          int4* dst = reinterpret_cast<int4*>(d.buckets + (size_t)(t & (ring - 1)) * (size_t)d.bcap + pos);
+          int4 x = src[0], y = src[1];
+          dst[0] = x;
+          dst[1] = y;
+        }
       }
       __syncwarp();
     }
-    __syncwarp();
   }
 }
 
