@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
   __shared__ int cnt;
   if (d.ctl->error) return;
   const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
-  int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
   bool coop = false;
-  if (n < d.N && d.inboxFill[n] > 0) {
+  if (threadIdx.x < NODE_SPAN && n < d.N && d.inboxFill[n] > 0) {
     if (split) {
       CoopSerial cs;  // message deliveries: one thread per node
       coop = nodeProcess(d, cs, n, 1) > 0;
@@ -543,7 +543,7 @@ class CudaBackend : public Backend {
     k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
     profEnd();
       profBegin(7);
-    k_node<<<(d.N + NODE_BLOCK - 1) / NODE_BLOCK, NODE_BLOCK, 0, st>>>(d);
+    k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
     profEnd();
       launches += 5;
     }
