@@ -61,6 +61,13 @@ int wtg_pingpong_init(wtg_net* net, int node_ct);
  *             acceleratedCallsCount, nodesDown }  (the fields of GSFSignatureParameters) */
 int wtg_gsf_init(wtg_net* net, const int* params7);
 
+/* new SanFerminSignature(params) — protocols/SanFerminSignature.java:112-129 (the constructor builds the nodes on
+ * network.rd, so a later wtg_set_seed does not change them) and .init() — :136-138.
+ * params6 = { nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount } (:41-110;
+ * shuffledLists / verbose are unused by the reference).  Device engine: power-of-two nodeCount, candidateCount 1. */
+int wtg_sanfermin_construct(wtg_net* net, const int* params6);
+int wtg_sanfermin_init(wtg_net* net);
+
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);
 /* network.time — Network.java:49 */
@@ -90,6 +97,11 @@ int wtg_node_attrs(wtg_net* net, int* x, int* y, int* extra, int* city, double* 
 
 /* PingPongNode.pong — protocols/PingPong.java:61 */
 int wtg_pingpong_pongs(wtg_net* net, int* out);
+
+/* SanFerminNode.aggValue, currentPrefixLength, done, thresholdDone, sentRequests, receivedRequests, isSwapping,
+ * thresholdAt — protocols/SanFerminSignature.java:157-208 */
+int wtg_sanfermin_node_scalars(wtg_net* net, int* agg, int* cpl, int* done, int* thr_done, int* sent_req, int* recv_req,
+                               int* swapping, long long* threshold_at);
 
 /* GSFNode.levels.size() — protocols/GSFSignature.java:168 */
 int wtg_gsf_levels(wtg_net* net);

@@ -276,4 +276,78 @@ int wo_gsf_test_last_finished(void* h) {
   return r0 * 1000 + r1 * 100 + r2 * 10 + r3;
 }
 
+
+// ---- SanFerminSignature -------------------------------------------------------------------
+void* wo_sf_create(int nodeCount, int threshold, int pairingTime, int signatureSize, int replyTimeout, int candidateCount,
+                   const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  SanFerminSignature::Params p;
+  p.nodeCount = nodeCount;
+  p.threshold = threshold;
+  p.pairingTime = pairingTime;
+  p.signatureSize = signatureSize;
+  p.replyTimeout = replyTimeout;
+  p.candidateCount = candidateCount;
+  p.nodeBuilderName = nodeBuilderName ? nodeBuilderName : "";
+  p.latencyNull = networkLatencyName == nullptr;
+  p.networkLatencyName = networkLatencyName ? networkLatencyName : "";
+  return new SanFerminSignature(p);
+  WO_CATCH(nullptr)
+}
+void wo_sf_destroy(void* h) { delete static_cast<SanFerminSignature*>(h); }
+void wo_sf_set_seed(void* h, int64_t s) { static_cast<SanFerminSignature*>(h)->network.rd.setSeed(s); }
+int wo_sf_init(void* h) {
+  WO_TRY
+  static_cast<SanFerminSignature*>(h)->init();
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_sf_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<SanFerminSignature*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+int wo_sf_time(void* h) { return static_cast<SanFerminSignature*>(h)->network.time; }
+int64_t wo_sf_msgs_live(void* h) { return static_cast<SanFerminSignature*>(h)->network.msgs.live; }
+uint64_t wo_sf_rng_state(void* h) { return static_cast<SanFerminSignature*>(h)->network.rd.seed; }
+void wo_sf_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<SanFerminSignature*>(h)->network.allNodes, out5N); }
+void wo_sf_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<SanFerminSignature*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+// per node: aggValue, currentPrefixLength, done, thresholdDone, sentRequests, receivedRequests, isSwapping ; thresholdAt (int64)
+void wo_sf_node_scalars(void* h, int32_t* agg, int32_t* cpl, int32_t* done, int32_t* thrDone, int32_t* sentReq, int32_t* recvReq,
+                        int32_t* swapping, int64_t* thresholdAt) {
+  auto* p = static_cast<SanFerminSignature*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) {
+    auto& n = *p->nodes[i];
+    agg[i] = n.aggValue;
+    cpl[i] = n.currentPrefixLength;
+    done[i] = n.done ? 1 : 0;
+    thrDone[i] = n.thresholdDone ? 1 : 0;
+    sentReq[i] = n.sentRequests;
+    recvReq[i] = n.receivedRequests;
+    swapping[i] = n.isSwapping ? 1 : 0;
+    thresholdAt[i] = n.thresholdAt;
+  }
+}
+// SanFerminHelper KATs (PT/SanFerminTest.java): candidate / own set of a node, pickNextNodes
+void wo_sf_helper_sets(int nodeId, int setSize, int level, int32_t* out4) {
+  SanFerminHelper h(nodeId, setSize, nullptr);
+  auto c = h.getCandidateSet(level);
+  auto o = h.getOwnSet(level);
+  out4[0] = c.first;
+  out4[1] = c.second;
+  out4[2] = o.first;
+  out4[3] = o.second;
+}
+int wo_sf_helper_pick(int nodeId, int setSize, int level, int howMany, int calls, int32_t* out, int cap) {
+  JavaRandom rd(0);
+  SanFerminHelper h(nodeId, setSize, &rd);
+  std::vector<int> r;
+  for (int i = 0; i < calls; ++i) r = h.pickNextNodes(level, howMany);
+  int n = std::min<int>(cap, static_cast<int>(r.size()));
+  for (int i = 0; i < n; ++i) out[i] = r[static_cast<size_t>(i)];
+  return static_cast<int>(r.size());
+}
+
 }  // extern "C"

@@ -3,13 +3,17 @@
 // CPU restatement of the reference protocols on the hot path:
 //   protocols/PingPong.java       -> PingPong
 //   protocols/GSFSignature.java   -> GSFSignature (GSFNode, SFLevel, SendSigs)
+//   protocols/SanFerminSignature.java + SanFerminHelper.java -> SanFerminSignature, SanFerminHelper
 // Line references are to those files.  PARITY STATUS: structure / schedule / liveness are
 // pinned by the reference's own tests (PT/GSFSignatureTest.java, PT/PingPongTest.java,
 // restated in tests/test_oracle_protocols.py); the protocol END STATE (bitmaps, doneAt) is
 // "parity unpinned" — the reference's tests hold no golden end state and no JVM is available.
 #pragma once
 #include <atomic>
+#include <map>
 #include <memory>
+#include <unordered_map>
+#include <unordered_set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -519,6 +523,278 @@ inline void GSFSignature::initFast(int threads) {
                                       [n] { return !n->toVerify.empty(); }, [n] { return !n->done; });
     }
   }
+}
+
+// ----------------------------------------------------------------------------------------
+// SanFerminHelper  (protocols/SanFerminHelper.java) — node ids == indices in allNodes
+// ----------------------------------------------------------------------------------------
+inline int javaLog2(int n) {  // MoreMath.log2
+  if (n <= 0) throw IllegalArgument("n");
+  int r = 0;
+  while ((1 << (r + 1)) > 0 && (1 << (r + 1)) <= n) ++r;
+  return r;
+}
+struct SanFerminHelper {
+  int nodeId = 0, setSize = 0;
+  std::string binaryId;
+  std::map<int, JBitSet> usedNodes;  // :25  level -> picked indices
+  JavaRandom* rd = nullptr;
+
+  static std::string toBinaryID(int nodeId, int setSize) {  // :169-172 + leftPadWithZeroes :159-167
+    int log2 = javaLog2(setSize);
+    std::string bin;
+    for (unsigned v = static_cast<unsigned>(nodeId); v != 0; v >>= 1) bin.insert(bin.begin(), static_cast<char>('0' + (v & 1)));
+    if (bin.empty()) bin = "0";
+    if (static_cast<int>(bin.size()) > log2) throw IllegalState("StringIndexOutOfBounds in leftPadWithZeroes");
+    return std::string(static_cast<size_t>(log2) - bin.size(), '0') + bin;
+  }
+  SanFerminHelper() = default;
+  SanFerminHelper(int id, int n, JavaRandom* r) : nodeId(id), setSize(n), binaryId(toBinaryID(id, n)), rd(r) {}
+
+  // [min, max) of allNodes.subList(min, max)
+  std::pair<int, int> getOwnSet(int level) const {  // :46-64
+    int mn = 0, mx = setSize;
+    for (int currLevel = 0; currLevel <= level && mn <= mx; currLevel++) {
+      int m = (mx + mn) / 2;
+      char ch = binaryId.at(static_cast<size_t>(currLevel));
+      if (ch == '0')
+        mx = m;
+      else if (ch == '1')
+        mn = m;
+      if (mx == mn) break;
+      if (mx - 1 == 0 || mn == setSize) break;
+    }
+    return {mn, mx};
+  }
+  std::pair<int, int> getCandidateSet(int level) const {  // :70-96
+    int mn = 0, mx = setSize;
+    for (int currLevel = 0; currLevel <= level && mn <= mx; currLevel++) {
+      int m = (mx + mn) / 2;
+      char ch = binaryId.at(static_cast<size_t>(currLevel));
+      if (ch == '0') {
+        if (currLevel == level)
+          mn = m;
+        else
+          mx = m;
+      } else if (ch == '1') {
+        if (currLevel == level)
+          mx = m;
+        else
+          mn = m;
+      }
+      if (mx == mn) break;
+      if (mx - 1 == 0 || mn == setSize) break;
+    }
+    return {mn, mx};
+  }
+  bool isCandidate(int node, int level) const {  // :99-101
+    auto c = getCandidateSet(level);
+    return node >= c.first && node < c.second;
+  }
+  std::vector<int> pickNextNodes(int level, int howMany) {  // :123-157
+    auto cs = getCandidateSet(level);
+    std::vector<int> candidateSet;
+    for (int i = cs.first; i < cs.second; ++i) candidateSet.push_back(i);
+    auto own = getOwnSet(level);
+    int idx = (nodeId >= own.first && nodeId < own.second) ? nodeId - own.first : -1;
+    if (idx == -1 || (own.second - own.first) < idx) throw IllegalState("pickNextNodes");
+    std::vector<int> newList;
+    JBitSet& set = usedNodes[level];  // getOrDefault + put: the same object is kept per level
+    if (!set.get(idx)) {
+      newList.push_back(candidateSet.at(static_cast<size_t>(idx)));
+      candidateSet.erase(candidateSet.begin() + idx);
+      set.set(idx);
+    }
+    int taken = 0;
+    for (int i = 0; i < static_cast<int>(candidateSet.size()) && taken < howMany; ++i) {
+      if (!set.get(i)) {
+        set.set(i);
+        newList.push_back(candidateSet[static_cast<size_t>(i)]);
+        ++taken;
+      }
+    }
+    javaShuffle(newList, *rd);
+    return newList;
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// SanFerminSignature  (protocols/SanFerminSignature.java)
+// ----------------------------------------------------------------------------------------
+struct SanFerminSignature {
+  struct Params {  // :41-110
+    int nodeCount = 32768 / 32, powerOfTwo = 10, threshold = 32768 / 32, pairingTime = 2, signatureSize = 48, replyTimeout = 300;
+    int candidateCount = 1;
+    bool shuffledLists = false;
+    std::string nodeBuilderName, networkLatencyName;
+    bool latencyNull = true;
+  };
+  enum Status { OK, NO };
+  struct SanFerminNode;
+  struct SwapReply : Message {  // :518-541
+    SanFerminSignature* p;
+    Status status;
+    int level, aggValue;
+    SwapReply(SanFerminSignature* pp, Status s, int l, int a) : p(pp), status(s), level(l), aggValue(a) {}
+    void action(Network&, Node& from, Node& to) override;
+    int size() const override { return 4 + p->params.signatureSize; }
+  };
+  struct SwapRequest : Message {  // :543-564
+    SanFerminSignature* p;
+    int level, aggValue;
+    SwapRequest(SanFerminSignature* pp, int l, int a) : p(pp), level(l), aggValue(a) {}
+    void action(Network&, Node& from, Node& to) override;
+    int size() const override { return 4 + p->params.signatureSize; }
+  };
+  struct SanFerminNode : Node {  // :148-511
+    SanFerminSignature* p;
+    std::string binaryId;
+    int currentPrefixLength;
+    SanFerminHelper candidateTree;
+    std::unordered_map<int, int> signatureCache, futurSigs;
+    std::unordered_set<int> pendingNodes;
+    bool isSwapping = false;
+    int aggValue = 1;
+    int64_t thresholdAt = 0;
+    bool thresholdDone = false, done = false;
+    int sentRequests = 0, receivedRequests = 0;
+
+    explicit SanFerminNode(SanFerminSignature* pp)
+        : Node(pp->network.rd, pp->nb), p(pp), binaryId(SanFerminHelper::toBinaryID(nodeId, pp->params.nodeCount)),
+          currentPrefixLength(pp->params.powerOfTwo) {}
+
+    void onSwapRequest(SanFerminNode& node, const SwapRequest& request) {  // :229-268
+      receivedRequests++;
+      if (done || request.level != currentPrefixLength) {
+        auto it = signatureCache.find(request.level);
+        if (it != signatureCache.end()) {
+          sendSwapReply(node, OK, request.level, it->second);
+        } else {
+          sendSwapReply(node, NO, currentPrefixLength, 0);
+          bool isCandidate = candidateTree.isCandidate(node.nodeId, request.level);
+          if (isCandidate) signatureCache[request.level] = request.aggValue;
+        }
+        return;
+      }
+      if (isSwapping) {
+        sendSwapReply(node, OK, request.level, aggValue);
+        return;
+      }
+      bool isCandidate = candidateTree.isCandidate(node.nodeId, currentPrefixLength);
+      bool goodLevel = request.level == currentPrefixLength;
+      if (isCandidate && goodLevel) transition(request.aggValue);
+    }
+    void onSwapReply(SanFerminNode& from, const SwapReply& reply) {  // :270-323
+      if (reply.level != currentPrefixLength || done) return;
+      if (isSwapping) return;
+      switch (reply.status) {
+        case OK:
+          if (!pendingNodes.count(from.nodeId)) {
+            bool isCandidate = candidateTree.isCandidate(from.nodeId, currentPrefixLength);
+            bool goodLevel = reply.level == currentPrefixLength;
+            if (isCandidate && goodLevel) transition(reply.aggValue);
+            return;
+          }
+          transition(reply.aggValue);
+          break;
+        case NO:
+          if (pendingNodes.count(from.nodeId)) {
+            std::vector<int> nodes = candidateTree.pickNextNodes(currentPrefixLength, p->params.candidateCount);
+            sendToNodes(nodes);
+          }
+          break;
+      }
+    }
+    void sendToNodes(const std::vector<int>& candidates) {  // :329-373
+      if (candidates.empty()) return;
+      for (int c : candidates) pendingNodes.insert(c);
+      sentRequests += static_cast<int>(candidates.size());
+      auto r = std::make_shared<SwapRequest>(p, currentPrefixLength, aggValue);
+      std::vector<Node*> dests;
+      for (int c : candidates) dests.push_back(p->nodes[static_cast<size_t>(c)].get());
+      p->network.send(r, *this, dests);
+      int currLevel = currentPrefixLength;
+      SanFerminNode* self = this;
+      p->network.registerTask(
+          [self, currLevel] {
+            if (!self->done && self->currentPrefixLength == currLevel) {
+              std::vector<int> newList = self->candidateTree.pickNextNodes(self->currentPrefixLength, self->p->params.candidateCount);
+              self->sendToNodes(newList);
+            }
+          },
+          p->network.time + p->params.replyTimeout, *this);
+    }
+    void goNextLevel() {  // :383-423
+      if (done) return;
+      bool enoughSigs = aggValue >= p->params.threshold;
+      bool noMoreSwap = currentPrefixLength == 0;
+      if (enoughSigs && !thresholdDone) {
+        thresholdDone = true;
+        thresholdAt = p->network.time + p->params.pairingTime * 2;
+      }
+      if (noMoreSwap && !done) {
+        doneAt = p->network.time + p->params.pairingTime * 2;
+        done = true;
+        return;
+      }
+      currentPrefixLength--;
+      signatureCache[currentPrefixLength] = aggValue;
+      isSwapping = false;
+      pendingNodes.clear();
+      auto fs = futurSigs.find(currentPrefixLength);
+      if (fs != futurSigs.end()) {
+        aggValue += fs->second;
+        goNextLevel();
+        return;
+      }
+      std::vector<int> newList = candidateTree.pickNextNodes(currentPrefixLength, p->params.candidateCount);
+      sendToNodes(newList);
+    }
+    void sendSwapReply(SanFerminNode& n, Status s, int level, int value) {  // :425-432
+      auto r = std::make_shared<SwapReply>(p, s, level, value);
+      std::vector<Node*> d{&n};
+      p->network.send(r, *this, d);
+    }
+    void transition(int toAggregate) {  // :438-455
+      isSwapping = true;
+      SanFerminNode* self = this;
+      p->network.registerTask(
+          [self, toAggregate] {
+            self->aggValue += toAggregate;
+            self->goNextLevel();
+          },
+          p->network.time + p->params.pairingTime, *this);
+    }
+  };
+
+  Params params;
+  Network network;
+  NodeBuilder nb;
+  std::vector<std::unique_ptr<SanFerminNode>> nodes;
+
+  // nodes are built in the constructor (:112-129): a later rd.setSeed() does not affect them
+  explicit SanFerminSignature(const Params& pr) : params(pr) {
+    params.powerOfTwo = javaLog2(params.nodeCount);
+    nb = nodeBuilderByName(params.nodeBuilderName);
+    network.setNetworkLatency(networkLatencyByName(params.networkLatencyName, params.latencyNull));
+    for (int i = 0; i < params.nodeCount; i++) {
+      nodes.push_back(std::make_unique<SanFerminNode>(this));
+      network.addNode(nodes.back().get());
+    }
+    for (auto& n : nodes) n->candidateTree = SanFerminHelper(n->nodeId, params.nodeCount, &network.rd);
+  }
+  void init() {  // :136-138
+    for (auto& up : nodes) {
+      SanFerminNode* n = up.get();
+      network.registerTask([n] { n->goNextLevel(); }, 1, *n);
+    }
+  }
+};
+inline void SanFerminSignature::SwapReply::action(Network&, Node& from, Node& to) {
+  static_cast<SanFerminNode&>(to).onSwapReply(static_cast<SanFerminNode&>(from), *this);
+}
+inline void SanFerminSignature::SwapRequest::action(Network&, Node& from, Node& to) {
+  static_cast<SanFerminNode&>(to).onSwapRequest(static_cast<SanFerminNode&>(from), *this);
 }
 
 }  // namespace wo

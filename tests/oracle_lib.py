@@ -35,6 +35,10 @@ def load():
     lib.wo_gpd_inverse.restype = C.c_double
     lib.wo_gpd_inverse.argtypes = [C.c_double] * 4
     lib.wo_latency.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.wo_sf_create.restype = C.c_void_p
+    lib.wo_sf_create.argtypes = [C.c_int] * 6 + [C.c_char_p, C.c_char_p]
+    lib.wo_sf_rng_state.restype = C.c_uint64
+    lib.wo_sf_msgs_live.restype = C.c_int64
     for name in ("wo_pp_create", "wo_gsf_create"):
         getattr(lib, name).restype = C.c_void_p
     lib.wo_pp_create.argtypes = [C.c_int, C.c_char_p, C.c_char_p]
@@ -209,4 +213,64 @@ class OracleGSF:
     def __del__(self):
         if getattr(self, "h", None):
             self.lib.wo_gsf_destroy(self.h)
+            self.h = None
+
+
+class OracleSanFermin:
+    """protocols/SanFerminSignature.java through the oracle (nodes are built by the constructor)."""
+
+    def __init__(self, node_count, threshold, pairing_time, signature_size, reply_timeout, candidate_count, node_builder, latency):
+        self.lib = load()
+        self.n = node_count
+        self.h = C.c_void_p(self.lib.wo_sf_create(node_count, threshold, pairing_time, signature_size, reply_timeout, candidate_count,
+                                                  _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+
+    def set_seed(self, s):
+        self.lib.wo_sf_set_seed(self.h, C.c_int64(s))
+
+    def init(self):
+        if self.lib.wo_sf_init(self.h) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def run_ms(self, ms):
+        r = self.lib.wo_sf_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    @property
+    def time(self):
+        return self.lib.wo_sf_time(self.h)
+
+    def msgs_live(self):
+        return self.lib.wo_sf_msgs_live(self.h)
+
+    def rng_state(self):
+        return int(self.lib.wo_sf_rng_state(self.h))
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_sf_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_sf_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def scalars(self):
+        a = [np.zeros(self.n, np.int32) for _ in range(7)]
+        t = np.zeros(self.n, np.int64)
+        self.lib.wo_sf_node_scalars(self.h, *[_p(v, C.c_int32) for v in a], _p(t, C.c_int64))
+        keys = ["agg", "cpl", "done", "threshold_done", "sent_requests", "received_requests", "swapping"]
+        d = dict(zip(keys, a))
+        d["threshold_at"] = t
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.wo_sf_destroy(self.h)
             self.h = None

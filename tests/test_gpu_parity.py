@@ -123,6 +123,59 @@ def test_gsf_4096_random_positions_no_tor():
     assert not bad, bad
 
 
+def _sf_compare(p, o, tag):
+    bad = []
+    if p.network().rng_state() != o.rng_state():
+        bad.append(f"{tag}: rd state")
+    if p.network().msgs_size() != o.msgs_live():
+        bad.append(f"{tag}: msgs.size()")
+    if not (p.network().counters() == o.counters()).all():
+        bad.append(f"{tag}: counters")
+    a, b = p.scalars(), o.scalars()
+    for k in a:
+        if not (a[k] == b[k]).all():
+            bad.append(f"{tag}: {k}")
+    return bad
+
+
+@pytest.mark.parametrize("n,nb,nl,seed,step", [(64, None, None, None, 1), (1024, None, None, None, 7),
+                                                 (1024, AWS_NB, AWS_NL, 5, 10), (4096, None, "IC3NetworkLatency", 2, 25)])
+def test_sanfermin_parity(n, nb, nl, seed, step):
+    """SanFerminSignature (swap requests / replies, timeouts, 2-candidate shuffled sends) vs the oracle."""
+    from tests.oracle_lib import OracleSanFermin
+    from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
+
+    p = SanFerminSignature(SanFerminSignatureParameters(n, n, 2, 48, 300, 1, False, nb, nl))
+    o = OracleSanFermin(n, n, 2, 48, 300, 1, nb, nl)
+    if seed is not None:  # after construction: node positions were already drawn (SanFerminSignature.java:112-129)
+        p.network().set_seed(seed)
+        o.set_seed(seed)
+    p.init(); o.init()
+    assert not _sf_compare(p, o, "init")
+    while o.time < 3500:
+        assert p.network().run_ms(step) == o.run_ms(step)
+        bad = _sf_compare(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert p.scalars()["done"].sum() > n // 2
+
+
+def test_sanfermin_16384_shipped_scenario():
+    """SanFerminSignature.sigsPerTime() parameters (SanFerminSignature.java:566-571): 16 384 nodes, runMs(10) to 6 s."""
+    from tests.oracle_lib import OracleSanFermin
+    from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
+
+    n = 16384
+    p = SanFerminSignature(SanFerminSignatureParameters(n, n, 2, 48, 300, 1, False, None, None))
+    o = OracleSanFermin(n, n, 2, 48, 300, 1, None, None)
+    p.init(); o.init()
+    for i in range(600):
+        assert p.network().run_ms(10) == o.run_ms(10)
+        if i % 50 == 49:
+            bad = _sf_compare(p, o, f"t={o.time}")
+            assert not bad, bad
+    assert not _sf_compare(p, o, "end")
+
+
 def test_error_paths():
     from wittgenstein_b200 import GSFSignature, GSFSignatureParameters, Network, PingPong, PingPongParameters, WtgError
 
@@ -146,6 +199,11 @@ def test_error_paths():
     g = GSFSignature(GSFSignatureParameters(64, 60, 3, 20, 10, 10, 0, NB, AWS_NL))
     with pytest.raises(WtgError):
         g.init()  # AWS latency with non-AWS builder (NetworkLatency.java:146-148)
+    from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
+    with pytest.raises(WtgError):
+        SanFerminSignature(SanFerminSignatureParameters(1000, 1000, 2, 48, 300, 1))  # power of two only on the device
+    with pytest.raises(WtgError):
+        SanFerminSignature(SanFerminSignatureParameters(1024, 1024, 2, 48, 300, 3))  # candidateCount 1 only
     # a capacity that is too small fails loudly instead of dropping events
     g = GSFSignature(GSFSignatureParameters(256, 250, 3, 20, 10, 10, 0, NB, NL), tunables={"qcap": 32})
     g.init()

@@ -173,3 +173,43 @@ def test_gsf_init_fast_equals_init():
         for _ in range(20):
             a.run_ms(10); b.run_ms(10)
         assert (a.verified() == b.verified()).all() and (a.counters() == b.counters()).all() and a.rng_state() == b.rng_state()
+
+
+def test_sanfermin_helper_kats():
+    """PT/SanFerminTest.java: candidate sets of node 1 of 8 (:26-46) and pickNextNodes (:48-59)."""
+    import ctypes as C
+    from tests.oracle_lib import load
+
+    lib = load()
+    o = np.zeros(4, np.int32)
+    sets = {}
+    for lvl in (2, 1, 0):
+        lib.wo_sf_helper_sets(1, 8, lvl, o.ctypes.data_as(C.POINTER(C.c_int32)))
+        sets[lvl] = range(int(o[0]), int(o[1]))
+    assert 0 in sets[2]
+    assert 3 in sets[1] and 0 not in sets[1]
+    assert 4 in sets[0] and 0 not in sets[0] and 3 not in sets[0]
+    lib.wo_sf_helper_sets(4, 8, 0, o.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert 1 in range(int(o[0]), int(o[1]))  # helper4.isCandidate(n1, 0)
+    out = np.zeros(16, np.int32)
+    k = lib.wo_sf_helper_pick(1, 8, 2, 10, 1, out.ctypes.data_as(C.POINTER(C.c_int32)), 16)
+    assert k == 1 and out[0] == 0
+    assert lib.wo_sf_helper_pick(1, 8, 2, 10, 2, out.ctypes.data_as(C.POINTER(C.c_int32)), 16) == 0
+
+
+def test_sanfermin_run_and_determinism():
+    from tests.oracle_lib import OracleSanFermin
+
+    a = OracleSanFermin(256, 256, 2, 48, 300, 1, None, None); a.init()
+    b = OracleSanFermin(256, 256, 2, 48, 300, 1, None, None); b.init()
+    for _ in range(400):
+        a.run_ms(10); b.run_ms(10)
+    sa, sb = a.scalars(), b.scalars()
+    for k in sa:
+        assert (sa[k] == sb[k]).all()
+    assert (a.counters() == b.counters()).all()
+    assert sa["done"].sum() > 200 and sa["agg"].max() == 256
+    # a finished node aggregated the whole tree; doneAt = time + 2 * pairing (SanFerminSignature.java:396)
+    done = sa["done"] == 1
+    assert (sa["cpl"][done] == 0).all()
+    assert (a.counters()[4][done] > 0).all()

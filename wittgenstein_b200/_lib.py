@@ -31,6 +31,9 @@ class Api:
         "set_tunable": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "pingpong_init": (C.c_int, [C.c_void_p, C.c_int]),
         "gsf_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "sanfermin_construct": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "sanfermin_init": (C.c_int, [C.c_void_p]),
+        "sanfermin_node_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 7 + [C.POINTER(C.c_longlong)]),
         "run_ms": (C.c_int, [C.c_void_p, C.c_int]),
         "time": (C.c_int, [C.c_void_p]),
         "node_count": (C.c_int, [C.c_void_p]),

@@ -107,6 +107,20 @@ int WTG_API(gsf_init)(void* h, const int* params7) {
     return 0;
   });
 }
+// params6 = { nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount }
+int WTG_API(sanfermin_construct)(void* h, const int* params6) {
+  return guard([&] {
+    wtg::SfParams p{params6[0], params6[1], params6[2], params6[3], params6[4], params6[5]};
+    ENG.sanferminConstruct(p);
+    return 0;
+  });
+}
+int WTG_API(sanfermin_init)(void* h) {
+  return guard([&] {
+    ENG.sanferminInit();
+    return 0;
+  });
+}
 int WTG_API(run_ms)(void* h, int ms) {
   return guard([&] { return ENG.runMs(ms); });
 }
@@ -185,6 +199,28 @@ int WTG_API(pingpong_pongs)(void* h, int* out) {
     ENG.requireInited();
     if (ENG.d.proto != wtg::PROTO_PINGPONG) throw std::logic_error("not a PingPong network");
     ENG.fetch(out, ENG.d.pong, (size_t)ENG.d.N);
+    return 0;
+  });
+}
+// aggValue, currentPrefixLength, done, thresholdDone, sentRequests, receivedRequests, isSwapping (int[N] each), thresholdAt (int64[N])
+int WTG_API(sanfermin_node_scalars)(void* h, int* agg, int* cpl, int* done, int* thrDone, int* sentReq, int* recvReq, int* swapping,
+                                    long long* thresholdAt) {
+  return guard([&] {
+    ENG.requireInited();
+    if (ENG.d.proto != wtg::PROTO_SANFERMIN) throw std::logic_error("not a SanFerminSignature network");
+    size_t n = (size_t)ENG.d.N;
+    std::vector<int> fl(n);
+    ENG.fetch(agg, ENG.d.sfAgg, n);
+    ENG.fetch(cpl, ENG.d.sfCpl, n);
+    ENG.fetch(fl.data(), ENG.d.sfFlags, n);
+    ENG.fetch(sentReq, ENG.d.sfSentReq, n);
+    ENG.fetch(recvReq, ENG.d.sfRecvReq, n);
+    ENG.fetch(thresholdAt, ENG.d.sfThresholdAt, n);
+    for (size_t i = 0; i < n; ++i) {
+      swapping[i] = fl[i] & 1;
+      done[i] = (fl[i] >> 1) & 1;
+      thrDone[i] = (fl[i] >> 2) & 1;
+    }
     return 0;
   });
 }

@@ -104,7 +104,10 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
   int n = blockIdx.x * NODE_SPAN + threadIdx.x;
   bool coop = false;
   if (threadIdx.x < NODE_SPAN && n < d.N && d.inboxFill[n] > 0) {
-    if (split) {
+    if (d.proto == PROTO_SANFERMIN) {
+      CoopSerial cs;  // every SanFermin handler is scalar: the node's events, in order, on one thread
+      nodeProcess(d, cs, n, 0);
+    } else if (split) {
       CoopSerial cs;  // message deliveries: one thread per node
       coop = nodeProcess(d, cs, n, 1) > 0;
     } else {

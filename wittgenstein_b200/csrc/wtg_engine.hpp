@@ -21,6 +21,10 @@ struct GsfParams {
   int nodeCount, threshold, pairingTime, timeoutPerLevelMs, periodDurationMs, acceleratedCallsCount, nodesDown;
 };
 
+struct SfParams {
+  int nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount;
+};
+
 struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
 };
@@ -452,6 +456,68 @@ class Engine {
   const uint64_t* hostJumpC() {
     hostJumpA();
     return hjc_;
+  }
+
+  // ---- SanFerminSignature: constructor builds the nodes (:112-129), init() registers goNextLevel at t=1 (:136-138) ----
+  SfParams sp{};
+  bool sfConstructed = false;
+  void sanferminConstruct(const SfParams& p) {
+    requireNotInited();
+    if (sfConstructed) throw std::logic_error("already constructed");
+    const int N = p.nodeCount;
+    if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("the B200 engine needs a power-of-two nodeCount >= 2 for SanFerminSignature");
+    if (p.candidateCount != 1) throw std::invalid_argument("the B200 engine supports candidateCount == 1 (the shipped scenario) for SanFerminSignature");
+    if (p.pairingTime <= 0 || p.replyTimeout <= 0) throw std::invalid_argument("pairingTime / replyTimeout must be positive");
+    checkLatencyBuilder();
+    sp = p;
+    hm.buildNodes(N);  // new SanFerminNode(nb) draws from network.rd here, before any later rd.setSeed()
+    sfConstructed = true;
+  }
+  void sanferminInit() {
+    requireNotInited();
+    if (!sfConstructed) throw std::logic_error("SanFerminSignature not constructed");
+    const int N = sp.nodeCount;
+    allocCommon(N, PROTO_SANFERMIN);
+    int P = 0;
+    while ((1 << (P + 1)) <= N) ++P;
+    d.sfP = P;
+    d.sfThreshold = sp.threshold;
+    d.sfPairing = sp.pairingTime;
+    d.sfSigSize = sp.signatureSize;
+    d.sfReplyTimeout = sp.replyTimeout;
+    d.sfCandCount = sp.candidateCount;
+    std::vector<int> cpl(N, P), agg(N, 1);
+    d.sfCpl = dupload(cpl);
+    d.sfAgg = dupload(agg);
+    d.sfFlags = dalloc<int>(N);
+    d.sfThresholdAt = dalloc<long long>(N);
+    d.sfSentReq = dalloc<int>(N);
+    d.sfRecvReq = dalloc<int>(N);
+    d.sfPendCnt = dalloc<int>(N);
+    d.sfPending = dalloc<int>((size_t)N * SF_PENDCAP);
+    d.sfUsedCnt = dalloc<int>(N);
+    d.sfUsed = dalloc<int>((size_t)N * SF_USEDCAP);
+    d.sfCacheMask = dalloc<uint32_t>(N);
+    d.sfCache = dalloc<int>((size_t)N * 32);
+    std::vector<Ev> tasks((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      Ev ev;
+      std::memset(&ev, 0, sizeof(ev));
+      ev.kind = EV_TASK;
+      ev.to = (uint32_t)i;
+      ev.from = (uint32_t)i;
+      ev.meta = SF_T_GO;
+      tasks[(size_t)i] = ev;
+    }
+    if (N > d.bcap) throw std::runtime_error("bucket capacity too small");
+    be->upload(d.buckets + (size_t)1 * d.bcap, tasks.data(), tasks.size() * sizeof(Ev));
+    be->upload(d.bucketCount + 1, &N, sizeof(int));
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    c.callId = 1;
+    c.rng = hm.rd.seed;
+    writeCtl(c);
+    inited = true;
   }
 
   // ---- runMs  (Network.java:318-338) ----

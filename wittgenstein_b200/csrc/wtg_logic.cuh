@@ -1142,6 +1142,256 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
 #endif
 
 // ------------------------------------------------------------------------------------------
+// SanFerminSignature handlers (protocols/SanFerminSignature.java, SanFerminHelper.java) — scalar: per-node
+// state is a handful of ints, so every event of a node is handled by one thread, in reference order.
+// Power-of-two node counts and candidateCount == 1 (the shipped scenario, SanFerminSignature.java:568-571).
+// ------------------------------------------------------------------------------------------
+struct SfEmit {  // what a handler asks the engine to do, in program order: at most one send, then one task
+  int nSend;     // 0, 1 (single destination) or 2 (two destinations, shuffled before the send)
+  uint32_t dst[2];
+  uint32_t sendMeta;
+  u64 sendPl;
+  bool task;
+  uint32_t taskMeta;
+  u64 taskPl;
+  int taskAt;
+};
+WTG_HD u64 sfPl(int level, int value) { return (u64)(uint32_t)level | ((u64)(uint32_t)value << 32); }
+WTG_HD bool sfIsCandidate(const Dev& d, int n, int node, int level) {  // SanFerminHelper.getCandidateSet :70-96 (N = 2^P)
+  int shift = d.sfP - 1 - level;
+  if (shift < 0) return false;
+  return (node >> shift) == ((n >> shift) ^ 1);
+}
+WTG_HD bool sfContains(const int* a, int cnt, int v) {
+  for (int i = 0; i < cnt; ++i)
+    if (a[i] == v) return true;
+  return false;
+}
+// SanFerminHelper.pickNextNodes(level, 1) :123-157 (without the shuffle, which the emit step performs)
+WTG_HD int sfPickNextNodes(const Dev& d, int n, int level, uint32_t* out) {
+  int shift = d.sfP - 1 - level;
+  int S = 1 << shift;
+  int ownMin = (n >> shift) << shift;
+  int candMin = ownMin ^ S;
+  int idx = n - ownMin;
+  int* used = d.sfUsed + (size_t)n * SF_USEDCAP;
+  int ucnt = d.sfUsedCnt[n];
+  int cnt = 0;
+  bool removed = false;
+  if (!sfContains(used, ucnt, idx)) {  // the deterministic counterpart first
+    out[cnt++] = (uint32_t)(candMin + idx);
+    removed = true;
+    if (ucnt < SF_USEDCAP) used[ucnt] = idx;
+    ++ucnt;
+  }
+  int size = removed ? S - 1 : S;  // candidateSet.remove(idx) shifts the list the stream below walks
+  int taken = 0;
+  for (int i = 0; i < size && taken < d.sfCandCount; ++i) {
+    if (!sfContains(used, ucnt < SF_USEDCAP ? ucnt : SF_USEDCAP, i)) {
+      if (ucnt < SF_USEDCAP) used[ucnt] = i;
+      ++ucnt;
+      out[cnt++] = (uint32_t)(removed ? (i < idx ? candMin + i : candMin + i + 1) : candMin + i);
+      ++taken;
+    }
+  }
+  if (ucnt > SF_USEDCAP) setError(d, ERR_QUEUE_OVERFLOW, n);
+  d.sfUsedCnt[n] = ucnt < SF_USEDCAP ? ucnt : SF_USEDCAP;
+  return cnt;
+}
+WTG_HD void sfSendToNodes(const Dev& d, int n, const uint32_t* list, int cnt, SfEmit& em) {  // :329-373
+  if (cnt == 0) return;
+  int* pend = d.sfPending + (size_t)n * SF_PENDCAP;
+  int pc = d.sfPendCnt[n];
+  for (int i = 0; i < cnt; ++i)
+    if (!sfContains(pend, pc, (int)list[i])) {
+      if (pc < SF_PENDCAP)
+        pend[pc++] = (int)list[i];
+      else
+        setError(d, ERR_QUEUE_OVERFLOW, n);
+    }
+  d.sfPendCnt[n] = pc;
+  d.sfSentReq[n] += cnt;
+  int cpl = d.sfCpl[n];
+  em.nSend = cnt;
+  em.dst[0] = list[0];
+  em.dst[1] = cnt > 1 ? list[1] : 0;
+  em.sendMeta = SF_REQ;
+  em.sendPl = sfPl(cpl, d.sfAgg[n]);
+  em.task = true;
+  em.taskMeta = SF_T_TIMEOUT;
+  em.taskPl = sfPl(cpl, 0);
+  em.taskAt = d.ctl->tick + d.sfReplyTimeout;
+}
+WTG_HD void sfGoNextLevel(const Dev& d, int n, SfEmit& em) {  // :383-423
+  int fl = d.sfFlags[n];
+  if (fl & 2) return;
+  int cpl = d.sfCpl[n];
+  int agg = d.sfAgg[n];
+  const int tick = d.ctl->tick;
+  if (agg >= d.sfThreshold && !(fl & 4)) {
+    fl |= 4;
+    d.sfThresholdAt[n] = tick + d.sfPairing * 2;
+  }
+  if (cpl == 0) {
+    d.doneAt[n] = tick + d.sfPairing * 2;
+    fl |= 2;
+    d.sfFlags[n] = fl;
+    return;
+  }
+  --cpl;
+  d.sfCpl[n] = cpl;
+  d.sfCache[(size_t)n * 32 + cpl] = agg;
+  d.sfCacheMask[n] |= 1u << cpl;
+  fl &= ~1;
+  d.sfFlags[n] = fl;
+  d.sfPendCnt[n] = 0;
+  d.sfUsedCnt[n] = 0;  // usedNodes of a level that was never picked from is a fresh BitSet
+  uint32_t list[4];
+  int cnt = sfPickNextNodes(d, n, cpl, list);
+  sfSendToNodes(d, n, list, cnt, em);
+}
+WTG_HD void sfReply(const Dev& d, int n, uint32_t to, uint32_t status, int level, int value, SfEmit& em) {  // :425-432
+  (void)d;
+  (void)n;
+  em.nSend = 1;
+  em.dst[0] = to;
+  em.sendMeta = status;
+  em.sendPl = sfPl(level, value);
+}
+WTG_HD void sfTransition(const Dev& d, int n, int toAggregate, SfEmit& em) {  // :438-455
+  d.sfFlags[n] |= 1;
+  em.task = true;
+  em.taskMeta = SF_T_TRANSITION;
+  em.taskPl = sfPl(0, toAggregate);
+  em.taskAt = d.ctl->tick + d.sfPairing;
+}
+WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, int item, int& outSlots, int& outDraws) {
+  SfEmit em;
+  em.nSend = 0;
+  em.task = false;
+  em.dst[0] = em.dst[1] = 0;
+  em.sendMeta = 0;
+  em.sendPl = 0;
+  em.taskMeta = 0;
+  em.taskPl = 0;
+  em.taskAt = 0;
+  const int level = (int)(uint32_t)pl, val = (int)(uint32_t)(pl >> 32);
+  const int msgBytes = 4 + d.sfSigSize;
+  if (type == SF_REQ || type == SF_REPLY_OK || type == SF_REPLY_NO) {
+    d.msgReceived[n] += 1;
+    d.bytesReceived[n] += msgBytes;
+    statAdd(d, n, ST_DELIVERIES, 1ULL);
+  } else {
+    statAdd(d, n, ST_TASKS, 1ULL);
+  }
+  int fl = d.sfFlags[n], cpl = d.sfCpl[n];
+  switch (type) {
+    case SF_REQ: {  // onSwapRequest :229-268
+      d.sfRecvReq[n] += 1;
+      if ((fl & 2) || level != cpl) {
+        if (level >= 0 && level < 32 && (d.sfCacheMask[n] >> level) & 1u) {
+          sfReply(d, n, from, SF_REPLY_OK, level, d.sfCache[(size_t)n * 32 + level], em);
+        } else {
+          sfReply(d, n, from, SF_REPLY_NO, cpl, 0, em);
+          if (level >= 0 && level < 32 && sfIsCandidate(d, n, (int)from, level)) {
+            d.sfCache[(size_t)n * 32 + level] = val;
+            d.sfCacheMask[n] |= 1u << level;
+          }
+        }
+      } else if (fl & 1) {
+        sfReply(d, n, from, SF_REPLY_OK, level, d.sfAgg[n], em);
+      } else if (sfIsCandidate(d, n, (int)from, cpl)) {
+        sfTransition(d, n, val, em);
+      }
+      break;
+    }
+    case SF_REPLY_OK:
+    case SF_REPLY_NO: {  // onSwapReply :270-323
+      if (level != cpl || (fl & 2)) break;
+      if (fl & 1) break;
+      bool pending = sfContains(d.sfPending + (size_t)n * SF_PENDCAP, d.sfPendCnt[n], (int)from);
+      if (type == SF_REPLY_OK) {
+        if (pending || sfIsCandidate(d, n, (int)from, cpl)) sfTransition(d, n, val, em);
+      } else if (pending) {
+        uint32_t list[4];
+        int cnt = sfPickNextNodes(d, n, cpl, list);
+        sfSendToNodes(d, n, list, cnt, em);
+      }
+      break;
+    }
+    case SF_T_GO:
+      sfGoNextLevel(d, n, em);
+      break;
+    case SF_T_TIMEOUT:  // :356-369
+      if (!(fl & 2) && cpl == level) {
+        uint32_t list[4];
+        int cnt = sfPickNextNodes(d, n, cpl, list);
+        sfSendToNodes(d, n, list, cnt, em);
+      }
+      break;
+    case SF_T_TRANSITION:  // :441-452
+      d.sfAgg[n] += val;
+      sfGoNextLevel(d, n, em);
+      break;
+    default:
+      break;
+  }
+  int nd = (em.nSend > 0 ? 1 : 0) + (em.task ? 1 : 0);
+  outSlots = nd;
+  outDraws = em.nSend == 0 ? 0 : em.nSend == 2 ? 2 : 1;
+  if (nd == 0) return;
+  CoopSerial cs;
+  int base = descAlloc(d, cs, n, nd);
+  if (base < 0) return;
+  int sub = 0;
+  if (em.nSend > 0) {
+    Desc ds;
+    ds.item = (uint32_t)(d.N + item);
+    ds.sub = 0;
+    ds.from = (uint32_t)n;
+    ds.evKind = EV_MSG;
+    ds.meta = em.sendMeta;
+    ds.pl = em.sendPl;
+    ds.target = 0;
+    ds.aux = 0;
+    if (em.nSend == 1) {
+      ds.dkind = DK_SEND_SINGLE;
+      ds.to = em.dst[0];
+      ds.nDest = 1;
+    } else {
+      int off = destAlloc(d, n, 2);
+      if (off >= 0) {
+        d.destScratch[off] = em.dst[0];
+        d.destScratch[off + 1] = em.dst[1];
+      }
+      ds.dkind = DK_SEND_MULTI;
+      ds.to = (uint32_t)(off < 0 ? 0 : off);
+      ds.nDest = off < 0 ? 0u : 2u;
+      ds.aux = DESC_SHUFFLE2;
+    }
+    d.desc[base + sub] = ds;
+    ++sub;
+    d.msgSent[n] += em.nSend;
+    d.bytesSent[n] += (long long)em.nSend * msgBytes;
+  }
+  if (em.task) {
+    Desc ds;
+    ds.dkind = DK_INSERT_AT;
+    ds.item = (uint32_t)(d.N + item);
+    ds.sub = (uint32_t)sub;
+    ds.from = (uint32_t)n;
+    ds.to = (uint32_t)n;
+    ds.nDest = 0;
+    ds.evKind = EV_TASK;
+    ds.meta = em.taskMeta;
+    ds.pl = em.taskPl;
+    ds.target = em.taskAt;
+    ds.aux = 0;
+    d.desc[base + sub] = ds;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // one delivery at node n (Network.receiveUntil :603-627 + the protocol's Message.action)
 // `ev` is the envelope, item its scan item.  Writes evSlots/evDraws[item].
 // ------------------------------------------------------------------------------------------
@@ -1178,6 +1428,10 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
       gsfCycle(d, c, n, item, slots, draws);
 #endif
     }
+  } else if (d.proto == PROTO_SANFERMIN) {
+    if (c.lane() == 0) sfHandle(d, n, from, meta, pl, item, slots, draws);
+    slots = c.bcast(slots, 0);
+    draws = c.bcast(draws, 0);
   } else if (d.proto == PROTO_PINGPONG) {
     if (c.lane() == 0) {
       d.msgReceived[n] += 1;
@@ -1375,14 +1629,23 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   ev.from = ds.from;
   ev.meta = ds.meta;
   ev.pl = ds.pl;
-  ev.aux = ds.aux;
+  ev.aux = ds.dkind == DK_INSERT_AT ? ds.aux : 0;
   ev.pad = 0;
   int target = -1;
   int sendTime = ctl.tick + 1;  // send(m, from, to) == send(m, time + 1, from, to)   Network.java:364-366
   if (ds.dkind == DK_INSERT_AT) {
     target = ds.target;
   } else {
-    int32_t seed = lcgNextIntAt(d, ctl.rng, (u64)(d.drawBase[ds.item] + (int)ds.sub));
+    u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
+    bool swap01 = false;
+    if (ds.dkind == DK_SEND_MULTI && (ds.aux & DESC_SHUFFLE2)) {
+      // Collections.shuffle of a 2-element list: swap(list, 1, rnd.nextInt(2))  (SanFerminHelper.java:155)
+      u64 st = lcgAdvance(d.jumpA, d.jumpC, ctl.rng, drawIdx + 1);
+      int32_t r31 = (int32_t)(uint32_t)(st >> 17);
+      swap01 = (int)(((long long)2 * (long long)r31) >> 31) == 0;
+      drawIdx += 1;
+    }
+    int32_t seed = lcgNextIntAt(d, ctl.rng, drawIdx);
     int from = (int)ds.from;
     if (ds.dkind == DK_SEND_SINGLE) {
       int to = (int)ds.to;
@@ -1397,7 +1660,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
       int arr[MAX_ACC];
       int cnt = 0;
       for (int i = 0; i < (int)ds.nDest; ++i) {
-        int to = (int)d.destScratch[ds.to + i];
+        int to = (int)d.destScratch[ds.to + ((swap01 && i < 2) ? 1 - i : i)];
         if (d.npart[from] == d.npart[to] && !d.ndown[from] && !d.ndown[to]) {
           int nt = latency(d, from, to, pseudoRandom(to, seed));
           if (nt < d.msgDiscardTime) {
@@ -1417,6 +1680,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
         ev.to = dst[0];
         target = arr[0];
       } else if (cnt > 1) {
+        ev.aux = 0;
         int ri = WTG_ATOMIC_ADD(&d.ctl->recTop, 1);
         int off = WTG_ATOMIC_ADD(&d.ctl->recDestTop, cnt);
         if (ri >= d.recCap || off + cnt > d.recDestCap) {

@@ -29,7 +29,7 @@ constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bi
 constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
 
 // protocols
-enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2 };
+enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3 };
 
 // event kinds (Ev.kind)
 enum : uint32_t {
@@ -52,6 +52,11 @@ WTG_HD uint32_t metaLevel(uint32_t m) { return (m >> 2) & 31u; }
 WTG_HD uint32_t metaK(uint32_t m) { return (m >> 7) & 31u; }
 // PingPong message types (Ev.meta)
 enum : uint32_t { PP_PING = 1, PP_PONG = 2 };
+// SanFermin message / task types (Ev.meta); Ev.pl = level | (value << 32)
+enum : uint32_t { SF_REQ = 1, SF_REPLY_OK = 2, SF_REPLY_NO = 3, SF_T_GO = 4, SF_T_TIMEOUT = 5, SF_T_TRANSITION = 6 };
+constexpr int SF_PENDCAP = 24;  // pendingNodes of the current level
+constexpr int SF_USEDCAP = 24;  // SanFerminHelper.usedNodes of the current level
+constexpr uint32_t DESC_SHUFFLE2 = 1u;  // Desc.aux: Collections.shuffle of the 2 destinations before the send (one extra draw)
 
 struct Ev {  // 32 bytes: one in-flight envelope / task
   uint32_t kind;
@@ -220,6 +225,20 @@ struct Dev {
   uint32_t* freeList; // [freeCap] level<<27 | slot
   // ---- PingPong ----
   int* pong;  // [N]
+  // ---- SanFermin ----
+  int sfThreshold, sfPairing, sfSigSize, sfReplyTimeout, sfCandCount, sfP;
+  int* sfCpl;        // [N] currentPrefixLength
+  int* sfAgg;        // [N] aggValue
+  int* sfFlags;      // [N] bit0 isSwapping, bit1 done, bit2 thresholdDone
+  long long* sfThresholdAt;  // [N]
+  int* sfSentReq;    // [N]
+  int* sfRecvReq;    // [N]
+  int* sfPendCnt;    // [N]
+  int* sfPending;    // [N][SF_PENDCAP]
+  int* sfUsedCnt;    // [N]
+  int* sfUsed;       // [N][SF_USEDCAP]
+  uint32_t* sfCacheMask;  // [N] levels present in signatureCache
+  int* sfCache;      // [N][32]
   // ---- GSF ----
   unsigned long long* verified;   // [N][W64]
   unsigned long long* indivSeen;  // [N][W64]

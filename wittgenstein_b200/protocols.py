@@ -130,3 +130,51 @@ class GSFSignature:
         card = self.scalars()["card"]
         down = self._net.attrs()["down"]
         return bool(((card < self.params.threshold) & (down == 0)).any())
+
+
+class SanFerminSignatureParameters:
+    """SanFerminSignature.SanFerminSignatureParameters (SanFerminSignature.java:41-110)."""
+
+    def __init__(self, node_count=32768 // 32, threshold=32768 // 32, pairing_time=2, signature_size=48, reply_timeout=300,
+                 candidate_count=1, shuffled_lists=False, node_builder_name=None, network_latency_name=None):
+        self.node_count = node_count
+        self.threshold = threshold
+        self.pairing_time = pairing_time
+        self.signature_size = signature_size
+        self.reply_timeout = reply_timeout
+        self.candidate_count = candidate_count
+        self.shuffled_lists = shuffled_lists  # unused by the reference as well
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+
+
+class SanFerminSignature:
+    """The reference builds its nodes in the constructor (SanFerminSignature.java:112-129); so does this mirror."""
+
+    def __init__(self, params, _api=None):
+        self.params = params
+        self._api = _api
+        self._net = Network(_api)
+        self._net.set_node_builder(params.node_builder_name)
+        self._net.set_network_latency(params.network_latency_name)
+        arr = np.array([params.node_count, params.threshold, params.pairing_time, params.signature_size, params.reply_timeout,
+                        params.candidate_count], np.int32)
+        self._net.api.check(self._net.api.sanfermin_construct(self._net.h, _p(arr, C.c_int)))
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return SanFerminSignature(self.params, self._api)
+
+    def init(self):
+        self._net.api.check(self._net.api.sanfermin_init(self._net.h))
+
+    def scalars(self):
+        n = self.params.node_count
+        a = [np.zeros(n, np.int32) for _ in range(7)]
+        t = np.zeros(n, np.int64)
+        self._net.api.check(self._net.api.sanfermin_node_scalars(self._net.h, *[_p(v, C.c_int) for v in a], _p(t, C.c_longlong)))
+        d = dict(zip(["agg", "cpl", "done", "threshold_done", "sent_requests", "received_requests", "swapping"], a))
+        d["threshold_at"] = t
+        return d
