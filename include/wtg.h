@@ -68,6 +68,12 @@ int wtg_gsf_init(wtg_net* net, const int* params7);
 int wtg_sanfermin_construct(wtg_net* net, const int* params6);
 int wtg_sanfermin_init(wtg_net* net);
 
+/* new Handel(params).init() — protocols/Handel.java:96-141, 957-1014.
+ * params11 = { nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
+ *              desynchronizedStart, byzantineSuicide, hiddenByzantine } (HandelParameters; window = WindowParameters()).
+ * hiddenByzantine != 0 is rejected (not built yet); badNodes is always drawn with Network.chooseBadNodes. */
+int wtg_handel_init(wtg_net* net, const int* params11);
+
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);
 /* network.time — Network.java:49 */
@@ -102,6 +108,19 @@ int wtg_pingpong_pongs(wtg_net* net, int* out);
  * thresholdAt — protocols/SanFerminSignature.java:157-208 */
 int wtg_sanfermin_node_scalars(wtg_net* net, int* agg, int* cpl, int* done, int* thr_done, int* sent_req, int* recv_req,
                                int* swapping, long long* threshold_at);
+
+/* HNode fields — protocols/Handel.java:280-298: 9 int arrays of N: startAt, nodePairingTime, sigsChecked, sigQueueSize,
+ * msgFiltered, currWindowSize, addedCycle, totalSigSize(), total length of the toVerifyAgg lists */
+int wtg_handel_node_scalars(wtg_net* net, int* out9N);
+/* HLevel bitsets as unions over levels, N rows of N/64 uint64 — :373-394; which: 0 totalIncoming, 1 lastAggVerified,
+ * 2 verifiedIndSignatures, 3 toVerifyInd, 4 finishedPeers, 5 HNode.blacklist (:287) */
+int wtg_handel_rows(wtg_net* net, int which, unsigned long long* outNW);
+/* HLevel.posInLevel, outgoingFinished, suicideBizAfter as N*L arrays — :397-406 */
+int wtg_handel_level_scalars(wtg_net* net, int* pos, int* outgoing_finished, int* suicide_biz_after);
+/* HLevel.peers (emission order) — :370 ; HNode.receptionRanks — :285 ; HNode.levels.size() */
+int wtg_handel_peers(wtg_net* net, int node, int level, int* out, int cap);
+int wtg_handel_ranks(wtg_net* net, int node, int* outN);
+int wtg_handel_levels(wtg_net* net);
 
 /* GSFNode.levels.size() — protocols/GSFSignature.java:168 */
 int wtg_gsf_levels(wtg_net* net);

@@ -350,4 +350,112 @@ int wo_sf_helper_pick(int nodeId, int setSize, int level, int howMany, int calls
   return static_cast<int>(r.size());
 }
 
+
+// ---- Handel -------------------------------------------------------------------------------
+// params10 = nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
+//            desynchronizedStart, byzantineSuicide
+void* wo_handel_create(const int* params10, const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  Handel::Params p;
+  p.nodeCount = params10[0];
+  p.threshold = params10[1];
+  p.pairingTime = params10[2];
+  p.levelWaitTime = params10[3];
+  p.extraCycle = params10[4];
+  p.disseminationPeriodMs = params10[5];
+  p.fastPath = params10[6];
+  p.nodesDown = params10[7];
+  p.desynchronizedStart = params10[8];
+  p.byzantineSuicide = params10[9] != 0;
+  p.nodeBuilderName = nodeBuilderName ? nodeBuilderName : "";
+  p.latencyNull = networkLatencyName == nullptr;
+  p.networkLatencyName = networkLatencyName ? networkLatencyName : "";
+  return new Handel(p);
+  WO_CATCH(nullptr)
+}
+void wo_handel_destroy(void* h) { delete static_cast<Handel*>(h); }
+void wo_handel_set_seed(void* h, int64_t s) { static_cast<Handel*>(h)->network.rd.setSeed(s); }
+int wo_handel_init(void* h) {
+  WO_TRY
+  static_cast<Handel*>(h)->init();
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_handel_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<Handel*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+double wo_handel_run_timed(void* h, int ms, int steps) {
+  auto* p = static_cast<Handel*>(h);
+  auto t0 = std::chrono::steady_clock::now();
+  try {
+    for (int i = 0; i < steps; ++i) p->network.runMs(ms);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+int wo_handel_time(void* h) { return static_cast<Handel*>(h)->network.time; }
+int64_t wo_handel_msgs_live(void* h) { return static_cast<Handel*>(h)->network.msgs.live; }
+uint64_t wo_handel_rng_state(void* h) { return static_cast<Handel*>(h)->network.rd.seed; }
+int wo_handel_continue_if(void* h) { return static_cast<Handel*>(h)->continueIf() ? 1 : 0; }
+int wo_handel_levels(void* h) { return static_cast<int>(static_cast<Handel*>(h)->node(0).levels.size()); }
+void wo_handel_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<Handel*>(h)->network.allNodes, out5N); }
+void wo_handel_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<Handel*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+// per node: startAt, pairing, sigsChecked, sigQueueSize, msgFiltered, currWindowSize, addedCycle, totalSigSize, sum of toVerifyAgg sizes
+void wo_handel_node_scalars(void* h, int32_t* out9N) {
+  auto* p = static_cast<Handel*>(h);
+  size_t n = p->nodes.size();
+  for (size_t i = 0; i < n; ++i) {
+    auto& nd = *p->nodes[i];
+    int q = 0;
+    for (auto& l : nd.levels) q += static_cast<int>(l.toVerifyAgg.size());
+    int v[9] = {nd.startAt, nd.nodePairingTime, nd.sigsChecked, nd.sigQueueSize, nd.msgFiltered, nd.currWindowSize, nd.addedCycle, nd.totalSigSize(), q};
+    for (int k = 0; k < 9; ++k) out9N[static_cast<size_t>(k) * n + i] = v[k];
+  }
+}
+// which: 0 totalIncoming, 1 lastAggVerified, 2 verifiedIndSignatures, 3 toVerifyInd, 4 finishedPeers (OR over levels), 5 blacklist
+void wo_handel_rows(void* h, int which, uint64_t* out, int words) {
+  auto* p = static_cast<Handel*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) {
+    uint64_t* row = out + i * static_cast<size_t>(words);
+    for (int w = 0; w < words; ++w) row[w] = 0;
+    if (which == 5) {
+      for (int w = 0; w < words; ++w) row[w] = p->nodes[i]->blacklist.rawWord(w);
+      continue;
+    }
+    for (auto& l : p->nodes[i]->levels) {
+      const JBitSet& b = which == 0 ? l.totalIncoming : which == 1 ? l.lastAggVerified : which == 2 ? l.verifiedIndSignatures : which == 3 ? l.toVerifyInd : l.finishedPeers;
+      for (int w = 0; w < words; ++w) row[w] |= b.rawWord(w);
+    }
+  }
+}
+// per (node, level): posInLevel, outgoingFinished, suicideBizAfter, toVerifyAgg.size()
+void wo_handel_level_scalars(void* h, int L, int32_t* pos, int32_t* fin, int32_t* biz, int32_t* qsz) {
+  auto* p = static_cast<Handel*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i)
+    for (int l = 0; l < L; ++l) {
+      size_t k = i * static_cast<size_t>(L) + static_cast<size_t>(l);
+      auto& lv = p->nodes[i]->levels[static_cast<size_t>(l)];
+      pos[k] = lv.posInLevel;
+      fin[k] = lv.outgoingFinished ? 1 : 0;
+      biz[k] = lv.suicideBizAfter;
+      qsz[k] = static_cast<int>(lv.toVerifyAgg.size());
+    }
+}
+int wo_handel_peers(void* h, int node, int level, int32_t* out, int cap) {
+  auto& pe = static_cast<Handel*>(h)->node(node).levels[static_cast<size_t>(level)].peers;
+  int c = std::min<int>(cap, static_cast<int>(pe.size()));
+  for (int i = 0; i < c; ++i) out[i] = pe[static_cast<size_t>(i)];
+  return static_cast<int>(pe.size());
+}
+void wo_handel_ranks(void* h, int node, int32_t* out) {
+  auto& r = static_cast<Handel*>(h)->node(node).receptionRanks;
+  for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
+}
+
 }  // extern "C"

@@ -4,6 +4,7 @@
 //   protocols/PingPong.java       -> PingPong
 //   protocols/GSFSignature.java   -> GSFSignature (GSFNode, SFLevel, SendSigs)
 //   protocols/SanFerminSignature.java + SanFerminHelper.java -> SanFerminSignature, SanFerminHelper
+//   protocols/Handel.java         -> Handel (HNode, HLevel, SendSigs, SigToVerify; HiddenByzantine not restated)
 // Line references are to those files.  PARITY STATUS: structure / schedule / liveness are
 // pinned by the reference's own tests (PT/GSFSignatureTest.java, PT/PingPongTest.java,
 // restated in tests/test_oracle_protocols.py); the protocol END STATE (bitmaps, doneAt) is
@@ -795,6 +796,409 @@ inline void SanFerminSignature::SwapReply::action(Network&, Node& from, Node& to
 }
 inline void SanFerminSignature::SwapRequest::action(Network&, Node& from, Node& to) {
   static_cast<SanFerminNode&>(to).onSwapRequest(static_cast<SanFerminNode&>(from), *this);
+}
+
+// ----------------------------------------------------------------------------------------
+// Handel  (protocols/Handel.java).  HiddenByzantine (:840-917) is not restated: requesting it throws.
+// ----------------------------------------------------------------------------------------
+struct Handel {
+  struct Params {  // :22-142
+    int nodeCount = 32, threshold = 31, pairingTime = 3, levelWaitTime = 50, extraCycle = 10, disseminationPeriodMs = 10;
+    int fastPath = 10, nodesDown = 0;
+    std::string nodeBuilderName, networkLatencyName;
+    bool latencyNull = false;
+    int desynchronizedStart = 0;
+    bool byzantineSuicide = false, hiddenByzantine = false;
+    int windowInitial = 16, windowMinimum = 1, windowMaximum = 128;  // WindowParameters() :157-159
+  };
+  static void validate(const Params& p) {  // :112-124
+    if (p.nodesDown >= p.nodeCount || p.nodesDown < 0 || p.threshold > p.nodeCount || (p.nodesDown + p.threshold > p.nodeCount))
+      throw IllegalArgument("nodeCount/threshold");
+    if (__builtin_popcount(static_cast<unsigned>(p.nodeCount)) != 1) throw IllegalArgument("We support only power of two nodes in this simulation");
+    if (p.byzantineSuicide && p.hiddenByzantine) throw IllegalArgument("Only one attack at a time");
+    if (p.hiddenByzantine) throw IllegalArgument("hiddenByzantine is not restated in the oracle");
+  }
+  // WindowParameters.newSize + ScoringExp(2, 4) :168-200
+  int windowNewSize(int curr, bool correct) const {
+    int updated = correct ? static_cast<int>(std::ceil(static_cast<double>(curr) * 2.0)) : static_cast<int>(std::floor(static_cast<double>(curr) / 4.0));
+    if (updated > params.windowMaximum) return params.windowMaximum;
+    if (updated < params.windowMinimum) return params.windowMinimum;
+    return updated;
+  }
+
+  struct HNode;
+  struct HLevel;
+  struct SigToVerify {  // :919-938
+    int from, level, rank;
+    JBitSet sig;
+    bool badSig;
+  };
+  using SigPtr = std::shared_ptr<SigToVerify>;
+  struct SendSigs : Message {  // :239-276
+    int level;
+    JBitSet sigs;
+    bool levelFinished;
+    int size_;
+    bool badSig = false;
+    SendSigs(const JBitSet& s, const HLevel& l);
+    int size() const override { return size_; }
+    void action(Network&, Node& from, Node& to) override;
+  };
+  struct HLevel {  // :364-643
+    HNode* node = nullptr;
+    int level = 0, size = 0;
+    std::vector<int> peers;  // node ids in emission order
+    JBitSet waitedSigs, lastAggVerified, totalIncoming, verifiedIndSignatures, toVerifyInd, finishedPeers, totalOutgoing;
+    std::vector<SigPtr> toVerifyAgg;
+    bool outgoingFinished = false;
+    int posInLevel = 0;
+    int suicideBizAfter = -1;
+
+    int expectedSigs() const { return size; }
+    bool incomingComplete() const { return waitedSigs.equals(totalIncoming); }     // :520-522
+    bool outgoingComplete() const { return totalOutgoing.cardinality() == size; }  // :524-526
+    bool isOpen() const;                                                           // :454-468
+    void doCycle();                                                                // :470-480
+    std::vector<int> getRemainingPeers(int peersCt);                               // :482-504
+    int sizeIfIncluded(const SigToVerify& sig) const {                             // :528-536
+      JBitSet c = sig.sig;
+      if (!c.intersects(totalIncoming)) c.or_(totalIncoming);
+      c.or_(verifiedIndSignatures);
+      return c.cardinality();
+    }
+    SigPtr createSuicideByzantineSig(int maxRank);  // :538-559
+    SigPtr bestToVerify();                          // :566-630
+  };
+  struct HNode : Node {  // :278-838
+    Handel* p;
+    int startAt;
+    std::vector<HLevel> levels;
+    int nodePairingTime;
+    std::vector<int> receptionRanks;
+    JBitSet blacklist;
+    int currWindowSize, addedCycle;
+    bool done = false;
+    int sigsChecked = 0, sigQueueSize = 0, msgFiltered = 0;
+
+    HNode(Handel* pp, int startAt_)
+        : Node(pp->network.rd, pp->nb), p(pp), startAt(startAt_),
+          nodePairingTime(static_cast<int>(std::max(1.0, pp->params.pairingTime * speedRatio))),
+          receptionRanks(static_cast<size_t>(pp->params.nodeCount), 0), currWindowSize(pp->params.windowInitial),
+          addedCycle(pp->params.extraCycle) {}
+    JBitSet allSigsAtLevel(int round) const {  // :667-680
+      JBitSet res;
+      int cMask = (1 << round) - 1;
+      int start = (cMask | nodeId) ^ cMask;
+      int end = std::min(nodeId | cMask, p->params.nodeCount - 1);
+      res.setRange(start, end + 1);
+      res.set(nodeId, false);
+      return res;
+    }
+    void initLevel() {  // :319-329, HLevel ctors :409-431
+      int rounded = roundPow2(p->params.nodeCount);
+      JBitSet allPreviousNodes;
+      levels.reserve(40);
+      levels.emplace_back();
+      HLevel& l0 = levels.back();
+      l0.node = this;
+      l0.level = 0;
+      l0.size = 1;
+      l0.outgoingFinished = true;
+      l0.lastAggVerified.set(nodeId);
+      l0.verifiedIndSignatures.set(nodeId);
+      l0.totalIncoming.set(nodeId);
+      l0.suicideBizAfter = p->params.byzantineSuicide ? 0 : -1;
+      for (int l = 1; (1LL << l) <= rounded; l++) {
+        allPreviousNodes.or_(levels.back().waitedSigs);
+        HLevel nl;
+        nl.node = this;
+        nl.level = levels.back().level + 1;
+        nl.waitedSigs.or_(allSigsAtLevel(nl.level));
+        nl.waitedSigs.andNot(allPreviousNodes);
+        nl.totalOutgoing.set(nodeId);
+        nl.size = nl.waitedSigs.cardinality();
+        nl.suicideBizAfter = p->params.byzantineSuicide ? 0 : -1;
+        levels.push_back(std::move(nl));
+      }
+    }
+    void dissemination() {  // :331-343
+      if (doneAt > 0) {
+        if (addedCycle > 0)
+          addedCycle--;
+        else
+          return;
+      }
+      for (HLevel& sfl : levels) sfl.doCycle();
+    }
+    bool hasSigToVerify() const { return sigQueueSize != 0; }
+    int totalSigSize() const {  // :349-352
+      const HLevel& last = levels.back();
+      return last.totalOutgoing.cardinality() + last.totalIncoming.cardinality();
+    }
+    int score(const HLevel& l, const JBitSet& sig) const {  // :651-664
+      if (l.lastAggVerified.cardinality() >= l.expectedSigs()) return 0;
+      if (!l.lastAggVerified.intersects(sig)) return l.lastAggVerified.cardinality() + sig.cardinality();
+      JBitSet withIndiv = l.verifiedIndSignatures;
+      withIndiv.or_(sig);
+      return std::max(0, withIndiv.cardinality() - l.lastAggVerified.cardinality());
+    }
+    static bool include(const JBitSet& big, const JBitSet& small) {  // BitSetUtils.include
+      JBitSet b = small;
+      b.or_(big);
+      return b.equals(big);
+    }
+    void updateVerifiedSignatures(const SigPtr& vs);  // :686-750
+    void onNewSig(HNode& from, const SendSigs& ssigs);  // :753-786
+    void checkSigs();                                   // :792-837
+  };
+
+  Params params;
+  Network network;
+  NodeBuilder nb;
+  std::vector<std::unique_ptr<HNode>> nodes;
+
+  explicit Handel(const Params& pr) : params(pr) {  // :212-216
+    validate(params);
+    network.setNetworkLatency(networkLatencyByName(params.networkLatencyName, params.latencyNull));
+  }
+  HNode& node(int i) { return *nodes[static_cast<size_t>(i)]; }
+
+  void setReceivingRanks() {  // :940-948
+    std::vector<int> expected(static_cast<size_t>(params.nodeCount));
+    for (int i = 0; i < params.nodeCount; ++i) expected[static_cast<size_t>(i)] = i;
+    for (auto& n : nodes) {
+      javaShuffle(expected, network.rd);
+      for (size_t i = 0; i < expected.size(); i++) n->receptionRanks[static_cast<size_t>(expected[i])] = static_cast<int>(i);
+    }
+  }
+  void init() {  // :957-1014
+    nb = nodeBuilderByName(params.nodeBuilderName);
+    std::vector<bool> badNodes = Network::chooseBadNodes(network.rd, params.nodeCount, params.nodesDown);
+    for (int i = 0; i < params.nodeCount; i++) {
+      int startAt = params.desynchronizedStart == 0 ? 0 : network.rd.nextInt(params.desynchronizedStart);
+      nodes.push_back(std::make_unique<HNode>(this, startAt));
+      if (badNodes[static_cast<size_t>(i)]) nodes.back()->stop();
+      network.addNode(nodes.back().get());
+    }
+    for (auto& up : nodes) {
+      HNode* n = up.get();
+      n->initLevel();
+      if (!n->isDown()) {
+        network.registerPeriodicTask([n] { n->dissemination(); }, n->startAt + 1, params.disseminationPeriodMs, *n);
+        network.registerConditionalTask([n] { n->checkSigs(); }, n->startAt + 1, n->nodePairingTime, *n,
+                                        [n] { return n->hasSigToVerify(); }, [n] { return !n->done; });
+      }
+    }
+    setReceivingRanks();
+    // emission lists: contact first the peers that gave you a good reception rank (:991-1013)
+    for (auto& up : nodes) {
+      HNode* sender = up.get();
+      if (sender->isDown()) continue;
+      for (HLevel& l : sender->levels) {
+        std::vector<std::vector<int>> emissionList(static_cast<size_t>(params.nodeCount));
+        for (int cur = l.waitedSigs.nextSetBit(0); cur >= 0; cur = l.waitedSigs.nextSetBit(cur + 1)) {
+          int recRank = node(cur).receptionRanks[static_cast<size_t>(sender->nodeId)];
+          emissionList[static_cast<size_t>(recRank)].push_back(cur);
+        }
+        if (!l.peers.empty()) throw IllegalState("peers not empty");  // buildEmissionList :506-518
+        for (auto& ranks : emissionList) {
+          if (!ranks.empty()) {
+            if (ranks.size() > 1) javaShuffle(ranks, network.rd);
+            l.peers.insert(l.peers.end(), ranks.begin(), ranks.end());
+          }
+        }
+      }
+    }
+  }
+  bool continueIf() const {  // Handel.newContIf :1044-1053
+    for (auto& n : nodes)
+      if (!n->isDown() && (n->doneAt == 0 || n->addedCycle > 0)) return true;
+    return false;
+  }
+};
+
+inline Handel::SendSigs::SendSigs(const JBitSet& s, const HLevel& l)  // :253-265
+    : level(l.level), sigs(s), levelFinished(l.incomingComplete()), size_(1 + l.expectedSigs() / 8 + 96 * 2) {
+  if (sigs.isEmpty() || sigs.cardinality() > l.size) throw IllegalState("bad level");
+}
+inline void Handel::SendSigs::action(Network&, Node& from, Node& to) {
+  static_cast<HNode&>(to).onNewSig(static_cast<HNode&>(from), *this);
+}
+inline bool Handel::HLevel::isOpen() const {
+  if (outgoingFinished) return false;
+  if (node->p->network.time >= (level - 1) * node->p->params.levelWaitTime) return true;
+  if (outgoingComplete()) return true;
+  return false;
+}
+inline void Handel::HLevel::doCycle() {
+  if (!isOpen()) return;
+  std::vector<int> dest = getRemainingPeers(1);
+  if (!dest.empty()) {
+    auto ss = std::make_shared<SendSigs>(totalOutgoing, *this);
+    node->p->network.send(ss, *node, node->p->node(dest[0]));
+  }
+}
+inline std::vector<int> Handel::HLevel::getRemainingPeers(int peersCt) {
+  std::vector<int> res;
+  int start = posInLevel;
+  while (peersCt > 0 && !outgoingFinished) {
+    int pid = peers.at(static_cast<size_t>(posInLevel++));
+    if (posInLevel >= static_cast<int>(peers.size())) posInLevel = 0;
+    if (!finishedPeers.get(pid) && !node->blacklist.get(pid)) {
+      res.push_back(pid);
+      peersCt--;
+    } else {
+      if (posInLevel == start) outgoingFinished = true;
+    }
+  }
+  return res;
+}
+inline Handel::SigPtr Handel::HLevel::createSuicideByzantineSig(int maxRank) {
+  bool reset = false;
+  for (int i = suicideBizAfter; i < static_cast<int>(peers.size()); i++) {
+    int pid = peers[static_cast<size_t>(i)];
+    if (node->p->node(pid).isDown() && !node->blacklist.get(pid)) {
+      if (!reset) {
+        suicideBizAfter = i;
+        reset = true;
+      }
+      if (node->receptionRanks[static_cast<size_t>(pid)] < maxRank)
+        return std::make_shared<SigToVerify>(SigToVerify{pid, level, node->receptionRanks[static_cast<size_t>(pid)], waitedSigs, true});
+    }
+  }
+  if (!reset) suicideBizAfter = -1;
+  return nullptr;
+}
+inline Handel::SigPtr Handel::HLevel::bestToVerify() {
+  if (toVerifyAgg.empty()) return nullptr;
+  if (node->currWindowSize < 1) throw IllegalState("window");
+  int windowIndex = toVerifyAgg[0]->rank;  // Collections.min(..., comparingInt(getRank)).rank
+  for (auto& s : toVerifyAgg) windowIndex = std::min(windowIndex, s->rank);
+  if (suicideBizAfter >= 0) {
+    SigPtr bSig = createSuicideByzantineSig(windowIndex + node->currWindowSize);
+    if (bSig) {
+      toVerifyAgg.push_back(bSig);
+      node->sigQueueSize++;
+      return bSig;
+    }
+  }
+  int curSignatureSize = totalIncoming.cardinality();
+  SigPtr bestOutside, bestInside;
+  int bestScoreInside = 0;
+  int removed = 0;
+  std::vector<SigPtr> curatedList;
+  for (auto& stv : toVerifyAgg) {
+    int s = sizeIfIncluded(*stv);
+    if (!node->blacklist.get(stv->from) && s > curSignatureSize) {
+      curatedList.push_back(stv);
+      if (stv->rank <= windowIndex + node->currWindowSize) {
+        int sc = node->score(*this, stv->sig);
+        if (sc > bestScoreInside) {
+          bestScoreInside = sc;
+          bestInside = stv;
+        }
+      } else {
+        if (!bestOutside || stv->rank < bestOutside->rank) bestOutside = stv;
+      }
+    } else {
+      removed++;
+    }
+  }
+  if (removed > 0) {  // replaceToVerifyAgg :632-642
+    int oldSize = static_cast<int>(toVerifyAgg.size());
+    toVerifyAgg = curatedList;
+    node->sigQueueSize -= oldSize;
+    node->sigQueueSize += static_cast<int>(toVerifyAgg.size());
+    if (node->sigQueueSize < 0) throw IllegalState("sigQueueSize<0");
+  }
+  if (bestInside) return bestInside;
+  if (bestOutside) return bestOutside;
+  return nullptr;
+}
+inline void Handel::HNode::updateVerifiedSignatures(const SigPtr& vs) {
+  if (vs->badSig) {
+    blacklist.set(vs->from);
+    if (!p->params.byzantineSuicide) throw IllegalState("We should not have invalid signatures in this scenario");
+    return;
+  }
+  HLevel& vsl = levels[static_cast<size_t>(vs->level)];
+  if (!include(vsl.waitedSigs, vs->sig)) throw IllegalState("bad signature received");
+  vsl.toVerifyInd.set(vs->from, false);
+  for (size_t i = 0; i < vsl.toVerifyAgg.size(); ++i)  // toVerifyAgg.remove(vs): identity
+    if (vsl.toVerifyAgg[i] == vs) {
+      vsl.toVerifyAgg.erase(vsl.toVerifyAgg.begin() + static_cast<long>(i));
+      break;
+    }
+  vsl.verifiedIndSignatures.set(vs->from);
+  bool improved = false;
+  if (!vsl.totalIncoming.get(vs->from)) {
+    vsl.totalIncoming.set(vs->from);
+    improved = true;
+  }
+  JBitSet all = vs->sig;
+  all.or_(vsl.verifiedIndSignatures);
+  if (all.cardinality() > vsl.verifiedIndSignatures.cardinality()) {
+    improved = true;
+    if (vsl.lastAggVerified.intersects(vs->sig)) vsl.lastAggVerified = JBitSet();
+    vsl.lastAggVerified.or_(vs->sig);
+    vsl.totalIncoming = JBitSet();
+    vsl.totalIncoming.or_(vsl.lastAggVerified);
+    vsl.totalIncoming.or_(vsl.verifiedIndSignatures);
+  }
+  if (!improved) return;
+  bool justCompleted = vsl.incomingComplete();
+  JBitSet cur;
+  for (HLevel& l : levels) {
+    if (l.level > vsl.level) {
+      l.totalOutgoing = JBitSet();
+      l.totalOutgoing.or_(cur);
+      if (justCompleted && p->params.fastPath > 0 && !l.outgoingFinished && l.outgoingComplete()) {
+        std::vector<int> peers = l.getRemainingPeers(p->params.fastPath);
+        auto sendSigs = std::make_shared<SendSigs>(l.totalOutgoing, l);
+        std::vector<Node*> dests;
+        for (int pid : peers) dests.push_back(&p->node(pid));
+        p->network.send(sendSigs, *this, dests);
+      }
+    }
+    cur.or_(l.totalIncoming);
+  }
+  if (doneAt == 0 && cur.cardinality() >= p->params.threshold) doneAt = p->network.time;
+}
+inline void Handel::HNode::onNewSig(HNode& from, const SendSigs& ssigs) {
+  if (doneAt > 0) {
+    msgFiltered++;
+    return;
+  }
+  if (p->network.time < startAt || blacklist.get(from.nodeId)) return;
+  HLevel& l = levels[static_cast<size_t>(ssigs.level)];
+  if (!include(l.waitedSigs, ssigs.sigs)) throw IllegalState("bad signatures received");
+  JBitSet cs = ssigs.sigs;
+  cs.and_(l.waitedSigs);
+  if (!cs.equals(ssigs.sigs) || ssigs.sigs.isEmpty()) throw IllegalState("bad message");
+  if (ssigs.levelFinished) l.finishedPeers.set(from.nodeId);
+  if (!l.verifiedIndSignatures.get(from.nodeId)) l.toVerifyInd.set(from.nodeId);
+  sigQueueSize++;
+  l.toVerifyAgg.push_back(std::make_shared<SigToVerify>(
+      SigToVerify{from.nodeId, l.level, receptionRanks[static_cast<size_t>(from.nodeId)], cs, ssigs.badSig}));
+}
+inline void Handel::HNode::checkSigs() {
+  std::vector<SigPtr> byLevels;
+  for (HLevel& l : levels) {
+    SigPtr ss = l.bestToVerify();
+    if (!ss) continue;
+    byLevels.push_back(ss);
+  }
+  if (byLevels.empty()) return;
+  SigPtr best = byLevels[static_cast<size_t>(p->network.rd.nextInt(static_cast<int>(byLevels.size())))];  // :788-790
+  HLevel& l = levels[static_cast<size_t>(best->level)];
+  int newSize = p->windowNewSize(currWindowSize, !best->badSig);
+  currWindowSize = std::min(newSize, l.size);
+  int& rk = receptionRanks[static_cast<size_t>(best->from)];
+  rk = static_cast<int>(static_cast<uint32_t>(rk) + static_cast<uint32_t>(p->params.nodeCount));
+  if (rk < 0) rk = std::numeric_limits<int>::max();
+  sigsChecked++;
+  HNode* self = this;
+  p->network.registerTask([self, best] { self->updateVerifiedSignatures(best); }, p->network.time + nodePairingTime, *this);
 }
 
 }  // namespace wo

@@ -44,6 +44,26 @@ class HostBackend : public Backend {
       for (int t = 0; t < tot; ++t) gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
       for (int n = 0; n < d.N; ++n) gsfCondSelect(d, c, n, keep.data());
     }
+    if (d.proto == PROTO_HANDEL) {
+      HScratch sc;
+      for (int n = 0; n < d.N; ++n)
+        if (hCondMark(d, n)) hCondScanQueue(d, c, n);
+      int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
+      for (int t = 0; t < tot; ++t) hScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
+      for (int n = 0; n < d.N; ++n) hCondSelect(d, c, n, &sc);
+      const char* force = std::getenv("WTG_EMU_FORCE_SERIAL_PICK");
+      bool serial = force && force[0] == '1';
+      pairScan(d, 2);
+      if (!serial)
+        for (int n = 0; n < d.N; ++n)
+          if (hCondPick(d, n, (u64)d.hDrawBase[n], false) > d.condDraws[n]) serial = true;
+      if (!serial) {
+        for (int n = 0; n < d.N; ++n) hCondPick(d, n, (u64)d.hDrawBase[n], true);
+      } else {
+        u64 idx = 0;
+        for (int n = 0; n < d.N; ++n) idx += (u64)hCondPick(d, n, idx, true);
+      }
+    }
     if (mode != 2) {
       int nEv = d.ctl->nEv;
       for (int i = 0; i < nEv; ++i) dispatchCount(d, i);

@@ -35,6 +35,12 @@ def load():
     lib.wo_gpd_inverse.restype = C.c_double
     lib.wo_gpd_inverse.argtypes = [C.c_double] * 4
     lib.wo_latency.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.wo_handel_create.restype = C.c_void_p
+    lib.wo_handel_create.argtypes = [C.POINTER(C.c_int), C.c_char_p, C.c_char_p]
+    lib.wo_handel_rng_state.restype = C.c_uint64
+    lib.wo_handel_msgs_live.restype = C.c_int64
+    lib.wo_handel_run_timed.restype = C.c_double
+    lib.wo_handel_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.wo_sf_create.restype = C.c_void_p
     lib.wo_sf_create.argtypes = [C.c_int] * 6 + [C.c_char_p, C.c_char_p]
     lib.wo_sf_rng_state.restype = C.c_uint64
@@ -273,4 +279,93 @@ class OracleSanFermin:
     def __del__(self):
         if getattr(self, "h", None):
             self.lib.wo_sf_destroy(self.h)
+            self.h = None
+
+
+class OracleHandel:
+    """protocols/Handel.java through the oracle."""
+
+    def __init__(self, node_count, threshold, pairing_time, level_wait_time, extra_cycle, dissemination_period_ms, fast_path,
+                 nodes_down, node_builder, latency, desynchronized_start=0, byzantine_suicide=False, seed=None):
+        self.lib = load()
+        self.n = node_count
+        arr = np.array([node_count, threshold, pairing_time, level_wait_time, extra_cycle, dissemination_period_ms, fast_path,
+                        nodes_down, desynchronized_start, 1 if byzantine_suicide else 0], np.int32)
+        self.h = C.c_void_p(self.lib.wo_handel_create(_p(arr, C.c_int), _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+        if seed is not None:
+            self.lib.wo_handel_set_seed(self.h, C.c_int64(seed))
+        self.words = max(1, node_count // 64)
+
+    def init(self):
+        if self.lib.wo_handel_init(self.h) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        self.L = self.lib.wo_handel_levels(self.h)
+
+    def run_ms(self, ms):
+        r = self.lib.wo_handel_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    def run_timed(self, ms, steps):
+        t = self.lib.wo_handel_run_timed(self.h, ms, steps)
+        if t < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return t
+
+    @property
+    def time(self):
+        return self.lib.wo_handel_time(self.h)
+
+    def msgs_live(self):
+        return self.lib.wo_handel_msgs_live(self.h)
+
+    def rng_state(self):
+        return int(self.lib.wo_handel_rng_state(self.h))
+
+    def continue_if(self):
+        return bool(self.lib.wo_handel_continue_if(self.h))
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_handel_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_handel_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def scalars(self):
+        out = np.zeros((9, self.n), np.int32)
+        self.lib.wo_handel_node_scalars(self.h, _p(out, C.c_int32))
+        keys = ["start_at", "pairing", "sigs_checked", "sig_queue_size", "msg_filtered", "window", "added_cycle", "total_sig_size", "queued"]
+        return {k: out[i] for i, k in enumerate(keys)}
+
+    def rows(self, which):
+        out = np.zeros((self.n, self.words), np.uint64)
+        self.lib.wo_handel_rows(self.h, which, _p(out, C.c_uint64), self.words)
+        return out
+
+    def level_scalars(self):
+        a = [np.zeros((self.n, self.L), np.int32) for _ in range(4)]
+        self.lib.wo_handel_level_scalars(self.h, self.L, *[_p(v, C.c_int32) for v in a])
+        return dict(pos=a[0], outgoing_finished=a[1], suicide_biz_after=a[2], queue=a[3])
+
+    def peers(self, node, level):
+        out = np.zeros(max(1, self.n), np.int32)
+        k = self.lib.wo_handel_peers(self.h, node, level, _p(out, C.c_int32), self.n)
+        return out[:k].copy()
+
+    def ranks(self, node):
+        out = np.zeros(self.n, np.int32)
+        self.lib.wo_handel_ranks(self.h, node, _p(out, C.c_int32))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.wo_handel_destroy(self.h)
             self.h = None

@@ -176,6 +176,82 @@ def test_sanfermin_16384_shipped_scenario():
     assert not _sf_compare(p, o, "end")
 
 
+def _handel_compare(p, o, tag, full=True):
+    bad = []
+    if p.network().rng_state() != o.rng_state():
+        bad.append(f"{tag}: rd state")
+    if p.network().msgs_size() != o.msgs_live():
+        bad.append(f"{tag}: msgs.size()")
+    if not (p.network().counters() == o.counters()).all():
+        bad.append(f"{tag}: counters")
+    a, b = p.scalars(), o.scalars()
+    for k in a:
+        if not (a[k] == b[k]).all():
+            bad.append(f"{tag}: {k}")
+    if full:
+        for w in range(6):
+            if not (p.rows(w) == o.rows(w)).all():
+                bad.append(f"{tag}: rows {w}")
+        l1, l2 = p.level_scalars(), o.level_scalars()
+        for k in l1:
+            if not (l1[k] == l2[k]).all():
+                bad.append(f"{tag}: level {k}")
+    return bad
+
+
+def _handel_pair(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=None):
+    from tests.oracle_lib import OracleHandel
+    from wittgenstein_b200 import Handel, HandelParameters
+
+    p = Handel(HandelParameters(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, False))
+    o = OracleHandel(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=seed)
+    if seed is not None:
+        p.network().set_seed(seed)
+    p.init(); o.init()
+    for node in (0, 1, n // 2, n - 1):
+        assert (p.ranks(node) == o.ranks(node)).all()
+        for l in range(p.levels):
+            assert (p.peers(node, l) == o.peers(node, l)).all()
+    a, b = p.network().attrs(), o.attrs()
+    for k in a:
+        assert (a[k] == b[k]).all()
+    assert not _handel_compare(p, o, "init")
+    return p, o
+
+
+def test_handel_64_test_copy_params_every_ms():
+    """PT/HandelTest parameters (64 nodes, 2 dead, desynchronised start 100 ms), compared after every ms."""
+    p, o = _handel_pair(64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False)
+    while o.time < 1200:
+        assert p.network().run_ms(1) == o.run_ms(1)
+        bad = _handel_compare(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert not p.continue_if() and not o.continue_if()
+
+
+@pytest.mark.parametrize("seed", [None, 3])
+def test_handel_1024_byzantine_suicide(seed):
+    """BASELINE config #3 scaled down: 25 % Byzantine (suicide attack), AWS regions, fast path 10."""
+    p, o = _handel_pair(1024, 760, 4, 50, 10, 20, 10, 256, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, True, seed=seed)
+    steps = 0
+    while o.continue_if() and o.time < 6000:
+        assert p.network().run_ms(10) == o.run_ms(10)
+        steps += 1
+        bad = _handel_compare(p, o, f"t={o.time}", full=(steps % 10 == 0))
+        assert not bad, bad
+    assert not p.continue_if()
+    assert not _handel_compare(p, o, "end")
+    assert (p.rows(5) != 0).any()  # somebody got blacklisted
+
+
+def test_handel_512_tor_desync_plain_dead():
+    p, o = _handel_pair(512, 450, 4, 50, 10, 20, 10, 51, AWS_NB, AWS_NL, 50, False, seed=1)
+    for step in (1, 3, 7, 20, 50, 100, 100, 300, 500, 1000):
+        assert p.network().run_ms(step) == o.run_ms(step)
+        bad = _handel_compare(p, o, f"t={o.time}")
+        assert not bad, bad
+
+
 def test_error_paths():
     from wittgenstein_b200 import GSFSignature, GSFSignatureParameters, Network, PingPong, PingPongParameters, WtgError
 
@@ -204,6 +280,11 @@ def test_error_paths():
         SanFerminSignature(SanFerminSignatureParameters(1000, 1000, 2, 48, 300, 1))  # power of two only on the device
     with pytest.raises(WtgError):
         SanFerminSignature(SanFerminSignatureParameters(1024, 1024, 2, 48, 300, 3))  # candidateCount 1 only
+    from wittgenstein_b200 import Handel, HandelParameters
+    with pytest.raises(WtgError):
+        HandelParameters(100, 90)  # Handel.java:118-120
+    with pytest.raises(WtgError):
+        Handel(HandelParameters(64, 60, hidden_byzantine=True, node_builder_name=NB, network_latency_name=NL)).init()
     # a capacity that is too small fails loudly instead of dropping events
     g = GSFSignature(GSFSignatureParameters(256, 250, 3, 20, 10, 10, 0, NB, NL), tunables={"qcap": 32})
     g.init()

@@ -213,3 +213,42 @@ def test_sanfermin_run_and_determinism():
     done = sa["done"] == 1
     assert (sa["cpl"][done] == 0).all()
     assert (a.counters()[4][done] > 0).all()
+
+
+def test_handel_liveness_and_determinism():
+    """PT/HandelTest.java: testRun (:36-49, done within 20 s) and testCopy (:13-34, lock-step every ms)."""
+    from tests.oracle_lib import OracleHandel
+
+    mk = lambda: OracleHandel(64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False)
+    p = mk(); p.init()
+    while p.time < 20000 and (p.counters()[4][p.attrs()["down"] == 0] == 0).any():
+        p.run_ms(1000)
+    assert (p.counters()[4][p.attrs()["down"] == 0] > 0).all()
+    a, b = mk(), mk()
+    a.init(); b.init()
+    while a.time < 2000:
+        a.run_ms(1); b.run_ms(1)
+        assert a.msgs_live() == b.msgs_live()
+        if a.time % 100 == 0:
+            assert (a.counters()[4] == b.counters()[4]).all()
+            assert (a.scalars()["total_sig_size"] == b.scalars()["total_sig_size"]).all()
+
+
+def test_handel_byzantine_suicide_blacklists():
+    from tests.oracle_lib import OracleHandel
+
+    q = OracleHandel(256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", "AwsRegionNetworkLatency", 0, True)
+    q.init()
+    while q.continue_if() and q.time < 10000:
+        q.run_ms(100)
+    assert not q.continue_if()
+    down = q.attrs()["down"] == 1
+    bl = q.rows(5)
+    ids = np.arange(256)
+    # only byzantine (down) nodes are ever blacklisted, and some are
+    listed = np.zeros(256, bool)
+    for n in range(256):
+        listed |= ((bl[n][ids // 64] >> (ids % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+    assert listed.any() and not (listed & ~down).any()
+    with pytest.raises(ValueError):
+        OracleHandel(100, 90, 4, 50, 10, 20, 10, 5, NB, NL)  # power of two only (Handel.java:118-120)

@@ -34,6 +34,13 @@ class Api:
         "sanfermin_construct": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "sanfermin_init": (C.c_int, [C.c_void_p]),
         "sanfermin_node_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 7 + [C.POINTER(C.c_longlong)]),
+        "handel_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "handel_node_scalars": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "handel_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
+        "handel_level_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),
+        "handel_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
+        "handel_ranks": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+        "handel_levels": (C.c_int, [C.c_void_p]),
         "run_ms": (C.c_int, [C.c_void_p, C.c_int]),
         "time": (C.c_int, [C.c_void_p]),
         "node_count": (C.c_int, [C.c_void_p]),

@@ -121,6 +121,15 @@ int WTG_API(sanfermin_init)(void* h) {
     return 0;
   });
 }
+// params11 = { nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
+//              desynchronizedStart, byzantineSuicide, hiddenByzantine }
+int WTG_API(handel_init)(void* h, const int* p) {
+  return guard([&] {
+    wtg::HandelParams hp{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10]};
+    ENG.handelInit(hp);
+    return 0;
+  });
+}
 int WTG_API(run_ms)(void* h, int ms) {
   return guard([&] { return ENG.runMs(ms); });
 }
@@ -224,11 +233,75 @@ int WTG_API(sanfermin_node_scalars)(void* h, int* agg, int* cpl, int* done, int*
     return 0;
   });
 }
+static void requireHandel(wtg::Engine& e) {
+  e.requireInited();
+  if (e.d.proto != wtg::PROTO_HANDEL) throw std::logic_error("not a Handel network");
+}
+// out9N: startAt, nodePairingTime, sigsChecked, sigQueueSize, msgFiltered, currWindowSize, addedCycle, totalSigSize(), sum of toVerifyAgg sizes
+int WTG_API(handel_node_scalars)(void* h, int* out9N) {
+  return guard([&] {
+    requireHandel(ENG);
+    size_t n = (size_t)ENG.d.N;
+    ENG.fetch(out9N + 0 * n, ENG.d.hStartAt, n);
+    ENG.fetch(out9N + 1 * n, ENG.d.pairing, n);
+    ENG.fetch(out9N + 2 * n, ENG.d.hSigsChecked, n);
+    ENG.fetch(out9N + 3 * n, ENG.d.hSigQueueSize, n);
+    ENG.fetch(out9N + 4 * n, ENG.d.hMsgFiltered, n);
+    ENG.fetch(out9N + 5 * n, ENG.d.hWindow, n);
+    ENG.fetch(out9N + 6 * n, ENG.d.hAddedCycle, n);
+    // totalSigSize() = |totalOutgoing(last)| + |totalIncoming(last)| (:349-352) = sum of |totalIncoming| over all levels
+    ENG.fetch(out9N + 7 * n, ENG.d.hTotal, n);
+    ENG.fetch(out9N + 8 * n, ENG.d.qLen, n);
+    return 0;
+  });
+}
+// which: 0 totalIncoming, 1 lastAggVerified, 2 verifiedIndSignatures, 3 toVerifyInd, 4 finishedPeers (unions over levels), 5 blacklist
+int WTG_API(handel_rows)(void* h, int which, unsigned long long* outNW) {
+  return guard([&] {
+    requireHandel(ENG);
+    const unsigned long long* src = which == 0 ? ENG.d.hTotInc : which == 1 ? ENG.d.hLastAgg : which == 2 ? ENG.d.hVerInd : which == 3 ? ENG.d.hToVerInd : which == 4 ? ENG.d.hFinPeers : ENG.d.hBlack;
+    ENG.fetch(outNW, src, (size_t)ENG.d.N * ENG.d.W64);
+    return 0;
+  });
+}
+// N*L arrays: posInLevel, outgoingFinished, suicideBizAfter
+int WTG_API(handel_level_scalars)(void* h, int* pos, int* outFin, int* biz) {
+  return guard([&] {
+    requireHandel(ENG);
+    size_t n = (size_t)ENG.d.N * ENG.d.L;
+    ENG.fetch(pos, ENG.d.hPos, n);
+    ENG.fetch(outFin, ENG.d.hOutFin, n);
+    ENG.fetch(biz, ENG.d.hBiz, n);
+    return 0;
+  });
+}
+int WTG_API(handel_peers)(void* h, int node, int level, int* out, int cap) {
+  return guard([&] {
+    requireHandel(ENG);
+    if (node < 0 || node >= ENG.d.N || level < 0 || level >= ENG.d.L) throw std::invalid_argument("node/level");
+    if (level == 0 || ENG.hm.nodes[(size_t)node].down) return 0;
+    int size = 1 << (level - 1);
+    int cnt = size < cap ? size : cap;
+    std::vector<unsigned> tmp((size_t)cnt);
+    ENG.fetch(tmp.data(), (const unsigned*)ENG.d.peers + (size_t)node * (size_t)(ENG.d.N - 1) + (size_t)(size - 1), (size_t)cnt);
+    for (int i = 0; i < cnt; ++i) out[i] = (int)tmp[(size_t)i];
+    return size;
+  });
+}
+int WTG_API(handel_ranks)(void* h, int node, int* outN) {
+  return guard([&] {
+    requireHandel(ENG);
+    if (node < 0 || node >= ENG.d.N) throw std::invalid_argument("node");
+    ENG.fetch(outN, ENG.d.hRanks + (size_t)node * ENG.d.N, (size_t)ENG.d.N);
+    return 0;
+  });
+}
 static void requireGsf(wtg::Engine& e) {
   e.requireInited();
   if (e.d.proto != wtg::PROTO_GSF) throw std::logic_error("not a GSFSignature network");
 }
 int WTG_API(gsf_levels)(void* h) { return ENG.d.L; }
+int WTG_API(handel_levels)(void* h) { return ENG.d.L; }
 int WTG_API(gsf_verified)(void* h, unsigned long long* outNW) {
   return guard([&] {
     requireGsf(ENG);

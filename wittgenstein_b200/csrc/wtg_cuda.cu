@@ -68,7 +68,13 @@ __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
   CoopWarp c;
   const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
   for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warpsPerGrid)
-    gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
+  {
+    uint32_t it = d.workList[stripedIndex(d.ctl->workCnt, per, t)];
+    if (d.proto == PROTO_HANDEL)
+      hScoreItem(d, c, it);
+    else
+      gsfScoreItem(d, c, it);
+  }
 }
 __global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
   extern __shared__ uint32_t keepAll[];
@@ -81,6 +87,45 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
   CoopWarp c;
   int warp = threadIdx.x >> 5;
   for (int k = warp; k < total; k += WARPS_PER_BLOCK) gsfCondSelect(d, c, list[k], keepAll + (size_t)warp * (size_t)(d.qcap / 32));
+}
+
+// ---- Handel conditional pass (checkSigs): scan -> score -> select -> draw scan -> pick ---------------------
+__global__ void __launch_bounds__(NODE_BLOCK) k_hcond_scan(Dev d) {
+  __shared__ int list[NODE_BLOCK];
+  __shared__ int cnt;
+  if (d.ctl->error) return;
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
+  bool due = threadIdx.x < NODE_SPAN && n < d.N && hCondMark(d, n);
+  int total = blockCompact(due, n, list, &cnt);
+  CoopWarp c;
+  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) hCondScanQueue(d, c, list[k]);
+}
+__global__ void __launch_bounds__(NODE_BLOCK) k_hcond_select(Dev d) {
+  __shared__ int list[NODE_BLOCK];
+  __shared__ int cnt;
+  __shared__ HScratch scratch[WARPS_PER_BLOCK];
+  if (d.ctl->error) return;
+  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
+  bool due = threadIdx.x < NODE_SPAN && n < d.N && d.condDue[n] != 0;
+  int total = blockCompact(due, n, list, &cnt);
+  CoopWarp c;
+  int warp = threadIdx.x >> 5;
+  for (int k = warp; k < total; k += WARPS_PER_BLOCK) hCondSelect(d, c, list[k], &scratch[warp]);
+}
+// does any nextInt(k) of this pass hit java.util.Random's rejection loop?  (probability ~ k / 2^31 per draw)
+__global__ void k_hpick_check(Dev d) {
+  if (d.ctl->error) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x)
+    if (d.hCandK[n] > 0 && hCondPick(d, n, (u64)d.hDrawBase[n], false) > d.condDraws[n]) d.ctl->hReject = 1;
+}
+__global__ void k_hpick_apply(Dev d) {
+  if (d.ctl->error) return;
+  if (!d.ctl->hReject) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x) hCondPick(d, n, (u64)d.hDrawBase[n], true);
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {  // a rejection shifts every later draw: redo the picks in node order
+    u64 idx = 0;
+    for (int n = 0; n < d.N; ++n) idx += (u64)hCondPick(d, n, idx, true);
+  }
 }
 
 // ---- dispatch -----------------------------------------------------------------------------
@@ -519,6 +564,28 @@ class CudaBackend : public Backend {
     profBegin(0);
     k_begin<<<1, 1, 0, st>>>(d, mode);
     profEnd();
+    if (d.proto == PROTO_HANDEL) {
+      profBegin(1);
+      k_hcond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      profEnd();
+      profBegin(14);
+      k_cond_score<<<sms * 8, 256, 0, st>>>(d);
+      profEnd();
+      profBegin(15);
+      k_hcond_select<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      profEnd();
+      profBegin(3);
+      k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 2);
+      profEnd();
+      profBegin(5);
+      k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 2);
+      profEnd();
+      profBegin(15);
+      k_hpick_check<<<sms, 256, 0, st>>>(d);
+      k_hpick_apply<<<sms, 256, 0, st>>>(d);
+      profEnd();
+      launches += 7;
+    }
     if (d.proto == PROTO_GSF) {
       size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);

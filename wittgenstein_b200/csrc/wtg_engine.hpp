@@ -25,6 +25,11 @@ struct SfParams {
   int nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount;
 };
 
+struct HandelParams {
+  int nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown, desynchronizedStart,
+      byzantineSuicide, hiddenByzantine;
+};
+
 struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
 };
@@ -169,6 +174,7 @@ class Engine {
     d.evSlots = dalloc<int>(d.itemCap);
     d.evDraws = dalloc<int>(d.itemCap);
     d.condFired = dalloc<int>(N);
+    d.condDraws = dalloc<int>(N);
     d.condDue = dalloc<int>(N);
     d.workCap = (int)std::max<long long>(1 << 16, 64LL * N) / ARENA_STRIPES * ARENA_STRIPES;
     d.workList = dalloc<uint32_t>(d.workCap);
@@ -514,6 +520,186 @@ class Engine {
     be->upload(d.bucketCount + 1, &N, sizeof(int));
     Ctl c;
     std::memset(&c, 0, sizeof(c));
+    c.callId = 1;
+    c.rng = hm.rd.seed;
+    writeCtl(c);
+    inited = true;
+  }
+
+  // ---- Handel.init()  (protocols/Handel.java:957-1014).  Everything init() draws from network.rd is sequential
+  //      (bad nodes, start times, node attributes, N cumulative shuffles for the reception ranks, tie shuffles of
+  //      the emission lists), so it runs on the host like in the reference; the tables are then uploaded. ----
+  HandelParams hp{};
+  void handelInit(const HandelParams& p) {
+    requireNotInited();
+    const int N = p.nodeCount;
+    if (p.nodesDown >= N || p.nodesDown < 0 || p.threshold > N || (p.nodesDown + p.threshold > N))  // :112-117
+      throw std::invalid_argument("nodeCount=" + std::to_string(N) + ", threshold=" + std::to_string(p.threshold));
+    if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("We support only power of two nodes in this simulation");  // :118-120
+    if (p.byzantineSuicide && p.hiddenByzantine) throw std::invalid_argument("Only one attack at a time");  // :122-124
+    if (p.hiddenByzantine) throw std::invalid_argument("hiddenByzantine is not supported by the B200 engine yet");
+    if (p.fastPath < 0 || p.fastPath > MAX_ACC) throw std::invalid_argument("fastPath must be in [0,16]");
+    if (p.disseminationPeriodMs <= 0 || p.pairingTime < 0 || p.desynchronizedStart < 0) throw std::invalid_argument("period/pairing/desynchronizedStart");
+    checkLatencyBuilder();
+    hp = p;
+    // Network.chooseBadNodes first (:960-963)
+    std::vector<char> bad((size_t)N, 0);
+    for (int setDown = 0; setDown < p.nodesDown;) {
+      int down = hm.rd.nextInt(N);
+      if (down != 1 && !bad[(size_t)down]) {
+        bad[(size_t)down] = 1;
+        setDown++;
+      }
+    }
+    std::vector<int> startAt((size_t)N, 0);
+    for (int i = 0; i < N; ++i) {  // :965-974
+      startAt[(size_t)i] = p.desynchronizedStart == 0 ? 0 : hm.rd.nextInt(p.desynchronizedStart);
+      hm.buildNodes(1);
+      if (bad[(size_t)i]) hm.nodes[(size_t)i].down = true;
+    }
+    int L = 1;
+    while ((1 << L) <= N) ++L;
+    allocCommon(N, PROTO_HANDEL);
+    for (int i = 0; i < N; ++i)
+      if (startAt[(size_t)i] + 1 >= d.ring) throw std::invalid_argument("desynchronizedStart exceeds the time ring");
+    d.L = L;
+    d.W64 = std::max(1, N / 64);
+    d.threshold = p.threshold;
+    d.period = p.disseminationPeriodMs;
+    d.hLevelWait = p.levelWaitTime;
+    d.hFastPath = p.fastPath;
+    d.hExtraCycle = p.extraCycle;
+    d.hByzSuicide = p.byzantineSuicide;
+    d.hWinInit = 16;  // WindowParameters() :157-159
+    d.hWinMin = 1;
+    d.hWinMax = 128;
+    d.qcap = (int)(tun.qcap ? tun.qcap : std::min<long long>(4096, std::max<long long>(64, 2LL * N)));
+    d.qcap = (d.qcap + 31) / 32 * 32;
+    size_t rowWords = (size_t)N * d.W64;
+    // level 0: own signature in lastAggVerified / verifiedIndSignatures / totalIncoming (:409-417); initLevel() runs for every node
+    std::vector<unsigned long long> diag(rowWords, 0);
+    for (int i = 0; i < N; ++i) diag[(size_t)i * d.W64 + (size_t)(i >> 6)] = 1ULL << (i & 63);
+    d.hLastAgg = dupload(diag);
+    d.hTotInc = dupload(diag);
+    d.hVerInd = dupload(diag);
+    d.hToVerInd = dalloc<unsigned long long>(rowWords);
+    d.hFinPeers = dalloc<unsigned long long>(rowWords);
+    d.hBlack = dalloc<unsigned long long>(rowWords);
+    std::vector<int> zerosNL((size_t)N * L, 0), outFin((size_t)N * L, 0), biz((size_t)N * L, p.byzantineSuicide ? 0 : -1), cnt0((size_t)N * L, 0);
+    std::vector<uint32_t> ver((size_t)N * L, 1);
+    for (int i = 0; i < N; ++i) {
+      outFin[(size_t)i * L] = 1;  // level 0: outgoingFinished = true
+      cnt0[(size_t)i * L] = 1;
+    }
+    d.hPos = dupload(zerosNL);
+    d.hOutFin = dupload(outFin);
+    d.hBiz = dupload(biz);
+    d.hCntLast = dupload(cnt0);
+    d.hCntInc = dupload(cnt0);
+    d.hCntInd = dupload(cnt0);
+    d.lvVer = dupload(ver);
+    std::vector<int> ones((size_t)N, 1), win((size_t)N, d.hWinInit), added((size_t)N, p.extraCycle), pairing((size_t)N), minStart((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      pairing[(size_t)i] = (int)std::max(1.0, p.pairingTime * hm.nodes[(size_t)i].speed);  // :282
+      minStart[(size_t)i] = startAt[(size_t)i] + 1;                                        // :981-982
+    }
+    d.hTotal = dupload(ones);
+    d.hWindow = dupload(win);
+    d.hAddedCycle = dupload(added);
+    d.pairing = dupload(pairing);
+    d.minStart = dupload(minStart);
+    d.stamp = dalloc<uint32_t>(N);
+    d.hStartAt = dupload(startAt);
+    d.hSigsChecked = dalloc<int>(N);
+    d.hSigQueueSize = dalloc<int>(N);
+    d.hMsgFiltered = dalloc<int>(N);
+    d.hSeq = dalloc<int>(N);
+    d.qLen = dalloc<int>(N);
+    d.hQueue = dalloc<HQEntry>((size_t)N * d.qcap);
+    d.qStamp = dalloc<uint32_t>((size_t)N * d.qcap);
+    d.hCand = dalloc<int>((size_t)N * 32);
+    d.hCandK = dalloc<int>(N);
+    d.hDrawBase = dalloc<int>(N);
+    // setReceivingRanks (:940-948): N cumulative shuffles of one list
+    std::vector<int> ranks((size_t)N * N);
+    {
+      std::vector<int> expected((size_t)N);
+      for (int i = 0; i < N; ++i) expected[(size_t)i] = i;
+      for (int n = 0; n < N; ++n) {
+        for (int i = N; i > 1; --i) std::swap(expected[(size_t)i - 1], expected[(size_t)hm.rd.nextInt(i)]);
+        int* row = ranks.data() + (size_t)n * N;
+        for (int i = 0; i < N; ++i) row[expected[(size_t)i]] = i;
+      }
+    }
+    // emission lists (:991-1013): receivers of each level sorted by the rank they gave the sender, ties shuffled
+    std::vector<uint32_t> peers((size_t)N * (size_t)(N - 1), 0);
+    {
+      std::vector<std::pair<int, int>> rr;  // (rank, receiver)
+      std::vector<int> group;
+      for (int sIdx = 0; sIdx < N; ++sIdx) {
+        if (hm.nodes[(size_t)sIdx].down) continue;
+        for (int l = 1; l < L; ++l) {
+          Blk wb = levelBlock(sIdx ^ (1 << (l - 1)), l);
+          rr.clear();
+          for (int r = wb.base; r < wb.base + wb.size; ++r) rr.push_back({ranks[(size_t)r * N + sIdx], r});
+          std::stable_sort(rr.begin(), rr.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+          uint32_t* out = peers.data() + (size_t)sIdx * (size_t)(N - 1) + (size_t)((1 << (l - 1)) - 1);
+          size_t o = 0;
+          for (size_t i = 0; i < rr.size();) {
+            size_t j = i;
+            while (j < rr.size() && rr[j].first == rr[i].first) ++j;
+            if (j - i > 1) {
+              group.clear();
+              for (size_t k = i; k < j; ++k) group.push_back(rr[k].second);
+              for (int m = (int)group.size(); m > 1; --m) std::swap(group[(size_t)m - 1], group[(size_t)hm.rd.nextInt(m)]);
+              for (int g : group) out[o++] = (uint32_t)g;
+            } else {
+              out[o++] = (uint32_t)rr[i].second;
+            }
+            i = j;
+          }
+        }
+      }
+    }
+    d.hRanks = dupload(ranks);
+    d.peerBits = 32;
+    d.peers = dupload(peers);
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
+    for (int l = INLINE_MAX_LEVEL + 1; l < L; ++l) {
+      long long slots = std::max<long long>(1024, perNode * N);
+      slots = (slots + POOL_STRIPES - 1) / POOL_STRIPES * POOL_STRIPES;
+      d.poolCap[l] = (int)slots;
+      d.pool[l] = dalloc<unsigned long long>((size_t)slots * (size_t)poolWords(l));
+      d.poolRef[l] = dalloc<int>((size_t)slots);
+      std::vector<uint32_t> fl((size_t)slots);
+      long long per = slots / POOL_STRIPES;
+      for (int sidx = 0; sidx < POOL_STRIPES; ++sidx) {
+        for (long long i = 0; i < per; ++i) fl[(size_t)(sidx * per + i)] = (uint32_t)(sidx * per + (per - 1 - i));
+        c.poolFreeCnt[l][sidx] = (int)per;
+      }
+      d.poolFree[l] = dupload(fl);
+      c.poolMinFree[l] = (int)slots;
+    }
+    // periodic dissemination at startAt + 1 for live nodes, in id order (:978-983)
+    std::vector<std::vector<Ev>> per((size_t)d.ring);
+    for (int i = 0; i < N; ++i)
+      if (!hm.nodes[(size_t)i].down) {
+        Ev ev;
+        std::memset(&ev, 0, sizeof(ev));
+        ev.kind = EV_PERIODIC;
+        ev.to = (uint32_t)i;
+        ev.from = (uint32_t)i;
+        per[(size_t)(startAt[(size_t)i] + 1)].push_back(ev);
+      }
+    for (int t = 0; t < d.ring; ++t)
+      if (!per[(size_t)t].empty()) {
+        if ((int)per[(size_t)t].size() > d.bcap) throw std::runtime_error("bucket capacity too small");
+        be->upload(d.buckets + (size_t)t * d.bcap, per[(size_t)t].data(), per[(size_t)t].size() * sizeof(Ev));
+        int cnt = (int)per[(size_t)t].size();
+        be->upload(d.bucketCount + t, &cnt, sizeof(int));
+      }
     c.callId = 1;
     c.rng = hm.rd.seed;
     writeCtl(c);

@@ -1391,6 +1391,10 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   }
 }
 
+}  // namespace wtg
+#include "wtg_handel.cuh"
+namespace wtg {
+
 // ------------------------------------------------------------------------------------------
 // one delivery at node n (Network.receiveUntil :603-627 + the protocol's Message.action)
 // `ev` is the envelope, item its scan item.  Writes evSlots/evDraws[item].
@@ -1405,6 +1409,24 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
     // dropped: a pooled payload dies with the envelope
     if (d.proto == PROTO_GSF && (ev.kind == EV_MSG || ev.kind == EV_TASK) && metaKind(meta) == PK_POOL && c.lane() == 0)
       freeDeferred(d, n, (int)metaLevel(meta), (uint32_t)pl);
+    if (d.proto == PROTO_HANDEL && (ev.kind == EV_MSG || ev.kind == EV_TASK) && metaKind(meta) == PK_POOL && c.lane() == 0)
+      hRelease(d, n, (int)metaLevel(meta), (uint32_t)pl, false);
+  } else if (d.proto == PROTO_HANDEL) {
+    if (ev.kind == EV_MSG || ev.kind == EV_MULTI) {
+      if (c.lane() == 0) {
+        d.msgReceived[n] += 1;
+        d.bytesReceived[n] += hMsgSize((int)metaLevel(meta));
+        statAdd(d, n, ST_DELIVERIES, 1ULL);
+        hOnNewSig(d, n, from, meta, pl);
+      }
+      c.sync();
+    } else if (ev.kind == EV_TASK) {
+      if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
+      hUpdate(d, c, n, from, meta, pl, ev.aux, item, slots, draws);
+    } else {
+      if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
+      hDissemination(d, c, n, item, slots, draws);
+    }
   } else if (d.proto == PROTO_GSF) {
     if (ev.kind == EV_MSG || ev.kind == EV_MULTI) {
       if (c.lane() == 0) {
@@ -1760,6 +1782,7 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
   c.nItems = 0;
   c.totalSlots = 0;
   c.totalDraws = 0;
+  c.hReject = 0;
   if (c.nEv > c.maxBucket) c.maxBucket = c.nEv;
 }
 WTG_HD void tickEnd(const Dev& d, int mode) {
@@ -1882,6 +1905,11 @@ struct Pair {
 };
 WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
   Pair p;
+  if (which == 2) {  // Handel: draws of the conditional pass, over nodes
+    p.a = d.condDraws[j];
+    p.b = 0;
+    return p;
+  }
   if (which == 0) {
     int nEv = d.ctl->nEv;
     if (j < nEv) {
@@ -1894,7 +1922,7 @@ WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
   } else {
     if (j < d.N) {
       p.a = d.condFired[j];
-      p.b = 0;
+      p.b = d.condDraws[j];
     } else {
       p.a = d.evSlots[j - d.N];
       p.b = d.evDraws[j - d.N];
@@ -1902,8 +1930,12 @@ WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
   }
   return p;
 }
-WTG_HD int scanCount(const Dev& d, int which) { return which == 0 ? d.ctl->nEv + d.N : d.N + d.ctl->nItems; }
+WTG_HD int scanCount(const Dev& d, int which) { return which == 2 ? d.N : which == 0 ? d.ctl->nEv + d.N : d.N + d.ctl->nItems; }
 WTG_HD void scanStore(const Dev& d, int which, int j, Pair ex) {
+  if (which == 2) {
+    d.hDrawBase[j] = ex.a;
+    return;
+  }
   if (which == 0) {
     int nEv = d.ctl->nEv;
     if (j < nEv)
@@ -1918,6 +1950,7 @@ WTG_HD void scanStore(const Dev& d, int which, int j, Pair ex) {
   }
 }
 WTG_HD void scanTotals(const Dev& d, int which, Pair tot) {
+  if (which == 2) return;
   if (which == 0) {
     d.ctl->nItems = tot.a;
     if (tot.a > d.itemCap || tot.b > d.itemCap) setError(d, ERR_INBOX_OVERFLOW, tot.a);

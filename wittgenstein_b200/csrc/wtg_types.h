@@ -29,7 +29,7 @@ constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bi
 constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
 
 // protocols
-enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3 };
+enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4 };
 
 // event kinds (Ev.kind)
 enum : uint32_t {
@@ -72,6 +72,16 @@ struct QEntry {  // 16 bytes: one entry of a GSF node's toVerify list
   uint32_t from;
   uint32_t meta;
   uint64_t pl;
+};
+
+struct HQEntry {  // 32 bytes: one Handel SigToVerify (protocols/Handel.java:919-938) + cached evaluation
+  uint32_t from;
+  uint32_t meta;  // payload kind | level << 2 | k << 7 | badSig << 12
+  uint64_t pl;
+  uint32_t rank;
+  uint32_t id;    // identity of the object (toVerifyAgg.remove(vs) is by reference)
+  int32_t s;      // sizeIfIncluded, valid while qStamp == lvVer of the level
+  int32_t score;  // score(level, sig)
 };
 
 struct MultiRec {  // multi-destination envelope: sorted destinations + explicit arrivals
@@ -130,6 +140,7 @@ struct Ctl {  // device-resident control block (one per engine)
   int error;               // first error code (0 = ok)
   int errorDetail;
   int recTop, recDestTop;  // multi-destination record arenas
+  int hReject;             // Handel: some nextInt(k) of this tick's conditional pass hit the rejection loop
   int maxBucket;
   unsigned long long statDraws, statEvents;
   int descCnt[ARENA_STRIPES];   // descriptors allocated this tick, per stripe (stripe = node id & 63)
@@ -209,6 +220,7 @@ struct Dev {
   int* condDue;       // [N] conditional task of node n is examined this tick and its queue is not empty
   uint32_t* workList; // [workCap] global queue-entry index (n*qcap+i) of stale pooled entries, striped
   int* condFired;     // [N]
+  int* condDraws;     // [N] rd draws consumed by the node's conditional task this tick (Handel: nextInt(k))
   Ev* condEv;         // [N] task created by the conditional task of node n
   int* condTarget;    // [N]
   int* slotBase;      // [N + itemCap]
@@ -225,6 +237,34 @@ struct Dev {
   uint32_t* freeList; // [freeCap] level<<27 | slot
   // ---- PingPong ----
   int* pong;  // [N]
+  // ---- Handel ----
+  int hLevelWait, hFastPath, hExtraCycle, hByzSuicide, hWinInit, hWinMin, hWinMax;
+  unsigned long long* hLastAgg;   // [N][W64] lastAggVerified (all levels of a node in one row)
+  unsigned long long* hTotInc;    // [N][W64] totalIncoming
+  unsigned long long* hVerInd;    // [N][W64] verifiedIndSignatures
+  unsigned long long* hToVerInd;  // [N][W64] toVerifyInd
+  unsigned long long* hFinPeers;  // [N][W64] finishedPeers
+  unsigned long long* hBlack;     // [N][W64] blacklist
+  int* hPos;        // [N][L] posInLevel
+  int* hOutFin;     // [N][L] outgoingFinished
+  int* hBiz;        // [N][L] suicideBizAfter
+  int* hCntLast;    // [N][L] |lastAggVerified|
+  int* hCntInc;     // [N][L] |totalIncoming|
+  int* hCntInd;     // [N][L] |verifiedIndSignatures|
+  int* hTotal;      // [N] sum of |totalIncoming| over levels
+  int* hWindow;     // [N] currWindowSize
+  int* hAddedCycle; // [N]
+  int* hSigsChecked;   // [N]
+  int* hSigQueueSize;  // [N]
+  int* hMsgFiltered;   // [N]
+  int* hStartAt;    // [N]
+  int* hSeq;        // [N] next SigToVerify id
+  int* hRanks;      // [N][N] receptionRanks
+  HQEntry* hQueue;  // [N][qcap] toVerifyAgg of all levels, arrival order
+  int* hCand;       // [N][32] per level: queue index of bestToVerify() or -1
+  int* hCandK;      // [N] number of levels with a candidate
+  int* hDrawBase;   // [N] exclusive scan of condDraws
+  int* poolRef[MAX_LEVELS];  // reference counts of pooled payloads (queue entry + pending update tasks)
   // ---- SanFermin ----
   int sfThreshold, sfPairing, sfSigSize, sfReplyTimeout, sfCandCount, sfP;
   int* sfCpl;        // [N] currentPrefixLength

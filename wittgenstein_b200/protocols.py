@@ -178,3 +178,93 @@ class SanFerminSignature:
         d = dict(zip(["agg", "cpl", "done", "threshold_done", "sent_requests", "received_requests", "swapping"], a))
         d["threshold_at"] = t
         return d
+
+
+class HandelParameters:
+    """Handel.HandelParameters (Handel.java:22-142); window = WindowParameters() (16, 1, 128, ScoringExp(2, 4))."""
+
+    def __init__(self, node_count=32, threshold=None, pairing_time=3, level_wait_time=50, extra_cycle=10,
+                 dissemination_period_ms=10, fast_path=10, nodes_down=0, node_builder_name=None, network_latency_name=None,
+                 desynchronized_start=0, byzantine_suicide=False, hidden_byzantine=False):
+        if threshold is None:
+            threshold = int(node_count * 0.99)
+        if nodes_down >= node_count or nodes_down < 0 or threshold > node_count or nodes_down + threshold > node_count:
+            raise WtgError(f"nodeCount={node_count}, threshold={threshold}")  # :112-117
+        if bin(node_count).count("1") != 1:
+            raise WtgError("We support only power of two nodes in this simulation")  # :118-120
+        if byzantine_suicide and hidden_byzantine:
+            raise WtgError("Only one attack at a time")  # :122-124
+        self.node_count = node_count
+        self.threshold = threshold
+        self.pairing_time = pairing_time
+        self.level_wait_time = level_wait_time
+        self.extra_cycle = extra_cycle
+        self.dissemination_period_ms = dissemination_period_ms
+        self.fast_path = fast_path
+        self.nodes_down = nodes_down
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+        self.desynchronized_start = desynchronized_start
+        self.byzantine_suicide = byzantine_suicide
+        self.hidden_byzantine = hidden_byzantine
+
+
+class Handel:
+    def __init__(self, params, _api=None, tunables=None):
+        self.params = params
+        self._api = _api
+        self._tunables = dict(tunables or {})
+        self._net = Network(_api)
+        self._net.set_network_latency(params.network_latency_name)  # Handel.java:214-215
+        for k, v in self._tunables.items():
+            self._net.set_tunable(k, v)
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return Handel(self.params, self._api, self._tunables)
+
+    def init(self):
+        p = self.params
+        self._net.set_node_builder(p.node_builder_name)  # :958
+        arr = np.array([p.node_count, p.threshold, p.pairing_time, p.level_wait_time, p.extra_cycle, p.dissemination_period_ms,
+                        p.fast_path, p.nodes_down, p.desynchronized_start, int(p.byzantine_suicide), int(p.hidden_byzantine)], np.int32)
+        self._net.api.check(self._net.api.handel_init(self._net.h, _p(arr, C.c_int)))
+        self.levels = self._net.api.handel_levels(self._net.h)
+        self.words = max(1, p.node_count // 64)
+
+    def scalars(self):
+        n = self.params.node_count
+        out = np.zeros((9, n), np.int32)
+        self._net.api.check(self._net.api.handel_node_scalars(self._net.h, _p(out, C.c_int)))
+        keys = ["start_at", "pairing", "sigs_checked", "sig_queue_size", "msg_filtered", "window", "added_cycle", "total_sig_size", "queued"]
+        return {k: out[i] for i, k in enumerate(keys)}
+
+    def rows(self, which):
+        out = np.zeros((self.params.node_count, self.words), np.uint64)
+        self._net.api.check(self._net.api.handel_rows(self._net.h, int(which), _p(out, C.c_ulonglong)))
+        return out
+
+    def level_scalars(self):
+        n, L = self.params.node_count, self.levels
+        a = [np.zeros((n, L), np.int32) for _ in range(3)]
+        self._net.api.check(self._net.api.handel_level_scalars(self._net.h, *[_p(v, C.c_int) for v in a]))
+        return dict(pos=a[0], outgoing_finished=a[1], suicide_biz_after=a[2])
+
+    def peers(self, node, level):
+        out = np.zeros(max(1, self.params.node_count), np.int32)
+        k = self._net.api.check(self._net.api.handel_peers(self._net.h, node, level, _p(out, C.c_int), self.params.node_count))
+        return out[:k].copy()
+
+    def ranks(self, node):
+        out = np.zeros(self.params.node_count, np.int32)
+        self._net.api.check(self._net.api.handel_ranks(self._net.h, node, _p(out, C.c_int)))
+        return out
+
+    def continue_if(self):
+        """Handel.newContIf (:1044-1053)."""
+        c = self._net.counters()
+        down = self._net.attrs()["down"]
+        sc = self.scalars()
+        return bool((((c[4] == 0) | (sc["added_cycle"] > 0)) & (down == 0)).any())
