@@ -990,22 +990,28 @@ struct Handel {
       }
     }
     setReceivingRanks();
-    // emission lists: contact first the peers that gave you a good reception rank (:991-1013)
+    // emission lists: contact first the peers that gave you a good reception rank (:991-1013).
+    // The reference allocates a nodeCount-sized List[] per (sender, level); here one array is reused and only the
+    // touched ranks are visited (in increasing rank order, like the array walk of buildEmissionList) — same result.
+    std::vector<std::vector<int>> emissionList(static_cast<size_t>(params.nodeCount));
+    std::vector<int> touched;
     for (auto& up : nodes) {
       HNode* sender = up.get();
       if (sender->isDown()) continue;
       for (HLevel& l : sender->levels) {
-        std::vector<std::vector<int>> emissionList(static_cast<size_t>(params.nodeCount));
+        touched.clear();
         for (int cur = l.waitedSigs.nextSetBit(0); cur >= 0; cur = l.waitedSigs.nextSetBit(cur + 1)) {
           int recRank = node(cur).receptionRanks[static_cast<size_t>(sender->nodeId)];
+          if (emissionList[static_cast<size_t>(recRank)].empty()) touched.push_back(recRank);
           emissionList[static_cast<size_t>(recRank)].push_back(cur);
         }
         if (!l.peers.empty()) throw IllegalState("peers not empty");  // buildEmissionList :506-518
-        for (auto& ranks : emissionList) {
-          if (!ranks.empty()) {
-            if (ranks.size() > 1) javaShuffle(ranks, network.rd);
-            l.peers.insert(l.peers.end(), ranks.begin(), ranks.end());
-          }
+        std::sort(touched.begin(), touched.end());
+        for (int rk : touched) {
+          auto& ranks = emissionList[static_cast<size_t>(rk)];
+          if (ranks.size() > 1) javaShuffle(ranks, network.rd);
+          l.peers.insert(l.peers.end(), ranks.begin(), ranks.end());
+          ranks.clear();
         }
       }
     }
