@@ -594,6 +594,10 @@ class Engine {
     d.hPos = dupload(zerosNL);
     d.hOutFin = dupload(outFin);
     d.hBiz = dupload(biz);
+    {
+      std::vector<int> nohit((size_t)N * L, -2147483647 - 1);
+      d.hBizNoHit = dupload(nohit);
+    }
     d.hCntLast = dupload(cnt0);
     d.hCntInc = dupload(cnt0);
     d.hCntInd = dupload(cnt0);

@@ -613,30 +613,63 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
     }
   }
   c.sync();
-  // 2. createSuicideByzantineSig (:538-559), one lane per level
-  for (int l = 1 + c.lane(); l < L; l += C::LANES) {
+  // 2. createSuicideByzantineSig (:538-559).  All lanes scan the emission list of one level together.
+  //    (a) suicideBizAfter = first peer at or after the old index that is down and not blacklisted (or -1);
+  //    (b) the injected signature comes from the first such peer whose reception rank is < maxRank.  Reception
+  //        ranks only grow and the blacklist only grows, so once a scan up to maxRank R found nobody, no later
+  //        call with maxRank <= R can find anybody: hBizNoHit caches R and skips the (long) scan (b).
+  for (int l = 1; l < L; ++l) {
     int biz = d.hBiz[n * L + l];
-    if (sc->count[l] > 0 && biz >= 0) {
-      const int size = 1 << (l - 1);
-      const int maxRank = sc->minRank[l] + window;
-      bool reset = false;
-      for (int i = biz; i < size; ++i) {
+    if (sc->count[l] <= 0 || biz < 0) continue;
+    const int size = 1 << (l - 1);
+    const int maxRank = sc->minRank[l] + window;
+    int first = -1;
+    for (int base = biz; base < size && first < 0; base += C::LANES) {
+      int i = base + c.lane();
+      bool cand = false;
+      if (i < size) {
         int p = (int)peerAt(d, n, l, i);
-        if (d.ndown[p] && !rowBit(blRow, p)) {
-          if (!reset) {
-            biz = i;
-            reset = true;
-          }
-          int rk = d.hRanks[(size_t)n * d.N + p];
-          if (rk < maxRank) {
-            sc->hitPeer[l] = p;
-            sc->hitRank[l] = rk;
-            break;
+        cand = d.ndown[p] && !rowBit(blRow, p);
+      }
+      uint32_t m = c.ballot(cand);
+      if (m) {
+#if defined(__CUDA_ARCH__)
+        first = base + __ffs(m) - 1;
+#else
+        first = base;
+#endif
+      }
+    }
+    int hitP = -1, hitR = 0;
+    if (first >= 0 && maxRank > d.hBizNoHit[n * L + l]) {
+      for (int base = first; base < size && hitP < 0; base += C::LANES) {
+        int i = base + c.lane();
+        bool hit = false;
+        int p = 0, rk = 0;
+        if (i < size) {
+          p = (int)peerAt(d, n, l, i);
+          if (d.ndown[p] && !rowBit(blRow, p)) {
+            rk = d.hRanks[(size_t)n * d.N + p];
+            hit = rk < maxRank;
           }
         }
+        uint32_t m = c.ballot(hit);
+        if (m) {
+#if defined(__CUDA_ARCH__)
+          int src = __ffs(m) - 1;
+#else
+          int src = 0;
+#endif
+          hitP = c.bcast(p, src);
+          hitR = c.bcast(rk, src);
+        }
       }
-      if (!reset) biz = -1;
-      d.hBiz[n * L + l] = biz;
+      if (hitP < 0 && c.lane() == 0) d.hBizNoHit[n * L + l] = maxRank;
+    }
+    if (c.lane() == 0) {
+      d.hBiz[n * L + l] = first;  // -1: no Byzantine peer left in this level
+      sc->hitPeer[l] = hitP;
+      sc->hitRank[l] = hitR;
     }
   }
   c.sync();
