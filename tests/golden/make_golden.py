@@ -1,0 +1,75 @@
+"""Generates tests/golden/*.json: end-state digests of seeded runs, produced by the CPU oracle.
+
+The reference is Java and cannot run in this environment (no JVM), so these vectors are NOT outputs of the
+reference itself: they pin the oracle (regression) and give the GPU engine a fixed target that does not depend on
+the oracle being rebuilt.  Regenerate with:  python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests.oracle_lib import OracleGSF, OracleHandel, OraclePingPong, OracleSanFermin  # noqa: E402
+
+AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
+NB, NL = "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+CASES = {
+    "pingpong_1000": dict(kind="pingpong", args=[1000, None, None], steps=[100] * 10),
+    "gsf_32": dict(kind="gsf", args=[32, 32, 3, 20, 10, 10, 0, NB, NL], steps=[1] * 300),
+    "gsf_256_aws_tor": dict(kind="gsf", args=[256, 204, 4, 50, 20, 10, 25, AWS_NB, AWS_NL], steps=[7] * 300),
+    "gsf_1024_aws_tor": dict(kind="gsf", args=[1024, 870, 4, 50, 20, 10, 102, AWS_NB, AWS_NL], steps=[10] * 200),
+    "sanfermin_1024": dict(kind="sanfermin", args=[1024, 1024, 2, 48, 300, 1, None, None], steps=[10] * 400),
+    "handel_64_desync": dict(kind="handel", args=[64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False], steps=[1] * 1200),
+    "handel_256_byz": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, True], steps=[10] * 300),
+}
+
+
+def run_case(c, make):
+    p = make(c["kind"], c["args"])
+    p.init()
+    for s in c["steps"]:
+        p.run_ms(s)
+    return p
+
+
+def state_digest(kind, p, net=None):
+    """p exposes the same read-back names for oracle and engine wrappers (see tests/test_golden.py)."""
+    counters = p.counters() if net is None else net.counters()
+    if kind == "pingpong":
+        return digest(counters, p.pongs())
+    if kind == "gsf":
+        sc = p.scalars()
+        return digest(counters, p.verified(), sc["sig_checked"], sc["sig_queue_size"], sc["to_verify"])
+    if kind == "sanfermin":
+        sc = p.scalars()
+        return digest(counters, sc["agg"], sc["cpl"], sc["done"], sc["sent_requests"], sc["received_requests"], sc["threshold_at"])
+    if kind == "handel":
+        sc = p.scalars()
+        return digest(counters, p.rows(0), p.rows(1), p.rows(2), p.rows(5), sc["sigs_checked"], sc["sig_queue_size"], sc["msg_filtered"], sc["window"])
+    raise ValueError(kind)
+
+
+def make_oracle(kind, args):
+    return {"pingpong": OraclePingPong, "gsf": OracleGSF, "sanfermin": OracleSanFermin, "handel": OracleHandel}[kind](*args)
+
+
+if __name__ == "__main__":
+    out = {}
+    for name, c in CASES.items():
+        p = run_case(c, make_oracle)
+        out[name] = {"kind": c["kind"], "args": c["args"], "steps": c["steps"], "time": p.time, "digest": state_digest(c["kind"], p)}
+        print(name, out[name]["time"], out[name]["digest"][:16])
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "end_states.json"), "w"), indent=1)
