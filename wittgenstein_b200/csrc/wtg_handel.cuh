@@ -298,7 +298,10 @@ WTG_HD void hUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u64
   outDraws = 0;
   if (c.lane() == 0) statAdd(d, n, ST_UPDATES, 1ULL);
   if (meta & HMETA_BAD) {  // :687-694
-    if (c.lane() == 0) hRow(d.hBlack, d, n)[from >> 6] |= 1ULL << (from & 63);
+    if (c.lane() == 0) {
+      hRow(d.hBlack, d, n)[from >> 6] |= 1ULL << (from & 63);
+      d.hBizNoHit[n * L + (int)metaLevel(meta)] = -2147483647 - 1;  // a candidate left: recompute the minimum lazily
+    }
     c.sync();
     return;
   }
@@ -615,9 +618,9 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
   c.sync();
   // 2. createSuicideByzantineSig (:538-559).  All lanes scan the emission list of one level together.
   //    (a) suicideBizAfter = first peer at or after the old index that is down and not blacklisted (or -1);
-  //    (b) the injected signature comes from the first such peer whose reception rank is < maxRank.  Reception
-  //        ranks only grow and the blacklist only grows, so once a scan up to maxRank R found nobody, no later
-  //        call with maxRank <= R can find anybody: hBizNoHit caches R and skips the (long) scan (b).
+  //    (b) the injected signature comes from the first such peer whose reception rank is < maxRank.  hBizNoHit
+  //        holds the exact minimum rank over the level's candidates (recomputed lazily after a candidate's rank
+  //        was bumped or it was blacklisted), so "nobody qualifies" is answered without walking the list.
   for (int l = 1; l < L; ++l) {
     int biz = d.hBiz[n * L + l];
     if (sc->count[l] <= 0 || biz < 0) continue;
@@ -641,30 +644,61 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
       }
     }
     int hitP = -1, hitR = 0;
-    if (first >= 0 && maxRank > d.hBizNoHit[n * L + l]) {
-      for (int base = first; base < size && hitP < 0; base += C::LANES) {
-        int i = base + c.lane();
-        bool hit = false;
-        int p = 0, rk = 0;
-        if (i < size) {
-          p = (int)peerAt(d, n, l, i);
-          if (d.ndown[p] && !rowBit(blRow, p)) {
-            rk = d.hRanks[(size_t)n * d.N + p];
-            hit = rk < maxRank;
+    if (first >= 0) {
+      const int HB_DIRTY = -2147483647 - 1;
+      int bmin = d.hBizNoHit[n * L + l];  // exact minimum rank over the level's candidates, or HB_DIRTY
+      if (bmin == HB_DIRTY) {
+        // full pass: minimum rank over all candidates and, on the way, the first one below maxRank
+        int lmin = 0x7fffffff;
+        for (int base = first; base < size; base += C::LANES) {
+          int i = base + c.lane();
+          bool hit = false;
+          int p = 0, rk = 0;
+          if (i < size) {
+            p = (int)peerAt(d, n, l, i);
+            if (d.ndown[p] && !rowBit(blRow, p)) {
+              rk = d.hRanks[(size_t)n * d.N + p];
+              if (rk < lmin) lmin = rk;
+              hit = rk < maxRank;
+            }
+          }
+          uint32_t m = c.ballot(hit);
+          if (m && hitP < 0) {
+#if defined(__CUDA_ARCH__)
+            int src = __ffs(m) - 1;
+#else
+            int src = 0;
+#endif
+            hitP = c.bcast(p, src);
+            hitR = c.bcast(rk, src);
           }
         }
-        uint32_t m = c.ballot(hit);
-        if (m) {
+        lmin = c.minv(lmin);
+        if (c.lane() == 0) d.hBizNoHit[n * L + l] = lmin;
+      } else if (maxRank > bmin) {  // somebody qualifies: find the first one in emission order
+        for (int base = first; base < size && hitP < 0; base += C::LANES) {
+          int i = base + c.lane();
+          bool hit = false;
+          int p = 0, rk = 0;
+          if (i < size) {
+            p = (int)peerAt(d, n, l, i);
+            if (d.ndown[p] && !rowBit(blRow, p)) {
+              rk = d.hRanks[(size_t)n * d.N + p];
+              hit = rk < maxRank;
+            }
+          }
+          uint32_t m = c.ballot(hit);
+          if (m) {
 #if defined(__CUDA_ARCH__)
-          int src = __ffs(m) - 1;
+            int src = __ffs(m) - 1;
 #else
-          int src = 0;
+            int src = 0;
 #endif
-          hitP = c.bcast(p, src);
-          hitR = c.bcast(rk, src);
+            hitP = c.bcast(p, src);
+            hitR = c.bcast(rk, src);
+          }
         }
       }
-      if (hitP < 0 && c.lane() == 0) d.hBizNoHit[n * L + l] = maxRank;
     }
     if (c.lane() == 0) {
       d.hBiz[n * L + l] = first;  // -1: no Byzantine peer left in this level
@@ -815,6 +849,7 @@ WTG_HD int hCondPick(const Dev& d, int n, u64 drawIdx, bool apply) {
   int nr = (int)((uint32_t)*rk + (uint32_t)d.N);
   if (nr < 0) nr = 0x7fffffff;
   *rk = nr;
+  if (d.ndown[e.from]) d.hBizNoHit[n * d.L + lvl] = -2147483647 - 1;  // a candidate's rank moved
   d.hSigsChecked[n] += 1;
   if (metaKind(e.meta) == PK_POOL) WTG_ATOMIC_ADD(&d.poolRef[metaLevel(e.meta)][(uint32_t)e.pl], 1);
   Ev ev;

@@ -248,7 +248,7 @@ struct Dev {
   int* hPos;        // [N][L] posInLevel
   int* hOutFin;     // [N][L] outgoingFinished
   int* hBiz;        // [N][L] suicideBizAfter
-  int* hBizNoHit;   // [N][L] largest maxRank for which no Byzantine peer of the level qualified (monotone cache)
+  int* hBizNoHit;   // [N][L] minimum reception rank over the level's non-blacklisted Byzantine peers (INT_MIN = recompute)
   int* hCntLast;    // [N][L] |lastAggVerified|
   int* hCntInc;     // [N][L] |totalIncoming|
   int* hCntInd;     // [N][L] |verifiedIndSignatures|
