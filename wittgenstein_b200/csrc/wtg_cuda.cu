@@ -141,26 +141,35 @@ __global__ void k_dispatch_scatter(Dev d) {
 }
 
 // ---- handlers: warp per node ----------------------------------------------------------------
+// pass 1: one thread per node.  GSF / PingPong: message deliveries (they commute with the node's tasks, see
+// nodeProcess); SanFermin: everything (all handlers are scalar).  Leaves nodeTasks[n] = 1 when a warp is needed.
+__global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
+  if (d.ctl->error) return;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.N) return;
+  int flag = 0;
+  if (d.inboxFill[n] > 0) {
+    CoopSerial cs;
+    if (d.proto == PROTO_SANFERMIN)
+      nodeProcess(d, cs, n, 0);
+    else if (d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG)
+      flag = nodeProcess(d, cs, n, 1) > 0 ? 1 : 0;
+    else
+      flag = 1;
+  }
+  d.nodeTasks[n] = flag;
+}
+// pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
+// events do not commute (Handel), all of the node's events in reference order.
 __global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
   if (d.ctl->error) return;
   const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
   int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool coop = false;
-  if (threadIdx.x < NODE_SPAN && n < d.N && d.inboxFill[n] > 0) {
-    if (d.proto == PROTO_SANFERMIN) {
-      CoopSerial cs;  // every SanFermin handler is scalar: the node's events, in order, on one thread
-      nodeProcess(d, cs, n, 0);
-    } else if (split) {
-      CoopSerial cs;  // message deliveries: one thread per node
-      coop = nodeProcess(d, cs, n, 1) > 0;
-    } else {
-      coop = true;
-    }
-  }
+  bool coop = threadIdx.x < NODE_SPAN && n < d.N && d.nodeTasks[n] != 0;
   int total = blockCompact(coop, n, list, &cnt);
-  CoopWarp c;  // tasks (updateVerifiedSignatures / doCycle): one warp per node
+  CoopWarp c;
   for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k], split ? 2 : 0);
 }
 
@@ -613,9 +622,10 @@ class CudaBackend : public Backend {
     k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
     profEnd();
       profBegin(7);
+    k_node_msgs<<<(d.N + 255) / 256, 256, 0, st>>>(d);
     k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
     profEnd();
-      launches += 5;
+      launches += 6;
     }
     profBegin(3);
     k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 1);

@@ -168,6 +168,7 @@ class Engine {
     d.inboxCnt = dalloc<int>(N);
     d.inboxOff = dalloc<int>(N);
     d.inboxFill = dalloc<int>(N);
+    d.nodeTasks = dalloc<int>(N);
     d.inbox = dalloc<unsigned long long>((size_t)d.itemCap);
     d.subCount = dalloc<int>(d.bcap);
     d.itemBase = dalloc<int>(d.bcap);

@@ -212,6 +212,7 @@ struct Dev {
   int* inboxCnt;      // [N]  events addressed to the node this tick
   int* inboxOff;      // [N]
   int* inboxFill;     // [N]
+  int* nodeTasks;     // [N] node still has task items to run after the per-thread message pass
   unsigned long long* inbox;  // [bcap*? ] (key<<32 | entry index)
   int* subCount;      // [bcap] deliveries (+ re-push) of the event at processing position p
   int* itemBase;      // [bcap] exclusive scan of subCount
