@@ -61,15 +61,20 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
   CoopWarp c;
   for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) gsfCondScanQueue(d, c, list[k]);
 }
+// blocks are assigned to arena stripes (blockIdx & 63), so an item is found without walking the 64 counters
 __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
   if (d.ctl->error) return;
   const int per = d.workCap / ARENA_STRIPES;
-  const int total = stripedTotal(d.ctl->workCnt, per);
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  int cnt = d.ctl->workCnt[stripe];
+  if (cnt > per) cnt = per;
+  const int warpsPerBlock = blockDim.x >> 5;
+  const int sub = (blockIdx.x >> 6) * warpsPerBlock + (threadIdx.x >> 5);
+  const int nsub = (gridDim.x >> 6) * warpsPerBlock;
   CoopWarp c;
-  const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-  for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warpsPerGrid)
-  {
-    uint32_t it = d.workList[stripedIndex(d.ctl->workCnt, per, t)];
+  const uint32_t* wl = d.workList + (size_t)stripe * per;
+  for (int t = sub; t < cnt; t += nsub) {
+    uint32_t it = wl[t];
     if (d.proto == PROTO_HANDEL)
       hScoreItem(d, c, it);
     else
@@ -298,14 +303,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
 // ---- emit ------------------------------------------------------------------------------------
 __global__ void k_emit(Dev d) {
   if (d.ctl->error) return;
+  // conditional-task inserts (one per node) ...
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) emitCond(d, i);
+  // ... then the handlers' descriptors, blocks assigned to arena stripes
   const int per = d.descCap / ARENA_STRIPES;
-  int total = d.N + stripedTotal(d.ctl->descCnt, per);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    if (i < d.N)
-      emitCond(d, i);
-    else
-      emitDesc(d, stripedIndex(d.ctl->descCnt, per, i - d.N));
-  }
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  int cnt = d.ctl->descCnt[stripe];
+  if (cnt > per) cnt = per;
+  const int sub = (blockIdx.x >> 6) * blockDim.x + threadIdx.x;
+  const int nsub = (gridDim.x >> 6) * blockDim.x;
+  for (int j = sub; j < cnt; j += nsub) emitDesc(d, stripe * per + j);
 }
 
 // ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
@@ -414,8 +421,12 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
 __global__ void k_free(Dev d) {
   if (d.ctl->error) return;
   const int per = d.freeCap / ARENA_STRIPES;
-  int n = stripedTotal(d.ctl->freeCnt, per);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) freeApply(d, stripedIndex(d.ctl->freeCnt, per, i));
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  int cnt = d.ctl->freeCnt[stripe];
+  if (cnt > per) cnt = per;
+  const int sub = (blockIdx.x >> 6) * blockDim.x + threadIdx.x;
+  const int nsub = (gridDim.x >> 6) * blockDim.x;
+  for (int j = sub; j < cnt; j += nsub) freeApply(d, stripe * per + j);
 }
 
 // ---- init kernels ---------------------------------------------------------------------------
@@ -578,7 +589,7 @@ class CudaBackend : public Backend {
       k_hcond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
       profEnd();
       profBegin(14);
-      k_cond_score<<<sms * 8, 256, 0, st>>>(d);
+      k_cond_score<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(15);
       k_hcond_select<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
@@ -601,7 +612,7 @@ class CudaBackend : public Backend {
       k_cond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
       profEnd();
       profBegin(14);
-      k_cond_score<<<sms * 8, 256, 0, st>>>(d);
+      k_cond_score<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(15);
       k_cond_select<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
@@ -634,7 +645,7 @@ class CudaBackend : public Backend {
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
     profEnd();
     profBegin(8);
-    k_emit<<<wide, 256, 0, st>>>(d);
+    k_emit<<<ARENA_STRIPES * 16, 256, 0, st>>>(d);
     profEnd();
     profBegin(9);
     k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
@@ -646,7 +657,7 @@ class CudaBackend : public Backend {
     k_ms_scatter<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
     profEnd();
     profBegin(12);
-    k_free<<<sms, 256, 0, st>>>(d);
+    k_free<<<ARENA_STRIPES * 2, 256, 0, st>>>(d);
     profEnd();
     profBegin(13);
     k_end<<<1, 1, 0, st>>>(d, mode);

@@ -649,6 +649,21 @@ WTG_HD int gsfLastFinished(const Dev& d, int n) {
   return k;
 }
 
+// same, with one lane per level: L independent loads instead of a chain of dependent ones
+template <class C>
+WTG_HD int gsfLastFinishedCoop(const Dev& d, C& c, int n) {
+  if (C::LANES == 1) return gsfLastFinished(d, n);
+  int l = c.lane();
+  bool complete = l >= 1 && l < d.L && d.cntVer[n * d.L + l] == (1 << (l - 1));
+  uint32_t m = c.ballot(complete);
+  uint32_t t = ~(m >> 1);
+#if defined(__CUDA_ARCH__)
+  return __ffs(t) - 1;
+#else
+  return __builtin_ctz(t);
+#endif
+}
+
 // onNewSig (GSFSignature.java:537-555) — executed by lane 0 only
 WTG_HD void gsfOnNewSig(const Dev& d, int n, uint32_t from, uint32_t meta, u64 pl) {
   int l = (int)metaLevel(meta);
@@ -843,7 +858,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
   c.sync();
 
   if (d.accel > 0) {  // :438-451
-    int kf = gsfLastFinished(d, n);
+    int kf = gsfLastFinishedCoop(d, c, n);
     // count the sends first so the descriptor block can be allocated in one go
     int nSend = 0;
     for (int cur = l; cur <= kf && cur < L - 1;) {
