@@ -51,6 +51,54 @@ __device__ __forceinline__ int blockCompact(bool active, int n, int* list, int* 
   __syncthreads();
   return *cnt;
 }
+// append node n to a striped list (stripe = global warp index & 63; a stripe receives at most listStripeCap nodes)
+__device__ __forceinline__ void listAppend(const Dev& d, bool active, int n, int* cnt, int* list) {
+  unsigned m = __ballot_sync(0xffffffffu, active);
+  if (!m) return;
+  int lane = threadIdx.x & 31;
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int stripe = gw & (ARENA_STRIPES - 1);
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&cnt[stripe], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (active) list[(size_t)stripe * d.listStripeCap + base + __popc(m & ((1u << lane) - 1u))] = n;
+}
+// conditional-task bookkeeping, one thread per node -> list of due nodes
+__global__ void __launch_bounds__(256) k_cond_mark(Dev d) {
+  if (d.ctl->error) return;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  bool due = false;
+  if (n < d.N) due = d.proto == PROTO_HANDEL ? hCondMark(d, n) : gsfCondMark(d, n);
+  listAppend(d, due, n, d.ctl->dueCnt, d.dueList);
+}
+// one warp per due node, blocks assigned to list stripes
+template <int PHASE>
+__global__ void __launch_bounds__(256) k_cond_nodes(Dev d) {
+  extern __shared__ uint32_t keepAll[];
+  __shared__ HScratch scratch[8];
+  if (d.ctl->error) return;
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  const int cnt = d.ctl->dueCnt[stripe];
+  const int warp = threadIdx.x >> 5;
+  const int sub = (blockIdx.x >> 6) * 8 + warp;
+  const int nsub = (gridDim.x >> 6) * 8;
+  const int* list = d.dueList + (size_t)stripe * d.listStripeCap;
+  CoopWarp c;
+  for (int t = sub; t < cnt; t += nsub) {
+    int n = list[t];
+    if (PHASE == 0) {
+      if (d.proto == PROTO_HANDEL)
+        hCondScanQueue(d, c, n);
+      else
+        gsfCondScanQueue(d, c, n);
+    } else {
+      if (d.proto == PROTO_HANDEL)
+        hCondSelect(d, c, n, &scratch[warp]);
+      else
+        gsfCondSelect(d, c, n, keepAll + (size_t)warp * (size_t)(d.qcap / 32));
+    }
+  }
+}
 __global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
   __shared__ int list[NODE_BLOCK];
   __shared__ int cnt;
@@ -151,9 +199,8 @@ __global__ void k_dispatch_scatter(Dev d) {
 __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
   if (d.ctl->error) return;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d.N) return;
   int flag = 0;
-  if (d.inboxFill[n] > 0) {
+  if (n < d.N && d.inboxFill[n] > 0) {
     CoopSerial cs;
     if (d.proto == PROTO_SANFERMIN)
       nodeProcess(d, cs, n, 0);
@@ -162,7 +209,18 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
     else
       flag = 1;
   }
-  d.nodeTasks[n] = flag;
+  listAppend(d, flag != 0, n, d.ctl->taskCnt, d.taskList);
+}
+__global__ void __launch_bounds__(256) k_node_tasks(Dev d) {
+  if (d.ctl->error) return;
+  const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  const int cnt = d.ctl->taskCnt[stripe];
+  const int sub = (blockIdx.x >> 6) * 8 + (threadIdx.x >> 5);
+  const int nsub = (gridDim.x >> 6) * 8;
+  const int* list = d.taskList + (size_t)stripe * d.listStripeCap;
+  CoopWarp c;
+  for (int t = sub; t < cnt; t += nsub) nodeProcess(d, c, list[t], split ? 2 : 0);
 }
 // pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
 // events do not commute (Handel), all of the node's events in reference order.
@@ -586,13 +644,14 @@ class CudaBackend : public Backend {
     profEnd();
     if (d.proto == PROTO_HANDEL) {
       profBegin(1);
-      k_hcond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+      k_cond_nodes<0><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(14);
       k_cond_score<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(15);
-      k_hcond_select<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      k_cond_nodes<1><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(3);
       k_scan_partial<<<wide, SCAN_THREADS, 0, st>>>(d, 2);
@@ -608,16 +667,19 @@ class CudaBackend : public Backend {
     }
     if (d.proto == PROTO_GSF) {
       size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
+      size_t smem8 = (size_t)8 * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);
-      k_cond_scan<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+      k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+      k_cond_nodes<0><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(14);
       k_cond_score<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(15);
-      k_cond_select<<<nodeBlocks, NODE_BLOCK, smem, st>>>(d);
+      k_cond_nodes<1><<<ARENA_STRIPES * 19, 256, smem8, st>>>(d);
       profEnd();
-      launches += 3;
+      (void)smem;
+      launches += 4;
     }
     if (mode != 2) {
       profBegin(2);
@@ -634,7 +696,7 @@ class CudaBackend : public Backend {
     profEnd();
       profBegin(7);
     k_node_msgs<<<(d.N + 255) / 256, 256, 0, st>>>(d);
-    k_node<<<nodeBlocks, NODE_BLOCK, 0, st>>>(d);
+    k_node_tasks<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
     profEnd();
       launches += 6;
     }

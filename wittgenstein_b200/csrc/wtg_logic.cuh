@@ -1793,6 +1793,8 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
     c.descCnt[t] = 0;
     c.destCnt[t] = 0;
     c.workCnt[t] = 0;
+    c.dueCnt[t] = 0;
+    c.taskCnt[t] = 0;
   }
   c.nItems = 0;
   c.totalSlots = 0;

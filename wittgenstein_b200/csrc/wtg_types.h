@@ -147,6 +147,8 @@ struct Ctl {  // device-resident control block (one per engine)
   int destCnt[ARENA_STRIPES];   // multi-send destination scratch, per stripe
   int freeCnt[ARENA_STRIPES];   // deferred payload frees, per stripe
   int workCnt[ARENA_STRIPES];   // stale pooled queue entries to re-score this tick, per stripe
+  int dueCnt[ARENA_STRIPES];    // nodes whose conditional task runs this tick, per stripe
+  int taskCnt[ARENA_STRIPES];   // nodes with task events this tick, per stripe
   int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
   int poolFreeCnt[MAX_LEVELS][POOL_STRIPES];   // free slots per (level, stripe)
 };
@@ -213,6 +215,9 @@ struct Dev {
   int* inboxOff;      // [N]
   int* inboxFill;     // [N]
   int* nodeTasks;     // [N] node still has task items to run after the per-thread message pass
+  int* dueList;       // [64][listStripeCap] nodes whose conditional task runs this tick
+  int* taskList;      // [64][listStripeCap] nodes with task events this tick
+  int listStripeCap;
   unsigned long long* inbox;  // [bcap*? ] (key<<32 | entry index)
   int* subCount;      // [bcap] deliveries (+ re-push) of the event at processing position p
   int* itemBase;      // [bcap] exclusive scan of subCount
