@@ -83,14 +83,17 @@ def make_gsf(n, seed):
 
 def event_counts(st0, st1):
     return {k: st1[k] - st0[k] for k in ("deliveries", "tasks", "cond_runs", "draws", "eval_entries", "eval_words", "updates",
-                                         "cycles", "sends", "multi_sends", "send_words", "events")}
+                                         "cycles", "sends", "multi_sends", "send_words", "events", "update_words", "reevaluated")}
 
 
 def algorithmic_bytes(ev):
     """minimal traffic per event type of this engine's layout (bytes)."""
     b = {}
-    b["k_cond"] = 16 * ev["eval_entries"] + 8 * ev["eval_words"] + 16 * ev["eval_entries"] + 64 * ev["cond_runs"]
-    b["k_node"] = 96 * ev["deliveries"] + 8 * ev["send_words"] + 48 * (ev["sends"] + ev["multi_sends"]) + 128 * ev["updates"] + 64 * ev["cycles"]
+    b["k_cond_scan"] = 20 * ev["eval_entries"] + 24 * ev["reevaluated"] + 64 * ev["cond_runs"]   # entry + stamp; re-scored: counters + 2 row words
+    b["k_cond_score"] = 8 * ev["eval_words"]                                                  # payload, verified, indivVerified blocks
+    b["k_cond_select"] = 4 * ev["eval_entries"] + 24 * ev["eval_entries"] // 2 + 64 * ev["cond_runs"]  # scores; about half the entries move
+    b["k_node"] = (96 * ev["deliveries"] + 8 * (ev["send_words"] + ev["update_words"]) + 48 * (ev["sends"] + ev["multi_sends"])
+                   + 128 * ev["updates"] + 64 * ev["cycles"])
     b["k_emit"] = (48 + 32 + 4) * (ev["sends"] + ev["multi_sends"] + ev["cycles"] + ev["cond_runs"])
     b["k_ms_scatter"] = (32 + 32 + 4) * (ev["sends"] + ev["multi_sends"] + ev["cycles"] + ev["cond_runs"])
     return b
@@ -324,7 +327,8 @@ def main():
                     "traffic": None, "peak_source": "measured" if peaks else "fallback",
                     "avg_launch_us": 1000.0 * kms / kcnt, "algorithmic_bytes_per_launch": ab[kname] / kcnt,
                     "share_of_step": kms / total_ms,
-                    "kernel_ms": {k: round(v[0], 3) for k, v in prof.items()}}
+                    "kernel_ms": {k: round(v[0], 3) for k, v in prof.items()},
+                    "kernel_gbs": {k: round(ab[k] / (v[0] / 1000.0) / 1e9, 1) for k, v in prof.items() if k in ab and v[0] > 0}}
 
     line = {"metric": "simulated-ms/sec, GSFSignature 131,072 nodes", "value": value, "unit": "simulated-ms/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

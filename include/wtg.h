@@ -135,8 +135,8 @@ int wtg_gsf_level_scalars(wtg_net* net, int* pos, int* remaining, int* card);
 /* SFLevel.peers of one node / level — :239 ; returns the list length */
 int wtg_gsf_peers(wtg_net* net, int node, int level, int* out, int cap);
 
-/* engine statistics (24 int64), see wittgenstein_b200/network.py:Network.stats for the keys */
-int wtg_stats(wtg_net* net, long long* out24);
+/* engine statistics (26 int64), see wittgenstein_b200/network.py:Network.stats for the keys */
+int wtg_stats(wtg_net* net, long long* out26);
 
 /* measurement hooks (no reference counterpart): a CUDA-event stopwatch on the engine's stream, and
  * per-kernel event timing of the tick pipeline (names[i] are static strings) */

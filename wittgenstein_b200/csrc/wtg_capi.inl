@@ -362,10 +362,10 @@ int WTG_API(gsf_peers)(void* h, int node, int level, int* out, int cap) {
     return size;
   });
 }
-// stats (int64 x 24): deliveries, tasks, condRuns, draws, evalEntries, evalWords, updates, cycles, sends,
+// stats (int64 x 26; the last two: updateWords, reEvaluatedEntries): deliveries, tasks, condRuns, draws, evalEntries, evalWords, updates, cycles, sends,
 // multiSends, sendWords, events, maxQueue, maxBucket, maxInbox, recTop, recDestTop, kernelLaunches,
 // minPoolFree (over levels), initDraws, ring, bcap, qcap, peerBits
-int WTG_API(stats)(void* h, long long* out24) {
+int WTG_API(stats)(void* h, long long* out24) {  // out24 must hold 26 values
   return guard([&] {
     ENG.requireInited();
     wtg::Ctl c = ENG.readCtl();
@@ -380,6 +380,8 @@ int WTG_API(stats)(void* h, long long* out24) {
                        (long long)st[wtg::ST_MAXINBOX], c.recTop, c.recDestTop, wtg::backendLaunches(ENG.be.get()),
                        minFree, (long long)ENG.initDraws, ENG.d.ring, ENG.d.bcap, ENG.d.qcap, ENG.d.peerBits};
     std::memcpy(out24, v, sizeof(v));
+    out24[24] = (long long)st[wtg::ST_UPDATEWORDS];
+    out24[25] = (long long)st[wtg::ST_EVALPOOL];
     return 0;
   });
 }

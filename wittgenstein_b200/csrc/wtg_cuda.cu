@@ -1,9 +1,10 @@
 // wittgenstein_b200 — CUDA backend (sm_100a): the kernels of the tick pipeline and the C ABI.
 //
 // One simulated millisecond = one pass of this kernel sequence over SoA state resident in HBM:
-//   k_begin -> k_cond (conditional tasks, warp per node) -> k_dispatch_count -> pair scan A ->
-//   k_dispatch_scatter -> k_node (handlers, warp per node) -> pair scan B -> k_emit (seed / latency /
-//   arrival) -> multisplit (count, column scan, stable scatter into the time ring) -> k_free -> k_end
+//   k_begin -> k_cond_mark / k_cond_nodes<scan> / k_cond_score / k_cond_nodes<select> (conditional tasks) ->
+//   k_dispatch_count -> pair scan A -> k_dispatch_scatter -> k_node_msgs (thread per node) / k_node_tasks (warp per
+//   node) -> pair scan B -> k_emit (seed / latency / arrival) -> multisplit (count, column scan, stable scatter
+//   into the time ring) -> k_free -> k_end
 // All sizes are read from the device control block, so a whole runMs window is enqueued without
 // a host round trip.  See DESIGN.md §4 for why this reproduces the reference's sequential order.
 #include <cuda_runtime.h>
@@ -26,7 +27,6 @@ namespace wtg {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int NODE_BLOCK = WARPS_PER_BLOCK * 32;
-constexpr int NODE_SPAN = 32;  // nodes covered by one block of the handler kernels
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -35,22 +35,6 @@ __global__ void k_begin(Dev d, int mode) { tickBegin(d, mode); }
 __global__ void k_end(Dev d, int mode) { tickEnd(d, mode); }
 
 // ---- conditional tasks (checkSigs): scan -> score -> select ---------------------------------------
-// A block covers NODE_BLOCK consecutive nodes: one thread per node decides whether the node has work, the
-// block compacts those nodes into shared memory, then its warps take them one by one.  (Launching a warp for
-// every node cost ~60 us per tick in block dispatch alone at 131 072 nodes: profiles/r01.)
-__device__ __forceinline__ int blockCompact(bool active, int n, int* list, int* cnt) {
-  if (threadIdx.x == 0) *cnt = 0;
-  __syncthreads();
-  unsigned m = __ballot_sync(0xffffffffu, active);
-  if (m) {
-    int lane = threadIdx.x & 31, base = 0;
-    if (lane == 0) base = atomicAdd(cnt, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (active) list[base + __popc(m & ((1u << lane) - 1u))] = n;
-  }
-  __syncthreads();
-  return *cnt;
-}
 // append node n to a striped list (stripe = global warp index & 63; a stripe receives at most listStripeCap nodes)
 __device__ __forceinline__ void listAppend(const Dev& d, bool active, int n, int* cnt, int* list) {
   unsigned m = __ballot_sync(0xffffffffu, active);
@@ -99,16 +83,6 @@ __global__ void __launch_bounds__(256) k_cond_nodes(Dev d) {
     }
   }
 }
-__global__ void __launch_bounds__(NODE_BLOCK) k_cond_scan(Dev d) {
-  __shared__ int list[NODE_BLOCK];
-  __shared__ int cnt;
-  if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool due = threadIdx.x < NODE_SPAN && n < d.N && gsfCondMark(d, n);
-  int total = blockCompact(due, n, list, &cnt);
-  CoopWarp c;
-  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) gsfCondScanQueue(d, c, list[k]);
-}
 // blocks are assigned to arena stripes (blockIdx & 63), so an item is found without walking the 64 counters
 __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
   if (d.ctl->error) return;
@@ -129,42 +103,7 @@ __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
       gsfScoreItem(d, c, it);
   }
 }
-__global__ void __launch_bounds__(NODE_BLOCK) k_cond_select(Dev d) {
-  extern __shared__ uint32_t keepAll[];
-  __shared__ int list[NODE_BLOCK];
-  __shared__ int cnt;
-  if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool due = threadIdx.x < NODE_SPAN && n < d.N && d.condDue[n] != 0;
-  int total = blockCompact(due, n, list, &cnt);
-  CoopWarp c;
-  int warp = threadIdx.x >> 5;
-  for (int k = warp; k < total; k += WARPS_PER_BLOCK) gsfCondSelect(d, c, list[k], keepAll + (size_t)warp * (size_t)(d.qcap / 32));
-}
-
 // ---- Handel conditional pass (checkSigs): scan -> score -> select -> draw scan -> pick ---------------------
-__global__ void __launch_bounds__(NODE_BLOCK) k_hcond_scan(Dev d) {
-  __shared__ int list[NODE_BLOCK];
-  __shared__ int cnt;
-  if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool due = threadIdx.x < NODE_SPAN && n < d.N && hCondMark(d, n);
-  int total = blockCompact(due, n, list, &cnt);
-  CoopWarp c;
-  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) hCondScanQueue(d, c, list[k]);
-}
-__global__ void __launch_bounds__(NODE_BLOCK) k_hcond_select(Dev d) {
-  __shared__ int list[NODE_BLOCK];
-  __shared__ int cnt;
-  __shared__ HScratch scratch[WARPS_PER_BLOCK];
-  if (d.ctl->error) return;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool due = threadIdx.x < NODE_SPAN && n < d.N && d.condDue[n] != 0;
-  int total = blockCompact(due, n, list, &cnt);
-  CoopWarp c;
-  int warp = threadIdx.x >> 5;
-  for (int k = warp; k < total; k += WARPS_PER_BLOCK) hCondSelect(d, c, list[k], &scratch[warp]);
-}
 // does any nextInt(k) of this pass hit java.util.Random's rejection loop?  (probability ~ k / 2^31 per draw)
 __global__ void k_hpick_check(Dev d) {
   if (d.ctl->error) return;
@@ -211,6 +150,8 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
   }
   listAppend(d, flag != 0, n, d.ctl->taskCnt, d.taskList);
 }
+// pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
+// events do not commute (Handel), all of the node's events in reference order; blocks assigned to list stripes.
 __global__ void __launch_bounds__(256) k_node_tasks(Dev d) {
   if (d.ctl->error) return;
   const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
@@ -222,20 +163,6 @@ __global__ void __launch_bounds__(256) k_node_tasks(Dev d) {
   CoopWarp c;
   for (int t = sub; t < cnt; t += nsub) nodeProcess(d, c, list[t], split ? 2 : 0);
 }
-// pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
-// events do not commute (Handel), all of the node's events in reference order.
-__global__ void __launch_bounds__(NODE_BLOCK) k_node(Dev d) {
-  __shared__ int list[NODE_BLOCK];
-  __shared__ int cnt;
-  if (d.ctl->error) return;
-  const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
-  int n = blockIdx.x * NODE_SPAN + threadIdx.x;
-  bool coop = threadIdx.x < NODE_SPAN && n < d.N && d.nodeTasks[n] != 0;
-  int total = blockCompact(coop, n, list, &cnt);
-  CoopWarp c;
-  for (int k = threadIdx.x >> 5; k < total; k += WARPS_PER_BLOCK) nodeProcess(d, c, list[k], split ? 2 : 0);
-}
-
 // ---- pair scans ---------------------------------------------------------------------------
 __device__ __forceinline__ Pair pairAdd(Pair x, Pair y) {
   Pair r;
@@ -636,7 +563,6 @@ class CudaBackend : public Backend {
   }
 
   void enqueueTick(const Dev& d, int mode) {
-    const int nodeBlocks = (d.N + NODE_SPAN - 1) / NODE_SPAN;
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
     profBegin(0);
@@ -666,7 +592,6 @@ class CudaBackend : public Backend {
       launches += 7;
     }
     if (d.proto == PROTO_GSF) {
-      size_t smem = (size_t)WARPS_PER_BLOCK * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       size_t smem8 = (size_t)8 * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);
       k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
@@ -678,7 +603,6 @@ class CudaBackend : public Backend {
       profBegin(15);
       k_cond_nodes<1><<<ARENA_STRIPES * 19, 256, smem8, st>>>(d);
       profEnd();
-      (void)smem;
       launches += 4;
     }
     if (mode != 2) {

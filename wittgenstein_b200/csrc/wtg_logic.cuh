@@ -846,7 +846,10 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
     d.cntUnion[n * L + l] = cU;
     d.totalCard[n] = total;
   }
-  if (kind == PK_POOL && c.lane() == 0) freeDeferred(d, n, l, (uint32_t)pl);
+  if (kind == PK_POOL && c.lane() == 0) {
+    freeDeferred(d, n, l, (uint32_t)pl);
+    statAdd(d, n, ST_UPDATEWORDS, (unsigned long long)((changed ? 4 : 3) * b.nw));  // read payload ∥ indiv ∥ verified, write verified
+  }
   c.sync();
 
   outSlots = 0;

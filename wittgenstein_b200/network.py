@@ -111,11 +111,11 @@ class Network:
         return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
 
     def stats(self):
-        out = np.zeros(24, np.int64)
+        out = np.zeros(26, np.int64)
         self.api.check(self.api.stats(self.h, _p(out, C.c_longlong)))
         keys = ["deliveries", "tasks", "cond_runs", "draws", "eval_entries", "eval_words", "updates", "cycles", "sends",
                 "multi_sends", "send_words", "events", "max_queue", "max_bucket", "max_inbox", "rec_top", "rec_dest_top",
-                "kernel_launches", "min_pool_free", "init_draws", "ring", "bcap", "qcap", "peer_bits"]
+                "kernel_launches", "min_pool_free", "init_draws", "ring", "bcap", "qcap", "peer_bits", "update_words", "reevaluated"]
         return dict(zip(keys, out.tolist()))
 
     # ---- measurement hooks ----
