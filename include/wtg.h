@@ -74,6 +74,15 @@ int wtg_sanfermin_init(wtg_net* net);
  * hiddenByzantine != 0 is rejected (not built yet); badNodes is always drawn with Network.chooseBadNodes. */
 int wtg_handel_init(wtg_net* net, const int* params11);
 
+/* new CasperIMD(params) — protocols/CasperIMD.java:81-88 (the constructor builds the observer node on network.rd) and
+ * .init(new ByzBlockProducerWF(byz_delay, genesis)) — :472-508 (init() itself uses byz_delay 0).
+ * params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime,
+ *             attestationConstructionTime } (CasperParemeters :18-71).  Node ids: 0 observer, 1 the Byzantine producer,
+ * 2.. the other producers, then the attesters.  Device engine: ByzBlockProducerWF only; with randomOnTies a vote tie
+ * between two branches is reported as an error (the tie-break draws from network.rd inside a handler, :250-253). */
+int wtg_casper_construct(wtg_net* net, const int* params6);
+int wtg_casper_init(wtg_net* net, int byz_delay);
+
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);
 /* network.time — Network.java:49 */
@@ -108,6 +117,21 @@ int wtg_pingpong_pongs(wtg_net* net, int* out);
  * thresholdAt — protocols/SanFerminSignature.java:157-208 */
 int wtg_sanfermin_node_scalars(wtg_net* net, int* agg, int* cpl, int* done, int* thr_done, int* sent_req, int* recv_req,
                                int* swapping, long long* threshold_at);
+
+/* CasperIMD read-backs.  Blocks are numbered in creation order (Block.id, core/Block.java:10,49; genesis = 0).
+ * wtg_casper_blocks: per block height, parent id (-1), producer node id (-1), proposalTime, number of attestations it
+ * includes (CasperBlock.attestationsByHeight, CasperIMD.java:152); returns the block count.
+ * wtg_casper_block_attestations: those attestations as (attester node id, attestation height); returns their number.
+ * wtg_casper_node_state: per node head id (BlockChainNode.head), attestations received and distinct heads among them
+ * (attestationsByHead, CasperIMD.java:197), blocks received incl. genesis (blocksReceivedByBlockId), |blocksToReevaluate|,
+ * and an order-free 64-bit hash over (attester, height, head id) of the received attestations.
+ * wtg_casper_byz: { toSend, h, late, onTime, delay } of the ByzBlockProducerWF (:512-518, 648-649). */
+int wtg_casper_block_count(wtg_net* net);
+int wtg_casper_blocks(wtg_net* net, int* height, int* parent, int* producer, int* proposal_time, int* included);
+int wtg_casper_block_attestations(wtg_net* net, int block, int* attester, int* height, int cap);
+int wtg_casper_node_state(wtg_net* net, int* head, int* atts_received, int* heads_with_atts, int* blocks_received,
+                          int* to_reevaluate, unsigned long long* att_hash);
+int wtg_casper_byz(wtg_net* net, int* out5);
 
 /* HNode fields — protocols/Handel.java:280-298: 9 int arrays of N: startAt, nodePairingTime, sigsChecked, sigQueueSize,
  * msgFiltered, currWindowSize, addedCycle, totalSigSize(), total length of the toVerifyAgg lists */

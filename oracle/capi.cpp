@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "casper.hpp"
 #include "protocols.hpp"
 
 using namespace wo;
@@ -458,4 +459,123 @@ void wo_handel_ranks(void* h, int node, int32_t* out) {
   for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
 }
 
+
+// ---- CasperIMD ------------------------------------------------------------------------------
+// params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime, attestationConstructionTime }
+void* wo_casper_create(const int* p, const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  return new CasperIMD(CasperIMD::makeParams(p[0], p[1] != 0, p[2], p[3], p[4], p[5], nodeBuilderName ? nodeBuilderName : "",
+                                             networkLatencyName ? networkLatencyName : "", networkLatencyName == nullptr));
+  WO_CATCH(nullptr)
+}
+void wo_casper_destroy(void* h) { delete static_cast<CasperIMD*>(h); }
+void wo_casper_set_seed(void* h, int64_t s) { static_cast<CasperIMD*>(h)->network.rd.setSeed(s); }
+int wo_casper_init(void* h, int byzDelay) {
+  WO_TRY
+  auto* ci = static_cast<CasperIMD*>(h);
+  ci->init(ci->newByzWF(byzDelay));
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_casper_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<CasperIMD*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+double wo_casper_run_timed(void* h, int ms, int step) {  // wall seconds of `ms` simulated ms in runMs(step) slices
+  WO_TRY
+  auto* ci = static_cast<CasperIMD*>(h);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int done = 0; done < ms; done += step) ci->network.runMs(std::min(step, ms - done));
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  WO_CATCH(-1.0)
+}
+int wo_casper_time(void* h) { return static_cast<CasperIMD*>(h)->network.time; }
+int wo_casper_node_count(void* h) { return static_cast<int>(static_cast<CasperIMD*>(h)->network.allNodes.size()); }
+int64_t wo_casper_msgs_live(void* h) { return static_cast<CasperIMD*>(h)->network.msgs.live; }
+int wo_casper_msgs_size_at(void* h, int t) { return static_cast<CasperIMD*>(h)->network.msgs.sizeAt(t); }
+uint64_t wo_casper_rng_state(void* h) { return static_cast<CasperIMD*>(h)->network.rd.seed; }
+int64_t wo_casper_deliveries(void* h) { return static_cast<CasperIMD*>(h)->network.statDeliveries; }
+void wo_casper_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<CasperIMD*>(h)->network.allNodes, out5N); }
+void wo_casper_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<CasperIMD*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+void wo_casper_stop_node(void* h, int id) { static_cast<CasperIMD*>(h)->network.getNodeById(id).stop(); }
+void wo_casper_start_node(void* h, int id) { static_cast<CasperIMD*>(h)->network.getNodeById(id).start(); }
+int wo_casper_partition(void* h, float part) {
+  WO_TRY
+  static_cast<CasperIMD*>(h)->network.partition(part);
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_casper_block_count(void* h) { return 1 + static_cast<int>(static_cast<CasperIMD*>(h)->blocks.size()); }
+// blocks in id order, genesis first; ids are reported relative to the instance (genesis 0, first block 1)
+void wo_casper_blocks(void* h, int32_t* height, int32_t* parent, int32_t* producer, int32_t* proposalTime, int32_t* included) {
+  auto* ci = static_cast<CasperIMD*>(h);
+  height[0] = 0;
+  parent[0] = -1;
+  producer[0] = -1;
+  proposalTime[0] = 0;
+  included[0] = 0;
+  for (size_t i = 0; i < ci->blocks.size(); ++i) {
+    auto& b = *ci->blocks[i];
+    size_t k = static_cast<size_t>(b.id);
+    height[k] = b.height;
+    parent[k] = static_cast<int32_t>(b.parent->id);
+    producer[k] = b.producer->nodeId;
+    proposalTime[k] = b.proposalTime;
+    int c = 0;
+    for (auto& kv : b.attestationsByHeight) c += static_cast<int>(kv.second.size());
+    included[k] = c;
+  }
+}
+int wo_casper_block_attestations(void* h, int block, int32_t* attester, int32_t* height, int cap) {
+  auto* ci = static_cast<CasperIMD*>(h);
+  if (block <= 0) return 0;
+  auto& b = *ci->blocks.at(static_cast<size_t>(block - 1));
+  int k = 0;
+  for (auto& kv : b.attestationsByHeight)
+    for (auto* a : kv.second) {
+      if (k < cap) {
+        attester[k] = a->attester->nodeId;
+        height[k] = a->height;
+      }
+      ++k;
+    }
+  return k;
+}
+static inline uint64_t casperAttMix(int attester, int height, int head) {
+  return static_cast<uint64_t>(static_cast<uint32_t>(attester)) * 0x9E3779B97F4A7C15ULL +
+         static_cast<uint64_t>(static_cast<uint32_t>(height)) * 0xC2B2AE3D27D4EB4FULL +
+         static_cast<uint64_t>(static_cast<uint32_t>(head)) * 0x165667B19E3779F9ULL;
+}
+void wo_casper_node_state(void* h, int32_t* head, int32_t* attsReceived, int32_t* headsWithAtts, int32_t* blocksReceived,
+                          int32_t* toReevaluate, uint64_t* attHash) {
+  auto* ci = static_cast<CasperIMD*>(h);
+  for (size_t i = 0; i < ci->network.allNodes.size(); ++i) {
+    auto* n = static_cast<CasperIMD::CasperNode*>(ci->network.allNodes[i]);
+    head[i] = static_cast<int32_t>(n->head->id);
+    int cnt = 0;
+    uint64_t hs = 0;
+    for (auto& kv : n->attestationsByHead)
+      for (auto* a : kv.second) {
+        ++cnt;
+        hs += casperAttMix(a->attester->nodeId, a->height, static_cast<int>(a->head->id));
+      }
+    attsReceived[i] = cnt;
+    headsWithAtts[i] = static_cast<int32_t>(n->attestationsByHead.size());
+    blocksReceived[i] = static_cast<int32_t>(n->blocksReceivedByBlockId.size());
+    toReevaluate[i] = static_cast<int32_t>(n->blocksToReevaluate.size());
+    attHash[i] = hs;
+  }
+}
+void wo_casper_byz(void* h, int32_t* out5) {
+  auto* ci = static_cast<CasperIMD*>(h);
+  auto* b = static_cast<CasperIMD::ByzBlockProducerWF*>(ci->bps.at(0));
+  out5[0] = b->toSend;
+  out5[1] = b->h;
+  out5[2] = b->late;
+  out5[3] = b->onTime;
+  out5[4] = b->delay;
+}
 }  // extern "C"

@@ -35,7 +35,10 @@ class HostBackend : public Backend {
   void tick(const Dev& d, int mode) override {
     CoopSerial c;
     std::vector<uint32_t> keep((size_t)std::max(1, d.qcap));
-    tickBegin(d, mode);
+    if (d.ffwd && mode == 1)
+      tickBeginFfwd(d, c);
+    else
+      tickBegin(d, mode);
     if (d.ctl->error) return;
     if (d.proto == PROTO_GSF) {
       for (int n = 0; n < d.N; ++n)
@@ -78,6 +81,11 @@ class HostBackend : public Backend {
     {
       int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
       for (int t = 0; t < tot; ++t) emitDesc(d, stripedIndex(d.ctl->descCnt, per, t));
+    }
+    if (d.allCap > 0) {
+      std::vector<int> tmp((size_t)d.N), hist((size_t)ALL_HIST);
+      int cnt = std::min(d.ctl->allCnt, d.allCap);
+      for (int j = 0; j < cnt; ++j) emitAll(d, c, d.allList[j], tmp.data(), hist.data());
     }
     // multisplit: stable append into the ring in creation order
     int G = d.ctl->totalSlots;

@@ -41,6 +41,14 @@ def load():
     lib.wo_handel_msgs_live.restype = C.c_int64
     lib.wo_handel_run_timed.restype = C.c_double
     lib.wo_handel_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.wo_casper_create.restype = C.c_void_p
+    lib.wo_casper_create.argtypes = [C.POINTER(C.c_int), C.c_char_p, C.c_char_p]
+    lib.wo_casper_rng_state.restype = C.c_uint64
+    lib.wo_casper_msgs_live.restype = C.c_int64
+    lib.wo_casper_deliveries.restype = C.c_int64
+    lib.wo_casper_run_timed.restype = C.c_double
+    lib.wo_casper_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.wo_casper_partition.argtypes = [C.c_void_p, C.c_float]
     lib.wo_sf_create.restype = C.c_void_p
     lib.wo_sf_create.argtypes = [C.c_int] * 6 + [C.c_char_p, C.c_char_p]
     lib.wo_sf_rng_state.restype = C.c_uint64
@@ -369,3 +377,107 @@ class OracleHandel:
         if getattr(self, "h", None):
             self.lib.wo_handel_destroy(self.h)
             self.h = None
+
+
+class OracleCasper:
+    """protocols/CasperIMD.java through the oracle; init(byz_delay) = init(new ByzBlockProducerWF(byz_delay, genesis))."""
+
+    def __init__(self, cycle_length, random_on_ties, block_producers_count, attesters_per_round, block_construction_time,
+                 attestation_construction_time, node_builder, latency):
+        self.lib = load()
+        arr = np.array([cycle_length, 1 if random_on_ties else 0, block_producers_count, attesters_per_round,
+                        block_construction_time, attestation_construction_time], np.int32)
+        self.n = 1 + block_producers_count + attesters_per_round * cycle_length
+        self.h = C.c_void_p(self.lib.wo_casper_create(_p(arr, C.c_int), _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+
+    def __del__(self):
+        try:
+            self.lib.wo_casper_destroy(self.h)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_seed(self, s):
+        self.lib.wo_casper_set_seed(self.h, C.c_int64(s))
+
+    def init(self, byz_delay=0):
+        if self.lib.wo_casper_init(self.h, int(byz_delay)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def run_ms(self, ms):
+        r = self.lib.wo_casper_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    def run_timed(self, ms, step):
+        r = self.lib.wo_casper_run_timed(self.h, ms, step)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return r
+
+    @property
+    def time(self):
+        return self.lib.wo_casper_time(self.h)
+
+    def msgs_live(self):
+        return self.lib.wo_casper_msgs_live(self.h)
+
+    def msgs_size_at(self, t):
+        return self.lib.wo_casper_msgs_size_at(self.h, t)
+
+    def rng_state(self):
+        return int(self.lib.wo_casper_rng_state(self.h))
+
+    def deliveries(self):
+        return int(self.lib.wo_casper_deliveries(self.h))
+
+    def stop_node(self, i):
+        self.lib.wo_casper_stop_node(self.h, i)
+
+    def start_node(self, i):
+        self.lib.wo_casper_start_node(self.h, i)
+
+    def partition(self, part):
+        if self.lib.wo_casper_partition(self.h, C.c_float(part)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_casper_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_casper_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def blocks(self):
+        nb = self.lib.wo_casper_block_count(self.h)
+        v = [np.zeros(nb, np.int32) for _ in range(5)]
+        self.lib.wo_casper_blocks(self.h, *[_p(x, C.c_int32) for x in v])
+        return dict(zip(["height", "parent", "producer", "proposal_time", "included"], v))
+
+    def block_attestations(self, block):
+        cap = 1 << 16
+        while True:
+            att, h = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            k = self.lib.wo_casper_block_attestations(self.h, int(block), _p(att, C.c_int32), _p(h, C.c_int32), cap)
+            if k <= cap:
+                return sorted(zip(att[:k].tolist(), h[:k].tolist()))
+            cap = k
+
+    def node_state(self):
+        v = [np.zeros(self.n, np.int32) for _ in range(5)]
+        hs = np.zeros(self.n, np.uint64)
+        self.lib.wo_casper_node_state(self.h, *[_p(x, C.c_int32) for x in v], _p(hs, C.c_uint64))
+        d = dict(zip(["head", "atts_received", "heads_with_atts", "blocks_received", "to_reevaluate"], v))
+        d["att_hash"] = hs
+        return d
+
+    def byz(self):
+        out = np.zeros(5, np.int32)
+        self.lib.wo_casper_byz(self.h, _p(out, C.c_int32))
+        return dict(zip(["to_send", "h", "late", "on_time", "delay"], out.tolist()))

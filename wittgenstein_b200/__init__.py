@@ -2,5 +2,5 @@
 Protocol / Network / Node / Message surface (hot path only: see DESIGN.md)."""
 from ._lib import WtgError  # noqa: F401
 from .network import Network  # noqa: F401
-from .protocols import (GSFSignature, GSFSignatureParameters, Handel, HandelParameters, PingPong,  # noqa: F401
+from .protocols import (CasperIMD, CasperParemeters, GSFSignature, GSFSignatureParameters, Handel, HandelParameters, PingPong,  # noqa: F401
                         PingPongParameters, SanFerminSignature, SanFerminSignatureParameters)

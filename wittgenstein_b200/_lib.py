@@ -34,6 +34,13 @@ class Api:
         "sanfermin_construct": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "sanfermin_init": (C.c_int, [C.c_void_p]),
         "sanfermin_node_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 7 + [C.POINTER(C.c_longlong)]),
+        "casper_construct": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "casper_init": (C.c_int, [C.c_void_p, C.c_int]),
+        "casper_block_count": (C.c_int, [C.c_void_p]),
+        "casper_blocks": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
+        "casper_block_attestations": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+        "casper_node_state": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_ulonglong)]),
+        "casper_byz": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_node_scalars": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),

@@ -90,6 +90,8 @@ int WTG_API(set_tunable)(void* h, const char* key, long long v) {
     else if (k == "desc_cap") ENG.tun.descCap = v;
     else if (k == "rec_cap") ENG.tun.recCap = v;
     else if (k == "ring") ENG.tun.ring = v;
+    else if (k == "casper_votes") ENG.tun.casperVotes = v;
+    else if (k == "casper_blocks") ENG.tun.casperBlocks = v;
     else throw std::invalid_argument("unknown tunable " + k);
     return 0;
   });
@@ -118,6 +120,142 @@ int WTG_API(sanfermin_construct)(void* h, const int* params6) {
 int WTG_API(sanfermin_init)(void* h) {
   return guard([&] {
     ENG.sanferminInit();
+    return 0;
+  });
+}
+// params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime, attestationConstructionTime }
+int WTG_API(casper_construct)(void* h, const int* p) {
+  return guard([&] {
+    wtg::CasperParams cp{p[0], p[1], p[2], p[3], p[4], p[5]};
+    ENG.casperConstruct(cp);
+    return 0;
+  });
+}
+int WTG_API(casper_init)(void* h, int byzDelay) {
+  return guard([&] {
+    ENG.casperInit(byzDelay);
+    return 0;
+  });
+}
+static void requireCasper(wtg::Engine& e) {
+  e.requireInited();
+  if (e.d.proto != wtg::PROTO_CASPER) throw std::logic_error("not a CasperIMD network");
+}
+static inline unsigned long long casperAttMix(int attester, int height, int head) {
+  return (unsigned long long)(unsigned)attester * 0x9E3779B97F4A7C15ULL + (unsigned long long)(unsigned)height * 0xC2B2AE3D27D4EB4FULL +
+         (unsigned long long)(unsigned)head * 0x165667B19E3779F9ULL;
+}
+int WTG_API(casper_block_count)(void* h) {
+  return guard([&] {
+    requireCasper(ENG);
+    wtg::CasperG g;
+    ENG.fetch(&g, ENG.d.cg, 1);
+    return g.nBlocks;
+  });
+}
+// per block (index == id, genesis first): height, parent id (-1), producer node id (-1), proposalTime, attestations included
+int WTG_API(casper_blocks)(void* h, int* height, int* parent, int* producer, int* proposalTime, int* included) {
+  return guard([&] {
+    requireCasper(ENG);
+    wtg::CasperG g;
+    ENG.fetch(&g, ENG.d.cg, 1);
+    size_t nb = (size_t)std::min(g.nBlocks, ENG.d.cMaxBlocks);
+    ENG.fetch(height, ENG.d.cbHeight, nb);
+    ENG.fetch(parent, ENG.d.cbParent, nb);
+    ENG.fetch(producer, ENG.d.cbProducer, nb);
+    ENG.fetch(proposalTime, ENG.d.cbTime, nb);
+    std::vector<unsigned long long> inc(nb * (size_t)ENG.d.cAttWords);
+    ENG.fetch(inc.data(), ENG.d.cbIncluded, inc.size());
+    for (size_t b = 0; b < nb; ++b) {
+      int c = 0;
+      for (int w = 0; w < ENG.d.cAttWords; ++w) c += __builtin_popcountll(inc[b * (size_t)ENG.d.cAttWords + (size_t)w]);
+      included[b] = c;
+    }
+    return (int)nb;
+  });
+}
+// the attestations a block includes, as (attester node id, attestation height) pairs in attestation-index order
+int WTG_API(casper_block_attestations)(void* h, int block, int* attester, int* height, int cap) {
+  return guard([&] {
+    requireCasper(ENG);
+    if (block < 0 || block >= ENG.d.cMaxBlocks) throw std::invalid_argument("block");
+    std::vector<unsigned long long> inc((size_t)ENG.d.cAttWords);
+    ENG.fetch(inc.data(), ENG.d.cbIncluded + (size_t)block * ENG.d.cAttWords, inc.size());
+    std::vector<int> ah((size_t)ENG.d.cMaxAtts);
+    ENG.fetch(ah.data(), ENG.d.attHeight, ah.size());
+    int k = 0;
+    for (int a = 0; a < ENG.d.cMaxAtts; ++a)
+      if ((inc[(size_t)a >> 6] >> (a & 63)) & 1ULL) {
+        if (k < cap) {
+          attester[k] = ENG.d.cFirstAtt + a % ENG.d.cAttCount;
+          height[k] = ah[(size_t)a];
+        }
+        ++k;
+      }
+    return k;
+  });
+}
+// per node: head block id, attestations received, distinct heads among them (attestationsByHead.size()), blocks received
+// (genesis included), |blocksToReevaluate|, and an order-free hash of the received attestations (attester, height, head)
+int WTG_API(casper_node_state)(void* h, int* head, int* attsReceived, int* headsWithAtts, int* blocksReceived, int* toReevaluate,
+                               unsigned long long* attHash) {
+  return guard([&] {
+    requireCasper(ENG);
+    const wtg::Dev& d = ENG.d;
+    size_t n = (size_t)d.N;
+    ENG.fetch(head, d.cHead, n);
+    std::vector<int> ah((size_t)d.cMaxAtts), ahd((size_t)d.cMaxAtts);
+    ENG.fetch(ah.data(), d.attHeight, ah.size());
+    ENG.fetch(ahd.data(), d.attHead, ahd.size());
+    std::vector<unsigned long long> br(n * (size_t)d.cBlkWords), tr(n * (size_t)d.cBlkWords);
+    ENG.fetch(br.data(), d.cBlkRecv, br.size());
+    ENG.fetch(tr.data(), d.cToReeval, tr.size());
+    std::vector<unsigned long long> row((size_t)d.cAttWords);
+    std::vector<unsigned char> seen((size_t)d.cMaxBlocks);
+    for (size_t i = 0; i < n; ++i) {
+      int b = 0, t = 0;
+      for (int w = 0; w < d.cBlkWords; ++w) {
+        b += __builtin_popcountll(br[i * (size_t)d.cBlkWords + (size_t)w]);
+        t += __builtin_popcountll(tr[i * (size_t)d.cBlkWords + (size_t)w]);
+      }
+      blocksReceived[i] = b;
+      toReevaluate[i] = t;
+      ENG.fetch(row.data(), d.cAttRecv + i * (size_t)d.cAttWords, row.size());
+      std::fill(seen.begin(), seen.end(), 0);
+      int cnt = 0, heads = 0;
+      unsigned long long hs = 0;
+      for (int w = 0; w < d.cAttWords; ++w) {
+        unsigned long long bits = row[(size_t)w];
+        while (bits) {
+          int a = w * 64 + __builtin_ctzll(bits);
+          bits &= bits - 1;
+          ++cnt;
+          int hb = ahd[(size_t)a];
+          if (!seen[(size_t)hb]) {
+            seen[(size_t)hb] = 1;
+            ++heads;
+          }
+          hs += casperAttMix(d.cFirstAtt + a % d.cAttCount, ah[(size_t)a], hb);
+        }
+      }
+      attsReceived[i] = cnt;
+      headsWithAtts[i] = heads;
+      attHash[i] = hs;
+    }
+    return 0;
+  });
+}
+// out5 = { toSend, h, late, onTime, delay } of the ByzBlockProducerWF (node 1)
+int WTG_API(casper_byz)(void* h, int* out5) {
+  return guard([&] {
+    requireCasper(ENG);
+    wtg::CasperG g;
+    ENG.fetch(&g, ENG.d.cg, 1);
+    out5[0] = g.byzToSend;
+    out5[1] = g.byzH;
+    out5[2] = g.byzLate;
+    out5[3] = g.byzOnTime;
+    out5[4] = ENG.d.cByzDelay;
     return 0;
   });
 }

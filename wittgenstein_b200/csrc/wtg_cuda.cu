@@ -31,7 +31,14 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void k_begin(Dev d, int mode) { tickBegin(d, mode); }
+__global__ void k_begin(Dev d, int mode) {  // one warp
+  if (d.ffwd && mode == 1) {
+    CoopWarp c;
+    tickBeginFfwd(d, c);
+  } else if (threadIdx.x == 0) {
+    tickBegin(d, mode);
+  }
+}
 __global__ void k_end(Dev d, int mode) { tickEnd(d, mode); }
 
 // ---- conditional tasks (checkSigs): scan -> score -> select ---------------------------------------
@@ -145,7 +152,21 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
       nodeProcess(d, cs, n, 0);
     else if (d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG)
       flag = nodeProcess(d, cs, n, 1) > 0 ? 1 : 0;
-    else
+    else if (d.proto == PROTO_CASPER) {  // an inbox of attestations only is scalar work; blocks and tasks get a warp
+      const u64* in = d.inbox + d.inboxOff[n];
+      const Ev* bucket = d.buckets + (size_t)(d.ctl->tick & (d.ring - 1)) * (size_t)d.bcap;
+      int cnt = d.inboxFill[n];
+      bool simple = true;
+      for (int r = 0; r < cnt && simple; ++r) {
+        const Ev& ev = bucket[inboxEntry(in[r])];
+        uint32_t meta = ev.kind == EV_MULTI ? d.rec[ev.aux].meta : ev.meta;
+        simple = (ev.kind == EV_MSG || ev.kind == EV_MULTI) && meta == CM_ATT;
+      }
+      if (simple)
+        nodeProcess(d, cs, n, 0);
+      else
+        flag = 1;
+    } else
       flag = 1;
   }
   listAppend(d, flag != 0, n, d.ctl->taskCnt, d.taskList);
@@ -298,6 +319,18 @@ __global__ void k_emit(Dev d) {
   const int sub = (blockIdx.x >> 6) * blockDim.x + threadIdx.x;
   const int nsub = (gridDim.x >> 6) * blockDim.x;
   for (int j = sub; j < cnt; j += nsub) emitDesc(d, stripe * per + j);
+}
+
+// sendAll descriptors: one warp each (arrival per destination, stable counting sort by arrival)
+__global__ void __launch_bounds__(128) k_emit_all(Dev d) {
+  __shared__ int hist[4][ALL_HIST];
+  if (d.ctl->error) return;
+  int cnt = d.ctl->allCnt;
+  if (cnt > d.allCap) cnt = d.allCap;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * 4 + warp, nw = gridDim.x * 4;
+  CoopWarp c;
+  for (int j = gw; j < cnt; j += nw) emitAll(d, c, d.allList[j], d.allTmp + (size_t)gw * d.N, hist[warp]);
 }
 
 // ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
@@ -566,7 +599,7 @@ class CudaBackend : public Backend {
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
     profBegin(0);
-    k_begin<<<1, 1, 0, st>>>(d, mode);
+    k_begin<<<1, 32, 0, st>>>(d, mode);
     profEnd();
     if (d.proto == PROTO_HANDEL) {
       profBegin(1);
@@ -632,6 +665,10 @@ class CudaBackend : public Backend {
     profEnd();
     profBegin(8);
     k_emit<<<ARENA_STRIPES * 16, 256, 0, st>>>(d);
+    if (d.allCap > 0) {
+      k_emit_all<<<d.allWarps / 4, 128, 0, st>>>(d);
+      launches += 1;
+    }
     profEnd();
     profBegin(9);
     k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);

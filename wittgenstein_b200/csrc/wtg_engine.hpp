@@ -30,8 +30,14 @@ struct HandelParams {
       byzantineSuicide, hiddenByzantine;
 };
 
+struct CasperParams {  // CasperParemeters (protocols/CasperIMD.java:18-71), in declaration order
+  int cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime, attestationConstructionTime;
+};
+
 struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
+  long long casperVotes = 0;   // CasperIMD: attestations one attester may publish in a run (default 6)
+  long long casperBlocks = 0;  // CasperIMD: blocks of a run (default from casperVotes)
 };
 
 struct Backend {
@@ -116,7 +122,8 @@ class Engine {
     d.proto = proto;
     d.msgDiscardTime = msgDiscardTime;
     int ring = 2048;
-    int need = hm.latMax + 64;
+    int need = hm.latMax + 64 + ringExtra;
+    if (farEnabled) need *= 2;  // envelopes are "near" up to ring/2 ms ahead
     while (ring < need) ring <<= 1;
     if (tun.ring) ring = (int)tun.ring;
     d.ring = ring;
@@ -129,7 +136,7 @@ class Engine {
     d.destScratchCap = d.descCap;
     d.newEvCap = d.descCap + N;
     d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * N));
-    d.recDestCap = d.recCap * 4 + N + 1024;
+    d.recDestCap = recDestOverride ? recDestOverride : d.recCap * 4 + N + 1024;
     d.freeCap = d.descCap;
     d.latKind = hm.latKind;
     d.latParam = hm.latParam;
@@ -197,7 +204,16 @@ class Engine {
     d.recDest = dalloc<uint32_t>(d.recDestCap);
     d.recArrival = dalloc<int>(d.recDestCap);
     d.freeList = dalloc<uint32_t>(d.freeCap);
+    if (farEnabled) {
+      d.ffwd = 1;
+      d.farCap = 2 * N + 1024;
+      d.far = dalloc<FarEv>(d.farCap);
+      d.farSel = dalloc<int>(d.farCap);
+    }
   }
+  int recDestOverride = 0;  // sendAll protocols size the destination arena themselves
+  int ringExtra = 0;        // longest handler-chosen delay of a near envelope (e.g. blockConstructionTime)
+  bool farEnabled = false;  // far-future calendar + fast-forward (protocols without conditional tasks)
 
   Ctl readCtl() {
     Ctl c;
@@ -714,6 +730,134 @@ class Engine {
     inited = true;
   }
 
+  // ---- CasperIMD: the constructor builds the observer (CasperIMD.java:81-88); init(byzantineNode) the producers and
+  //      attesters with their periodic tasks (:478-508) ----
+  CasperParams cp{};
+  bool casperConstructed = false;
+  void casperConstruct(const CasperParams& p) {
+    requireNotInited();
+    if (casperConstructed) throw std::logic_error("already constructed");
+    if (p.cycleLength <= 0 || p.blockProducersCount <= 0 || p.attestersPerRound <= 0) throw std::invalid_argument("cycleLength / blockProducersCount / attestersPerRound must be positive");
+    if (p.blockConstructionTime <= 0 || p.attestationConstructionTime <= 0) throw std::invalid_argument("construction times must be positive (sendTime > time, Network.java:470-473)");
+    checkLatencyBuilder();
+    cp = p;
+    hm.buildNodes(1);  // network.addObserver(new CasperNode(false, genesis) {})
+    casperConstructed = true;
+  }
+  void casperInit(int byzDelay) {
+    requireNotInited();
+    if (!casperConstructed) throw std::logic_error("CasperIMD not constructed");
+    const int attCount = cp.attestersPerRound * cp.cycleLength;
+    const int N = 1 + cp.blockProducersCount + attCount;
+    if (CASPER_SLOT + byzDelay <= 0) throw std::invalid_argument("the Byzantine producer's first slot would start in the past");
+    hm.buildNodes(N - 1);  // byzantine producer, producers 1.., attesters — in this order (:479-507); registering tasks draws nothing
+    ringExtra = std::max(cp.blockConstructionTime, cp.attestationConstructionTime);
+    farEnabled = true;
+    const long long slots = 4LL * (cp.attestersPerRound + 2) + 64;  // sendAll envelopes alive at once, with margin
+    if (slots * N > 0x7fffffffLL) throw std::invalid_argument("attestersPerRound x nodes too large for the sendAll arena");
+    recDestOverride = (int)(slots * N);
+    if (!tun.recCap) tun.recCap = slots;
+    allocCommon(N, PROTO_CASPER);
+    const int maxVotes = (int)(tun.casperVotes ? tun.casperVotes : 6);
+    long long maxBlocks = tun.casperBlocks ? tun.casperBlocks : (long long)cp.cycleLength * (maxVotes + 1) + 64;
+    maxBlocks = (maxBlocks + 63) / 64 * 64;
+    if (maxBlocks > 64 * CASPER_MAX_BLKWORDS) maxBlocks = 64 * CASPER_MAX_BLKWORDS;
+    d.cCycle = cp.cycleLength;
+    d.cBpCount = cp.blockProducersCount;
+    d.cAttPerRound = cp.attestersPerRound;
+    d.cAttCount = attCount;
+    d.cBlockTime = cp.blockConstructionTime;
+    d.cAttTime = cp.attestationConstructionTime;
+    d.cRandomTies = cp.randomOnTies;
+    d.cByzDelay = byzDelay;
+    d.cMaxBlocks = (int)maxBlocks;
+    d.cBlkWords = (int)(maxBlocks / 64);
+    d.cMaxAtts = (attCount * maxVotes + 63) / 64 * 64;
+    d.cAttWords = d.cMaxAtts / 64;
+    d.cFirstAtt = 1 + cp.blockProducersCount;
+    std::vector<uint8_t> kind((size_t)N, CK_ATTESTER);
+    kind[0] = CK_OBSERVER;
+    kind[1] = CK_BYZ_WF;
+    for (int i = 1; i < cp.blockProducersCount; ++i) kind[(size_t)(1 + i)] = CK_PRODUCER;
+    d.cKind = dupload(kind);
+    d.cHead = dalloc<int>(N);
+    d.cVotes = dalloc<int>(N);
+    d.cAttRecv = dalloc<unsigned long long>((size_t)N * d.cAttWords);
+    std::vector<unsigned long long> br((size_t)N * d.cBlkWords, 0);
+    for (int i = 0; i < N; ++i) br[(size_t)i * d.cBlkWords] = 1ULL;  // blocksReceivedByBlockId.put(genesis.id, genesis)
+    d.cBlkRecv = dupload(br);
+    d.cToReeval = dalloc<unsigned long long>((size_t)N * d.cBlkWords);
+    std::vector<int> minus1((size_t)d.cMaxBlocks, -1);
+    d.cbHeight = dalloc<int>(d.cMaxBlocks);
+    d.cbParent = dupload(minus1);
+    d.cbProducer = dupload(minus1);
+    d.cbTime = dalloc<int>(d.cMaxBlocks);
+    d.cbIncluded = dalloc<unsigned long long>((size_t)d.cMaxBlocks * d.cAttWords);
+    d.attHead = dalloc<int>(d.cMaxAtts);
+    d.attHeight = dalloc<int>(d.cMaxAtts);
+    CasperG g;
+    std::memset(&g, 0, sizeof(g));
+    g.nBlocks = 1;
+    g.byzToSend = 1;
+    d.cg = dalloc<CasperG>(1);
+    be->upload(d.cg, &g, sizeof(g));
+    // sendAll machinery: records recycled over recSlots slots of N destinations
+    d.allCap = N + 64;
+    d.allList = dalloc<int>(d.allCap);
+    d.allWarps = 512;
+    d.allTmp = dalloc<int>((size_t)d.allWarps * N);
+    d.recSlots = std::min<int>(d.recCap, std::max(1, d.recDestCap / N));
+    // periodic tasks in registration order (:481-506): near ones straight into their bucket, the others into the calendar
+    struct Reg {
+      int node, startAt;
+    };
+    std::vector<Reg> regs;
+    regs.push_back({1, CASPER_SLOT + byzDelay});
+    for (int i = 1; i < cp.blockProducersCount; ++i) regs.push_back({1 + i, CASPER_SLOT * (i + 1)});
+    for (int i = 0; i < attCount; ++i) regs.push_back({d.cFirstAtt + i, CASPER_SLOT * (1 + i % cp.cycleLength) + 4000});
+    std::vector<FarEv> far;
+    std::vector<std::vector<Ev>> near((size_t)d.ring);
+    int farMin = 0x7fffffff;
+    unsigned long long seq = 0;
+    for (const Reg& r : regs) {
+      Ev ev;
+      std::memset(&ev, 0, sizeof(ev));
+      ev.kind = EV_PERIODIC;
+      ev.to = (uint32_t)r.node;
+      ev.from = (uint32_t)r.node;
+      if (r.startAt < d.ring / 2) {
+        near[(size_t)r.startAt].push_back(ev);
+      } else {
+        FarEv f;
+        std::memset(&f, 0, sizeof(f));
+        f.ev = ev;
+        f.target = r.startAt;
+        f.key = seq;
+        far.push_back(f);
+        farMin = std::min(farMin, r.startAt);
+      }
+      ++seq;
+    }
+    if ((int)far.size() > d.farCap) throw std::runtime_error("calendar capacity too small");
+    if (!far.empty()) be->upload(d.far, far.data(), far.size() * sizeof(FarEv));
+    for (int t = 0; t < d.ring; ++t)
+      if (!near[(size_t)t].empty()) {
+        if ((int)near[(size_t)t].size() > d.bcap) throw std::runtime_error("bucket capacity too small");
+        be->upload(d.buckets + (size_t)t * d.bcap, near[(size_t)t].data(), near[(size_t)t].size() * sizeof(Ev));
+        int cnt = (int)near[(size_t)t].size();
+        be->upload(d.bucketCount + t, &cnt, sizeof(int));
+      }
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    c.callId = 1;
+    c.rng = hm.rd.seed;
+    c.farCnt = (int)far.size();
+    c.farMin = farMin;
+    c.nextEvent = 0;  // unknown: the first window looks for itself
+    writeCtl(c);
+    inited = true;
+  }
+
   // ---- runMs  (Network.java:318-338) ----
   int runMs(int ms) {
     requireInited();
@@ -725,6 +869,28 @@ class Engine {
     c.until = (int)endAt;
     c.callId += 1;  // a new nextMessage() call starts with the window
     c.didSomething = 0;
+    if (d.ffwd) {  // no conditional tasks: only the milliseconds that hold an envelope are run
+      if (c.nextEvent > endAt) {  // nothing arrives in this window
+        c.time = (int)endAt;
+        writeCtl(c);
+        time = (int)endAt;
+        return 0;
+      }
+      c.idle = 0;
+      writeCtl(c);
+      for (long long done = 0;;) {
+        int batch = (int)std::min<long long>(8, std::max<long long>(1, ms - done));
+        be->ticks(d, batch);
+        done += batch;
+        c = readCtl();
+        if (c.error) throwDeviceError(c);
+        if (c.idle) break;
+        if (done > 2LL * ms + 16) throw std::runtime_error("internal: fast-forward did not converge");
+      }
+      time = (int)endAt;
+      if (c.time != time) throw std::runtime_error("internal: device clock out of step");
+      return c.didSomething ? 1 : 0;
+    }
     writeCtl(c);
     if (pendingAtNow) {
       be->tick(d, 0);
@@ -741,8 +907,10 @@ class Engine {
   void throwDeviceError(const Ctl& c) {
     static const char* names[] = {"ok", "time-bucket capacity exceeded", "toVerify queue capacity exceeded", "payload pool exhausted",
                                   "arrival beyond the time ring", "descriptor arena exceeded", "multi-destination record arena exceeded",
-                                  "deferred-free list exceeded", "internal error", "inbox overflow"};
-    throw std::runtime_error(std::string("device engine error: ") + names[c.error < 10 ? c.error : 8] + " (detail " + std::to_string(c.errorDetail) + ")");
+                                  "deferred-free list exceeded", "internal error", "inbox overflow", "far-future calendar exceeded",
+                                  "the protocol reached a state where the reference throws (IllegalState/IllegalArgument)",
+                                  "situation not supported by the device path"};
+    throw std::runtime_error(std::string("device engine error: ") + names[c.error < 13 ? c.error : 8] + " (detail " + std::to_string(c.errorDetail) + ")");
   }
 
   int msgsSize() {
@@ -752,14 +920,22 @@ class Engine {
     be->download(bc.data(), d.bucketCount, sizeof(int) * d.ring);
     long long s = 0;
     for (int v : bc) s += v;
+    if (d.farCap > 0) s += readCtl().farCnt;
     return (int)s;
   }
   int msgsSizeAt(int t) {
     requireInited();
-    if (t < time || t >= time + d.ring) return 0;
-    int v;
+    if (t < time) return 0;
+    int v = 0;
     be->sync();
-    be->download(&v, d.bucketCount + (t & ringMask), sizeof(int));
+    if (t < time + d.ring) be->download(&v, d.bucketCount + (t & ringMask), sizeof(int));
+    if (d.farCap > 0) {
+      Ctl c = readCtl();
+      std::vector<FarEv> far((size_t)c.farCnt);
+      if (c.farCnt) be->download(far.data(), d.far, far.size() * sizeof(FarEv));
+      for (const FarEv& f : far)
+        if (f.target == t) ++v;
+    }
     return v;
   }
 

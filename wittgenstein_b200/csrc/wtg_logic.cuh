@@ -1411,6 +1411,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
 
 }  // namespace wtg
 #include "wtg_handel.cuh"
+#include "wtg_casper.cuh"
 namespace wtg {
 
 // ------------------------------------------------------------------------------------------
@@ -1468,6 +1469,8 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
       gsfCycle(d, c, n, item, slots, draws);
 #endif
     }
+  } else if (d.proto == PROTO_CASPER) {
+    casperDeliver(d, c, n, ev.kind, meta, pl, item, slots, draws);
   } else if (d.proto == PROTO_SANFERMIN) {
     if (c.lane() == 0) sfHandle(d, n, from, meta, pl, item, slots, draws);
     slots = c.bcast(slots, 0);
@@ -1658,6 +1661,7 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
 WTG_HD void emitDesc(const Dev& d, int di) {
   const Ctl& ctl = *d.ctl;
   const Desc& ds = d.desc[di];
+  if (ds.dkind == DK_SEND_ALL) return;  // built by emitAll
   int g = d.slotBase[ds.item] + (int)ds.sub;
   if (g >= d.newEvCap) {
     setError(d, ERR_DESC_OVERFLOW, g);
@@ -1748,7 +1752,12 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     }
     if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL) freeDirect(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
   }
-  if (target >= 0 && target - ctl.tick >= d.ring) {
+  if (d.farCap > 0) {
+    if (target >= 0 && target - ctl.tick >= farHorizon(d)) {
+      farAppend(d, ev, target, g);
+      target = -1;
+    }
+  } else if (target >= 0 && target - ctl.tick >= d.ring) {
     setError(d, ERR_FAR_FUTURE, target);
     target = -1;
   }
@@ -1803,6 +1812,7 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
   c.totalSlots = 0;
   c.totalDraws = 0;
   c.hReject = 0;
+  c.allCnt = 0;
   if (c.nEv > c.maxBucket) c.maxBucket = c.nEv;
 }
 WTG_HD void tickEnd(const Dev& d, int mode) {
@@ -1816,6 +1826,7 @@ WTG_HD void tickEnd(const Dev& d, int mode) {
   }
   if (mode != 2) d.bucketCount[c.tick & (d.ring - 1)] = 0;
   for (int t = 0; t < ARENA_STRIPES; ++t) c.freeCnt[t] = 0;
+  if (d.proto == PROTO_CASPER && d.cg->createdThisTick > 1) setError(d, ERR_UNSUPPORTED, 4);
   if (d.proto == PROTO_GSF && (c.tick & 15) == 0)
     for (int l = INLINE_MAX_LEVEL + 1; l < d.L; ++l) {
       int f = 0;

@@ -29,7 +29,7 @@ constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bi
 constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
 
 // protocols
-enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4 };
+enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4, PROTO_CASPER = 5 };
 
 // event kinds (Ev.kind)
 enum : uint32_t {
@@ -56,6 +56,12 @@ enum : uint32_t { PP_PING = 1, PP_PONG = 2 };
 enum : uint32_t { SF_REQ = 1, SF_REPLY_OK = 2, SF_REPLY_NO = 3, SF_T_GO = 4, SF_T_TIMEOUT = 5, SF_T_TRANSITION = 6 };
 constexpr int SF_PENDCAP = 24;  // pendingNodes of the current level
 constexpr int SF_USEDCAP = 24;  // SanFerminHelper.usedNodes of the current level
+// CasperIMD message / task types (Ev.meta); Ev.pl = attestation index, block index, or block | height << 32
+enum : uint32_t { CM_ATT = 1, CM_BLOCK = 2, CT_BUILD = 3 };
+// CasperIMD node kinds (CasperIMD.java: observer :87, BlockProducer :365, Attester :444, ByzBlockProducerWF :647)
+enum : uint8_t { CK_OBSERVER = 0, CK_PRODUCER = 1, CK_ATTESTER = 2, CK_BYZ_WF = 6 };
+constexpr int CASPER_SLOT = 8000;  // CasperParemeters.SLOT_DURATION (CasperIMD.java:19)
+constexpr int CASPER_MAX_BLKWORDS = 8;  // at most 512 blocks per run on the device
 constexpr uint32_t DESC_SHUFFLE2 = 1u;  // Desc.aux: Collections.shuffle of the 2 destinations before the send (one extra draw)
 
 struct Ev {  // 32 bytes: one in-flight envelope / task
@@ -98,7 +104,8 @@ struct MultiRec {  // multi-destination envelope: sorted destinations + explicit
 enum : uint32_t {
   DK_SEND_SINGLE = 0,  // network.send(msg, from, to): one rd.nextInt()
   DK_SEND_MULTI = 1,   // network.send(msg, from, dests): one rd.nextInt()
-  DK_INSERT_AT = 2     // sendArriveAt / registerTask / multi-dest re-push: no draw
+  DK_INSERT_AT = 2,    // sendArriveAt / registerTask / multi-dest re-push: no draw
+  DK_SEND_ALL = 3      // network.sendAll(msg, sendTime, from): one rd.nextInt(); Desc.target = sendTime
 };
 struct Desc {  // 48 bytes
   uint32_t dkind;
@@ -124,6 +131,20 @@ enum : int {
   LAT_DIST = 5         // tab[dist]                      IC3NetworkLatency
 };
 
+struct FarEv {  // an envelope whose arrival lies beyond the time ring's horizon (periodic tasks with long periods)
+  Ev ev;
+  int target;
+  int pad;
+  unsigned long long key;  // (creation tick << 32) | creation index: insertion order among far envelopes
+};
+
+struct CasperG {  // CasperIMD: block counter and the Byzantine producer's scalars (CasperIMD.java:511-518, 648-649)
+  int nBlocks;    // blocks created so far, genesis included (Block.blockId, per engine)
+  int byzToSend, byzH, byzLate, byzOnTime;
+  int createdThisTick;  // two blocks created in one millisecond would need the reference's event order for their ids
+  int pad[2];
+};
+
 struct Ctl {  // device-resident control block (one per engine)
   int time;       // network.time
   int until;      // end of the current runMs window (inclusive)
@@ -141,6 +162,10 @@ struct Ctl {  // device-resident control block (one per engine)
   int errorDetail;
   int recTop, recDestTop;  // multi-destination record arenas
   int hReject;             // Handel: some nextInt(k) of this tick's conditional pass hit the rejection loop
+  int farCnt, farMin;      // far-future calendar: entries, earliest arrival (INT_MAX when empty)
+  int idle;                // fast-forward: nothing left to do before `until`
+  int nextEvent;           // fast-forward: earliest arrival after `until` known when the window went idle
+  int allCnt;              // sendAll descriptors of this tick
   int maxBucket;
   unsigned long long statDraws, statEvents;
   int descCnt[ARENA_STRIPES];   // descriptors allocated this tick, per stripe (stripe = node id & 63)
@@ -170,7 +195,10 @@ enum : int {
   ERR_REC_OVERFLOW = 6,
   ERR_FREE_OVERFLOW = 7,
   ERR_INTERNAL = 8,
-  ERR_INBOX_OVERFLOW = 9
+  ERR_INBOX_OVERFLOW = 9,
+  ERR_FAR_OVERFLOW = 10,
+  ERR_PROTO_STATE = 11,   // the reference would have thrown IllegalStateException / IllegalArgumentException in a handler
+  ERR_UNSUPPORTED = 12    // a situation the device path does not implement (detail says which)
 };
 
 // All device pointers + sizes; passed by value to kernels.
@@ -241,8 +269,36 @@ struct Dev {
   uint32_t* recDest;  // [recDestCap]
   int* recArrival;    // [recDestCap]
   uint32_t* freeList; // [freeCap] level<<27 | slot
+  // ---- far-future calendar / fast-forward over empty ticks (protocols without conditional tasks) ----
+  int ffwd;       // 1: a tick is the next non-empty millisecond of the window, not the next millisecond
+  int farCap;     // 0: arrivals beyond the ring are an error
+  FarEv* far;     // [farCap]
+  int* farSel;    // [farCap] scratch of the migration pass
+  // ---- sendAll ----
+  int allCap;     // sendAll descriptors per tick
+  int* allList;   // [allCap] descriptor indices
+  int* allTmp;    // [allWarps][N] unsorted arrivals of one sendAll
+  int allWarps;
+  int recSlots;   // sendAll records are recycled round-robin over this many slots of N destinations each
   // ---- PingPong ----
   int* pong;  // [N]
+  // ---- CasperIMD ----
+  int cCycle, cBpCount, cAttPerRound, cAttCount, cBlockTime, cAttTime, cRandomTies, cByzDelay;
+  int cMaxBlocks, cMaxAtts, cAttWords, cBlkWords, cFirstAtt;
+  CasperG* cg;
+  uint8_t* cKind;   // [N]
+  int* cHead;       // [N] block index of the node's head
+  int* cVotes;      // [N] attestations published so far (attesters)
+  unsigned long long* cAttRecv;   // [N][cAttWords] attestations received (attestationsByHead, all heads)
+  unsigned long long* cBlkRecv;   // [N][cBlkWords] blocksReceivedByBlockId
+  unsigned long long* cToReeval;  // [N][cBlkWords] blocksToReevaluate
+  int* cbHeight;    // [cMaxBlocks]
+  int* cbParent;    // [cMaxBlocks] (-1 for genesis)
+  int* cbProducer;  // [cMaxBlocks] node id (-1 for genesis)
+  int* cbTime;      // [cMaxBlocks] proposalTime
+  unsigned long long* cbIncluded;  // [cMaxBlocks][cAttWords] attestations newly included by the block
+  int* attHead;     // [cMaxAtts] block index the attestation votes for
+  int* attHeight;   // [cMaxAtts] slot of the vote
   // ---- Handel ----
   int hLevelWait, hFastPath, hExtraCycle, hByzSuicide, hWinInit, hWinMin, hWinMax;
   unsigned long long* hLastAgg;   // [N][W64] lastAggVerified (all levels of a node in one row)

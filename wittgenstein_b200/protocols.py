@@ -180,6 +180,84 @@ class SanFerminSignature:
         return d
 
 
+class CasperParemeters:
+    """CasperIMD.CasperParemeters (CasperIMD.java:18-71; the reference's spelling)."""
+
+    SLOT_DURATION = 8000
+
+    def __init__(self, cycle_length=4, random_on_ties=True, block_producers_count=2, attesters_per_round=20,
+                 block_construction_time=1000, attestation_construction_time=1, node_builder_name=None, network_latency_name=None):
+        self.cycle_length = cycle_length
+        self.random_on_ties = random_on_ties
+        self.block_producers_count = block_producers_count
+        self.attesters_per_round = attesters_per_round
+        self.attesters_count = attesters_per_round * cycle_length
+        self.block_construction_time = block_construction_time
+        self.attestation_construction_time = attestation_construction_time
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+
+
+class CasperIMD:
+    """CasperIMD (protocols/CasperIMD.java).  The constructor adds the observer (node 0, :81-88); init(byz_delay) is
+    init(new ByzBlockProducerWF(byz_delay, genesis)) (:472-508): node 1 is the Byzantine producer, then the other
+    producers, then the attesters.  Blocks are identified by their creation rank (genesis = 0)."""
+
+    def __init__(self, params, _api=None):
+        self.params = params
+        self._api = _api
+        self._net = Network(_api)
+        self._net.set_node_builder(params.node_builder_name)
+        self._net.set_network_latency(params.network_latency_name)
+        arr = np.array([params.cycle_length, 1 if params.random_on_ties else 0, params.block_producers_count,
+                        params.attesters_per_round, params.block_construction_time, params.attestation_construction_time], np.int32)
+        self._net.api.check(self._net.api.casper_construct(self._net.h, _p(arr, C.c_int)))
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return CasperIMD(self.params, self._api)
+
+    def node_count(self):
+        return 1 + self.params.block_producers_count + self.params.attesters_count
+
+    def init(self, byz_delay=0):
+        self._net.api.check(self._net.api.casper_init(self._net.h, int(byz_delay)))
+
+    def blocks(self):
+        a = self._net.api
+        nb = a.check(a.casper_block_count(self._net.h))
+        v = [np.zeros(nb, np.int32) for _ in range(5)]
+        a.check(a.casper_blocks(self._net.h, *[_p(x, C.c_int) for x in v]))
+        return dict(zip(["height", "parent", "producer", "proposal_time", "included"], v))
+
+    def block_attestations(self, block):
+        a = self._net.api
+        cap = 1 << 16
+        while True:
+            att, h = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            k = a.check(a.casper_block_attestations(self._net.h, int(block), _p(att, C.c_int), _p(h, C.c_int), cap))
+            if k <= cap:
+                return sorted(zip(att[:k].tolist(), h[:k].tolist()))
+            cap = k
+
+    def node_state(self):
+        n = self.node_count()
+        v = [np.zeros(n, np.int32) for _ in range(5)]
+        hs = np.zeros(n, np.uint64)
+        a = self._net.api
+        a.check(a.casper_node_state(self._net.h, *[_p(x, C.c_int) for x in v], _p(hs, C.c_ulonglong)))
+        d = dict(zip(["head", "atts_received", "heads_with_atts", "blocks_received", "to_reevaluate"], v))
+        d["att_hash"] = hs
+        return d
+
+    def byz(self):
+        out = np.zeros(5, np.int32)
+        self._net.api.check(self._net.api.casper_byz(self._net.h, _p(out, C.c_int)))
+        return dict(zip(["to_send", "h", "late", "on_time", "delay"], out.tolist()))
+
+
 class HandelParameters:
     """Handel.HandelParameters (Handel.java:22-142); window = WindowParameters() (16, 1, 128, ScoringExp(2, 4))."""
 
