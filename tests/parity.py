@@ -56,3 +56,33 @@ def run_lockstep(p, o, step, until, full_every=1):
         i += 1
         bad = compare_gsf(p, o, f"t={o.time}", full=(i % full_every == 0))
         assert not bad, bad
+
+
+def compare_casper(p, o, tag, atts=False):
+    """p: wittgenstein_b200.CasperIMD, o: tests.oracle_lib.OracleCasper.  Returns a list of mismatches."""
+    bad = []
+    net = p.network()
+    if net.time != o.time:
+        bad.append(f"{tag}: time {net.time} vs {o.time}")
+    if net.rng_state() != o.rng_state():
+        bad.append(f"{tag}: rd state differs")
+    if net.msgs_size() != o.msgs_live():
+        bad.append(f"{tag}: msgs.size() {net.msgs_size()} vs {o.msgs_live()}")
+    if not (net.counters() == o.counters()).all():
+        d = net.counters() != o.counters()
+        bad.append(f"{tag}: counters differ rows={np.argwhere(d.any(axis=1)).ravel().tolist()} nodes={np.argwhere(d.any(axis=0))[:5].ravel().tolist()}")
+    a, b = p.node_state(), o.node_state()
+    for k in a:
+        if not (a[k] == b[k]).all():
+            bad.append(f"{tag}: node {k} differs at {np.argwhere(a[k] != b[k])[:5].ravel().tolist()}")
+    a, b = p.blocks(), o.blocks()
+    for k in a:
+        if len(a[k]) != len(b[k]) or not (a[k] == b[k]).all():
+            bad.append(f"{tag}: blocks {k} differ")
+    if p.byz() != o.byz():
+        bad.append(f"{tag}: byzantine producer {p.byz()} vs {o.byz()}")
+    if atts and not bad:
+        for i in range(1, len(a["height"])):
+            if p.block_attestations(i) != o.block_attestations(i):
+                bad.append(f"{tag}: attestations of block {i} differ")
+    return bad

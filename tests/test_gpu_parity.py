@@ -176,6 +176,97 @@ def test_sanfermin_16384_shipped_scenario():
     assert not _sf_compare(p, o, "end")
 
 
+def _casper_pair(cyc, bpc, apr, nb, nl, seed, delay, until):
+    from tests.oracle_lib import OracleCasper
+    from wittgenstein_b200 import CasperIMD, CasperParemeters
+
+    p = CasperIMD(CasperParemeters(cyc, False, bpc, apr, 1000, 1, nb, nl))
+    o = OracleCasper(cyc, False, bpc, apr, 1000, 1, nb, nl)
+    if seed is not None:  # after construction: the observer was already drawn (CasperIMD.java:87)
+        p.network().set_seed(seed)
+        o.set_seed(seed)
+    p.network().set_tunable("casper_votes", until // (8000 * cyc) + 3)
+    p.init(delay); o.init(delay)
+    return p, o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cyc,bpc,apr,nb,nl,seed,delay,step,until", [
+    (5, 5, 80, None, None, None, 0, 1000, 60000),            # the fixture of PT/CasperIMDTest.java:11-13 through init()
+    (2, 2, 6, None, None, None, 0, 1, 20000),                # runMs(1) slicing
+    (3, 3, 20, None, None, None, 9000, 500, 200000),         # the Byzantine block arrives after its successor: forks + vote counting
+    (3, 3, 20, None, None, None, -7500, 500, 120000),        # ByzBlockProducerWF "late" path
+    (4, 2, 16, AWS_NB, AWS_NL, 7, 3000, 1000, 300000),       # AWS regions, Tor, re-seeded, several cycles
+    (1, 2, 2, None, "NetworkNoLatency", None, 0, 1000, 40000),  # PT/CasperByzantineTest.java:8-15
+])
+def test_casper_parity(cyc, bpc, apr, nb, nl, seed, delay, step, until):
+    """CasperIMD (blocks, attestations, fork choice, ByzBlockProducerWF) vs the oracle, every step."""
+    from tests.parity import compare_casper
+
+    p, o = _casper_pair(cyc, bpc, apr, nb, nl, seed, delay, until)
+    assert not compare_casper(p, o, "init")
+    for t in (8000 + delay, 12000, 20000):
+        assert p.network().msgs_size_at(t) == o.msgs_size_at(t)
+    while o.time < until:
+        assert p.network().run_ms(step) == o.run_ms(step)
+        bad = compare_casper(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert not compare_casper(p, o, "end", atts=True)
+    assert len(p.blocks()["height"]) > 2
+
+
+@pytest.mark.gpu
+def test_casper_byzantine_wf_schedule():
+    """PT/CasperByzantineTest.java:12-36 through the engine: observer head heights at 9 / 10 / 18 / 26 s."""
+    from wittgenstein_b200 import CasperIMD, CasperParemeters
+
+    p = CasperIMD(CasperParemeters(1, False, 2, 2, 1000, 1, None, "NetworkNoLatency"))
+    p.init(0)
+    net = p.network()
+    net.run_ms(9000)
+    assert p.node_state()["head"][0] == 0
+    net.run_ms(1000)
+    b = p.blocks()
+    assert b["height"][p.node_state()["head"][0]] == 1 and b["producer"][p.node_state()["head"][0]] == 1
+    net.run_ms(8000)
+    b = p.blocks()
+    assert b["height"][p.node_state()["head"][0]] == 2 and b["producer"][p.node_state()["head"][0]] != 1
+    net.run_ms(8000)
+    b = p.blocks()
+    assert b["height"][p.node_state()["head"][0]] == 3 and b["producer"][p.node_state()["head"][0]] == 1
+
+
+@pytest.mark.gpu
+def test_casper_stopped_nodes_and_partition():
+    """Stopped attesters neither vote nor receive; a partition drops cross-partition deliveries (Network.java:478-486, 606)."""
+    from tests.parity import compare_casper
+
+    p, o = _casper_pair(3, 3, 24, None, None, 4, 0, 120000)
+    for i in (10, 11, 40):
+        p.network().stop_node(i); o.stop_node(i)
+    for k in range(60):
+        assert p.network().run_ms(1000) == o.run_ms(1000)
+        if k == 20:
+            p.network().partition(0.4); o.partition(0.4)
+        if k == 30:
+            p.network().start_node(11); o.start_node(11)
+        bad = compare_casper(p, o, f"t={o.time}")
+        assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_casper_errors():
+    from wittgenstein_b200 import CasperIMD, CasperParemeters, WtgError
+
+    with pytest.raises(WtgError):
+        CasperIMD(CasperParemeters(0, False, 2, 2, 1000, 1))
+    p = CasperIMD(CasperParemeters(4, False, 3, 8, 1000, 1))
+    p.init(8000)  # the Byzantine producer and producer 2 would both create a block in millisecond 16000
+    with pytest.raises(WtgError):
+        for _ in range(10):
+            p.network().run_ms(4000)
+
+
 def _handel_compare(p, o, tag, full=True):
     bad = []
     if p.network().rng_state() != o.rng_state():

@@ -9,7 +9,7 @@
 //   * per node: attestations received (one bitmap over attestation indices = every set of attestationsByHead),
 //     blocks received, blocksToReevaluate (bitmaps over block indices), head;
 //   * per block: the attestations it newly includes (bitmap) = attestationsByHeight flattened (the height is attHeight).
-// blocksToReevaluate is folded in ascending block id (the reference's HashSet order is JVM-dependent, see oracle/casper.hpp).
+// blocksToReevaluate is folded in ascending block id (the reference's HashSet order is JVM-dependent).
 #pragma once
 
 namespace wtg {
