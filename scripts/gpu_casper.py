@@ -27,6 +27,15 @@ if oms:
         if bad:
             print("MISMATCH", bad); sys.exit(1)
     print("oracle parity OK to t=%d; oracle %.1f s wall, %d deliveries (%.0f sim-ms/s)" % (o.time, tc, o.deliveries(), oms / tc), flush=True)
+if os.environ.get("PROFILE"):
+    net.profile_enable(True)
+    for _ in range(5):
+        net.run_ms(8000)
+    prof = net.profile_read()
+    net.profile_enable(False)
+    tot = sum(v[0] for v in prof.values())
+    print("per-kernel ms over 5 slots (total %.1f):" % tot, {k: (round(v[0], 2), v[1]) for k, v in prof.items() if v[1]}, flush=True)
+    oms = net.time
 net.timer_start()
 t1 = time.time()
 while net.time < total:

@@ -69,10 +69,11 @@ class HostBackend : public Backend {
     }
     if (mode != 2) {
       int nEv = d.ctl->nEv;
-      for (int i = 0; i < nEv; ++i) dispatchCount(d, i);
+      const bool coopDispatch = d.allCap > 0;
+      for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchCountCoop(d, c, i) : dispatchCount(d, i);
       pairScan(d, 0);
       if (d.ctl->error) return;
-      for (int i = 0; i < nEv; ++i) dispatchScatter(d, i);
+      for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchScatterCoop(d, c, i) : dispatchScatter(d, i);
       for (int n = 0; n < d.N; ++n) nodeProcess(d, c, n, 0);
     }
     pairScan(d, 1);

@@ -131,11 +131,23 @@ __global__ void k_hpick_apply(Dev d) {
 __global__ void k_dispatch_count(Dev d) {
   if (d.ctl->error) return;
   int nEv = d.ctl->nEv;
+  if (d.allCap > 0) {  // sendAll protocols: a warp per bucket entry
+    CoopWarp c;
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = gw; i < nEv; i += nw) dispatchCountCoop(d, c, i);
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEv; i += gridDim.x * blockDim.x) dispatchCount(d, i);
 }
 __global__ void k_dispatch_scatter(Dev d) {
   if (d.ctl->error) return;
   int nEv = d.ctl->nEv;
+  if (d.allCap > 0) {
+    CoopWarp c;
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = gw; i < nEv; i += nw) dispatchScatterCoop(d, c, i);
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEv; i += gridDim.x * blockDim.x) dispatchScatter(d, i);
 }
 

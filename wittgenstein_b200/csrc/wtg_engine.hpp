@@ -878,8 +878,10 @@ class Engine {
       }
       c.idle = 0;
       writeCtl(c);
+      int grow = 8;
       for (long long done = 0;;) {
-        int batch = (int)std::min<long long>(8, std::max<long long>(1, ms - done));
+        int batch = (int)std::min<long long>(grow, std::max<long long>(1, ms - done));
+        if (grow < 64) grow *= 2;  // busy windows: fewer host round trips
         be->ticks(d, batch);
         done += batch;
         c = readCtl();

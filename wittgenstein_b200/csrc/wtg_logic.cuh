@@ -1655,6 +1655,86 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
   }
 }
 
+// Cooperative variants for protocols whose envelopes fan out to thousands of destinations (sendAll): one coop per
+// bucket entry; the destinations that arrive in this tick are found by bisection of the sorted arrivals and
+// handled a lane each.  Same results as dispatchCount / dispatchScatter.
+WTG_HD int multiUpper(const Dev& d, const MultiRec& rc, int tick) {  // first index >= cur whose arrival is after `tick`
+  int lo = (int)rc.cur, hi = (int)rc.n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (d.recArrival[rc.off + mid] <= tick)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+template <class C>
+WTG_HD void dispatchCountCoop(const Dev& d, C& c, int i) {
+  const Ctl& ctl = *d.ctl;
+  int p = ctl.nEv - 1 - i;
+  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  if (ev.kind == EV_MULTI) {
+    const MultiRec& rc = d.rec[ev.aux];
+    int cur = (int)rc.cur, up = multiUpper(d, rc, ctl.tick);
+    for (int j = cur + c.lane(); j < up; j += C::LANES) WTG_ATOMIC_ADD(&d.inboxCnt[d.recDest[rc.off + j]], 1);
+    if (c.lane() == 0) d.subCount[p] = (up - cur) + (up < (int)rc.n ? 1 : 0);
+  } else if (c.lane() == 0) {
+    WTG_ATOMIC_ADD(&d.inboxCnt[ev.to], 1);
+    d.subCount[p] = 1;
+  }
+}
+template <class C>
+WTG_HD void dispatchScatterCoop(const Dev& d, C& c, int i) {
+  const Ctl& ctl = *d.ctl;
+  int p = ctl.nEv - 1 - i;
+  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  int item0 = d.itemBase[p];
+  if (ev.kind != EV_MULTI) {
+    if (c.lane() == 0) {
+      int to = (int)ev.to;
+      int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+      d.inbox[s] = inboxMake(item0, i);
+    }
+    return;
+  }
+  MultiRec& rc = d.rec[ev.aux];
+  const int cur = (int)rc.cur, up = multiUpper(d, rc, ctl.tick), m = up - cur;
+  for (int j = cur + c.lane(); j < up; j += C::LANES) {
+    int to = (int)d.recDest[rc.off + j];
+    int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+    d.inbox[s] = inboxMake(item0 + (j - cur), i);
+  }
+  c.sync();
+  if (c.lane() == 0) {
+    if (up < (int)rc.n) {  // Network.java:629-632: re-push for the next destination, after the handler ran
+      int dst_ = i & (ARENA_STRIPES - 1), dper_ = d.descCap / ARENA_STRIPES;
+      int di = WTG_ATOMIC_ADD(&d.ctl->descCnt[dst_], 1);
+      if (di < dper_) {
+        Desc ds;
+        ds.dkind = DK_INSERT_AT;
+        ds.item = (uint32_t)(d.N + item0 + m);
+        ds.sub = 0;
+        ds.from = rc.from;
+        ds.to = d.recDest[rc.off + up];
+        ds.nDest = 0;
+        ds.evKind = EV_MULTI;
+        ds.meta = 0;
+        ds.pl = 0;
+        ds.target = d.recArrival[rc.off + up];
+        ds.aux = ev.aux;
+        d.desc[dst_ * dper_ + di] = ds;
+      } else {
+        setError(d, ERR_DESC_OVERFLOW, di);
+      }
+      d.evSlots[item0 + m] = 1;
+      d.evDraws[item0 + m] = 0;
+    }
+    rc.cur = (uint32_t)up;
+  }
+  c.sync();
+}
+
 // ------------------------------------------------------------------------------------------
 // emit: turn one descriptor into a new envelope (seed -> latency -> arrival), in creation order
 // ------------------------------------------------------------------------------------------
