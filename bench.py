@@ -164,8 +164,161 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+CASPER_NB, CASPER_NL = "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"
+
+
+def casper_cfg():
+    # CasperParemeters(64, false, 5, 256, 1000, 1, RANDOM builder, ByDistanceWJitter) -> 16 390 nodes
+    return dict(cycle_length=64, random_on_ties=False, block_producers_count=5, attesters_per_round=256,
+                block_construction_time=1000, attestation_construction_time=1, node_builder_name=CASPER_NB,
+                network_latency_name=CASPER_NL)
+
+
+def casper_oracle():
+    from tests.oracle_lib import OracleCasper
+
+    c = casper_cfg()
+    o = OracleCasper(c["cycle_length"], False, c["block_producers_count"], c["attesters_per_round"], 1000, 1, CASPER_NB, CASPER_NL)
+    o.init(0)
+    return o
+
+
+def casper_workload(K, W):
+    return (f"CasperIMD 16390 nodes (64-slot cycles, 5 producers incl. ByzBlockProducerWF(0), 256 attesters per slot), {CASPER_NB}, "
+            f"{CASPER_NL}; step = runMs(8000) = one slot of one run; {W} warm-up slots then {K} timed slots of the same network")
+
+
+def run_casper_reference(args):
+    o = casper_oracle()
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        o.run_ms(8000)
+    d0 = o.deliveries()
+    wall = o.run_timed(8000 * K, 8000)
+    val = 8000 * K / wall
+    print(json.dumps({"impl": "reference", "metric": "simulated-ms/sec, CasperIMD 16,390 nodes", "value": val, "unit": "simulated-ms/s",
+                      "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1000 * wall / K, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitmaps / int32", "data": "synthetic",
+                      "config": {"workload": casper_workload(K, W), "note": "reference = C++ oracle port, 1 thread; Java reference not runnable here (no JVM)"},
+                      "msgs_per_s": (o.deliveries() - d0) / wall,
+                      "cpu_baseline": {"value": val, "unit": "simulated-ms/s", "cores": 1, "kind": "port", "sample": f"slots {W}..{W+K} of the run"},
+                      "e2e": {"value": val, "unit": "simulated-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks):
+    """--workload casper: SURVEY.md §8d config #4 on the device engine (replicas with different seeds for N > 1)."""
+    import torch
+
+    from wittgenstein_b200 import CasperIMD, CasperParemeters
+
+    K, W = args.steps, args.warmup
+
+    def make():
+        p = CasperIMD(CasperParemeters(**casper_cfg()))
+        p.network().set_seed(rank)
+        p.network().set_tunable("casper_votes", (K + W) // 64 + 3)
+        p.init(0)
+        return p
+
+    # pass 1: device-timed
+    p = make()
+    net = p.network()
+    for _ in range(W):
+        net.run_ms(8000)
+    st0 = net.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    net.timer_start()
+    for _ in range(K):
+        net.run_ms(8000)
+    dev_ms = max_over_ranks(net.timer_stop_ms())
+    torch.cuda.synchronize()
+    barrier()
+    sampler.stop_flag = True
+    st1 = net.stats()
+    heads_end = p.heads()
+    nblocks = len(p.blocks()["height"])
+    del p, net
+    # pass 2: end to end with the read-backs a caller makes after every slot (heads + the five node counters)
+    p = make()
+    net = p.network()
+    for _ in range(W):
+        net.run_ms(8000)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(K):
+        net.run_ms(8000)
+        heads = p.heads()
+        cnt = net.counters()
+        d2h = heads.nbytes + cnt.nbytes
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert (heads == heads_end).all(), "e2e pass diverged from the device-timed pass"
+    del p, net
+    # pass 3: per-kernel timing
+    prof = {}
+    if not args.no_profile:
+        p = make()
+        net = p.network()
+        for _ in range(W):
+            net.run_ms(8000)
+        net.profile_enable(True)
+        for _ in range(K):
+            net.run_ms(8000)
+        prof = net.profile_read()
+        net.profile_enable(False)
+        del p, net
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        o = casper_oracle()
+        t1 = time.time()
+        wall = o.run_timed(8000 * 6, 8000)
+        cpu = {"value": 48000 / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
+               "sample": f"oracle (C++ restatement, 1 thread), same configuration, slots 0..6 ({o.deliveries()} deliveries) in {wall:.1f} s",
+               "msgs_per_s": o.deliveries() / wall}
+        del o
+    deliveries = st1["deliveries"] - st0["deliveries"]
+    tasks = st1["tasks"] - st0["tasks"]
+    value = sum_over_ranks(K * 8000) / (dev_ms / 1000.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {"metric": "simulated-ms/sec, CasperIMD 16,390 nodes", "value": value, "unit": "simulated-ms/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bitmaps / int32", "data": "synthetic",
+            "config": {"workload": casper_workload(K, W), "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas",
+                       "l2": "launch-bound: ~340 non-empty milliseconds per slot, ~12 k deliveries each; working set (attestation bitmaps 200 MB) exceeds L2",
+                       "blocks_at_end": nblocks},
+            "msgs_per_s": sum_over_ranks(deliveries + tasks) / (dev_ms / 1000.0),
+            "e2e": {"value": sum_over_ranks(K * 8000) / e2e_s, "unit": "simulated-ms/s", "h2d_bytes_per_step": 6000, "d2h_bytes_per_step": int(d2h + 18000)},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]), "clocks": sampler.summary()}
+    if prof:
+        kname, (kms, kcnt) = max(prof.items(), key=lambda kv: kv[1][0])
+        total_ms = sum(v[0] for v in prof.values())
+        ab = 104 * deliveries  # Casper deliver = 96 B + 8 B bitmap RMW
+        line["roofline"] = {"bound": "hbm", "kernel": "whole tick pipeline (no kernel dominates: each is at its launch floor)",
+                            "achieved": ab / (dev_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s", "frac": ab / (dev_ms / 1000.0) / 1e9 / peak,
+                            "traffic": None, "peak_source": "measured" if peaks else "fallback", "top_kernel": kname,
+                            "share_of_step": kms / total_ms, "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+                            "ticks": int(prof.get("k_begin", (0, 0))[1])}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="gsf", choices=["gsf", "casper"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=22)
     ap.add_argument("--warmup", type=int, default=3)
@@ -186,7 +339,7 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args)
+            run_casper_reference(args) if args.workload == "casper" else run_reference(args)
         return
 
     import torch
@@ -221,6 +374,10 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.workload == "casper":
+        run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks)
+        return
 
     n, K, W, S = args.nodes, args.steps, args.warmup, args.step_ms
     seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)

@@ -131,6 +131,7 @@ int wtg_casper_blocks(wtg_net* net, int* height, int* parent, int* producer, int
 int wtg_casper_block_attestations(wtg_net* net, int block, int* attester, int* height, int cap);
 int wtg_casper_node_state(wtg_net* net, int* head, int* atts_received, int* heads_with_atts, int* blocks_received,
                           int* to_reevaluate, unsigned long long* att_hash);
+int wtg_casper_heads(wtg_net* net, int* head); /* BlockChainNode.head of every node (block id) */
 int wtg_casper_byz(wtg_net* net, int* out5);
 
 /* HNode fields — protocols/Handel.java:280-298: 9 int arrays of N: startAt, nodePairingTime, sigsChecked, sigQueueSize,

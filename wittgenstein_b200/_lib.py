@@ -40,6 +40,7 @@ class Api:
         "casper_blocks": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
         "casper_block_attestations": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
         "casper_node_state": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_ulonglong)]),
+        "casper_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "casper_byz": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_node_scalars": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

@@ -245,6 +245,13 @@ int WTG_API(casper_node_state)(void* h, int* head, int* attsReceived, int* heads
     return 0;
   });
 }
+int WTG_API(casper_heads)(void* h, int* head) {
+  return guard([&] {
+    requireCasper(ENG);
+    ENG.fetch(head, ENG.d.cHead, (size_t)ENG.d.N);
+    return 0;
+  });
+}
 // out5 = { toSend, h, late, onTime, delay } of the ByzBlockProducerWF (node 1)
 int WTG_API(casper_byz)(void* h, int* out5) {
   return guard([&] {

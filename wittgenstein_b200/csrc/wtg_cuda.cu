@@ -485,7 +485,8 @@ class CudaBackend : public Backend {
   cudaGraphExec_t tickGraph = nullptr;
   const void* graphFor = nullptr;
   bool useGraph = true;
-  long long launches = 0;
+  long long launches = 0;      // kernels enqueued (graph replays counted kernel by kernel)
+  long long graphKernels = 0;
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   // per-kernel profiling
   static constexpr int NK = 16;
@@ -719,14 +720,18 @@ class CudaBackend : public Backend {
     if (!tickGraph || graphFor != (const void*)d.ctl) {
       if (tickGraph) cudaGraphExecDestroy(tickGraph);
       cudaGraph_t g;
+      long long before = launches;
       CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       enqueueTick(d, 1);
       CUDA_OK(cudaStreamEndCapture(st, &g));
+      graphKernels = launches - before;  // kernels per replay
+      launches = before;
       CUDA_OK(cudaGraphInstantiate(&tickGraph, g, 0));
       cudaGraphDestroy(g);
       graphFor = (const void*)d.ctl;
     }
     for (int i = 0; i < count; ++i) CUDA_OK(cudaGraphLaunch(tickGraph, st));
+    launches += graphKernels * count;
   }
   void gsfInitNodes(const Dev& d) override {
     k_gsf_init_nodes<<<(d.N + 255) / 256, 256, 0, st>>>(d);

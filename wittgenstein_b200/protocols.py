@@ -252,6 +252,11 @@ class CasperIMD:
         d["att_hash"] = hs
         return d
 
+    def heads(self):
+        out = np.zeros(self.node_count(), np.int32)
+        self._net.api.check(self._net.api.casper_heads(self._net.h, _p(out, C.c_int)))
+        return out
+
     def byz(self):
         out = np.zeros(5, np.int32)
         self._net.api.check(self._net.api.casper_byz(self._net.h, _p(out, C.c_int)))
