@@ -13,7 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from tests.oracle_lib import OracleGSF, OracleHandel, OraclePingPong, OracleSanFermin  # noqa: E402
+from tests.oracle_lib import OracleCasper, OracleGSF, OracleHandel, OraclePingPong, OracleSanFermin  # noqa: E402
 
 AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
 NB, NL = "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"
@@ -34,12 +34,18 @@ CASES = {
     "sanfermin_1024": dict(kind="sanfermin", args=[1024, 1024, 2, 48, 300, 1, None, None], steps=[10] * 400),
     "handel_64_desync": dict(kind="handel", args=[64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False], steps=[1] * 1200),
     "handel_256_byz": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, True], steps=[10] * 300),
+    # casper args: cycleLength, randomOnTies, producers, attestersPerRound, blockTime, attestationTime, builder, latency ; byzDelay
+    "casper_3x20_forks": dict(kind="casper", args=[3, False, 3, 20, 1000, 1, None, None], delay=9000, steps=[500] * 400),
+    "casper_4x16_aws_late": dict(kind="casper", args=[4, False, 2, 16, 1000, 1, "AWS_SPEED=GAUSSIAN_TOR=0.33", AWS_NL], delay=-7000, steps=[1000] * 200),
 }
 
 
 def run_case(c, make):
     p = make(c["kind"], c["args"])
-    p.init()
+    if c["kind"] == "casper":
+        p.init(c["delay"])
+    else:
+        p.init()
     for s in c["steps"]:
         p.run_ms(s)
     return p
@@ -59,11 +65,17 @@ def state_digest(kind, p, net=None):
     if kind == "handel":
         sc = p.scalars()
         return digest(counters, p.rows(0), p.rows(1), p.rows(2), p.rows(5), sc["sigs_checked"], sc["sig_queue_size"], sc["msg_filtered"], sc["window"])
+    if kind == "casper":
+        st, b = p.node_state(), p.blocks()
+        atts = [np.array(p.block_attestations(i), np.int32).reshape(-1, 2) for i in range(1, len(b["height"]))]
+        return digest(counters, st["head"], st["atts_received"], st["heads_with_atts"], st["blocks_received"], st["to_reevaluate"],
+                      st["att_hash"], b["height"], b["parent"], b["producer"], b["proposal_time"], b["included"], *atts)
     raise ValueError(kind)
 
 
 def make_oracle(kind, args):
-    return {"pingpong": OraclePingPong, "gsf": OracleGSF, "sanfermin": OracleSanFermin, "handel": OracleHandel}[kind](*args)
+    return {"pingpong": OraclePingPong, "gsf": OracleGSF, "sanfermin": OracleSanFermin, "handel": OracleHandel,
+            "casper": OracleCasper}[kind](*args)
 
 
 if __name__ == "__main__":
@@ -71,5 +83,7 @@ if __name__ == "__main__":
     for name, c in CASES.items():
         p = run_case(c, make_oracle)
         out[name] = {"kind": c["kind"], "args": c["args"], "steps": c["steps"], "time": p.time, "digest": state_digest(c["kind"], p)}
+        if "delay" in c:
+            out[name]["delay"] = c["delay"]
         print(name, out[name]["time"], out[name]["digest"][:16])
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "end_states.json"), "w"), indent=1)
