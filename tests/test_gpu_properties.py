@@ -45,3 +45,38 @@ def test_gsf_invariants_and_determinism(n):
     assert a.network().rng_state() == b.network().rng_state()
     down = a.network().attrs()["down"] == 1
     assert (prev[down] == 1).all()
+
+
+@pytest.mark.gpu
+def test_run_multiple_times_concurrent_equals_sequential_and_oracle():
+    """RunMultipleTimes (C/RunMultipleTimes.java:41-85): seeds in flight concurrently give the sequential result, and the
+    averaged stats equal the oracle's over the same seeds."""
+    import numpy as np
+
+    from tests.oracle_lib import OracleGSF
+    from wittgenstein_b200 import (DoneAtStatGetter, GSFSignature, GSFSignatureParameters, MsgReceivedStatGetter, RunMultipleTimes)
+    from wittgenstein_b200.run_multiple import avg, get_stats_on
+
+    args = (256, 204, 4, 50, 20, 10, 25, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency")
+    p = GSFSignature(GSFSignatureParameters(*args))
+    cont = lambda c: c.continue_if()  # noqa: E731
+    r_seq = RunMultipleTimes(p, 4, 0, [DoneAtStatGetter(), MsgReceivedStatGetter()])
+    seq = r_seq.run(cont, concurrency=1)
+    r_con = RunMultipleTimes(p, 4, 0, [DoneAtStatGetter(), MsgReceivedStatGetter()])
+    con = r_con.run(cont, concurrency=4)
+    assert seq == con and r_seq.end_times == r_con.end_times
+    done, recv = [], []
+    for seed in range(4):
+        o = OracleGSF(*args, seed=seed)
+        o.init()
+        while True:
+            did = o.run_ms(10)
+            live = o.attrs()["down"] == 0
+            more = bool(((o.scalars()["card"] < args[1]) & live).any())
+            if not ((not did) or more):
+                break
+        assert o.time == r_seq.end_times[seed]
+        c = o.counters()
+        done.append(get_stats_on(c[4][live]))
+        recv.append(get_stats_on(c[0][live]))
+    assert avg(done) == seq[0] and avg(recv) == seq[1]

@@ -4,3 +4,5 @@ from ._lib import WtgError  # noqa: F401
 from .network import Network  # noqa: F401
 from .protocols import (CasperIMD, CasperParemeters, GSFSignature, GSFSignatureParameters, Handel, HandelParameters, PingPong,  # noqa: F401
                         PingPongParameters, SanFerminSignature, SanFerminSignatureParameters)
+from .run_multiple import (DoneAtStatGetter, MsgReceivedStatGetter, RunMultipleTimes, SimpleStats,  # noqa: F401
+                           cont_until_done)

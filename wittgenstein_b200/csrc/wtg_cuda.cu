@@ -481,6 +481,8 @@ __global__ void k_gsf_shuffle(Dev d, int l, u64 s0, const int* liveRank, const u
 class CudaBackend : public Backend {
  public:
   cudaStream_t st = nullptr;
+  int devId = 0;  // every entry point binds it: callers may drive different networks from different host threads
+  void bind() const { cudaSetDevice(devId); }
   int sms = 148;
   cudaGraphExec_t tickGraph = nullptr;
   const void* graphFor = nullptr;
@@ -510,6 +512,7 @@ class CudaBackend : public Backend {
     const char* e2 = std::getenv("WTG_DEVICE");
     if (e2) dev = std::atoi(e2) % cnt;
     CUDA_OK(cudaSetDevice(dev));
+    devId = dev;
     cudaDeviceProp p;
     CUDA_OK(cudaGetDeviceProperties(&p, dev));
     sms = p.multiProcessorCount;
@@ -522,6 +525,7 @@ class CudaBackend : public Backend {
     if (st) cudaStreamDestroy(st);
   }
   void* alloc(size_t bytes) override {
+    bind();
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) throw std::runtime_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
@@ -530,18 +534,22 @@ class CudaBackend : public Backend {
   }
   void release(void* p) override { cudaFree(p); }
   void upload(void* dst, const void* src, size_t bytes) override {
+    bind();
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));
   }
   void download(void* dst, const void* src, size_t bytes) override {
+    bind();
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
   }
   void sync() override {
+    bind();
     CUDA_OK(cudaStreamSynchronize(st));
     drainProfile();
   }
   void timerStart() override {
+    bind();
     if (!tm0) {
       CUDA_OK(cudaEventCreate(&tm0));
       CUDA_OK(cudaEventCreate(&tm1));
@@ -706,11 +714,13 @@ class CudaBackend : public Backend {
     CUDA_OK(cudaFuncSetAttribute(k_ms_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
   }
   void tick(const Dev& d, int mode) override {
+    bind();
     configure(d);
     enqueueTick(d, mode);
     CUDA_OK(cudaGetLastError());
   }
   void ticks(const Dev& d, int count) override {
+    bind();
     configure(d);
     if (!useGraph || profiling || count < 4) {
       for (int i = 0; i < count; ++i) enqueueTick(d, 1);
