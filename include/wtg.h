@@ -71,7 +71,7 @@ int wtg_sanfermin_init(wtg_net* net);
 /* new Handel(params).init() — protocols/Handel.java:96-141, 957-1014.
  * params11 = { nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
  *              desynchronizedStart, byzantineSuicide, hiddenByzantine } (HandelParameters; window = WindowParameters()).
- * hiddenByzantine != 0 is rejected (not built yet); badNodes is always drawn with Network.chooseBadNodes. */
+ * HiddenByzantine (:840-917) is supported; badNodes is always drawn with Network.chooseBadNodes. */
 int wtg_handel_init(wtg_net* net, const int* params11);
 
 /* new CasperIMD(params) — protocols/CasperIMD.java:81-88 (the constructor builds the observer node on network.rd) and

@@ -355,7 +355,7 @@ int wo_sf_helper_pick(int nodeId, int setSize, int level, int howMany, int calls
 // ---- Handel -------------------------------------------------------------------------------
 // params10 = nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
 //            desynchronizedStart, byzantineSuicide
-void* wo_handel_create(const int* params10, const char* nodeBuilderName, const char* networkLatencyName) {
+void* wo_handel_create(const int* params10,  /* 11 values: the 11th is hiddenByzantine */ const char* nodeBuilderName, const char* networkLatencyName) {
   WO_TRY
   Handel::Params p;
   p.nodeCount = params10[0];
@@ -368,6 +368,7 @@ void* wo_handel_create(const int* params10, const char* nodeBuilderName, const c
   p.nodesDown = params10[7];
   p.desynchronizedStart = params10[8];
   p.byzantineSuicide = params10[9] != 0;
+  p.hiddenByzantine = params10[10] != 0;
   p.nodeBuilderName = nodeBuilderName ? nodeBuilderName : "";
   p.latencyNull = networkLatencyName == nullptr;
   p.networkLatencyName = networkLatencyName ? networkLatencyName : "";

@@ -4,7 +4,7 @@
 //   protocols/PingPong.java       -> PingPong
 //   protocols/GSFSignature.java   -> GSFSignature (GSFNode, SFLevel, SendSigs)
 //   protocols/SanFerminSignature.java + SanFerminHelper.java -> SanFerminSignature, SanFerminHelper
-//   protocols/Handel.java         -> Handel (HNode, HLevel, SendSigs, SigToVerify; HiddenByzantine not restated)
+//   protocols/Handel.java         -> Handel (HNode, HLevel, SendSigs, SigToVerify, HiddenByzantine)
 // Line references are to those files.  PARITY STATUS: structure / schedule / liveness are
 // pinned by the reference's own tests (PT/GSFSignatureTest.java, PT/PingPongTest.java,
 // restated in tests/test_oracle_protocols.py); the protocol END STATE (bitmaps, doneAt) is
@@ -799,7 +799,7 @@ inline void SanFerminSignature::SwapRequest::action(Network&, Node& from, Node& 
 }
 
 // ----------------------------------------------------------------------------------------
-// Handel  (protocols/Handel.java).  HiddenByzantine (:840-917) is not restated: requesting it throws.
+// Handel  (protocols/Handel.java), HiddenByzantine (:840-917) included.
 // ----------------------------------------------------------------------------------------
 struct Handel {
   struct Params {  // :22-142
@@ -816,7 +816,6 @@ struct Handel {
       throw IllegalArgument("nodeCount/threshold");
     if (__builtin_popcount(static_cast<unsigned>(p.nodeCount)) != 1) throw IllegalArgument("We support only power of two nodes in this simulation");
     if (p.byzantineSuicide && p.hiddenByzantine) throw IllegalArgument("Only one attack at a time");
-    if (p.hiddenByzantine) throw IllegalArgument("hiddenByzantine is not restated in the oracle");
   }
   // WindowParameters.newSize + ScoringExp(2, 4) :168-200
   int windowNewSize(int curr, bool correct) const {
@@ -879,6 +878,11 @@ struct Handel {
     int currWindowSize, addedCycle;
     bool done = false;
     int sigsChecked = 0, sigQueueSize = 0, msgFiltered = 0;
+    // HiddenByzantine (:840-917): one per honest node when params.hiddenByzantine (:303)
+    bool hasHidden = false, hbNoByzantinePeers = false;
+    SigPtr hbLast;
+    HNode* firstByzantine(HLevel& l);            // :844-858
+    SigPtr attack(const SigPtr& currentBest);    // :861-916
 
     HNode(Handel* pp, int startAt_)
         : Node(pp->network.rd, pp->nb), p(pp), startAt(startAt_),
@@ -978,6 +982,7 @@ struct Handel {
       int startAt = params.desynchronizedStart == 0 ? 0 : network.rd.nextInt(params.desynchronizedStart);
       nodes.push_back(std::make_unique<HNode>(this, startAt));
       if (badNodes[static_cast<size_t>(i)]) nodes.back()->stop();
+      nodes.back()->hasHidden = params.hiddenByzantine && !badNodes[static_cast<size_t>(i)];  // :303, :968
       network.addNode(nodes.back().get());
     }
     for (auto& up : nodes) {
@@ -1196,6 +1201,7 @@ inline void Handel::HNode::checkSigs() {
   }
   if (byLevels.empty()) return;
   SigPtr best = byLevels[static_cast<size_t>(p->network.rd.nextInt(static_cast<int>(byLevels.size())))];  // :788-790
+  if (hasHidden && best->level == static_cast<int>(levels.size()) - 1) best = attack(best);  // :813-817
   HLevel& l = levels[static_cast<size_t>(best->level)];
   int newSize = p->windowNewSize(currWindowSize, !best->badSig);
   currWindowSize = std::min(newSize, l.size);
@@ -1205,6 +1211,48 @@ inline void Handel::HNode::checkSigs() {
   sigsChecked++;
   HNode* self = this;
   p->network.registerTask([self, best] { self->updateVerifiedSignatures(best); }, p->network.time + nodePairingTime, *this);
+}
+
+inline Handel::HNode* Handel::HNode::firstByzantine(HLevel& l) {
+  HNode* best = nullptr;
+  int bestRank = std::numeric_limits<int>::max();
+  for (int pid : l.peers) {
+    HNode* pn = p->nodes[static_cast<size_t>(pid)].get();
+    if (pn->isDown() && receptionRanks[static_cast<size_t>(pid)] < bestRank && !l.totalIncoming.get(pid)) {
+      bestRank = receptionRanks[static_cast<size_t>(pid)];
+      best = pn;
+      if (bestRank == 0) return pn;
+    }
+  }
+  return best;
+}
+inline Handel::SigPtr Handel::HNode::attack(const SigPtr& currentBest) {
+  if (hbNoByzantinePeers) return currentBest;
+  if (hbLast == currentBest) {  // a previous attack finally worked
+    hbLast = nullptr;
+    return currentBest;
+  }
+  HLevel& l = levels[static_cast<size_t>(currentBest->level)];
+  if (hbLast) {
+    for (auto& s : l.toVerifyAgg)
+      if (s == hbLast) return currentBest;  // still in the list: the attack failed this time
+    if (!l.totalIncoming.get(hbLast->from)) throw IllegalState("byz signature pruned!");
+    hbLast = nullptr;
+  }
+  HNode* fb = firstByzantine(l);
+  if (fb == nullptr) {
+    hbNoByzantinePeers = true;
+    return currentBest;
+  }
+  if (receptionRanks[static_cast<size_t>(fb->nodeId)] >= currentBest->rank) return currentBest;
+  JBitSet cur;
+  cur.set(fb->nodeId);
+  SigPtr bad = std::make_shared<SigToVerify>(SigToVerify{fb->nodeId, l.level, receptionRanks[static_cast<size_t>(fb->nodeId)], cur, false});
+  l.toVerifyAgg.push_back(bad);
+  sigQueueSize++;
+  SigPtr newBest = l.bestToVerify();
+  if (newBest != bad) hbLast = bad;
+  return newBest;
 }
 
 }  // namespace wo

@@ -6,9 +6,9 @@ from tests.oracle_lib import OracleHandel
 from wittgenstein_b200 import Handel, HandelParameters
 a=sys.argv
 N=int(a[1]); thr=int(a[2]); pairing=int(a[3]); lw=int(a[4]); extra=int(a[5]); period=int(a[6]); fp=int(a[7]); down=int(a[8])
-nb=a[9]; nl=a[10]; desync=int(a[11]); byz=int(a[12]); step=int(a[13]); T=int(a[14]); seed=int(a[15]) if len(a)>15 else None
-p=Handel(HandelParameters(N,thr,pairing,lw,extra,period,fp,down,nb,nl,desync,bool(byz),False), _api=emu_lib.api())
-o=OracleHandel(N,thr,pairing,lw,extra,period,fp,down,nb,nl,desync,bool(byz),seed=seed)
+nb=a[9]; nl=a[10]; desync=int(a[11]); byz=int(a[12]); step=int(a[13]); T=int(a[14]); seed=int(a[15]) if len(a)>15 and a[15]!='-' else None; hid=bool(int(a[16])) if len(a)>16 else False
+p=Handel(HandelParameters(N,thr,pairing,lw,extra,period,fp,down,nb,nl,desync,bool(byz),hid), _api=emu_lib.api())
+o=OracleHandel(N,thr,pairing,lw,extra,period,fp,down,nb,nl,desync,bool(byz),seed=seed,hidden_byzantine=hid)
 if seed is not None: p.network().set_seed(seed)
 p.init(); o.init()
 def cmp(tag, full=True):

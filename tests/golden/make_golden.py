@@ -34,6 +34,7 @@ CASES = {
     "sanfermin_1024": dict(kind="sanfermin", args=[1024, 1024, 2, 48, 300, 1, None, None], steps=[10] * 400),
     "handel_64_desync": dict(kind="handel", args=[64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False], steps=[1] * 1200),
     "handel_256_byz": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, True], steps=[10] * 300),
+    "handel_256_hidden": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, False], hidden=True, steps=[10] * 300),
     # casper args: cycleLength, randomOnTies, producers, attestersPerRound, blockTime, attestationTime, builder, latency ; byzDelay
     "casper_3x20_forks": dict(kind="casper", args=[3, False, 3, 20, 1000, 1, None, None], delay=9000, steps=[500] * 400),
     "casper_4x16_aws_late": dict(kind="casper", args=[4, False, 2, 16, 1000, 1, "AWS_SPEED=GAUSSIAN_TOR=0.33", AWS_NL], delay=-7000, steps=[1000] * 200),
@@ -41,7 +42,7 @@ CASES = {
 
 
 def run_case(c, make):
-    p = make(c["kind"], c["args"])
+    p = make(c["kind"], c["args"], hidden=c.get("hidden", False))
     if c["kind"] == "casper":
         p.init(c["delay"])
     else:
@@ -73,7 +74,9 @@ def state_digest(kind, p, net=None):
     raise ValueError(kind)
 
 
-def make_oracle(kind, args):
+def make_oracle(kind, args, hidden=False):
+    if hidden:
+        return OracleHandel(*args, hidden_byzantine=True)
     return {"pingpong": OraclePingPong, "gsf": OracleGSF, "sanfermin": OracleSanFermin, "handel": OracleHandel,
             "casper": OracleCasper}[kind](*args)
 
@@ -85,5 +88,7 @@ if __name__ == "__main__":
         out[name] = {"kind": c["kind"], "args": c["args"], "steps": c["steps"], "time": p.time, "digest": state_digest(c["kind"], p)}
         if "delay" in c:
             out[name]["delay"] = c["delay"]
+        if c.get("hidden"):
+            out[name]["hidden"] = True
         print(name, out[name]["time"], out[name]["digest"][:16])
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "end_states.json"), "w"), indent=1)

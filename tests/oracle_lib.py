@@ -294,11 +294,11 @@ class OracleHandel:
     """protocols/Handel.java through the oracle."""
 
     def __init__(self, node_count, threshold, pairing_time, level_wait_time, extra_cycle, dissemination_period_ms, fast_path,
-                 nodes_down, node_builder, latency, desynchronized_start=0, byzantine_suicide=False, seed=None):
+                 nodes_down, node_builder, latency, desynchronized_start=0, byzantine_suicide=False, seed=None, hidden_byzantine=False):
         self.lib = load()
         self.n = node_count
         arr = np.array([node_count, threshold, pairing_time, level_wait_time, extra_cycle, dissemination_period_ms, fast_path,
-                        nodes_down, desynchronized_start, 1 if byzantine_suicide else 0], np.int32)
+                        nodes_down, desynchronized_start, 1 if byzantine_suicide else 0, 1 if hidden_byzantine else 0], np.int32)
         self.h = C.c_void_p(self.lib.wo_handel_create(_p(arr, C.c_int), _b(node_builder), _b(latency)))
         if not self.h:
             raise ValueError(self.lib.wo_last_error().decode())

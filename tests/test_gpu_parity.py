@@ -290,12 +290,12 @@ def _handel_compare(p, o, tag, full=True):
     return bad
 
 
-def _handel_pair(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=None):
+def _handel_pair(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=None, hidden=False):
     from tests.oracle_lib import OracleHandel
     from wittgenstein_b200 import Handel, HandelParameters
 
-    p = Handel(HandelParameters(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, False))
-    o = OracleHandel(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=seed)
+    p = Handel(HandelParameters(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, hidden))
+    o = OracleHandel(n, thr, pairing, lw, extra, period, fp, down, nb, nl, desync, byz, seed=seed, hidden_byzantine=hidden)
     if seed is not None:
         p.network().set_seed(seed)
     p.init(); o.init()
@@ -333,6 +333,27 @@ def test_handel_1024_byzantine_suicide(seed):
     assert not p.continue_if()
     assert not _handel_compare(p, o, "end")
     assert (p.rows(5) != 0).any()  # somebody got blacklisted
+
+
+@pytest.mark.parametrize("n,thr,down,nb,nl,desync,seed,step,until", [
+    (64, 40, 16, NB, NL, 0, None, 5, 2500),
+    (128, 100, 20, NB, NL, 50, 9, 1, 1500),
+    (1024, 700, 256, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, 3, 10, 3000),  # last level is pooled: the injected signature gets a slab
+])
+def test_handel_hidden_byzantine(n, thr, down, nb, nl, desync, seed, step, until):
+    """HiddenByzantine.attack (P/Handel.java:840-917): low-value signatures of down peers injected at the last level."""
+    p, o = _handel_pair(n, thr, 4, 50, 10, 20, 10, down, nb, nl, desync, False, seed=seed, hidden=True)
+    k = 0
+    while o.time < until:
+        assert p.network().run_ms(step) == o.run_ms(step)
+        k += 1
+        bad = _handel_compare(p, o, f"t={o.time}", full=(k % 5 == 0))
+        assert not bad, bad
+    assert not _handel_compare(p, o, "end")
+    # the attack leaves its trace: some honest node counts a down node's signature in its last level
+    down_ids = np.flatnonzero(p.network().attrs()["down"])
+    inc = p.rows(0)
+    assert any(((inc[:, d >> 6] >> np.uint64(d & 63)) & np.uint64(1)).any() for d in down_ids)
 
 
 def test_handel_512_tor_desync_plain_dead():
@@ -374,8 +395,6 @@ def test_error_paths():
     from wittgenstein_b200 import Handel, HandelParameters
     with pytest.raises(WtgError):
         HandelParameters(100, 90)  # Handel.java:118-120
-    with pytest.raises(WtgError):
-        Handel(HandelParameters(64, 60, hidden_byzantine=True, node_builder_name=NB, network_latency_name=NL)).init()
     # a capacity that is too small fails loudly instead of dropping events
     g = GSFSignature(GSFSignatureParameters(256, 250, 3, 20, 10, 10, 0, NB, NL), tunables={"qcap": 32})
     g.init()

@@ -557,7 +557,6 @@ class Engine {
       throw std::invalid_argument("nodeCount=" + std::to_string(N) + ", threshold=" + std::to_string(p.threshold));
     if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("We support only power of two nodes in this simulation");  // :118-120
     if (p.byzantineSuicide && p.hiddenByzantine) throw std::invalid_argument("Only one attack at a time");  // :122-124
-    if (p.hiddenByzantine) throw std::invalid_argument("hiddenByzantine is not supported by the B200 engine yet");
     if (p.fastPath < 0 || p.fastPath > MAX_ACC) throw std::invalid_argument("fastPath must be in [0,16]");
     if (p.disseminationPeriodMs <= 0 || p.pairingTime < 0 || p.desynchronizedStart < 0) throw std::invalid_argument("period/pairing/desynchronizedStart");
     checkLatencyBuilder();
@@ -644,6 +643,13 @@ class Engine {
     d.hCand = dalloc<int>((size_t)N * 32);
     d.hCandK = dalloc<int>(N);
     d.hDrawBase = dalloc<int>(N);
+    d.hHidden = p.hiddenByzantine ? 1 : 0;
+    d.hbNoPeers = dalloc<int>(N);
+    {
+      std::vector<int> m1((size_t)N, -1);
+      d.hbLastId = dupload(m1);
+    }
+    d.hbLastFrom = dalloc<int>(N);
     // setReceivingRanks (:940-948): N cumulative shuffles of one list
     std::vector<int> ranks((size_t)N * N);
     {

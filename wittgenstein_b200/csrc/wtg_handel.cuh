@@ -807,6 +807,117 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
   c.sync();
 }
 
+// HiddenByzantine.attack (:861-916) on the level-(L-1) candidate `ci` of node n; returns the queue index of the
+// signature to verify.  Scalar: runs inside the pick, after the level draw.  Nothing changed the node's state since
+// the select phase, so every queued entry of the level is still improving and carries a fresh (s, score); only the
+// injected signature can be curated away by the second bestToVerify() (:566-630).
+WTG_HD int hHiddenAttack(const Dev& d, int n, int ci) {
+  const int L = d.L, lvl = L - 1;
+  HQEntry* q = d.hQueue + (size_t)n * d.qcap;
+  uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
+  if (d.hbNoPeers[n]) return ci;
+  const HQEntry cur = q[ci];
+  if (d.hbLastId[n] >= 0 && (uint32_t)d.hbLastId[n] == cur.id) {  // last == currentBest: a previous attack worked
+    d.hbLastId[n] = -1;
+    return ci;
+  }
+  int len = d.qLen[n];
+  const u64* incRow = hRow(d.hTotInc, d, n);
+  if (d.hbLastId[n] >= 0) {
+    for (int i = 0; i < len; ++i)
+      if ((int)metaLevel(q[i].meta) == lvl && q[i].id == (uint32_t)d.hbLastId[n]) return ci;  // still queued
+    if (!rowBit(incRow, d.hbLastFrom[n])) {  // IllegalStateException("byz signature pruned!")
+      setError(d, ERR_PROTO_STATE, 20);
+      return ci;
+    }
+    d.hbLastId[n] = -1;
+  }
+  // firstByzantine (:844-858): lowest reception rank among the down peers not yet in totalIncoming, first in emission order
+  const int size = 1 << (lvl - 1);
+  int fb = -1, bestRank = 0x7fffffff;
+  for (int i = 0; i < size; ++i) {
+    int p = (int)peerAt(d, n, lvl, i);
+    if (!d.ndown[p]) continue;
+    int rk = d.hRanks[(size_t)n * d.N + p];
+    if (rk < bestRank && !rowBit(incRow, p)) {
+      bestRank = rk;
+      fb = p;
+      if (rk == 0) break;
+    }
+  }
+  if (fb < 0) {
+    d.hbNoPeers[n] = 1;
+    return ci;
+  }
+  if (bestRank >= (int)cur.rank) return ci;  // we can't improve it
+  if (len + 1 > d.qcap) {
+    setError(d, ERR_QUEUE_OVERFLOW, n);
+    return ci;
+  }
+  HQEntry bad;
+  bad.from = (uint32_t)fb;
+  bad.rank = (uint32_t)bestRank;
+  HEval r;
+  if (lvl <= INLINE_MAX_LEVEL) {  // sig = {firstByzantine}
+    bad.meta = metaMake(PK_INLINE, (uint32_t)lvl, 0);
+    bad.pl = 1ULL << (fb & 63);
+    r = hEvalScalar(d, n, bad);
+  } else {
+    uint32_t slot = 0;
+    if (!poolAlloc(d, lvl, n, slot)) return ci;
+    d.poolRef[lvl][slot] = 1;
+    Blk fbk = levelBlock(fb, lvl);
+    u64* slab = d.pool[lvl] + (size_t)slot * (size_t)fbk.nw;
+    for (int w = 0; w < fbk.nw; ++w) slab[w] = 0;
+    slab[(fb >> 6) - fbk.w0] = 1ULL << (fb & 63);
+    bad.meta = metaMake(PK_POOL, (uint32_t)lvl, 0);
+    bad.pl = (u64)slot | (1ULL << 32);
+    CoopSerial cs;
+    r = hEvalPool(d, cs, n, (uint32_t)fb, bad.meta, bad.pl);
+  }
+  bad.id = (uint32_t)d.hSeq[n]++;
+  bad.s = r.s;
+  bad.score = r.score;
+  const int bi = len;
+  q[bi] = bad;
+  qst[bi] = d.lvVer[(size_t)n * L + lvl];
+  d.qLen[n] = ++len;
+  d.hSigQueueSize[n] += 1;
+  // l.bestToVerify() again: the window index is the lowest rank of the whole list, curated entries included (:574-575)
+  int minRank = 0x7fffffff;
+  for (int i = 0; i < len; ++i)
+    if ((int)metaLevel(q[i].meta) == lvl && (int)q[i].rank < minRank) minRank = (int)q[i].rank;
+  const bool badKept = !rowBit(hRow(d.hBlack, d, n), fb) && bad.s > d.hCntInc[n * L + lvl];
+  if (!badKept) {  // replaceToVerifyAgg (:616-618, 632-642)
+    d.qLen[n] = --len;
+    d.hSigQueueSize[n] -= 1;
+    if (metaKind(bad.meta) == PK_POOL) hRelease(d, n, lvl, (uint32_t)bad.pl, false);
+  }
+  const int lim = minRank + d.hWindow[n];
+  int bestIn = -1, bestInScore = 0, bestOut = -1;
+  for (int i = 0; i < len; ++i) {
+    if ((int)metaLevel(q[i].meta) != lvl) continue;
+    if ((int)q[i].rank <= lim) {
+      if (q[i].score > bestInScore) {
+        bestInScore = q[i].score;
+        bestIn = i;
+      }
+    } else if (bestOut < 0 || q[i].rank < q[bestOut].rank) {
+      bestOut = i;
+    }
+  }
+  int nb = bestIn >= 0 ? bestIn : bestOut;
+  if (nb < 0) {  // cannot happen: the list holds at least currentBest
+    setError(d, ERR_INTERNAL, 21);
+    return ci;
+  }
+  if (nb != bi || !badKept) {
+    d.hbLastId[n] = (int)bad.id;
+    d.hbLastFrom[n] = fb;
+  }
+  return nb;
+}
+
 // phase D: pick the level with network.rd.nextInt(k) and finish checkSigs (:808-837).  `drawIdx` = index of this
 // node's draw in the stream after ctl.rng (exclusive scan of condDraws over nodes).  Returns the number of
 // stream values consumed (1, or more when nextInt's rejection loop fires).
@@ -835,7 +946,9 @@ WTG_HD int hCondPick(const Dev& d, int n, u64 drawIdx, bool apply) {
       }
       ++seen;
     }
-  HQEntry e = d.hQueue[(size_t)n * d.qcap + d.hCand[(size_t)n * 32 + lvl]];
+  int ci = d.hCand[(size_t)n * 32 + lvl];
+  if (d.hHidden && lvl == d.L - 1) ci = hHiddenAttack(d, n, ci);  // :813-817
+  HQEntry e = d.hQueue[(size_t)n * d.qcap + ci];
   const bool bad = (e.meta & HMETA_BAD) != 0;
   // window (:821-822): ScoringExp(2,4) ceil(curr*2) / floor(curr/4), clamped to [min,max], then to the level size
   int curr = d.hWindow[n];

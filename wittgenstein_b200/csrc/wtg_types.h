@@ -327,6 +327,10 @@ struct Dev {
   int* hCand;       // [N][32] per level: queue index of bestToVerify() or -1
   int* hCandK;      // [N] number of levels with a candidate
   int* hDrawBase;   // [N] exclusive scan of condDraws
+  int hHidden;      // params.hiddenByzantine: every honest node carries a HiddenByzantine (Handel.java:303, 840-917)
+  int* hbNoPeers;   // [N] HiddenByzantine.noByzantinePeers
+  int* hbLastId;    // [N] id of HiddenByzantine.last (-1 = null)
+  int* hbLastFrom;  // [N] last.from
   int* poolRef[MAX_LEVELS];  // reference counts of pooled payloads (queue entry + pending update tasks)
   // ---- SanFermin ----
   int sfThreshold, sfPairing, sfSigSize, sfReplyTimeout, sfCandCount, sfP;
