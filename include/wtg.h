@@ -78,10 +78,12 @@ int wtg_handel_init(wtg_net* net, const int* params11);
  * .init(new ByzBlockProducerWF(byz_delay, genesis)) — :472-508 (init() itself uses byz_delay 0).
  * params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime,
  *             attestationConstructionTime } (CasperParemeters :18-71).  Node ids: 0 observer, 1 the Byzantine producer,
- * 2.. the other producers, then the attesters.  Device engine: ByzBlockProducerWF only; with randomOnTies a vote tie
+ * 2.. the other producers, then the attesters.  Device engine: with randomOnTies a vote tie
  * between two branches is reported as an error (the tie-break draws from network.rd inside a handler, :250-253). */
 int wtg_casper_construct(wtg_net* net, const int* params6);
 int wtg_casper_init(wtg_net* net, int byz_delay);
+/* .init(new ByzBlockProducer / SF / NS / WF (byz_delay, genesis)) — kind 3 / 4 / 5 / 6 (CasperIMD.java:511-707) */
+int wtg_casper_init_byz(wtg_net* net, int kind, int byz_delay);
 
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);
@@ -125,14 +127,15 @@ int wtg_sanfermin_node_scalars(wtg_net* net, int* agg, int* cpl, int* done, int*
  * wtg_casper_node_state: per node head id (BlockChainNode.head), attestations received and distinct heads among them
  * (attestationsByHead, CasperIMD.java:197), blocks received incl. genesis (blocksReceivedByBlockId), |blocksToReevaluate|,
  * and an order-free 64-bit hash over (attester, height, head id) of the received attestations.
- * wtg_casper_byz: { toSend, h, late, onTime, delay } of the ByzBlockProducerWF (:512-518, 648-649). */
+ * wtg_casper_byz: { toSend, h, late, onTime, delay, onDirectFather, onOlderAncestor, incNotTheBestFather, skipped } of the
+ * Byzantine producer (:512-518, 615, 648-649). */
 int wtg_casper_block_count(wtg_net* net);
 int wtg_casper_blocks(wtg_net* net, int* height, int* parent, int* producer, int* proposal_time, int* included);
 int wtg_casper_block_attestations(wtg_net* net, int block, int* attester, int* height, int cap);
 int wtg_casper_node_state(wtg_net* net, int* head, int* atts_received, int* heads_with_atts, int* blocks_received,
                           int* to_reevaluate, unsigned long long* att_hash);
 int wtg_casper_heads(wtg_net* net, int* head); /* BlockChainNode.head of every node (block id) */
-int wtg_casper_byz(wtg_net* net, int* out5);
+int wtg_casper_byz(wtg_net* net, int* out9);
 
 /* HNode fields — protocols/Handel.java:280-298: 9 int arrays of N: startAt, nodePairingTime, sigsChecked, sigQueueSize,
  * msgFiltered, currWindowSize, addedCycle, totalSigSize(), total length of the toVerifyAgg lists */

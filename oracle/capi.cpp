@@ -478,6 +478,16 @@ int wo_casper_init(void* h, int byzDelay) {
   return 0;
   WO_CATCH(-1)
 }
+int wo_casper_init_byz(void* h, int kind, int byzDelay) {  // 3 plain, 4 SF, 5 NS, 6 WF
+  WO_TRY
+  auto* ci = static_cast<CasperIMD*>(h);
+  CasperIMD::ByzBlockProducer* b = kind == 3 ? ci->newByz(byzDelay) : kind == 4 ? static_cast<CasperIMD::ByzBlockProducer*>(ci->newByzSF(byzDelay))
+                                   : kind == 5 ? static_cast<CasperIMD::ByzBlockProducer*>(ci->newByzNS(byzDelay))
+                                               : static_cast<CasperIMD::ByzBlockProducer*>(ci->newByzWF(byzDelay));
+  ci->init(b);
+  return 0;
+  WO_CATCH(-1)
+}
 int wo_casper_run_ms(void* h, int ms) {
   WO_TRY
   return static_cast<CasperIMD*>(h)->network.runMs(ms) ? 1 : 0;
@@ -572,11 +582,17 @@ void wo_casper_node_state(void* h, int32_t* head, int32_t* attsReceived, int32_t
 }
 void wo_casper_byz(void* h, int32_t* out5) {
   auto* ci = static_cast<CasperIMD*>(h);
-  auto* b = static_cast<CasperIMD::ByzBlockProducerWF*>(ci->bps.at(0));
+  auto* b = static_cast<CasperIMD::ByzBlockProducer*>(ci->bps.at(0));
+  auto* wf = dynamic_cast<CasperIMD::ByzBlockProducerWF*>(b);
+  auto* ns = dynamic_cast<CasperIMD::ByzBlockProducerNS*>(b);
   out5[0] = b->toSend;
   out5[1] = b->h;
-  out5[2] = b->late;
-  out5[3] = b->onTime;
+  out5[2] = wf ? wf->late : 0;
+  out5[3] = wf ? wf->onTime : 0;
   out5[4] = b->delay;
+  out5[5] = b->onDirectFather;
+  out5[6] = b->onOlderAncestor;
+  out5[7] = b->incNotTheBestFather;
+  out5[8] = ns ? ns->skipped : 0;
 }
 }  // extern "C"

@@ -17,7 +17,8 @@ p=CasperIMD(CasperParemeters(cyc,False,bpc,apr,1000,1,nb,nl), _api=api)
 o=OracleCasper(cyc,False,bpc,apr,1000,1,nb,nl)
 if seed is not None: p.network().set_seed(seed); o.set_seed(seed)
 p.network().set_tunable('casper_votes', T//(8000*cyc)+3)
-p.init(delay); o.init(delay)
+kind=os.environ.get('BYZ','WF')
+p.init(delay, kind); o.init(delay, kind)
 def cmp(tag):
     ok=True
     if p.network().rng_state()!=o.rng_state(): print(tag,"rng differ"); ok=False

@@ -401,8 +401,8 @@ class OracleCasper:
     def set_seed(self, s):
         self.lib.wo_casper_set_seed(self.h, C.c_int64(s))
 
-    def init(self, byz_delay=0):
-        if self.lib.wo_casper_init(self.h, int(byz_delay)) != 0:
+    def init(self, byz_delay=0, byz_kind="WF"):
+        if self.lib.wo_casper_init_byz(self.h, {"plain": 3, "SF": 4, "NS": 5, "WF": 6}[byz_kind], int(byz_delay)) != 0:
             raise RuntimeError(self.lib.wo_last_error().decode())
 
     def run_ms(self, ms):
@@ -478,6 +478,7 @@ class OracleCasper:
         return d
 
     def byz(self):
-        out = np.zeros(5, np.int32)
+        out = np.zeros(9, np.int32)
         self.lib.wo_casper_byz(self.h, _p(out, C.c_int32))
-        return dict(zip(["to_send", "h", "late", "on_time", "delay"], out.tolist()))
+        return dict(zip(["to_send", "h", "late", "on_time", "delay", "on_direct_father", "on_older_ancestor", "inc_not_the_best_father",
+                         "skipped"], out.tolist()))

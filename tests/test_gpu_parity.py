@@ -176,7 +176,7 @@ def test_sanfermin_16384_shipped_scenario():
     assert not _sf_compare(p, o, "end")
 
 
-def _casper_pair(cyc, bpc, apr, nb, nl, seed, delay, until):
+def _casper_pair(cyc, bpc, apr, nb, nl, seed, delay, until, kind="WF"):
     from tests.oracle_lib import OracleCasper
     from wittgenstein_b200 import CasperIMD, CasperParemeters
 
@@ -186,7 +186,7 @@ def _casper_pair(cyc, bpc, apr, nb, nl, seed, delay, until):
         p.network().set_seed(seed)
         o.set_seed(seed)
     p.network().set_tunable("casper_votes", until // (8000 * cyc) + 3)
-    p.init(delay); o.init(delay)
+    p.init(delay, kind); o.init(delay, kind)
     return p, o
 
 
@@ -213,6 +213,22 @@ def test_casper_parity(cyc, bpc, apr, nb, nl, seed, delay, step, until):
         assert not bad, bad
     assert not compare_casper(p, o, "end", atts=True)
     assert len(p.blocks()["height"]) > 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,cyc,bpc,apr,delay,until", [("plain", 3, 3, 20, 9000, 150000), ("SF", 4, 3, 12, 3000, 250000),
+                                                         ("NS", 2, 4, 10, -3000, 250000)])
+def test_casper_other_byzantine_producers(kind, cyc, bpc, apr, delay, until):
+    """ByzBlockProducer / ByzBlockProducerSF / ByzBlockProducerNS (P/CasperIMD.java:511-640) vs the oracle."""
+    from tests.parity import compare_casper
+
+    p, o = _casper_pair(cyc, bpc, apr, None, None, None, delay, until, kind)
+    while o.time < until:
+        assert p.network().run_ms(1000) == o.run_ms(1000)
+        bad = compare_casper(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert not compare_casper(p, o, "end", atts=True)
+    assert p.byz()["on_direct_father"] + p.byz()["on_older_ancestor"] + p.byz()["skipped"] > 0 or kind == "NS"
 
 
 @pytest.mark.gpu

@@ -36,6 +36,7 @@ class Api:
         "sanfermin_node_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 7 + [C.POINTER(C.c_longlong)]),
         "casper_construct": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "casper_init": (C.c_int, [C.c_void_p, C.c_int]),
+        "casper_init_byz": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
         "casper_block_count": (C.c_int, [C.c_void_p]),
         "casper_blocks": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
         "casper_block_attestations": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),

@@ -137,6 +137,13 @@ int WTG_API(casper_init)(void* h, int byzDelay) {
     return 0;
   });
 }
+// kind: 3 ByzBlockProducer, 4 ByzBlockProducerSF, 5 ByzBlockProducerNS, 6 ByzBlockProducerWF (CasperIMD.java:511-707)
+int WTG_API(casper_init_byz)(void* h, int kind, int byzDelay) {
+  return guard([&] {
+    ENG.casperInit(byzDelay, kind);
+    return 0;
+  });
+}
 static void requireCasper(wtg::Engine& e) {
   e.requireInited();
   if (e.d.proto != wtg::PROTO_CASPER) throw std::logic_error("not a CasperIMD network");
@@ -252,7 +259,7 @@ int WTG_API(casper_heads)(void* h, int* head) {
     return 0;
   });
 }
-// out5 = { toSend, h, late, onTime, delay } of the ByzBlockProducerWF (node 1)
+// out9 = { toSend, h, late, onTime, delay, onDirectFather, onOlderAncestor, incNotTheBestFather, skipped } of node 1
 int WTG_API(casper_byz)(void* h, int* out5) {
   return guard([&] {
     requireCasper(ENG);
@@ -263,6 +270,10 @@ int WTG_API(casper_byz)(void* h, int* out5) {
     out5[2] = g.byzLate;
     out5[3] = g.byzOnTime;
     out5[4] = ENG.d.cByzDelay;
+    out5[5] = g.byzDirect;
+    out5[6] = g.byzOlder;
+    out5[7] = g.byzNotBest;
+    out5[8] = g.byzSkipped;
     return 0;
   });
 }

@@ -284,6 +284,20 @@ WTG_HD void cOnAttestation(const Dev& d, int n, int a) {
   if (rowBit(d.cBlkRecv + (size_t)n * d.cBlkWords, hb)) d.cToReeval[(size_t)n * d.cBlkWords + (hb >> 6)] |= 1ULL << (hb & 63);
 }
 
+// blocksReceivedByHeight.get(hh).iterator().next(): the received block of that height with the lowest id, -1 if none
+WTG_HD int cFirstAtHeight(const Dev& d, int n, int hh) {
+  const u64* br = d.cBlkRecv + (size_t)n * d.cBlkWords;
+  for (int w = 0; w < d.cBlkWords; ++w) {
+    u64 bits = br[w];
+    while (bits) {
+      int b = w * 64 + WTG_CTZ64(bits);
+      bits &= bits - 1;
+      if (b != 0 && d.cbHeight[b] == hh) return b;  // genesis is only in blocksReceivedByBlockId (BlockChainNode.java:26)
+    }
+  }
+  return -1;
+}
+
 // periodic tasks: Attester.vote (:455-464), BlockProducer (:376-381, 430-436), ByzBlockProducerWF (:656-665, reevaluateH :529-542)
 // followed by the re-arm of PeriodicTask.action (messages/PeriodicTask.java:40-47)
 template <class C>
@@ -315,6 +329,63 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
     int base = descAlloc(d, c, n, 2);
     if (c.lane() == 0 && base >= 0 && nb >= 0) {
       d.cHead[n] = nb;
+      cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
+      cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
+    }
+    slots = 2;
+    draws = 1;
+  } else if (kind == CK_BYZ || kind == CK_BYZ_SF || kind == CK_BYZ_NS) {  // :544-564, 588-603, 617-634
+    const int toSend = d.cg->byzToSend;
+    cReevaluate(d, c, n);  // reevaluateH (:529-542)
+    int head = d.cHead[n];
+    while (d.cbHeight[head] >= toSend) head = d.cbParent[head];
+    const int h = (tick - d.cByzDelay) / CASPER_SLOT;
+    if (h != toSend) {
+      setError(d, ERR_PROTO_STATE, 3);
+      return;
+    }
+    int direct = 0, older = 0, notBest = 0, skipped = 0;
+    if (kind == CK_BYZ) {
+      if (d.cbHeight[head] == h - 1) {
+        direct = 1;
+      } else {
+        older = 1;
+        int pf = cFirstAtHeight(d, n, h - 1);
+        if (pf < 0) {  // blocksReceivedByHeight.get(h - 1) is null: NullPointerException in the reference
+          setError(d, ERR_PROTO_STATE, 6);
+          return;
+        }
+        if (d.cbHeight[d.cbParent[pf]] != h - 1) notBest = 1;
+      }
+    } else if (kind == CK_BYZ_SF) {
+      if (head != 0 && d.cbHeight[head] == h - 1) {
+        head = d.cbParent[head];
+        direct = 1;
+      } else {
+        older = 1;
+      }
+    } else {
+      if (head != 0 && d.cbHeight[head] == h - 1 && d.cbHeight[d.cbParent[head]] == h - 3) {
+        int b = cFirstAtHeight(d, n, h - 2);
+        if (b < 0) {
+          setError(d, ERR_PROTO_STATE, 6);
+          return;
+        }
+        head = b;
+        skipped = 1;
+      }
+    }
+    c.sync();
+    int nb = cBuildBlock(d, c, n, head, toSend);
+    int base = descAlloc(d, c, n, 2);
+    if (c.lane() == 0 && base >= 0 && nb >= 0) {
+      d.cg->byzH = h;
+      d.cg->byzDirect += direct;
+      d.cg->byzOlder += older;
+      d.cg->byzNotBest += notBest;
+      d.cg->byzSkipped += skipped;
+      d.cHead[n] = nb;
+      d.cg->byzToSend = toSend + d.cBpCount;
       cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
       cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
     }

@@ -750,12 +750,13 @@ class Engine {
     hm.buildNodes(1);  // network.addObserver(new CasperNode(false, genesis) {})
     casperConstructed = true;
   }
-  void casperInit(int byzDelay) {
+  void casperInit(int byzDelay, int byzKind = CK_BYZ_WF) {
     requireNotInited();
     if (!casperConstructed) throw std::logic_error("CasperIMD not constructed");
     const int attCount = cp.attestersPerRound * cp.cycleLength;
     const int N = 1 + cp.blockProducersCount + attCount;
     if (CASPER_SLOT + byzDelay <= 0) throw std::invalid_argument("the Byzantine producer's first slot would start in the past");
+    if (byzKind != CK_BYZ && byzKind != CK_BYZ_SF && byzKind != CK_BYZ_NS && byzKind != CK_BYZ_WF) throw std::invalid_argument("unknown Byzantine producer kind");
     hm.buildNodes(N - 1);  // byzantine producer, producers 1.., attesters — in this order (:479-507); registering tasks draws nothing
     ringExtra = std::max(cp.blockConstructionTime, cp.attestationConstructionTime);
     farEnabled = true;
@@ -783,7 +784,7 @@ class Engine {
     d.cFirstAtt = 1 + cp.blockProducersCount;
     std::vector<uint8_t> kind((size_t)N, CK_ATTESTER);
     kind[0] = CK_OBSERVER;
-    kind[1] = CK_BYZ_WF;
+    kind[1] = (uint8_t)byzKind;
     for (int i = 1; i < cp.blockProducersCount; ++i) kind[(size_t)(1 + i)] = CK_PRODUCER;
     d.cKind = dupload(kind);
     d.cHead = dalloc<int>(N);

@@ -59,7 +59,7 @@ constexpr int SF_USEDCAP = 24;  // SanFerminHelper.usedNodes of the current leve
 // CasperIMD message / task types (Ev.meta); Ev.pl = attestation index, block index, or block | height << 32
 enum : uint32_t { CM_ATT = 1, CM_BLOCK = 2, CT_BUILD = 3 };
 // CasperIMD node kinds (CasperIMD.java: observer :87, BlockProducer :365, Attester :444, ByzBlockProducerWF :647)
-enum : uint8_t { CK_OBSERVER = 0, CK_PRODUCER = 1, CK_ATTESTER = 2, CK_BYZ_WF = 6 };
+enum : uint8_t { CK_OBSERVER = 0, CK_PRODUCER = 1, CK_ATTESTER = 2, CK_BYZ = 3, CK_BYZ_SF = 4, CK_BYZ_NS = 5, CK_BYZ_WF = 6 };
 constexpr int CASPER_SLOT = 8000;  // CasperParemeters.SLOT_DURATION (CasperIMD.java:19)
 constexpr int CASPER_MAX_BLKWORDS = 8;  // at most 512 blocks per run on the device
 constexpr uint32_t DESC_SHUFFLE2 = 1u;  // Desc.aux: Collections.shuffle of the 2 destinations before the send (one extra draw)
@@ -142,6 +142,7 @@ struct CasperG {  // CasperIMD: block counter and the Byzantine producer's scala
   int nBlocks;    // blocks created so far, genesis included (Block.blockId, per engine)
   int byzToSend, byzH, byzLate, byzOnTime;
   int createdThisTick;  // two blocks created in one millisecond would need the reference's event order for their ids
+  int byzDirect, byzOlder, byzNotBest, byzSkipped;  // onDirectFather, onOlderAncestor, incNotTheBestFather (:515-517), skipped (:615)
   int pad[2];
 };
 

@@ -222,8 +222,10 @@ class CasperIMD:
     def node_count(self):
         return 1 + self.params.block_producers_count + self.params.attesters_count
 
-    def init(self, byz_delay=0):
-        self._net.api.check(self._net.api.casper_init(self._net.h, int(byz_delay)))
+    BYZ_KINDS = {"plain": 3, "SF": 4, "NS": 5, "WF": 6}  # ByzBlockProducer, ...SF, ...NS, ...WF (CasperIMD.java:511-707)
+
+    def init(self, byz_delay=0, byz_kind="WF"):
+        self._net.api.check(self._net.api.casper_init_byz(self._net.h, self.BYZ_KINDS[byz_kind], int(byz_delay)))
 
     def blocks(self):
         a = self._net.api
@@ -258,9 +260,10 @@ class CasperIMD:
         return out
 
     def byz(self):
-        out = np.zeros(5, np.int32)
+        out = np.zeros(9, np.int32)
         self._net.api.check(self._net.api.casper_byz(self._net.h, _p(out, C.c_int)))
-        return dict(zip(["to_send", "h", "late", "on_time", "delay"], out.tolist()))
+        return dict(zip(["to_send", "h", "late", "on_time", "delay", "on_direct_father", "on_older_ancestor", "inc_not_the_best_father",
+                         "skipped"], out.tolist()))
 
 
 class HandelParameters:
