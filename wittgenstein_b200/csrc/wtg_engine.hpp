@@ -955,6 +955,10 @@ class Engine {
     uint8_t v = down ? 1 : 0;
     be->sync();
     be->upload(d.ndown + id, &v, 1);
+    if (d.proto == PROTO_HANDEL) {  // the cached per-level minimum rank of the down peers is stale now
+      std::vector<int> dirty((size_t)d.N * d.L, -2147483647 - 1);
+      be->upload(d.hBizNoHit, dirty.data(), dirty.size() * sizeof(int));
+    }
   }
   void uploadPartitions() {
     std::vector<uint8_t> part(d.N);

@@ -300,7 +300,9 @@ WTG_HD void hUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u64
   if (meta & HMETA_BAD) {  // :687-694
     if (c.lane() == 0) {
       hRow(d.hBlack, d, n)[from >> 6] |= 1ULL << (from & 63);
-      d.hBizNoHit[n * L + (int)metaLevel(meta)] = -2147483647 - 1;  // a candidate left: recompute the minimum lazily
+      // a candidate left: the cached minimum rank of the level only changes if it was the one holding it
+      int* bm = &d.hBizNoHit[n * L + (int)metaLevel(meta)];
+      if (*bm == d.hRanks[(size_t)n * d.N + from]) *bm = -2147483647 - 1;
     }
     c.sync();
     return;
@@ -621,7 +623,27 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
   //    (b) the injected signature comes from the first such peer whose reception rank is < maxRank.  hBizNoHit
   //        holds the exact minimum rank over the level's candidates (recomputed lazily after a candidate's rank
   //        was bumped or it was blacklisted), so "nobody qualifies" is answered without walking the list.
+  // One lane per level first answers the common case from cached state: the peer at the old index is still a
+  // candidate (so suicideBizAfter does not move) and the level's cached minimum rank says nobody is below maxRank.
+  // Only the levels that need a walk of the emission list take the cooperative path below.
+  uint32_t slowLevels = 0xFFFFFFFEu;
+#if defined(__CUDA_ARCH__)
+  if (C::LANES == 32) {
+    const int l = c.lane();
+    bool slow = false;
+    if (l >= 1 && l < L && sc->count[l] > 0) {
+      int biz = d.hBiz[n * L + l];
+      if (biz >= 0) {
+        int p = (int)peerAt(d, n, l, biz);
+        int bmin = d.hBizNoHit[n * L + l];
+        slow = !(d.ndown[p] && !rowBit(blRow, p)) || bmin == (-2147483647 - 1) || sc->minRank[l] + window > bmin;
+      }
+    }
+    slowLevels = c.ballot(slow);
+  }
+#endif
   for (int l = 1; l < L; ++l) {
+    if (!((slowLevels >> l) & 1u)) continue;
     int biz = d.hBiz[n * L + l];
     if (sc->count[l] <= 0 || biz < 0) continue;
     const int size = 1 << (l - 1);
@@ -650,52 +672,68 @@ WTG_HD void hCondSelect(const Dev& d, C& c, int n, HScratch* sc) {
       if (bmin == HB_DIRTY) {
         // full pass: minimum rank over all candidates and, on the way, the first one below maxRank
         int lmin = 0x7fffffff;
-        for (int base = first; base < size; base += C::LANES) {
-          int i = base + c.lane();
-          bool hit = false;
-          int p = 0, rk = 0;
-          if (i < size) {
-            p = (int)peerAt(d, n, l, i);
-            if (d.ndown[p] && !rowBit(blRow, p)) {
-              rk = d.hRanks[(size_t)n * d.N + p];
-              if (rk < lmin) lmin = rk;
-              hit = rk < maxRank;
-            }
+        constexpr int FU = 4;  // chunks of the emission list in flight per lane (the walk is a chain of dependent loads)
+        for (int base = first; base < size; base += C::LANES * FU) {
+          int pp[FU], rr[FU];
+          bool cc[FU];
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            int i = base + u * C::LANES + c.lane();
+            pp[u] = i < size ? (int)peerAt(d, n, l, i) : -1;
           }
-          uint32_t m = c.ballot(hit);
-          if (m && hitP < 0) {
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            cc[u] = pp[u] >= 0 && d.ndown[pp[u]] && !rowBit(blRow, pp[u]);
+            rr[u] = pp[u] >= 0 ? d.hRanks[(size_t)n * d.N + pp[u]] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            bool hit = false;
+            if (cc[u]) {
+              if (rr[u] < lmin) lmin = rr[u];
+              hit = rr[u] < maxRank;
+            }
+            uint32_t m = c.ballot(hit);
+            if (m && hitP < 0) {
 #if defined(__CUDA_ARCH__)
-            int src = __ffs(m) - 1;
+              int src = __ffs(m) - 1;
 #else
-            int src = 0;
+              int src = 0;
 #endif
-            hitP = c.bcast(p, src);
-            hitR = c.bcast(rk, src);
+              hitP = c.bcast(pp[u], src);
+              hitR = c.bcast(rr[u], src);
+            }
           }
         }
         lmin = c.minv(lmin);
         if (c.lane() == 0) d.hBizNoHit[n * L + l] = lmin;
       } else if (maxRank > bmin) {  // somebody qualifies: find the first one in emission order
-        for (int base = first; base < size && hitP < 0; base += C::LANES) {
-          int i = base + c.lane();
-          bool hit = false;
-          int p = 0, rk = 0;
-          if (i < size) {
-            p = (int)peerAt(d, n, l, i);
-            if (d.ndown[p] && !rowBit(blRow, p)) {
-              rk = d.hRanks[(size_t)n * d.N + p];
-              hit = rk < maxRank;
-            }
+        constexpr int FU = 4;
+        for (int base = first; base < size && hitP < 0; base += C::LANES * FU) {
+          int pp[FU], rr[FU];
+          bool cc[FU];
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            int i = base + u * C::LANES + c.lane();
+            pp[u] = i < size ? (int)peerAt(d, n, l, i) : -1;
           }
-          uint32_t m = c.ballot(hit);
-          if (m) {
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            cc[u] = pp[u] >= 0 && d.ndown[pp[u]] && !rowBit(blRow, pp[u]);
+            rr[u] = pp[u] >= 0 ? d.hRanks[(size_t)n * d.N + pp[u]] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            uint32_t m = c.ballot(cc[u] && rr[u] < maxRank);
+            if (m && hitP < 0) {
 #if defined(__CUDA_ARCH__)
-            int src = __ffs(m) - 1;
+              int src = __ffs(m) - 1;
 #else
-            int src = 0;
+              int src = 0;
 #endif
-            hitP = c.bcast(p, src);
-            hitR = c.bcast(rk, src);
+              hitP = c.bcast(pp[u], src);
+              hitR = c.bcast(rr[u], src);
+            }
           }
         }
       }
@@ -959,10 +997,12 @@ WTG_HD int hCondPick(const Dev& d, int n, u64 drawIdx, bool apply) {
   d.hWindow[n] = upd < lsz ? upd : lsz;
   // :825-828 put the sender at the end of the ranking
   int* rk = &d.hRanks[(size_t)n * d.N + e.from];
-  int nr = (int)((uint32_t)*rk + (uint32_t)d.N);
+  const int oldRank = *rk;
+  int nr = (int)((uint32_t)oldRank + (uint32_t)d.N);
   if (nr < 0) nr = 0x7fffffff;
   *rk = nr;
-  if (d.ndown[e.from]) d.hBizNoHit[n * d.L + lvl] = -2147483647 - 1;  // a candidate's rank moved
+  // a candidate's rank grew: the level's cached minimum only changes if this candidate held it
+  if (d.ndown[e.from] && d.hBizNoHit[n * d.L + lvl] == oldRank) d.hBizNoHit[n * d.L + lvl] = -2147483647 - 1;
   d.hSigsChecked[n] += 1;
   if (metaKind(e.meta) == PK_POOL) WTG_ATOMIC_ADD(&d.poolRef[metaLevel(e.meta)][(uint32_t)e.pl], 1);
   Ev ev;
