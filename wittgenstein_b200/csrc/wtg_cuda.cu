@@ -54,6 +54,22 @@ __device__ __forceinline__ void listAppend(const Dev& d, bool active, int n, int
   base = __shfl_sync(0xffffffffu, base, 0);
   if (active) list[(size_t)stripe * d.listStripeCap + base + __popc(m & ((1u << lane) - 1u))] = n;
 }
+// same, with a 64-bit payload per entry
+__device__ __forceinline__ void listAppendW(const Dev& d, bool active, int n, u64 word, int* cnt, int* list, u64* words) {
+  unsigned m = __ballot_sync(0xffffffffu, active);
+  if (!m) return;
+  int lane = threadIdx.x & 31;
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int stripe = gw & (ARENA_STRIPES - 1);
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&cnt[stripe], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (active) {
+    size_t at = (size_t)stripe * d.listStripeCap + base + __popc(m & ((1u << lane) - 1u));
+    list[at] = n;
+    words[at] = word;
+  }
+}
 // conditional-task bookkeeping, one thread per node -> list of due nodes
 __global__ void __launch_bounds__(256) k_cond_mark(Dev d) {
   if (d.ctl->error) return;
@@ -158,12 +174,17 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
   if (d.ctl->error) return;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int flag = 0;
+  u64 word = ~0ULL;
   if (n < d.N && d.inboxFill[n] > 0) {
     CoopSerial cs;
     if (d.proto == PROTO_SANFERMIN)
       nodeProcess(d, cs, n, 0);
-    else if (d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG)
-      flag = nodeProcess(d, cs, n, 1) > 0 ? 1 : 0;
+    else if (d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG) {
+      u64 w = 0;
+      int tasks = nodeProcess(d, cs, n, 1, &w);
+      flag = tasks > 0 ? 1 : 0;
+      if (tasks == 1) word = w;
+    }
     else if (d.proto == PROTO_CASPER) {  // an inbox of attestations only is scalar work; blocks and tasks get a warp
       const u64* in = d.inbox + d.inboxOff[n];
       const Ev* bucket = d.buckets + (size_t)(d.ctl->tick & (d.ring - 1)) * (size_t)d.bcap;
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
     } else
       flag = 1;
   }
-  listAppend(d, flag != 0, n, d.ctl->taskCnt, d.taskList);
+  listAppendW(d, flag != 0, n, word, d.ctl->taskCnt, d.taskList, d.taskWord);
 }
 // pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
 // events do not commute (Handel), all of the node's events in reference order; blocks assigned to list stripes.
@@ -193,8 +214,16 @@ __global__ void __launch_bounds__(256) k_node_tasks(Dev d) {
   const int sub = (blockIdx.x >> 6) * 8 + (threadIdx.x >> 5);
   const int nsub = (gridDim.x >> 6) * 8;
   const int* list = d.taskList + (size_t)stripe * d.listStripeCap;
+  const u64* words = d.taskWord + (size_t)stripe * d.listStripeCap;
   CoopWarp c;
-  for (int t = sub; t < cnt; t += nsub) nodeProcess(d, c, list[t], split ? 2 : 0);
+  for (int t = sub; t < cnt; t += nsub) {
+    const int n = list[t];
+    const u64 w = words[t];
+    if (split && w != ~0ULL)
+      nodeSingleTask(d, c, n, w);
+    else
+      nodeProcess(d, c, n, split ? 2 : 0);
+  }
 }
 // ---- pair scans ---------------------------------------------------------------------------
 __device__ __forceinline__ Pair pairAdd(Pair x, Pair y) {

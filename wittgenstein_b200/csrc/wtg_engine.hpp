@@ -179,6 +179,7 @@ class Engine {
     d.listStripeCap = ((N + 31) / 32 + ARENA_STRIPES - 1) / ARENA_STRIPES * 32 + 32;
     d.dueList = dalloc<int>((size_t)ARENA_STRIPES * d.listStripeCap);
     d.taskList = dalloc<int>((size_t)ARENA_STRIPES * d.listStripeCap);
+    d.taskWord = dalloc<unsigned long long>((size_t)ARENA_STRIPES * d.listStripeCap);
     d.inbox = dalloc<unsigned long long>((size_t)d.itemCap);
     d.subCount = dalloc<int>(d.bcap);
     d.itemBase = dalloc<int>(d.bcap);

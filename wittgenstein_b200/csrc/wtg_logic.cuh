@@ -97,7 +97,7 @@ WTG_HD void statAdd(const Dev& d, int n, int idx, unsigned long long v) {
 }
 WTG_HD void statMax(const Dev& d, int n, int idx, unsigned long long v) {
   unsigned long long* p = &d.stats[(size_t)(n & (STAT_SLOTS - 1)) * ST_COUNT + idx];
-  if (*p < v) WTG_ATOMIC_MAX(p, v);
+  WTG_ATOMIC_MAX(p, v);  // result unused: compiles to a reduction, no round trip
 }
 WTG_HD void setError(const Dev& d, int code, int detail) {
   if (WTG_ATOMIC_CAS(&d.ctl->error, 0, code) == 0) d.ctl->errorDetail = detail;
@@ -738,7 +738,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
   int cSig = kind == PK_INDIV ? 1 : kind == PK_FULL ? (1 << k) : kind == PK_INLINE ? WTG_POPC64(pl) : (int)(pl >> 32);
   if (c.lane() == 0) {
     statAdd(d, n, ST_UPDATES, 1ULL);
-    d.lvVer[n * L + l] += 1;  // cached scores of this level's queue entries are stale from here on
+    WTG_ATOMIC_ADD(&d.lvVer[n * L + l], 1u);  // cached scores of this level's queue entries are stale from here on (no read-back)
   }
 
   // :387-389  if (sigs.cardinality() == 1) sfl.indivVerifiedSig.set(from.nodeId);
@@ -1529,7 +1529,7 @@ WTG_HD int inboxEntry(u64 w) { return (int)(w & 0xFFFFFFFFULL); }
 // disjoint state of the node, so deliveries can run one thread per node and only tasks need a whole warp.
 // Returns the number of items skipped by the filter.
 template <class C>
-WTG_HD int nodeProcess(const Dev& d, C& c, int n, int filter) {
+WTG_HD int nodeProcess(const Dev& d, C& c, int n, int filter, u64* skippedWord = nullptr) {
   int cnt = d.inboxFill[n];
   if (cnt == 0) return 0;
   const u64* in = d.inbox + d.inboxOff[n];
@@ -1562,6 +1562,7 @@ WTG_HD int nodeProcess(const Dev& d, C& c, int n, int filter) {
     bool isTask = ev.kind == EV_TASK || ev.kind == EV_PERIODIC;
     if ((filter == 1 && isTask) || (filter == 2 && !isTask)) {
       ++skipped;
+      if (skippedWord) *skippedWord = w;
       continue;
     }
     uint32_t from = ev.from, meta = ev.meta;
@@ -1574,11 +1575,19 @@ WTG_HD int nodeProcess(const Dev& d, C& c, int n, int filter) {
     }
     deliver(d, c, n, ev, from, meta, pl, item);
   }
-  if (c.lane() == 0 && (filter == 0 || filter == 2 || skipped == 0)) {
-    statMax(d, n, ST_MAXINBOX, (unsigned long long)cnt);
-    d.inboxFill[n] = 0;  // ready for the next tick
+  if (c.lane() == 0) {
+    if (filter != 2) statMax(d, n, ST_MAXINBOX, (unsigned long long)cnt);
+    if (filter == 0 || filter == 2 || skipped == 0) d.inboxFill[n] = 0;  // ready for the next tick
   }
   return skipped;
+}
+// the only task of node n this tick, handed over by the message pass (saves re-reading the inbox)
+template <class C>
+WTG_HD void nodeSingleTask(const Dev& d, C& c, int n, u64 w) {
+  const Ev* bucket = d.buckets + (size_t)(d.ctl->tick & (d.ring - 1)) * (size_t)d.bcap;
+  Ev ev = bucket[inboxEntry(w)];
+  deliver(d, c, n, ev, ev.from, ev.meta, ev.pl, inboxItem(w));
+  if (c.lane() == 0) d.inboxFill[n] = 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -246,6 +246,7 @@ struct Dev {
   int* nodeTasks;     // [N] node still has task items to run after the per-thread message pass
   int* dueList;       // [64][listStripeCap] nodes whose conditional task runs this tick
   int* taskList;      // [64][listStripeCap] nodes with task events this tick
+  unsigned long long* taskWord;  // [64][listStripeCap] inbox word of the node's only task, ~0 when it has several
   int listStripeCap;
   unsigned long long* inbox;  // [bcap*? ] (key<<32 | entry index)
   int* subCount;      // [bcap] deliveries (+ re-push) of the event at processing position p
