@@ -45,7 +45,8 @@ class HostBackend : public Backend {
         if (gsfCondMark(d, n)) gsfCondScanQueue(d, c, n);
       int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
       for (int t = 0; t < tot; ++t) gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
-      for (int n = 0; n < d.N; ++n) gsfCondSelect(d, c, n, keep.data());
+      for (int n = 0; n < d.N; ++n)
+        if (d.condDue[n]) gsfCondSelect(d, c, n, keep.data());
     }
     if (d.proto == PROTO_HANDEL) {
       HScratch sc;

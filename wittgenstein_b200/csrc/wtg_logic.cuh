@@ -76,6 +76,8 @@ struct CoopSerial {
   WTG_HD int bcast(int v, int) const { return v; }
   WTG_HD u64 bcast64(u64 v, int) const { return v; }
   WTG_HD void sync() const {}
+  // value held by lane `src` of a per-lane table (serial: read the table itself)
+  WTG_HD int gather(int, int src, const int* table) const { return table[src]; }
 };
 #if defined(__CUDACC__)
 struct CoopWarp {
@@ -89,6 +91,7 @@ struct CoopWarp {
   __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
   __device__ __forceinline__ u64 bcast64(u64 v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ int gather(int mine, int src, const int*) const { return __shfl_sync(0xffffffffu, mine, src); }
 };
 #endif
 
@@ -280,25 +283,29 @@ WTG_HD int gsfScoreFrom(int l, int size, int cV, int cSig, bool inter, int cWI, 
 }
 
 // O(1) kinds: evaluated by a single lane
+WTG_HD int gsfScoreScalarC(const Dev& d, int n, const QEntry& e, int cV, int cI, int cU);
 WTG_HD int gsfScoreScalar(const Dev& d, int n, const QEntry& e) {
+  int l = (int)metaLevel(e.meta);
+  return gsfScoreScalarC(d, n, e, d.cntVer[n * d.L + l], d.cntIndiv[n * d.L + l], d.cntUnion[n * d.L + l]);
+}
+// same with the level's cardinalities (|verified|, |indivVerified|, |verified ∪ indivVerified|) supplied by the caller
+WTG_HD int gsfScoreScalarC(const Dev& d, int n, const QEntry& e, int cV, int cI, int cU) {
   int l = (int)metaLevel(e.meta);
   int kind = (int)metaKind(e.meta);
   int size = 1 << (l - 1);
-  int cV = d.cntVer[n * d.L + l];
   if (cV >= size) return 0;
   const u64* rowV = d.verified + (size_t)n * d.W64;
   const u64* rowI = d.indivVer + (size_t)n * d.W64;
   if (kind == PK_FULL) {
     int k = (int)metaK(e.meta);
     int c = 1 << k;
-    bool interIndiv = d.cntIndiv[n * d.L + l] > 0;
+    bool interIndiv = cI > 0;
     return gsfScoreFrom(l, size, cV, c, cV > 0, c, c, interIndiv);
   }
   if (kind == PK_INDIV) {
     int f = (int)e.from;
     bool inV = (rowV[f >> 6] >> (f & 63)) & 1ULL;
     bool inI = (rowI[f >> 6] >> (f & 63)) & 1ULL;
-    int cI = d.cntIndiv[n * d.L + l], cU = d.cntUnion[n * d.L + l];
     return gsfScoreFrom(l, size, cV, 1, inV, cI + (inI ? 0 : 1), cU + ((inI || inV) ? 0 : 1), inI);
   }
   // PK_INLINE
@@ -399,6 +406,10 @@ WTG_HD void gsfCondScanQueue(const Dev& d, C& c, int n) {
   const int st = n & (ARENA_STRIPES - 1);
   const int per = d.workCap / ARENA_STRIPES;
   int reeval = 0;
+  // lane l keeps level l's version and cardinalities: per entry they come from a shuffle instead of a dependent load
+  const int myL = c.lane() < d.L ? c.lane() : 0;
+  const int verMine = (int)ver[myL];
+  const int cvMine = d.cntVer[n * d.L + myL], ciMine = d.cntIndiv[n * d.L + myL], cuMine = d.cntUnion[n * d.L + myL];
   for (int base0 = 0; base0 < len; base0 += C::LANES * COND_UNROLL) {
     QEntry e[COND_UNROLL];
     uint32_t es[COND_UNROLL];
@@ -419,14 +430,17 @@ WTG_HD void gsfCondScanQueue(const Dev& d, C& c, int n) {
     for (int u = 0; u < COND_UNROLL; ++u) {
       int i = base0 + u * C::LANES + c.lane();
       bool stalePool = false;
+      const int lv = (int)metaLevel(e[u].meta);
+      const uint32_t v = (uint32_t)c.gather(verMine, lv, reinterpret_cast<const int*>(ver));
+      const int cV = c.gather(cvMine, lv, d.cntVer + n * d.L), cI = c.gather(ciMine, lv, d.cntIndiv + n * d.L),
+                cU = c.gather(cuMine, lv, d.cntUnion + n * d.L);
       if (i < len) {
-        uint32_t v = ver[metaLevel(e[u].meta)];
         if (es[u] != v) {
           ++reeval;
           if (metaKind(e[u].meta) == PK_POOL) {
             stalePool = true;
           } else {
-            qsc[i] = gsfScoreScalar(d, n, e[u]);
+            qsc[i] = gsfScoreScalarC(d, n, e[u], cV, cI, cU);
             qst[i] = v;
           }
         }
@@ -471,10 +485,10 @@ WTG_HD void gsfScoreItem(const Dev& d, C& c, uint32_t item) {
 
 // keepBits: scratch of qcap/LANES words private to this coop
 template <class C>
-WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {
-  if (!d.condDue[n]) return;
+WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {  // n is due (callers walk the due list)
   const Ctl& ctl = *d.ctl;
   int len = d.qLen[n];
+  const int pairing = d.pairing[n];
   QEntry* q = d.queue + (size_t)n * d.qcap;
   int* qsc = d.qScore + (size_t)n * d.qcap;
   uint32_t* qst = d.qStamp + (size_t)n * d.qcap;
@@ -583,7 +597,7 @@ WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {
   if (c.lane() == 0) {
     d.qLen[n] = w;
     if (found) {  // registerTask(updateVerifiedSignatures, time + nodePairingTime, this)  :575-581
-      d.sigChecked[n] += 1;
+      WTG_ATOMIC_ADD(&d.sigChecked[n], 1);
       d.sigQueueSize[n] = w;
       Ev ev;
       ev.kind = EV_TASK;
@@ -594,7 +608,7 @@ WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {
       ev.aux = 0;
       ev.pad = 0;
       d.condEv[n] = ev;
-      d.condTarget[n] = ctl.tick + d.pairing[n];
+      d.condTarget[n] = ctl.tick + pairing;
     }
     d.condFired[n] = found ? 1 : 0;
   }
