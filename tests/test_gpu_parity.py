@@ -277,6 +277,11 @@ def test_casper_errors():
     with pytest.raises(WtgError):
         CasperIMD(CasperParemeters(0, False, 2, 2, 1000, 1))
     p = CasperIMD(CasperParemeters(4, False, 3, 8, 1000, 1))
+    p.init(0)
+    p.network().partition(0.5)
+    with pytest.raises(WtgError):
+        p.network().end_partition()  # BlockChainNetwork.endPartition re-sends every head: not offered, and says so
+    p = CasperIMD(CasperParemeters(4, False, 3, 8, 1000, 1))
     p.init(8000)  # the Byzantine producer and producer 2 would both create a block in millisecond 16000
     with pytest.raises(WtgError):
         for _ in range(10):

@@ -986,6 +986,8 @@ class Engine {
   }
   void endPartition() {
     requireInited();
+    if (d.proto == PROTO_CASPER)  // BlockChainNetwork.endPartition (BlockChainNetwork.java:46-54) also makes every node re-send its head
+      throw std::logic_error("endPartition of a block-chain network (full re-send of every node's head) is not supported by the B200 engine");
     partitionsInX.clear();
     uploadPartitions();
   }
