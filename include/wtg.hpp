@@ -1,0 +1,260 @@
+// wittgenstein_b200 — C++ host-side mirror of the reference classes for the accelerated path, over the C ABI of wtg.h.
+//
+// The reference is Java and no JVM exists in the build image, so the host side above the C ABI is written in C++ with the
+// reference's names, argument order and error behaviour (unchecked exceptions -> wtg_b200::WtgError):
+//   core/Network.java            -> Network          (rd.setSeed, runMs, run, time, msgs.size(), partition, ...)
+//   protocols/PingPong.java      -> PingPong / PingPongParameters
+//   protocols/GSFSignature.java  -> GSFSignature / GSFSignatureParameters
+//   protocols/SanFerminSignature.java -> SanFerminSignature / SanFerminSignatureParameters
+//   protocols/Handel.java        -> Handel / HandelParameters
+//   protocols/CasperIMD.java     -> CasperIMD / CasperParemeters (the reference's spelling)
+// Header-only; link with wittgenstein_b200/libwtg_b200.so.  tests/cpp/mirror_parity.cpp drives it against the CPU oracle.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "wtg.h"
+
+namespace wtg_b200 {
+
+struct WtgError : std::runtime_error {  // IllegalArgumentException / IllegalStateException of the reference
+  using std::runtime_error::runtime_error;
+};
+inline int check(int rc) {
+  if (rc < 0) throw WtgError(wtg_last_error());
+  return rc;
+}
+inline const char* cstr(const std::string& s) { return s.empty() ? nullptr : s.c_str(); }  // "" stands for Java null
+
+struct NodeCounters {  // Node.java:72-79
+  std::vector<long long> msgReceived, msgSent, bytesSent, bytesReceived, doneAt;
+};
+
+// core/Network.java
+class Network {
+ public:
+  struct Rd {  // network.rd
+    Network* net;
+    void setSeed(long long seed) { check(wtg_set_seed(net->h, seed)); }  // RunMultipleTimes.java:47
+  } rd{this};
+
+  Network() : h(wtg_create()) {
+    if (!h) throw WtgError(wtg_last_error());
+  }
+  ~Network() { wtg_destroy(h); }
+  Network(const Network&) = delete;
+  Network& operator=(const Network&) = delete;
+
+  void setNetworkLatency(const std::string& registryName) { check(wtg_set_network_latency(h, cstr(registryName))); }
+  void setNetworkLatency(const std::vector<int>& distribProp, const std::vector<int>& distribVal) {  // Network.java:665-667
+    check(wtg_set_network_latency_measured(h, distribProp.data(), distribVal.data(), (int)distribProp.size()));
+  }
+  void setNodeBuilder(const std::string& registryName) { check(wtg_set_node_builder(h, cstr(registryName))); }
+  void setMsgDiscardTime(int ms) { check(wtg_set_msg_discard_time(h, ms)); }
+  void setTunable(const std::string& key, long long v) { check(wtg_set_tunable(h, key.c_str(), v)); }
+
+  bool runMs(int ms) { return check(wtg_run_ms(h, ms)) == 1; }  // Network.java:318-338
+  bool run(int seconds) { return runMs(seconds * 1000); }       // :306-308
+  int time() const { return wtg_time(h); }
+  int nodeCount() const { return wtg_node_count(h); }
+  struct Msgs {  // network.msgs
+    const Network* net;
+    int size() const { return check(wtg_msgs_size(net->h)); }
+    int sizeAt(int t) const { return check(wtg_msgs_size_at(net->h, t)); }
+  } msgs{this};
+
+  void stopNode(int id) { check(wtg_stop_node(h, id)); }    // node.stop()
+  void startNode(int id) { check(wtg_start_node(h, id)); }  // node.start()
+  void partition(float part) { check(wtg_partition(h, part)); }
+  void endPartition() { check(wtg_end_partition(h)); }
+  unsigned long long rngState() const { return wtg_rng_state(h); }
+
+  NodeCounters counters() const {
+    size_t n = (size_t)nodeCount();
+    std::vector<long long> raw(5 * n);
+    check(wtg_node_counters(h, raw.data()));
+    NodeCounters c;
+    c.msgReceived.assign(raw.begin(), raw.begin() + n);
+    c.msgSent.assign(raw.begin() + n, raw.begin() + 2 * n);
+    c.bytesSent.assign(raw.begin() + 2 * n, raw.begin() + 3 * n);
+    c.bytesReceived.assign(raw.begin() + 3 * n, raw.begin() + 4 * n);
+    c.doneAt.assign(raw.begin() + 4 * n, raw.end());
+    return c;
+  }
+  std::vector<unsigned char> down() const {  // Node.isDown()
+    std::vector<unsigned char> d((size_t)nodeCount());
+    check(wtg_node_attrs(h, nullptr, nullptr, nullptr, nullptr, nullptr, d.data()));
+    return d;
+  }
+  wtg_net* handle() const { return h; }
+
+ private:
+  wtg_net* h;
+};
+
+// protocols/PingPong.java:34-50
+struct PingPongParameters {
+  int nodeCt = 1000;
+  std::string nodeBuilderName, networkLatencyName;
+};
+class PingPong {
+ public:
+  explicit PingPong(const PingPongParameters& p) : params(p) {
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+  }
+  Network& network() { return net; }
+  void init() { check(wtg_pingpong_init(net.handle(), params.nodeCt)); }  // :82-87
+  std::vector<int> pong() {
+    std::vector<int> v((size_t)params.nodeCt);
+    check(wtg_pingpong_pongs(net.handle(), v.data()));
+    return v;
+  }
+  const PingPongParameters params;
+
+ private:
+  Network net;
+};
+
+// protocols/GSFSignature.java:27-107
+struct GSFSignatureParameters {
+  int nodeCount, threshold, pairingTime, timeoutPerLevelMs, periodDurationMs, acceleratedCallsCount, nodesDown;
+  std::string nodeBuilderName, networkLatencyName;
+};
+class GSFSignature {
+ public:
+  explicit GSFSignature(const GSFSignatureParameters& p) : params(p) {
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+  }
+  Network& network() { return net; }
+  void init() {  // :611-635
+    int a[7] = {params.nodeCount, params.threshold, params.pairingTime, params.timeoutPerLevelMs, params.periodDurationMs,
+                params.acceleratedCallsCount, params.nodesDown};
+    check(wtg_gsf_init(net.handle(), a));
+  }
+  int words() const { return params.nodeCount < 64 ? 1 : params.nodeCount / 64; }
+  std::vector<unsigned long long> verifiedSignatures() {  // GSFNode.verifiedSignatures, N rows of words()
+    std::vector<unsigned long long> v((size_t)params.nodeCount * (size_t)words());
+    check(wtg_gsf_verified(net.handle(), v.data()));
+    return v;
+  }
+  struct Scalars {
+    std::vector<int> nodePairingTime, sigChecked, sigQueueSize, toVerifySize, cardinality;
+  };
+  Scalars scalars() {
+    size_t n = (size_t)params.nodeCount;
+    Scalars s{std::vector<int>(n), std::vector<int>(n), std::vector<int>(n), std::vector<int>(n), std::vector<int>(n)};
+    check(wtg_gsf_node_scalars(net.handle(), s.nodePairingTime.data(), s.sigChecked.data(), s.sigQueueSize.data(), s.toVerifySize.data(),
+                               s.cardinality.data()));
+    return s;
+  }
+  bool continueIf() {  // newConfIf :670-682
+    Scalars s = scalars();
+    std::vector<unsigned char> d = net.down();
+    for (int i = 0; i < params.nodeCount; ++i)
+      if (!d[(size_t)i] && s.cardinality[(size_t)i] < params.threshold) return true;
+    return false;
+  }
+  const GSFSignatureParameters params;
+
+ private:
+  Network net;
+};
+
+// protocols/SanFerminSignature.java:41-110
+struct SanFerminSignatureParameters {
+  int nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount;
+  std::string nodeBuilderName, networkLatencyName;
+};
+class SanFerminSignature {
+ public:
+  explicit SanFerminSignature(const SanFerminSignatureParameters& p) : params(p) {  // the constructor builds the nodes (:112-129)
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+    int a[6] = {p.nodeCount, p.threshold, p.pairingTime, p.signatureSize, p.replyTimeout, p.candidateCount};
+    check(wtg_sanfermin_construct(net.handle(), a));
+  }
+  Network& network() { return net; }
+  void init() { check(wtg_sanfermin_init(net.handle())); }
+  const SanFerminSignatureParameters params;
+
+ private:
+  Network net;
+};
+
+// protocols/Handel.java:22-142
+struct HandelParameters {
+  int nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown;
+  std::string nodeBuilderName, networkLatencyName;
+  int desynchronizedStart = 0;
+  bool byzantineSuicide = false, hiddenByzantine = false;
+};
+class Handel {
+ public:
+  explicit Handel(const HandelParameters& p) : params(p) {
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+  }
+  Network& network() { return net; }
+  void init() {  // :957-1014
+    int a[11] = {params.nodeCount, params.threshold, params.pairingTime, params.levelWaitTime, params.extraCycle,
+                 params.disseminationPeriodMs, params.fastPath, params.nodesDown, params.desynchronizedStart,
+                 params.byzantineSuicide ? 1 : 0, params.hiddenByzantine ? 1 : 0};
+    check(wtg_handel_init(net.handle(), a));
+  }
+  std::vector<unsigned long long> totalIncoming() {  // union over levels, N rows of N/64 words
+    std::vector<unsigned long long> v((size_t)params.nodeCount * (size_t)(params.nodeCount < 64 ? 1 : params.nodeCount / 64));
+    check(wtg_handel_rows(net.handle(), 0, v.data()));
+    return v;
+  }
+  const HandelParameters params;
+
+ private:
+  Network net;
+};
+
+// protocols/CasperIMD.java:18-71
+struct CasperParemeters {
+  int cycleLength = 4;
+  bool randomOnTies = true;
+  int blockProducersCount = 2, attestersPerRound = 20, blockConstructionTime = 1000, attestationConstructionTime = 1;
+  std::string nodeBuilderName, networkLatencyName;
+};
+class CasperIMD {
+ public:
+  enum ByzKind { ByzBlockProducer = 3, ByzBlockProducerSF = 4, ByzBlockProducerNS = 5, ByzBlockProducerWF = 6 };
+  explicit CasperIMD(const CasperParemeters& p) : params(p) {  // adds the observer (:81-88)
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+    int a[6] = {p.cycleLength, p.randomOnTies ? 1 : 0, p.blockProducersCount, p.attestersPerRound, p.blockConstructionTime,
+                p.attestationConstructionTime};
+    check(wtg_casper_construct(net.handle(), a));
+  }
+  Network& network() { return net; }
+  int nodeCount() const { return 1 + params.blockProducersCount + params.attestersPerRound * params.cycleLength; }
+  void init() { init(ByzBlockProducerWF, 0); }  // :472-476
+  void init(ByzKind kind, int delay) { check(wtg_casper_init_byz(net.handle(), (int)kind, delay)); }
+  std::vector<int> heads() {  // BlockChainNode.head (block id) of every node; node 0 is network.observer
+    std::vector<int> v((size_t)nodeCount());
+    check(wtg_casper_heads(net.handle(), v.data()));
+    return v;
+  }
+  struct Blocks {
+    std::vector<int> height, parent, producer, proposalTime, included;
+  };
+  Blocks blocks() {
+    size_t nb = (size_t)check(wtg_casper_block_count(net.handle()));
+    Blocks b{std::vector<int>(nb), std::vector<int>(nb), std::vector<int>(nb), std::vector<int>(nb), std::vector<int>(nb)};
+    check(wtg_casper_blocks(net.handle(), b.height.data(), b.parent.data(), b.producer.data(), b.proposalTime.data(), b.included.data()));
+    return b;
+  }
+  const CasperParemeters params;
+
+ private:
+  Network net;
+};
+
+}  // namespace wtg_b200
