@@ -348,32 +348,11 @@ def main():
 
     if rank == 0:
         g.build()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    from wittgenstein_b200.replicas import Replicas
 
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
-    os.environ["WTG_DEVICE"] = str(local)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    rep = Replicas("nccl")
+    dist = rep.dist
+    barrier, max_over_ranks, sum_over_ranks = rep.barrier, rep.max_over_ranks, rep.sum_over_ranks
 
     if args.workload == "casper":
         run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks)
