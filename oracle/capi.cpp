@@ -595,4 +595,24 @@ void wo_casper_byz(void* h, int32_t* out5) {
   out5[7] = b->incNotTheBestFather;
   out5[8] = ns ? ns->skipped : 0;
 }
+
+// ---- network controls of any protocol (Node.stop/start, Network.partition/endPartition/setMsgDiscardTime) ----------
+// op: 0 stop(arg), 1 start(arg), 2 partition(arg / 10000.f), 3 endPartition, 4 setMsgDiscardTime(arg)
+static int netCtl(Network& net, int op, int arg) {
+  WO_TRY
+  switch (op) {
+    case 0: net.getNodeById(arg).stop(); break;
+    case 1: net.getNodeById(arg).start(); break;
+    case 2: net.partition(static_cast<float>(arg) / 10000.f); break;
+    case 3: net.endPartition(); break;
+    case 4: net.setMsgDiscardTime(arg); break;
+    default: throw IllegalArgument("op");
+  }
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_pp_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<PingPong*>(h)->network, op, arg); }
+int wo_gsf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<GSFSignature*>(h)->network, op, arg); }
+int wo_sf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<SanFerminSignature*>(h)->network, op, arg); }
+int wo_handel_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<Handel*>(h)->network, op, arg); }
 }  // extern "C"

@@ -75,7 +75,34 @@ def _b(s):
     return None if s is None else s.encode()
 
 
-class OraclePingPong:
+class _NetCtl:
+    """Node.stop/start, Network.partition/endPartition/setMsgDiscardTime on the oracle's network (prefix set by the subclass)."""
+
+    _ctl = None
+
+    def _c(self, op, arg=0):
+        if getattr(self.lib, self._ctl)(self.h, op, int(arg)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def stop_node(self, i):
+        self._c(0, i)
+
+    def start_node(self, i):
+        self._c(1, i)
+
+    def partition(self, part):
+        self._c(2, round(part * 10000))
+
+    def end_partition(self):
+        self._c(3)
+
+    def set_msg_discard_time(self, ms):
+        self._c(4, ms)
+
+
+class OraclePingPong(_NetCtl):
+    _ctl = "wo_pp_net_ctl"
+
     """protocols/PingPong.java through the oracle."""
 
     def __init__(self, node_ct=1000, node_builder=None, latency=None, seed=None):
@@ -126,7 +153,9 @@ class OraclePingPong:
             self.h = None
 
 
-class OracleGSF:
+class OracleGSF(_NetCtl):
+    _ctl = "wo_gsf_net_ctl"
+
     """protocols/GSFSignature.java through the oracle."""
 
     def __init__(self, node_count, threshold, pairing_time, timeout_per_level_ms, period_ms, accelerated_calls, nodes_down,
@@ -230,7 +259,9 @@ class OracleGSF:
             self.h = None
 
 
-class OracleSanFermin:
+class OracleSanFermin(_NetCtl):
+    _ctl = "wo_sf_net_ctl"
+
     """protocols/SanFerminSignature.java through the oracle (nodes are built by the constructor)."""
 
     def __init__(self, node_count, threshold, pairing_time, signature_size, reply_timeout, candidate_count, node_builder, latency):
@@ -290,7 +321,9 @@ class OracleSanFermin:
             self.h = None
 
 
-class OracleHandel:
+class OracleHandel(_NetCtl):
+    _ctl = "wo_handel_net_ctl"
+
     """protocols/Handel.java through the oracle."""
 
     def __init__(self, node_count, threshold, pairing_time, level_wait_time, extra_cycle, dissemination_period_ms, fast_path,

@@ -6,6 +6,7 @@ import pytest
 
 from tests.oracle_lib import OracleGSF, OraclePingPong
 from tests.parity import compare_gsf, compare_init, run_lockstep
+from wittgenstein_b200 import GSFSignature, GSFSignatureParameters, PingPong, PingPongParameters  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -422,3 +423,71 @@ def test_error_paths():
     with pytest.raises(WtgError):
         for _ in range(100):
             g.network().run_ms(10)
+
+
+@pytest.mark.gpu
+def test_gsf_stop_start_partition_discard_midrun():
+    """Node.stop/start (Node.java:120-127), Network.partition/endPartition (Network.java:693-707) and setMsgDiscardTime
+    (:103-106) applied between runMs windows: dropped sends still count as sent (:476-486), stopped nodes neither receive
+    (:606) nor re-arm their periodic task, partitions cut deliveries both at send and at arrival time."""
+    args = (128, 100, 3, 20, 10, 10, 8, AWS_NB, AWS_NL)
+    p = GSFSignature(GSFSignatureParameters(*args))
+    o = OracleGSF(*args, seed=5)
+    p.network().set_seed(5)
+    p.network().set_msg_discard_time(180)
+    o.set_msg_discard_time(180)
+    p.init(); o.init()
+    plan = {5: ("stop", 7), 8: ("stop", 64), 12: ("partition", 0.3), 20: ("partition", 0.7), 30: ("start", 7), 45: ("end_partition", None),
+            60: ("start", 64)}
+    for k in range(120):
+        if k in plan:
+            op, arg = plan[k]
+            for tgt in (p.network(), o):
+                fn = getattr(tgt, {"stop": "stop_node", "start": "start_node"}.get(op, op))
+                fn() if arg is None else fn(arg)
+        assert p.network().run_ms(10) == o.run_ms(10)
+        bad = compare_gsf(p, o, f"t={o.time}", full=(k % 4 == 0))
+        assert not bad, bad
+    assert not compare_gsf(p, o, "end")
+
+
+@pytest.mark.gpu
+def test_pingpong_discard_and_partition():
+    p = PingPong(PingPongParameters(1000, AWS_NB, AWS_NL))
+    o = OraclePingPong(1000, AWS_NB, AWS_NL)
+    for tgt in (p.network(), o):
+        tgt.set_msg_discard_time(120)
+    p.init(); o.init()
+    for k in range(12):
+        if k == 1:
+            p.network().partition(0.5); o.partition(0.5)
+        if k == 3:
+            p.network().stop_node(0); o.stop_node(0)  # the pinger itself
+        if k == 5:
+            p.network().start_node(0); o.start_node(0)
+            p.network().end_partition(); o.end_partition()
+        assert p.network().run_ms(50) == o.run_ms(50)
+        assert (p.pongs() == o.pongs()).all()
+        assert (p.network().counters() == o.counters()).all()
+        assert p.network().msgs_size() == o.msgs_size()
+
+
+@pytest.mark.gpu
+def test_sanfermin_with_stopped_nodes_and_partition():
+    from tests.oracle_lib import OracleSanFermin
+    from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
+
+    p = SanFerminSignature(SanFerminSignatureParameters(256, 256, 2, 48, 300, 1, False, None, None))
+    o = OracleSanFermin(256, 256, 2, 48, 300, 1, None, None)
+    p.init(); o.init()
+    for k in range(150):
+        if k == 2:
+            for i in (3, 77, 200):
+                p.network().stop_node(i); o.stop_node(i)
+        if k == 10:
+            p.network().partition(0.4); o.partition(0.4)
+        if k == 40:
+            p.network().end_partition(); o.end_partition()
+        assert p.network().run_ms(20) == o.run_ms(20)
+        bad = _sf_compare(p, o, f"t={o.time}")
+        assert not bad, bad
