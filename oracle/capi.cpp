@@ -615,4 +615,60 @@ int wo_pp_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<PingPong
 int wo_gsf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<GSFSignature*>(h)->network, op, arg); }
 int wo_sf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<SanFerminSignature*>(h)->network, op, arg); }
 int wo_handel_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<Handel*>(h)->network, op, arg); }
+
+// ---- SanFerminCappos ---------------------------------------------------------------------------
+// params6 = { nodeCount, threshold, pairingTime, signatureSize, timeout, candidateCount }  (the constructor's order, :86-94)
+void* wo_cappos_create(const int* p6, const char* nodeBuilderName, const char* networkLatencyName) {
+  WO_TRY
+  SanFerminCappos::Params p;
+  p.nodeCount = p6[0];
+  p.threshold = p6[1];
+  p.pairingTime = p6[2];
+  p.signatureSize = p6[3];
+  p.timeout = p6[4];
+  p.candidateCount = p6[5];
+  p.nodeBuilderName = nodeBuilderName ? nodeBuilderName : "";
+  p.latencyNull = networkLatencyName == nullptr;
+  p.networkLatencyName = networkLatencyName ? networkLatencyName : "";
+  return new SanFerminCappos(p);
+  WO_CATCH(nullptr)
+}
+void wo_cappos_destroy(void* h) { delete static_cast<SanFerminCappos*>(h); }
+void wo_cappos_set_seed(void* h, int64_t s) { static_cast<SanFerminCappos*>(h)->network.rd.setSeed(s); }
+int wo_cappos_init(void* h) {
+  WO_TRY
+  static_cast<SanFerminCappos*>(h)->init();
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_cappos_run_ms(void* h, int ms) {
+  WO_TRY
+  return static_cast<SanFerminCappos*>(h)->network.runMs(ms) ? 1 : 0;
+  WO_CATCH(-1)
+}
+int wo_cappos_time(void* h) { return static_cast<SanFerminCappos*>(h)->network.time; }
+int64_t wo_cappos_msgs_live(void* h) { return static_cast<SanFerminCappos*>(h)->network.msgs.live; }
+uint64_t wo_cappos_rng_state(void* h) { return static_cast<SanFerminCappos*>(h)->network.rd.seed; }
+void wo_cappos_node_counters(void* h, int64_t* out5N) { nodeCounters(static_cast<SanFerminCappos*>(h)->network.allNodes, out5N); }
+void wo_cappos_node_attrs(void* h, int32_t* x, int32_t* y, int32_t* extra, int32_t* city, double* speed, uint8_t* down) {
+  nodeAttrs(static_cast<SanFerminCappos*>(h)->network.allNodes, x, y, extra, city, speed, down);
+}
+int wo_cappos_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<SanFerminCappos*>(h)->network, op, arg); }
+// per node: currentPrefixLength, totalNumberOfSigs(-1), done, thresholdDone, isSwapping, cached levels (bit mask) ; thresholdAt
+void wo_cappos_node_scalars(void* h, int32_t* cpl, int32_t* sigs, int32_t* done, int32_t* thrDone, int32_t* swapping, int32_t* cacheMask,
+                            int64_t* thresholdAt) {
+  auto* p = static_cast<SanFerminCappos*>(h);
+  for (size_t i = 0; i < p->nodes.size(); ++i) {
+    auto& n = *p->nodes[i];
+    cpl[i] = n.currentPrefixLength;
+    sigs[i] = n.totalNumberOfSigs(-1);
+    done[i] = n.done ? 1 : 0;
+    thrDone[i] = n.thresholdDone ? 1 : 0;
+    swapping[i] = n.isSwapping ? 1 : 0;
+    int m = 0;
+    for (auto& kv : n.signatureCache) m |= 1 << kv.first;
+    cacheMask[i] = m;
+    thresholdAt[i] = n.thresholdAt;
+  }
+}
 }  // extern "C"

@@ -799,6 +799,146 @@ inline void SanFerminSignature::SwapRequest::action(Network&, Node& from, Node& 
 }
 
 // ----------------------------------------------------------------------------------------
+// SanFerminCappos  (protocols/SanFerminCappos.java)
+// ----------------------------------------------------------------------------------------
+struct SanFerminCappos {
+  struct Params {  // :43-104
+    int nodeCount = 32768 / 16, pairingTime = 2, signatureSize = 48, candidateCount = 50, threshold = 32768 / 32, timeout = 150;
+    std::string nodeBuilderName, networkLatencyName;
+    bool latencyNull = true;
+  };
+  struct SanFerminNode;
+  struct Swap : Message {  // :439-463
+    SanFerminCappos* p;
+    bool wantReply;
+    int level, aggValue;
+    Swap(SanFerminCappos* pp, int l, int a, bool r) : p(pp), wantReply(r), level(l), aggValue(a) {}
+    void action(Network&, Node& from, Node& to) override;
+    int size() const override { return 4 + p->params.signatureSize; }
+  };
+  struct SanFerminNode : Node {  // :144-437
+    SanFerminCappos* p;
+    SanFerminHelper helper;
+    int currentPrefixLength;
+    std::map<int, std::vector<int>> signatureCache;  // HashMap<Integer, List<Integer>>: only containsKey / max / filtered sums are observed
+    bool isSwapping = false;
+    int aggValue = 1;
+    int64_t thresholdAt = 0;
+    bool thresholdDone = false, done = false;
+
+    explicit SanFerminNode(SanFerminCappos* pp)
+        : Node(pp->network.rd, pp->nb), p(pp), currentPrefixLength(javaLog2(pp->params.nodeCount)) {}
+
+    void onSwap(SanFerminNode& from, const Swap& swap) {  // :201-241
+      bool wantReply = swap.wantReply;
+      if (done || swap.level != currentPrefixLength) {
+        bool isValueCached = signatureCache.count(swap.level) != 0;
+        if (wantReply && isValueCached) {
+          sendSwap({&from}, swap.level, getBestCachedSig(swap.level), false);
+        } else {
+          if (helper.isCandidate(from.nodeId, swap.level)) putCachedSig(swap.level, swap.aggValue);
+        }
+        return;
+      }
+      if (wantReply) sendSwap({&from}, swap.level, totalNumberOfSigs(swap.level), false);
+      bool isCandidate = helper.isCandidate(from.nodeId, currentPrefixLength);
+      if (isCandidate && !isSwapping) transition(swap.level, swap.aggValue);
+    }
+    void tryNextNodes(const std::vector<int>& candidates) {  // :248-296
+      if (candidates.empty()) return;
+      for (int c : candidates)
+        if (!helper.isCandidate(c, currentPrefixLength)) throw IllegalState("tryNextNodes: not a candidate");
+      std::vector<Node*> dests;
+      for (int c : candidates) dests.push_back(p->nodes[static_cast<size_t>(c)].get());
+      sendSwap(dests, currentPrefixLength, totalNumberOfSigs(currentPrefixLength + 1), true);
+      int currLevel = currentPrefixLength;
+      p->network.registerTask(
+          [this, currLevel] {
+            if (!done && currentPrefixLength == currLevel) tryNextNodes(helper.pickNextNodes(currentPrefixLength, p->params.candidateCount));
+          },
+          p->network.time + p->params.timeout, *this);
+    }
+    void goNextLevel() {  // :306-344
+      if (done) return;
+      bool enoughSigs = totalNumberOfSigs(currentPrefixLength) >= p->params.threshold;
+      bool noMoreSwap = currentPrefixLength == 0;
+      if (enoughSigs && !thresholdDone) {
+        thresholdDone = true;
+        thresholdAt = p->network.time + p->params.pairingTime * 2;
+      }
+      if (noMoreSwap && !done) {
+        doneAt = p->network.time + p->params.pairingTime * 2;
+        p->finishedNodes.push_back(this);
+        done = true;
+        return;
+      }
+      currentPrefixLength--;
+      isSwapping = false;
+      if (signatureCache.count(currentPrefixLength)) {
+        goNextLevel();
+        return;
+      }
+      tryNextNodes(helper.pickNextNodes(currentPrefixLength, p->params.candidateCount));
+    }
+    void sendSwap(const std::vector<Node*>& nodes, int level, int value, bool wantReply) {  // :346-349
+      p->network.send(std::make_shared<Swap>(p, level, value, wantReply), *this, nodes);
+    }
+    int totalNumberOfSigs(int level) const {  // :351-358
+      int sum = 0;
+      for (auto& kv : signatureCache)
+        if (kv.first >= level) sum += *std::max_element(kv.second.begin(), kv.second.end());
+      return sum + 1;
+    }
+    void transition(int level, int toAggregate) {  // :364-374
+      isSwapping = true;
+      p->network.registerTask(
+          [this, level, toAggregate] {
+            putCachedSig(level, toAggregate);
+            goNextLevel();
+          },
+          p->network.time + p->params.pairingTime, *this);
+    }
+    int getBestCachedSig(int level) const {  // :376-380
+      const auto& v = signatureCache.at(level);
+      return *std::max_element(v.begin(), v.end());
+    }
+    void putCachedSig(int level, int value) {  // :382-393
+      signatureCache[level].push_back(value);
+      bool enoughSigs = totalNumberOfSigs(currentPrefixLength) >= p->params.threshold;
+      if (enoughSigs && !thresholdDone) {
+        thresholdDone = true;
+        thresholdAt = p->network.time + p->params.pairingTime * 2;
+      }
+    }
+  };
+
+  Params params;
+  Network network;
+  NodeBuilder nb;
+  std::vector<std::unique_ptr<SanFerminNode>> nodes;
+  std::vector<SanFerminNode*> finishedNodes;
+
+  explicit SanFerminCappos(const Params& pr) : params(pr) {  // :106-112
+    nb = nodeBuilderByName(pr.nodeBuilderName);
+    network.setNetworkLatency(networkLatencyByName(pr.networkLatencyName, pr.latencyNull));
+  }
+  void init() {  // :120-134
+    for (int i = 0; i < params.nodeCount; i++) {
+      nodes.push_back(std::make_unique<SanFerminNode>(this));
+      network.addNode(nodes.back().get());
+    }
+    for (auto& n : nodes) n->helper = SanFerminHelper(n->nodeId, params.nodeCount, &network.rd);
+    for (auto& up : nodes) {
+      SanFerminNode* n = up.get();
+      network.registerTask([n] { n->goNextLevel(); }, 1, *n);
+    }
+  }
+};
+inline void SanFerminCappos::Swap::action(Network&, Node& from, Node& to) {
+  static_cast<SanFerminNode&>(to).onSwap(static_cast<SanFerminNode&>(from), *this);
+}
+
+// ----------------------------------------------------------------------------------------
 // Handel  (protocols/Handel.java), HiddenByzantine (:840-917) included.
 // ----------------------------------------------------------------------------------------
 struct Handel {

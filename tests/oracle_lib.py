@@ -49,6 +49,10 @@ def load():
     lib.wo_casper_run_timed.restype = C.c_double
     lib.wo_casper_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.wo_casper_partition.argtypes = [C.c_void_p, C.c_float]
+    lib.wo_cappos_create.restype = C.c_void_p
+    lib.wo_cappos_create.argtypes = [C.POINTER(C.c_int), C.c_char_p, C.c_char_p]
+    lib.wo_cappos_rng_state.restype = C.c_uint64
+    lib.wo_cappos_msgs_live.restype = C.c_int64
     lib.wo_sf_create.restype = C.c_void_p
     lib.wo_sf_create.argtypes = [C.c_int] * 6 + [C.c_char_p, C.c_char_p]
     lib.wo_sf_rng_state.restype = C.c_uint64
@@ -515,3 +519,64 @@ class OracleCasper:
         self.lib.wo_casper_byz(self.h, _p(out, C.c_int32))
         return dict(zip(["to_send", "h", "late", "on_time", "delay", "on_direct_father", "on_older_ancestor", "inc_not_the_best_father",
                          "skipped"], out.tolist()))
+
+
+class OracleCappos(_NetCtl):
+    """protocols/SanFerminCappos.java through the oracle."""
+
+    _ctl = "wo_cappos_net_ctl"
+
+    def __init__(self, node_count, threshold, pairing_time, signature_size, timeout, candidate_count, node_builder, latency, seed=None):
+        self.lib = load()
+        self.n = node_count
+        arr = np.array([node_count, threshold, pairing_time, signature_size, timeout, candidate_count], np.int32)
+        self.h = C.c_void_p(self.lib.wo_cappos_create(_p(arr, C.c_int), _b(node_builder), _b(latency)))
+        if not self.h:
+            raise ValueError(self.lib.wo_last_error().decode())
+        if seed is not None:
+            self.lib.wo_cappos_set_seed(self.h, C.c_int64(seed))
+
+    def __del__(self):
+        try:
+            self.lib.wo_cappos_destroy(self.h)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def init(self):
+        if self.lib.wo_cappos_init(self.h) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
+    def run_ms(self, ms):
+        r = self.lib.wo_cappos_run_ms(self.h, ms)
+        if r < 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+        return bool(r)
+
+    @property
+    def time(self):
+        return self.lib.wo_cappos_time(self.h)
+
+    def msgs_live(self):
+        return self.lib.wo_cappos_msgs_live(self.h)
+
+    def rng_state(self):
+        return int(self.lib.wo_cappos_rng_state(self.h))
+
+    def counters(self):
+        out = np.zeros((5, self.n), np.int64)
+        self.lib.wo_cappos_node_counters(self.h, _p(out, C.c_int64))
+        return out
+
+    def attrs(self):
+        x = np.zeros(self.n, np.int32); y = np.zeros(self.n, np.int32); e = np.zeros(self.n, np.int32)
+        c = np.zeros(self.n, np.int32); s = np.zeros(self.n, np.float64); d = np.zeros(self.n, np.uint8)
+        self.lib.wo_cappos_node_attrs(self.h, _p(x, C.c_int32), _p(y, C.c_int32), _p(e, C.c_int32), _p(c, C.c_int32), _p(s, C.c_double), _p(d, C.c_uint8))
+        return dict(x=x, y=y, extra=e, city=c, speed=s, down=d)
+
+    def scalars(self):
+        a = [np.zeros(self.n, np.int32) for _ in range(6)]
+        t = np.zeros(self.n, np.int64)
+        self.lib.wo_cappos_node_scalars(self.h, *[_p(v, C.c_int32) for v in a], _p(t, C.c_int64))
+        d = dict(zip(["cpl", "sigs", "done", "threshold_done", "swapping", "cache_mask"], a))
+        d["threshold_at"] = t
+        return d
