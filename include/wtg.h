@@ -50,7 +50,7 @@ int wtg_set_node_builder(wtg_net* net, const char* name);
 int wtg_set_msg_discard_time(wtg_net* net, int ms);
 
 /* device capacities (no reference counterpart): "bcap", "qcap", "pool_slots_per_node", "desc_cap",
- * "rec_cap", "ring".  Exceeding a capacity makes wtg_run_ms fail loudly; it never drops events. */
+ * "rec_cap", "ring", "casper_votes", "casper_blocks"; "force_shuffle_serial" (test hook).  Exceeding a capacity makes wtg_run_ms fail loudly; it never drops events. */
 int wtg_set_tunable(wtg_net* net, const char* key, long long value);
 
 /* new PingPong(params).init() — protocols/PingPong.java:52-57, 82-87 */
@@ -67,6 +67,11 @@ int wtg_gsf_init(wtg_net* net, const int* params7);
  * shuffledLists / verbose are unused by the reference).  Device engine: power-of-two nodeCount, candidateCount 1. */
 int wtg_sanfermin_construct(wtg_net* net, const int* params6);
 int wtg_sanfermin_init(wtg_net* net);
+
+/* new SanFerminCappos(params).init() — protocols/SanFerminCappos.java:106-134.
+ * params6 = { nodeCount, threshold, pairingTime, signatureSize, timeout, candidateCount } (SanFerminParameters :86-103).
+ * Device engine: power-of-two nodeCount, candidateCount <= 63. */
+int wtg_cappos_init(wtg_net* net, const int* params6);
 
 /* new Handel(params).init() — protocols/Handel.java:96-141, 957-1014.
  * params11 = { nodeCount, threshold, pairingTime, levelWaitTime, extraCycle, disseminationPeriodMs, fastPath, nodesDown,
@@ -136,6 +141,14 @@ int wtg_casper_node_state(wtg_net* net, int* head, int* atts_received, int* head
                           int* to_reevaluate, unsigned long long* att_hash);
 int wtg_casper_heads(wtg_net* net, int* head); /* BlockChainNode.head of every node (block id) */
 int wtg_casper_byz(wtg_net* net, int* out9);
+
+/* SanFerminCappos.SanFerminNode: currentPrefixLength, totalNumberOfSigs(-1), done, thresholdDone, isSwapping, the levels
+ * present in signatureCache (bit mask), thresholdAt — protocols/SanFerminCappos.java:155-180, 351-358 */
+int wtg_cappos_node_scalars(wtg_net* net, int* cpl, int* sigs, int* done, int* thr_done, int* swapping, int* cache_mask,
+                            long long* threshold_at);
+/* java.util.Collections.shuffle(list, rnd) with rnd in 48-bit state `state` (JDK: for i = size; i > 1; i-- swap(i-1,
+ * rnd.nextInt(i))); runs on the host the code the emit kernel uses; returns the number of values drawn from the stream */
+int wtg_java_shuffle(unsigned long long state, int n, int* inout);
 
 /* HNode fields — protocols/Handel.java:280-298: 9 int arrays of N: startAt, nodePairingTime, sigsChecked, sigQueueSize,
  * msgFiltered, currWindowSize, addedCycle, totalSigSize(), total length of the toVerifyAgg lists */

@@ -80,6 +80,11 @@ class HostBackend : public Backend {
     pairScan(d, 1);
     if (d.ctl->error) return;
     for (int n = 0; n < d.N; ++n) emitCond(d, n);
+    if (d.shufCap > 0) {
+      int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
+      for (int t = 0; t < tot; ++t) shuffleCheck(d, stripedIndex(d.ctl->descCnt, per, t));
+      shuffleSerial(d);
+    }
     {
       int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
       for (int t = 0; t < tot; ++t) emitDesc(d, stripedIndex(d.ctl->descCnt, per, t));

@@ -13,7 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from tests.oracle_lib import OracleCasper, OracleGSF, OracleHandel, OraclePingPong, OracleSanFermin  # noqa: E402
+from tests.oracle_lib import OracleCappos, OracleCasper, OracleGSF, OracleHandel, OraclePingPong, OracleSanFermin  # noqa: E402
 
 AWS_NB, AWS_NL = "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency"
 NB, NL = "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"
@@ -35,6 +35,7 @@ CASES = {
     "handel_64_desync": dict(kind="handel", args=[64, 60, 6, 10, 5, 5, 10, 2, NB, NL, 100, False], steps=[1] * 1200),
     "handel_256_byz": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, True], steps=[10] * 300),
     "handel_256_hidden": dict(kind="handel", args=[256, 180, 4, 50, 10, 20, 10, 64, "AWS_SPEED=GAUSSIAN_TOR=0.00", AWS_NL, 0, False], hidden=True, steps=[10] * 300),
+    "cappos_512_k50": dict(kind="cappos", args=[512, 256, 2, 48, 150, 50, None, None], steps=[10] * 400),
     # casper args: cycleLength, randomOnTies, producers, attestersPerRound, blockTime, attestationTime, builder, latency ; byzDelay
     "casper_3x20_forks": dict(kind="casper", args=[3, False, 3, 20, 1000, 1, None, None], delay=9000, steps=[500] * 400),
     "casper_4x16_aws_late": dict(kind="casper", args=[4, False, 2, 16, 1000, 1, "AWS_SPEED=GAUSSIAN_TOR=0.33", AWS_NL], delay=-7000, steps=[1000] * 200),
@@ -66,6 +67,9 @@ def state_digest(kind, p, net=None):
     if kind == "handel":
         sc = p.scalars()
         return digest(counters, p.rows(0), p.rows(1), p.rows(2), p.rows(5), sc["sigs_checked"], sc["sig_queue_size"], sc["msg_filtered"], sc["window"])
+    if kind == "cappos":
+        sc = p.scalars()
+        return digest(counters, sc["cpl"], sc["sigs"], sc["done"], sc["threshold_done"], sc["swapping"], sc["cache_mask"], sc["threshold_at"])
     if kind == "casper":
         st, b = p.node_state(), p.blocks()
         atts = [np.array(p.block_attestations(i), np.int32).reshape(-1, 2) for i in range(1, len(b["height"]))]
@@ -78,7 +82,7 @@ def make_oracle(kind, args, hidden=False):
     if hidden:
         return OracleHandel(*args, hidden_byzantine=True)
     return {"pingpong": OraclePingPong, "gsf": OracleGSF, "sanfermin": OracleSanFermin, "handel": OracleHandel,
-            "casper": OracleCasper}[kind](*args)
+            "casper": OracleCasper, "cappos": OracleCappos}[kind](*args)
 
 
 if __name__ == "__main__":

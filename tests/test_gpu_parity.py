@@ -491,3 +491,43 @@ def test_sanfermin_with_stopped_nodes_and_partition():
         assert p.network().run_ms(20) == o.run_ms(20)
         bad = _sf_compare(p, o, f"t={o.time}")
         assert not bad, bad
+
+
+def _cappos_compare(p, o, tag):
+    bad = []
+    if p.network().rng_state() != o.rng_state():
+        bad.append(f"{tag}: rd state")
+    if p.network().msgs_size() != o.msgs_live():
+        bad.append(f"{tag}: msgs.size()")
+    if not (p.network().counters() == o.counters()).all():
+        bad.append(f"{tag}: counters")
+    a, b = p.scalars(), o.scalars()
+    for k in a:
+        if not (a[k] == b[k]).all():
+            bad.append(f"{tag}: {k}")
+    return bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,nb,nl,seed,step,until,force", [
+    (64, 3, None, None, None, 1, 2500, False),
+    (1024, 50, AWS_NB, AWS_NL, 4, 10, 4000, False),          # the shipped candidateCount (SanFerminCappos.java:79, 471)
+    (512, 7, None, None, 2, 10, 4000, True),                   # draw indices re-derived serially on every tick
+    (4096, 50, None, None, None, 20, 5000, False),
+])
+def test_cappos_parity(n, k, nb, nl, seed, step, until, force):
+    """SanFerminCappos (swaps with / without reply, cached levels, timeouts, candidateCount-wide shuffled requests) vs the oracle."""
+    from tests.oracle_lib import OracleCappos
+    from wittgenstein_b200 import SanFerminCappos, SanFerminCapposParameters
+
+    p = SanFerminCappos(SanFerminCapposParameters(n, n // 2, 2, 48, 150, k, nb, nl), tunables={"force_shuffle_serial": 1} if force else None)
+    o = OracleCappos(n, n // 2, 2, 48, 150, k, nb, nl, seed=seed)
+    if seed is not None:
+        p.network().set_seed(seed)
+    p.init(); o.init()
+    assert not _cappos_compare(p, o, "init")
+    while o.time < until:
+        assert p.network().run_ms(step) == o.run_ms(step)
+        bad = _cappos_compare(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert p.scalars()["done"].sum() > n // 2

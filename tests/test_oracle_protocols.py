@@ -252,3 +252,19 @@ def test_handel_byzantine_suicide_blacklists():
     assert listed.any() and not (listed & ~down).any()
     with pytest.raises(ValueError):
         OracleHandel(100, 90, 4, 50, 10, 20, 10, 5, NB, NL)  # power of two only (Handel.java:118-120)
+
+
+def test_cappos_oracle_liveness_and_threshold():
+    """SanFerminCappos.sigsPerTime parameters scaled down (SanFerminCappos.java:465-471): everybody finishes, the threshold is
+    reached before the end, and a finished node holds at least the threshold."""
+    from tests.oracle_lib import OracleCappos
+
+    o = OracleCappos(1024, 512, 2, 48, 150, 50, "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter")
+    o.init()
+    for _ in range(600):
+        o.run_ms(10)
+    s = o.scalars()
+    assert s["done"].sum() >= 1000
+    done = s["done"] == 1
+    assert (s["sigs"][done] >= 512).all()
+    assert (s["threshold_at"][done] > 0).all() and (s["threshold_at"][done] <= o.counters()[4][done]).all()

@@ -43,6 +43,9 @@ class Api:
         "casper_node_state": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_ulonglong)]),
         "casper_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "casper_byz": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "cappos_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+        "cappos_node_scalars": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_longlong)]),
+        "java_shuffle": (C.c_int, [C.c_ulonglong, C.c_int, C.POINTER(C.c_int)]),
         "handel_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_node_scalars": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
         "handel_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),

@@ -91,6 +91,7 @@ int WTG_API(set_tunable)(void* h, const char* key, long long v) {
     else if (k == "rec_cap") ENG.tun.recCap = v;
     else if (k == "ring") ENG.tun.ring = v;
     else if (k == "casper_votes") ENG.tun.casperVotes = v;
+    else if (k == "force_shuffle_serial") ENG.forceShufSerial = v != 0;
     else if (k == "casper_blocks") ENG.tun.casperBlocks = v;
     else throw std::invalid_argument("unknown tunable " + k);
     return 0;
@@ -121,6 +122,54 @@ int WTG_API(sanfermin_init)(void* h) {
   return guard([&] {
     ENG.sanferminInit();
     return 0;
+  });
+}
+// params6 = { nodeCount, threshold, pairingTime, signatureSize, timeout, candidateCount }
+int WTG_API(cappos_init)(void* h, const int* p) {
+  return guard([&] {
+    wtg::CapposParams cp{p[0], p[1], p[2], p[3], p[4], p[5]};
+    ENG.capposInit(cp);
+    return 0;
+  });
+}
+// per node: currentPrefixLength, totalNumberOfSigs(-1), done, thresholdDone, isSwapping, mask of cached levels ; thresholdAt
+int WTG_API(cappos_node_scalars)(void* h, int* cpl, int* sigs, int* done, int* thrDone, int* swapping, int* cacheMask, long long* thresholdAt) {
+  return guard([&] {
+    ENG.requireInited();
+    if (ENG.d.proto != wtg::PROTO_CAPPOS) throw std::logic_error("not a SanFerminCappos network");
+    size_t n = (size_t)ENG.d.N;
+    std::vector<int> fl(n), cache(n * 32);
+    std::vector<uint32_t> mask(n);
+    ENG.fetch(cpl, ENG.d.sfCpl, n);
+    ENG.fetch(fl.data(), ENG.d.sfFlags, n);
+    ENG.fetch(mask.data(), ENG.d.sfCacheMask, n);
+    ENG.fetch(cache.data(), ENG.d.sfCache, n * 32);
+    ENG.fetch(thresholdAt, ENG.d.sfThresholdAt, n);
+    for (size_t i = 0; i < n; ++i) {
+      int s = 1;
+      for (int l = 0; l < 32; ++l)
+        if ((mask[i] >> l) & 1u) s += cache[i * 32 + (size_t)l];
+      sigs[i] = s;
+      swapping[i] = fl[i] & 1;
+      done[i] = (fl[i] >> 1) & 1;
+      thrDone[i] = (fl[i] >> 2) & 1;
+      cacheMask[i] = (int)mask[i];
+    }
+    return 0;
+  });
+}
+// Collections.shuffle(list, rnd) for a java.util.Random whose 48-bit state is `state` (host-side run of the code the emit
+// kernel uses for shuffled multi-sends, nextInt's rejection loop included); returns the number of values drawn
+int WTG_API(java_shuffle)(unsigned long long state, int n, int* inout) {
+  return guard([&] {
+    if (n < 0) throw std::invalid_argument("n");
+    unsigned long long ja[48], jc[48];
+    wtg::lcgJumpTables((uint64_t*)ja, (uint64_t*)jc);
+    std::vector<uint32_t> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[(size_t)i] = (uint32_t)inout[i];
+    int used = wtg::javaShuffleAt((const wtg::u64*)ja, (const wtg::u64*)jc, state & ((1ULL << 48) - 1), 0, v.data(), n);
+    for (int i = 0; i < n; ++i) inout[i] = (int)v[(size_t)i];
+    return used;
   });
 }
 // params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime, attestationConstructionTime }

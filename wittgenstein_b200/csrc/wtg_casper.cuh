@@ -793,6 +793,7 @@ WTG_HD void tickBeginFfwd(const Dev& d, C& c) {
     ctl.totalDraws = 0;
     ctl.hReject = 0;
     ctl.allCnt = 0;
+    ctl.shufReject = 0;
     if (d.cg) d.cg->createdThisTick = 0;
   }
   c.sync();

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
   u64 word = ~0ULL;
   if (n < d.N && d.inboxFill[n] > 0) {
     CoopSerial cs;
-    if (d.proto == PROTO_SANFERMIN)
+    if (d.proto == PROTO_SANFERMIN || d.proto == PROTO_CAPPOS)
       nodeProcess(d, cs, n, 0);
     else if (d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG) {
       u64 w = 0;
@@ -345,6 +345,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(Dev d, int which) {
     if (tile == nTiles - 1 && threadIdx.x == 0) scanTotals(d, which, pairAdd(tileBase, total));
     __syncthreads();
   }
+}
+
+// ---- shuffled multi-sends: optimistic draw indices, checked; re-derived serially when a rejection shifted them ----
+__global__ void k_shuffle_check(Dev d) {
+  if (d.ctl->error) return;
+  const int per = d.descCap / ARENA_STRIPES;
+  const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
+  int cnt = d.ctl->descCnt[stripe];
+  if (cnt > per) cnt = per;
+  const int sub = (blockIdx.x >> 6) * blockDim.x + threadIdx.x;
+  const int nsub = (gridDim.x >> 6) * blockDim.x;
+  for (int j = sub; j < cnt; j += nsub) shuffleCheck(d, stripe * per + j);
+}
+__global__ void k_shuffle_serial(Dev d) {
+  if (d.ctl->error) return;
+  shuffleSerial(d);
 }
 
 // ---- emit ------------------------------------------------------------------------------------
@@ -714,6 +730,11 @@ class CudaBackend : public Backend {
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
     profEnd();
     profBegin(8);
+    if (d.shufCap > 0) {
+      k_shuffle_check<<<ARENA_STRIPES * 4, 256, 0, st>>>(d);
+      k_shuffle_serial<<<1, 1, 0, st>>>(d);
+      launches += 2;
+    }
     k_emit<<<ARENA_STRIPES * 16, 256, 0, st>>>(d);
     if (d.allCap > 0) {
       k_emit_all<<<d.allWarps / 4, 128, 0, st>>>(d);

@@ -30,6 +30,10 @@ struct HandelParams {
       byzantineSuicide, hiddenByzantine;
 };
 
+struct CapposParams {  // SanFerminCappos.SanFerminParameters (protocols/SanFerminCappos.java:86-103), constructor order
+  int nodeCount, threshold, pairingTime, signatureSize, timeout, candidateCount;
+};
+
 struct CasperParams {  // CasperParemeters (protocols/CasperIMD.java:18-71), in declaration order
   int cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime, attestationConstructionTime;
 };
@@ -133,7 +137,7 @@ class Engine {
     d.itemCap = (int)(2 * bcap + 1024);
     d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 32LL * N));
     d.descCap = (d.descCap + ARENA_STRIPES - 1) / ARENA_STRIPES * ARENA_STRIPES;
-    d.destScratchCap = d.descCap;
+    d.destScratchCap = destScratchOverride ? destScratchOverride : d.descCap;
     d.newEvCap = d.descCap + N;
     d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * N));
     d.recDestCap = recDestOverride ? recDestOverride : d.recCap * 4 + N + 1024;
@@ -213,6 +217,8 @@ class Engine {
     }
   }
   int recDestOverride = 0;  // sendAll protocols size the destination arena themselves
+  int destScratchOverride = 0;
+  bool forceShufSerial = false;  // tunable force_shuffle_serial (test hook)
   int ringExtra = 0;        // longest handler-chosen delay of a near envelope (e.g. blockConstructionTime)
   bool farEnabled = false;  // far-future calendar + fast-forward (protocols without conditional tasks)
 
@@ -731,6 +737,67 @@ class Engine {
         int cnt = (int)per[(size_t)t].size();
         be->upload(d.bucketCount + t, &cnt, sizeof(int));
       }
+    c.callId = 1;
+    c.rng = hm.rd.seed;
+    writeCtl(c);
+    inited = true;
+  }
+
+  // ---- SanFerminCappos.init()  (protocols/SanFerminCappos.java:120-134): nodes, helpers, goNextLevel at t = 1 ----
+  CapposParams qp{};
+  void capposInit(const CapposParams& p) {
+    requireNotInited();
+    const int N = p.nodeCount;
+    if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("the B200 engine needs a power-of-two nodeCount >= 2 for SanFerminCappos");
+    if (p.candidateCount < 1 || p.candidateCount + 1 > SHUFFLE_MAX) throw std::invalid_argument("candidateCount must be in [1, 63]");
+    if (p.pairingTime <= 0 || p.timeout <= 0) throw std::invalid_argument("pairingTime / timeout must be positive");
+    checkLatencyBuilder();
+    qp = p;
+    hm.buildNodes(N);
+    int P = 0;
+    while ((1 << (P + 1)) <= N) ++P;
+    const long long perSend = p.candidateCount + 1;
+    destScratchOverride = (int)std::min<long long>(0x7fffffffLL, (2 * perSend * N + 4096 + ARENA_STRIPES - 1) / ARENA_STRIPES * ARENA_STRIPES);
+    if (!tun.recCap) tun.recCap = std::max<long long>(65536, 4LL * N * (P + 1));
+    recDestOverride = (int)std::min<long long>(0x7fffffffLL, (long long)tun.recCap * perSend / 2 + N + 1024);
+    allocCommon(N, PROTO_CAPPOS);
+    d.sfP = P;
+    d.sfThreshold = p.threshold;
+    d.sfPairing = p.pairingTime;
+    d.sfSigSize = p.signatureSize;
+    d.sfTimeout = p.timeout;
+    d.sfCandCount = p.candidateCount;
+    std::vector<int> cpl(N, P);
+    d.sfCpl = dupload(cpl);
+    d.sfFlags = dalloc<int>(N);
+    d.sfThresholdAt = dalloc<long long>(N);
+    d.sfCacheMask = dalloc<uint32_t>(N);
+    d.sfCache = dalloc<int>((size_t)N * 32);
+    d.sfUsedWords = std::max(1, N / 128);
+    d.sfUsedBits = dalloc<unsigned long long>((size_t)N * d.sfUsedWords);
+    d.shufCap = d.newEvCap;
+    d.forceShufSerial = forceShufSerial ? 1 : 0;
+    d.byG = dalloc<int>(d.newEvCap);
+    {
+      std::vector<int> m1((size_t)d.newEvCap, -1);
+      d.byGTick = dupload(m1);
+    }
+    d.descDraw = dalloc<int>(d.descCap);
+    std::vector<Ev> tasks((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      Ev ev;
+      std::memset(&ev, 0, sizeof(ev));
+      ev.kind = EV_TASK;
+      ev.to = (uint32_t)i;
+      ev.from = (uint32_t)i;
+      ev.meta = CP_T_GO;
+      tasks[(size_t)i] = ev;
+    }
+    if (N > d.bcap) throw std::runtime_error("bucket capacity too small");
+    be->upload(d.buckets + (size_t)1 * d.bcap, tasks.data(), tasks.size() * sizeof(Ev));
+    be->upload(d.bucketCount + 1, &N, sizeof(int));
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
     c.callId = 1;
     c.rng = hm.rd.seed;
     writeCtl(c);

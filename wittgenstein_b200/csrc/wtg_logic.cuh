@@ -1426,6 +1426,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
 }  // namespace wtg
 #include "wtg_handel.cuh"
 #include "wtg_casper.cuh"
+#include "wtg_cappos.cuh"
 namespace wtg {
 
 // ------------------------------------------------------------------------------------------
@@ -1485,6 +1486,10 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
     }
   } else if (d.proto == PROTO_CASPER) {
     casperDeliver(d, c, n, ev.kind, meta, pl, item, slots, draws);
+  } else if (d.proto == PROTO_CAPPOS) {
+    if (c.lane() == 0) cpHandle(d, n, from, meta, pl, item, slots, draws);
+    slots = c.bcast(slots, 0);
+    draws = c.bcast(draws, 0);
   } else if (d.proto == PROTO_SANFERMIN) {
     if (c.lane() == 0) sfHandle(d, n, from, meta, pl, item, slots, draws);
     slots = c.bcast(slots, 0);
@@ -1784,6 +1789,13 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     target = ds.target;
   } else {
     u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
+    if (d.shufCap > 0) {  // protocols with k-element shuffles: draws per descriptor vary (wtg_cappos.cuh)
+      drawIdx = ctl.shufReject ? (u64)d.descDraw[di] : descDrawOptimistic(d, di);
+      if (ds.dkind == DK_SEND_MULTI && (ds.aux & DESC_SHUFFLEK)) {
+        emitShuffled(d, di, g, drawIdx);
+        return;
+      }
+    }
     bool swap01 = false;
     if (ds.dkind == DK_SEND_MULTI && (ds.aux & DESC_SHUFFLE2)) {
       // Collections.shuffle of a 2-element list: swap(list, 1, rnd.nextInt(2))  (SanFerminHelper.java:155)
@@ -1916,6 +1928,7 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
   c.totalDraws = 0;
   c.hReject = 0;
   c.allCnt = 0;
+  c.shufReject = 0;
   if (c.nEv > c.maxBucket) c.maxBucket = c.nEv;
 }
 WTG_HD void tickEnd(const Dev& d, int mode) {

@@ -29,7 +29,7 @@ constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bi
 constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
 
 // protocols
-enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4, PROTO_CASPER = 5 };
+enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4, PROTO_CASPER = 5, PROTO_CAPPOS = 6 };
 
 // event kinds (Ev.kind)
 enum : uint32_t {
@@ -62,6 +62,10 @@ enum : uint32_t { CM_ATT = 1, CM_BLOCK = 2, CT_BUILD = 3 };
 enum : uint8_t { CK_OBSERVER = 0, CK_PRODUCER = 1, CK_ATTESTER = 2, CK_BYZ = 3, CK_BYZ_SF = 4, CK_BYZ_NS = 5, CK_BYZ_WF = 6 };
 constexpr int CASPER_SLOT = 8000;  // CasperParemeters.SLOT_DURATION (CasperIMD.java:19)
 constexpr int CASPER_MAX_BLKWORDS = 8;  // at most 512 blocks per run on the device
+// SanFerminCappos message / task types (Ev.meta); Ev.pl = level | (value << 32)
+enum : uint32_t { CP_SWAP_REPLY = 1, CP_SWAP = 2, CP_T_GO = 4, CP_T_TIMEOUT = 5, CP_T_TRANSITION = 6 };
+constexpr int SHUFFLE_MAX = 64;          // longest destination list shuffled before a send (candidateCount + 1)
+constexpr uint32_t DESC_SHUFFLEK = 2u;   // Desc.aux: Collections.shuffle of the nDest destinations before the send (nDest - 1 draws + rejections)
 constexpr uint32_t DESC_SHUFFLE2 = 1u;  // Desc.aux: Collections.shuffle of the 2 destinations before the send (one extra draw)
 
 struct Ev {  // 32 bytes: one in-flight envelope / task
@@ -167,6 +171,7 @@ struct Ctl {  // device-resident control block (one per engine)
   int idle;                // fast-forward: nothing left to do before `until`
   int nextEvent;           // fast-forward: earliest arrival after `until` known when the window went idle
   int allCnt;              // sendAll descriptors of this tick
+  int shufReject;          // some Collections.shuffle of this tick hit nextInt's rejection loop: draw indices are re-derived serially
   int maxBucket;
   unsigned long long statDraws, statEvents;
   int descCnt[ARENA_STRIPES];   // descriptors allocated this tick, per stripe (stripe = node id & 63)
@@ -282,6 +287,12 @@ struct Dev {
   int* allTmp;    // [allWarps][N] unsorted arrivals of one sendAll
   int allWarps;
   int recSlots;   // sendAll records are recycled round-robin over this many slots of N destinations each
+  // ---- shuffled multi-sends (Collections.shuffle inside a handler, SanFerminHelper.java:155) ----
+  int shufCap;      // 0: protocol has no k-element shuffles
+  int forceShufSerial;  // test hook: always take the serial re-derivation path
+  int* byG;         // [newEvCap] descriptor index of creation index g ...
+  int* byGTick;     // [newEvCap] ... valid when it equals the tick
+  int* descDraw;    // [descCap] corrected draw index of a descriptor (valid when ctl->shufReject)
   // ---- PingPong ----
   int* pong;  // [N]
   // ---- CasperIMD ----
@@ -348,6 +359,9 @@ struct Dev {
   int* sfUsed;       // [N][SF_USEDCAP]
   uint32_t* sfCacheMask;  // [N] levels present in signatureCache
   int* sfCache;      // [N][32]
+  int sfTimeout;     // SanFerminCappos: params.timeout
+  int sfUsedWords;   // words of a row of sfUsedBits
+  unsigned long long* sfUsedBits;  // [N][sfUsedWords] SanFerminHelper.usedNodes of the current level
   // ---- GSF ----
   unsigned long long* verified;   // [N][W64]
   unsigned long long* indivSeen;  // [N][W64]

@@ -266,6 +266,55 @@ class CasperIMD:
                          "skipped"], out.tolist()))
 
 
+class SanFerminCapposParameters:
+    """SanFerminCappos.SanFerminParameters (SanFerminCappos.java:43-104)."""
+
+    def __init__(self, node_count=32768 // 16, threshold=32768 // 32, pairing_time=2, signature_size=48, timeout=150, candidate_count=50,
+                 node_builder_name=None, network_latency_name=None):
+        self.node_count = node_count
+        self.threshold = threshold
+        self.pairing_time = pairing_time
+        self.signature_size = signature_size
+        self.timeout = timeout
+        self.candidate_count = candidate_count
+        self.node_builder_name = node_builder_name
+        self.network_latency_name = network_latency_name
+
+
+class SanFerminCappos:
+    """SanFerminCappos (protocols/SanFerminCappos.java); nodes are built by init() (:120-134)."""
+
+    def __init__(self, params, _api=None, tunables=None):
+        self.params = params
+        self._api = _api
+        self._tunables = dict(tunables or {})
+        self._net = Network(_api)
+        self._net.set_node_builder(params.node_builder_name)
+        self._net.set_network_latency(params.network_latency_name)
+        for k, v in self._tunables.items():
+            self._net.set_tunable(k, v)
+
+    def network(self):
+        return self._net
+
+    def copy(self):
+        return SanFerminCappos(self.params, self._api, self._tunables)
+
+    def init(self):
+        p = self.params
+        arr = np.array([p.node_count, p.threshold, p.pairing_time, p.signature_size, p.timeout, p.candidate_count], np.int32)
+        self._net.api.check(self._net.api.cappos_init(self._net.h, _p(arr, C.c_int)))
+
+    def scalars(self):
+        n = self.params.node_count
+        a = [np.zeros(n, np.int32) for _ in range(6)]
+        t = np.zeros(n, np.int64)
+        self._net.api.check(self._net.api.cappos_node_scalars(self._net.h, *[_p(v, C.c_int) for v in a], _p(t, C.c_longlong)))
+        d = dict(zip(["cpl", "sigs", "done", "threshold_done", "swapping", "cache_mask"], a))
+        d["threshold_at"] = t
+        return d
+
+
 class HandelParameters:
     """Handel.HandelParameters (Handel.java:22-142); window = WindowParameters() (16, 1, 128, ScoringExp(2, 4))."""
 
