@@ -64,7 +64,7 @@ int wtg_gsf_init(wtg_net* net, const int* params7);
 /* new SanFerminSignature(params) — protocols/SanFerminSignature.java:112-129 (the constructor builds the nodes on
  * network.rd, so a later wtg_set_seed does not change them) and .init() — :136-138.
  * params6 = { nodeCount, threshold, pairingTime, signatureSize, replyTimeout, candidateCount } (:41-110;
- * shuffledLists / verbose are unused by the reference).  Device engine: power-of-two nodeCount, candidateCount 1. */
+ * shuffledLists / verbose are unused by the reference).  Device engine: power-of-two nodeCount, candidateCount <= 63. */
 int wtg_sanfermin_construct(wtg_net* net, const int* params6);
 int wtg_sanfermin_init(wtg_net* net);
 

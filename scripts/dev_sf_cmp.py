@@ -5,9 +5,10 @@ from tests import emu_lib
 from tests.oracle_lib import OracleSanFermin
 from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
 N=int(sys.argv[1]); step=int(sys.argv[2]); T=int(sys.argv[3]); nb=sys.argv[4] if len(sys.argv)>4 else None; nl=sys.argv[5] if len(sys.argv)>5 else None
-seed=int(sys.argv[6]) if len(sys.argv)>6 else None
-p=SanFerminSignature(SanFerminSignatureParameters(N,N,2,48,300,1,False,nb,nl), _api=emu_lib.api())
-o=OracleSanFermin(N,N,2,48,300,1,nb,nl)
+seed=int(sys.argv[6]) if len(sys.argv)>6 and sys.argv[6]!='-' else None
+k=int(sys.argv[7]) if len(sys.argv)>7 else 1
+p=SanFerminSignature(SanFerminSignatureParameters(N,N,2,48,300,k,False,None if nb=='-' else nb,None if nl=='-' else nl), _api=emu_lib.api())
+o=OracleSanFermin(N,N,2,48,300,k,None if nb=='-' else nb,None if nl=='-' else nl)
 if seed is not None: p.network().set_seed(seed); o.set_seed(seed)
 p.init(); o.init()
 def cmp(tag):

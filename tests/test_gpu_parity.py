@@ -160,6 +160,28 @@ def test_sanfermin_parity(n, nb, nl, seed, step):
     assert p.scalars()["done"].sum() > n // 2
 
 
+@pytest.mark.parametrize("n,k,seed,force", [(256, 3, None, False), (1024, 10, 7, False), (512, 50, 2, True)])
+def test_sanfermin_several_candidates(n, k, seed, force):
+    """candidateCount > 1: pickNextNodes hands out k + 1 nodes, shuffled on the network RNG before the request is sent
+    (SanFerminHelper.java:123-157); `force` re-derives the draw indices serially on every tick."""
+    from tests.oracle_lib import OracleSanFermin
+    from wittgenstein_b200 import SanFerminSignature, SanFerminSignatureParameters
+
+    p = SanFerminSignature(SanFerminSignatureParameters(n, n, 2, 48, 300, k, False, None, None))
+    o = OracleSanFermin(n, n, 2, 48, 300, k, None, None)
+    if force:
+        p.network().set_tunable("force_shuffle_serial", 1)
+    if seed is not None:
+        p.network().set_seed(seed)
+        o.set_seed(seed)
+    p.init(); o.init()
+    while o.time < 3500:
+        assert p.network().run_ms(10) == o.run_ms(10)
+        bad = _sf_compare(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert p.scalars()["done"].sum() > n // 2
+
+
 def test_sanfermin_16384_shipped_scenario():
     """SanFerminSignature.sigsPerTime() parameters (SanFerminSignature.java:566-571): 16 384 nodes, runMs(10) to 6 s."""
     from tests.oracle_lib import OracleSanFermin
@@ -413,7 +435,7 @@ def test_error_paths():
     with pytest.raises(WtgError):
         SanFerminSignature(SanFerminSignatureParameters(1000, 1000, 2, 48, 300, 1))  # power of two only on the device
     with pytest.raises(WtgError):
-        SanFerminSignature(SanFerminSignatureParameters(1024, 1024, 2, 48, 300, 3))  # candidateCount 1 only
+        SanFerminSignature(SanFerminSignatureParameters(1024, 1024, 2, 48, 300, 64))  # candidateCount + 1 destinations per request: at most 64
     from wittgenstein_b200 import Handel, HandelParameters
     with pytest.raises(WtgError):
         HandelParameters(100, 90)  # Handel.java:118-120

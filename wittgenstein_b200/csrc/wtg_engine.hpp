@@ -499,7 +499,7 @@ class Engine {
     if (sfConstructed) throw std::logic_error("already constructed");
     const int N = p.nodeCount;
     if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("the B200 engine needs a power-of-two nodeCount >= 2 for SanFerminSignature");
-    if (p.candidateCount != 1) throw std::invalid_argument("the B200 engine supports candidateCount == 1 (the shipped scenario) for SanFerminSignature");
+    if (p.candidateCount < 1 || p.candidateCount + 1 > SHUFFLE_MAX) throw std::invalid_argument("candidateCount must be in [1, 63]");
     if (p.pairingTime <= 0 || p.replyTimeout <= 0) throw std::invalid_argument("pairingTime / replyTimeout must be positive");
     checkLatencyBuilder();
     sp = p;
@@ -510,6 +510,14 @@ class Engine {
     requireNotInited();
     if (!sfConstructed) throw std::logic_error("SanFerminSignature not constructed");
     const int N = sp.nodeCount;
+    {
+      int P0 = 0;
+      while ((1 << (P0 + 1)) <= N) ++P0;
+      const long long perSend = sp.candidateCount + 1;
+      destScratchOverride = (int)std::min<long long>(0x7fffffffLL, (2 * perSend * N + 4096 + ARENA_STRIPES - 1) / ARENA_STRIPES * ARENA_STRIPES);
+      if (!tun.recCap) tun.recCap = std::max<long long>(65536, 4LL * N * (P0 + 1));
+      recDestOverride = (int)std::min<long long>(0x7fffffffLL, (long long)tun.recCap * perSend / 2 + N + 1024);
+    }
     allocCommon(N, PROTO_SANFERMIN);
     int P = 0;
     while ((1 << (P + 1)) <= N) ++P;
@@ -526,12 +534,19 @@ class Engine {
     d.sfThresholdAt = dalloc<long long>(N);
     d.sfSentReq = dalloc<int>(N);
     d.sfRecvReq = dalloc<int>(N);
-    d.sfPendCnt = dalloc<int>(N);
-    d.sfPending = dalloc<int>((size_t)N * SF_PENDCAP);
-    d.sfUsedCnt = dalloc<int>(N);
-    d.sfUsed = dalloc<int>((size_t)N * SF_USEDCAP);
     d.sfCacheMask = dalloc<uint32_t>(N);
     d.sfCache = dalloc<int>((size_t)N * 32);
+    d.sfUsedWords = std::max(1, N / 128);
+    d.sfUsedBits = dalloc<unsigned long long>((size_t)N * d.sfUsedWords);
+    d.sfPendBits = dalloc<unsigned long long>((size_t)N * d.sfUsedWords);
+    d.shufCap = d.newEvCap;
+    d.forceShufSerial = forceShufSerial ? 1 : 0;
+    d.byG = dalloc<int>(d.newEvCap);
+    {
+      std::vector<int> m1((size_t)d.newEvCap, -1);
+      d.byGTick = dupload(m1);
+    }
+    d.descDraw = dalloc<int>(d.descCap);
     std::vector<Ev> tasks((size_t)N);
     for (int i = 0; i < N; ++i) {
       Ev ev;

@@ -1176,11 +1176,11 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
 // ------------------------------------------------------------------------------------------
 // SanFerminSignature handlers (protocols/SanFerminSignature.java, SanFerminHelper.java) — scalar: per-node
 // state is a handful of ints, so every event of a node is handled by one thread, in reference order.
-// Power-of-two node counts and candidateCount == 1 (the shipped scenario, SanFerminSignature.java:568-571).
+// Power-of-two node counts; candidateCount up to SHUFFLE_MAX - 1 (the shipped scenario uses 1, SanFerminSignature.java:568-571).
 // ------------------------------------------------------------------------------------------
 struct SfEmit {  // what a handler asks the engine to do, in program order: at most one send, then one task
-  int nSend;     // 0, 1 (single destination) or 2 (two destinations, shuffled before the send)
-  uint32_t dst[2];
+  int nSend;     // 0, 1 (single destination) or more (shuffled before the send)
+  uint32_t dst[SHUFFLE_MAX];
   uint32_t sendMeta;
   u64 sendPl;
   bool task;
@@ -1194,59 +1194,31 @@ WTG_HD bool sfIsCandidate(const Dev& d, int n, int node, int level) {  // SanFer
   if (shift < 0) return false;
   return (node >> shift) == ((n >> shift) ^ 1);
 }
-WTG_HD bool sfContains(const int* a, int cnt, int v) {
-  for (int i = 0; i < cnt; ++i)
-    if (a[i] == v) return true;
-  return false;
-}
-// SanFerminHelper.pickNextNodes(level, 1) :123-157 (without the shuffle, which the emit step performs)
-WTG_HD int sfPickNextNodes(const Dev& d, int n, int level, uint32_t* out) {
-  int shift = d.sfP - 1 - level;
-  int S = 1 << shift;
-  int ownMin = (n >> shift) << shift;
-  int candMin = ownMin ^ S;
-  int idx = n - ownMin;
-  int* used = d.sfUsed + (size_t)n * SF_USEDCAP;
-  int ucnt = d.sfUsedCnt[n];
-  int cnt = 0;
-  bool removed = false;
-  if (!sfContains(used, ucnt, idx)) {  // the deterministic counterpart first
-    out[cnt++] = (uint32_t)(candMin + idx);
-    removed = true;
-    if (ucnt < SF_USEDCAP) used[ucnt] = idx;
-    ++ucnt;
-  }
-  int size = removed ? S - 1 : S;  // candidateSet.remove(idx) shifts the list the stream below walks
-  int taken = 0;
-  for (int i = 0; i < size && taken < d.sfCandCount; ++i) {
-    if (!sfContains(used, ucnt < SF_USEDCAP ? ucnt : SF_USEDCAP, i)) {
-      if (ucnt < SF_USEDCAP) used[ucnt] = i;
-      ++ucnt;
-      out[cnt++] = (uint32_t)(removed ? (i < idx ? candMin + i : candMin + i + 1) : candMin + i);
-      ++taken;
-    }
-  }
-  if (ucnt > SF_USEDCAP) setError(d, ERR_QUEUE_OVERFLOW, n);
-  d.sfUsedCnt[n] = ucnt < SF_USEDCAP ? ucnt : SF_USEDCAP;
-  return cnt;
+// SanFerminHelper.pickNextNodes(level, candidateCount) :123-157 without the shuffle (the emit step performs it); the
+// helper's usedNodes of the current level is a bitmap (wtg_cappos.cuh)
+WTG_HD int cpPickNextNodes(const Dev& d, int n, int level, uint32_t* out);
+WTG_HD int sfPickNextNodes(const Dev& d, int n, int level, uint32_t* out) { return cpPickNextNodes(d, n, level, out); }
+// pendingNodes (:189) holds candidates of the current level only: a bitmap over positions in the candidate block
+WTG_HD bool sfPendingHas(const Dev& d, int n, int node) {
+  int shift = d.sfP - 1 - d.sfCpl[n];
+  if (shift < 0 || !sfIsCandidate(d, n, node, d.sfCpl[n])) return false;
+  int pos = node & ((1 << shift) - 1);
+  return (d.sfPendBits[(size_t)n * d.sfUsedWords + (pos >> 6)] >> (pos & 63)) & 1ULL;
 }
 WTG_HD void sfSendToNodes(const Dev& d, int n, const uint32_t* list, int cnt, SfEmit& em) {  // :329-373
   if (cnt == 0) return;
-  int* pend = d.sfPending + (size_t)n * SF_PENDCAP;
-  int pc = d.sfPendCnt[n];
-  for (int i = 0; i < cnt; ++i)
-    if (!sfContains(pend, pc, (int)list[i])) {
-      if (pc < SF_PENDCAP)
-        pend[pc++] = (int)list[i];
-      else
-        setError(d, ERR_QUEUE_OVERFLOW, n);
-    }
-  d.sfPendCnt[n] = pc;
-  d.sfSentReq[n] += cnt;
   int cpl = d.sfCpl[n];
+  {
+    const int shift = d.sfP - 1 - cpl;
+    u64* pend = d.sfPendBits + (size_t)n * d.sfUsedWords;
+    for (int i = 0; i < cnt; ++i) {  // every picked node is a candidate of the current level
+      int pos = (int)list[i] & ((1 << shift) - 1);
+      pend[pos >> 6] |= 1ULL << (pos & 63);
+    }
+  }
+  d.sfSentReq[n] += cnt;
   em.nSend = cnt;
-  em.dst[0] = list[0];
-  em.dst[1] = cnt > 1 ? list[1] : 0;
+  for (int i = 0; i < cnt; ++i) em.dst[i] = list[i];
   em.sendMeta = SF_REQ;
   em.sendPl = sfPl(cpl, d.sfAgg[n]);
   em.task = true;
@@ -1276,9 +1248,16 @@ WTG_HD void sfGoNextLevel(const Dev& d, int n, SfEmit& em) {  // :383-423
   d.sfCacheMask[n] |= 1u << cpl;
   fl &= ~1;
   d.sfFlags[n] = fl;
-  d.sfPendCnt[n] = 0;
-  d.sfUsedCnt[n] = 0;  // usedNodes of a level that was never picked from is a fresh BitSet
-  uint32_t list[4];
+  {  // pendingNodes.clear(); usedNodes of a level that was never picked from is a fresh BitSet
+    int words = ((1 << (d.sfP - 1 - cpl)) + 63) / 64;
+    u64* used = d.sfUsedBits + (size_t)n * d.sfUsedWords;
+    u64* pend = d.sfPendBits + (size_t)n * d.sfUsedWords;
+    for (int w = 0; w < words; ++w) {
+      used[w] = 0;
+      pend[w] = 0;
+    }
+  }
+  uint32_t list[SHUFFLE_MAX];
   int cnt = sfPickNextNodes(d, n, cpl, list);
   sfSendToNodes(d, n, list, cnt, em);
 }
@@ -1341,11 +1320,11 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
     case SF_REPLY_NO: {  // onSwapReply :270-323
       if (level != cpl || (fl & 2)) break;
       if (fl & 1) break;
-      bool pending = sfContains(d.sfPending + (size_t)n * SF_PENDCAP, d.sfPendCnt[n], (int)from);
+      bool pending = sfPendingHas(d, n, (int)from);
       if (type == SF_REPLY_OK) {
         if (pending || sfIsCandidate(d, n, (int)from, cpl)) sfTransition(d, n, val, em);
       } else if (pending) {
-        uint32_t list[4];
+        uint32_t list[SHUFFLE_MAX];
         int cnt = sfPickNextNodes(d, n, cpl, list);
         sfSendToNodes(d, n, list, cnt, em);
       }
@@ -1356,7 +1335,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
       break;
     case SF_T_TIMEOUT:  // :356-369
       if (!(fl & 2) && cpl == level) {
-        uint32_t list[4];
+        uint32_t list[SHUFFLE_MAX];
         int cnt = sfPickNextNodes(d, n, cpl, list);
         sfSendToNodes(d, n, list, cnt, em);
       }
@@ -1370,7 +1349,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   }
   int nd = (em.nSend > 0 ? 1 : 0) + (em.task ? 1 : 0);
   outSlots = nd;
-  outDraws = em.nSend == 0 ? 0 : em.nSend == 2 ? 2 : 1;
+  outDraws = em.nSend;  // nSend - 1 shuffle draws, then the send's seed
   if (nd == 0) return;
   CoopSerial cs;
   int base = descAlloc(d, cs, n, nd);
@@ -1391,15 +1370,13 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
       ds.to = em.dst[0];
       ds.nDest = 1;
     } else {
-      int off = destAlloc(d, n, 2);
-      if (off >= 0) {
-        d.destScratch[off] = em.dst[0];
-        d.destScratch[off + 1] = em.dst[1];
-      }
+      int off = destAlloc(d, n, 2 * em.nSend);  // destinations, then room for their arrivals
+      if (off >= 0)
+        for (int i = 0; i < em.nSend; ++i) d.destScratch[off + i] = em.dst[i];
       ds.dkind = DK_SEND_MULTI;
       ds.to = (uint32_t)(off < 0 ? 0 : off);
-      ds.nDest = off < 0 ? 0u : 2u;
-      ds.aux = DESC_SHUFFLE2;
+      ds.nDest = off < 0 ? 0u : (uint32_t)em.nSend;
+      ds.aux = DESC_SHUFFLEK;
     }
     d.desc[base + sub] = ds;
     ++sub;

@@ -54,8 +54,6 @@ WTG_HD uint32_t metaK(uint32_t m) { return (m >> 7) & 31u; }
 enum : uint32_t { PP_PING = 1, PP_PONG = 2 };
 // SanFermin message / task types (Ev.meta); Ev.pl = level | (value << 32)
 enum : uint32_t { SF_REQ = 1, SF_REPLY_OK = 2, SF_REPLY_NO = 3, SF_T_GO = 4, SF_T_TIMEOUT = 5, SF_T_TRANSITION = 6 };
-constexpr int SF_PENDCAP = 24;  // pendingNodes of the current level
-constexpr int SF_USEDCAP = 24;  // SanFerminHelper.usedNodes of the current level
 // CasperIMD message / task types (Ev.meta); Ev.pl = attestation index, block index, or block | height << 32
 enum : uint32_t { CM_ATT = 1, CM_BLOCK = 2, CT_BUILD = 3 };
 // CasperIMD node kinds (CasperIMD.java: observer :87, BlockProducer :365, Attester :444, ByzBlockProducerWF :647)
@@ -353,15 +351,12 @@ struct Dev {
   long long* sfThresholdAt;  // [N]
   int* sfSentReq;    // [N]
   int* sfRecvReq;    // [N]
-  int* sfPendCnt;    // [N]
-  int* sfPending;    // [N][SF_PENDCAP]
-  int* sfUsedCnt;    // [N]
-  int* sfUsed;       // [N][SF_USEDCAP]
   uint32_t* sfCacheMask;  // [N] levels present in signatureCache
   int* sfCache;      // [N][32]
   int sfTimeout;     // SanFerminCappos: params.timeout
   int sfUsedWords;   // words of a row of sfUsedBits
   unsigned long long* sfUsedBits;  // [N][sfUsedWords] SanFerminHelper.usedNodes of the current level
+  unsigned long long* sfPendBits;  // [N][sfUsedWords] SanFerminSignature: pendingNodes (positions in the current candidate block)
   // ---- GSF ----
   unsigned long long* verified;   // [N][W64]
   unsigned long long* indivSeen;  // [N][W64]
