@@ -327,23 +327,33 @@ WTG_HD int gsfScorePool(const Dev& d, C& c, int n, uint32_t from, uint32_t meta,
   const u64* sig = d.pool[l] + (size_t)(uint32_t)pl * (size_t)b.nw;
   int cWI = 0, cWIV = 0, inter = 0, interI = 0;
 #if defined(__CUDA_ARCH__)
-  {  // 128-bit loads, two independent triples in flight per lane (nw is even for pooled levels)
+  {  // 128-bit loads, four independent triples in flight per lane (nw is even for pooled levels)
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(sig);
     const ulonglong2* v2 = reinterpret_cast<const ulonglong2*>(rowV);
     const ulonglong2* i2 = reinterpret_cast<const ulonglong2*>(rowI);
     const int n2 = b.nw >> 1;
-    for (int w = c.lane(); w < n2; w += 64) {
-      ulonglong2 sa = s2[w], va = v2[w], ia = i2[w];
-      ulonglong2 sb = make_ulonglong2(0, 0), vb = sb, ib = sb;
-      if (w + 32 < n2) {
-        sb = s2[w + 32];
-        vb = v2[w + 32];
-        ib = i2[w + 32];
+    for (int w0 = c.lane(); w0 < n2; w0 += 128) {
+      ulonglong2 sv[4], vv[4], iv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int w = w0 + 32 * u;
+        if (w < n2) {
+          sv[u] = s2[w];
+          vv[u] = v2[w];
+          iv[u] = i2[w];
+        } else {
+          sv[u] = make_ulonglong2(0, 0);
+          vv[u] = sv[u];
+          iv[u] = sv[u];
+        }
       }
-      cWI += __popcll(ia.x | sa.x) + __popcll(ia.y | sa.y) + __popcll(ib.x | sb.x) + __popcll(ib.y | sb.y);
-      cWIV += __popcll(ia.x | sa.x | va.x) + __popcll(ia.y | sa.y | va.y) + __popcll(ib.x | sb.x | vb.x) + __popcll(ib.y | sb.y | vb.y);
-      inter |= ((sa.x & va.x) | (sa.y & va.y) | (sb.x & vb.x) | (sb.y & vb.y)) != 0;
-      interI |= ((sa.x & ia.x) | (sa.y & ia.y) | (sb.x & ib.x) | (sb.y & ib.y)) != 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cWI += __popcll(iv[u].x | sv[u].x) + __popcll(iv[u].y | sv[u].y);
+        cWIV += __popcll(iv[u].x | sv[u].x | vv[u].x) + __popcll(iv[u].y | sv[u].y | vv[u].y);
+        inter |= ((sv[u].x & vv[u].x) | (sv[u].y & vv[u].y)) != 0;
+        interI |= ((sv[u].x & iv[u].x) | (sv[u].y & iv[u].y)) != 0;
+      }
     }
   }
 #else
