@@ -6,6 +6,7 @@
 //   protocols/PingPong.java      -> PingPong / PingPongParameters
 //   protocols/GSFSignature.java  -> GSFSignature / GSFSignatureParameters
 //   protocols/SanFerminSignature.java -> SanFerminSignature / SanFerminSignatureParameters
+//   protocols/SanFerminCappos.java -> SanFerminCappos / SanFerminCapposParameters
 //   protocols/Handel.java        -> Handel / HandelParameters
 //   protocols/CasperIMD.java     -> CasperIMD / CasperParemeters (the reference's spelling)
 // Header-only; link with wittgenstein_b200/libwtg_b200.so.  tests/cpp/mirror_parity.cpp drives it against the CPU oracle.
@@ -180,6 +181,28 @@ class SanFerminSignature {
   Network& network() { return net; }
   void init() { check(wtg_sanfermin_init(net.handle())); }
   const SanFerminSignatureParameters params;
+
+ private:
+  Network net;
+};
+
+// protocols/SanFerminCappos.java:43-104
+struct SanFerminCapposParameters {
+  int nodeCount, threshold, pairingTime, signatureSize, timeout, candidateCount;
+  std::string nodeBuilderName, networkLatencyName;
+};
+class SanFerminCappos {
+ public:
+  explicit SanFerminCappos(const SanFerminCapposParameters& p) : params(p) {
+    net.setNodeBuilder(p.nodeBuilderName);
+    net.setNetworkLatency(p.networkLatencyName);
+  }
+  Network& network() { return net; }
+  void init() {  // :120-134
+    int a[6] = {params.nodeCount, params.threshold, params.pairingTime, params.signatureSize, params.timeout, params.candidateCount};
+    check(wtg_cappos_init(net.handle(), a));
+  }
+  const SanFerminCapposParameters params;
 
  private:
   Network net;

@@ -166,6 +166,27 @@ static void testHandel() {
   ASSERT_EQ(live, 62);
 }
 
+// SanFerminCappos.sigsPerTime scaled down (SanFerminCappos.java:465-471), every 10 ms against the oracle
+static void testCappos() {
+  SanFerminCappos p(SanFerminCapposParameters{512, 256, 2, 48, 150, 50, "", ""});
+  wo::SanFerminCappos::Params op;
+  op.nodeCount = 512;
+  op.threshold = 256;
+  op.candidateCount = 50;
+  wo::SanFerminCappos o(op);
+  p.init();
+  o.init();
+  for (int i = 0; i < 400; ++i) {
+    ASSERT_EQ(p.network().runMs(10), o.network.runMs(10));
+    ASSERT_EQ(p.network().rngState(), o.network.rd.seed);
+    ASSERT_TRUE(sameCounters(p.network().counters(), o.nodes));
+  }
+  NodeCounters c = p.network().counters();
+  int done = 0;
+  for (int n = 0; n < 512; ++n) done += c.doneAt[(size_t)n] > 0;
+  ASSERT_TRUE(done > 500);
+}
+
 // error behaviour: the reference's unchecked exceptions surface as WtgError
 static void testErrors() {
   bool thrown = false;
@@ -193,6 +214,7 @@ int main() {
   testCasperByzantineWF();
   testCasperForks();
   testHandel();
+  testCappos();
   testErrors();
   if (g_fail) {
     std::printf("MIRROR PARITY FAILED: %d\n", g_fail);
