@@ -6,6 +6,11 @@
 // :665-677, partition :693-707, msgs.size() :204-210, time :49, rd :32; Protocol.init() of
 // protocols/PingPong.java:82-87 and protocols/GSFSignature.java:611-635.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <functional>
+#include <thread>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -672,6 +677,15 @@ class Engine {
       d.hbLastId = dupload(m1);
     }
     d.hbLastFrom = dalloc<int>(N);
+    const bool timing_ = std::getenv("WTG_INIT_TIMING") != nullptr;
+    auto t0_ = std::chrono::steady_clock::now();
+    auto lap_ = [&](const char* what) {
+      if (!timing_) return;
+      auto t1 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[handel init] %s: %.2f s\n", what, std::chrono::duration<double>(t1 - t0_).count());
+      t0_ = t1;
+    };
+    lap_("nodes + rows");
     // setReceivingRanks (:940-948): N cumulative shuffles of one list
     std::vector<int> ranks((size_t)N * N);
     {
@@ -683,39 +697,78 @@ class Engine {
         for (int i = 0; i < N; ++i) row[expected[(size_t)i]] = i;
       }
     }
+    lap_("reception ranks");
     // emission lists (:991-1013): receivers of each level sorted by the rank they gave the sender, ties shuffled
     std::vector<uint32_t> peers((size_t)N * (size_t)(N - 1), 0);
     {
-      std::vector<std::pair<int, int>> rr;  // (rank, receiver)
-      std::vector<int> group;
-      for (int sIdx = 0; sIdx < N; ++sIdx) {
-        if (hm.nodes[(size_t)sIdx].down) continue;
+      // The order of every list is a pure function of the rank table; only the shuffles of equal-rank runs draw from the
+      // network RNG, and they must do so in (sender, level, position) order.  So: (1) transpose the table once (the list
+      // of sender s reads column s); (2) sort all lists on all host threads; (3) one sequential pass shuffles the ties.
+      std::vector<int> ranksT((size_t)N * N);
+      const int TB = 64;
+      auto transposeRows = [&](int r0, int r1) {
+        for (int rb = r0; rb < r1; rb += TB)
+          for (int cb = 0; cb < N; cb += TB)
+            for (int r = rb; r < std::min(rb + TB, r1); ++r)
+              for (int c = cb; c < std::min(cb + TB, N); ++c) ranksT[(size_t)c * N + r] = ranks[(size_t)r * N + c];
+      };
+      auto sortSender = [&](int sIdx, std::vector<unsigned long long>& keys) {
+        if (hm.nodes[(size_t)sIdx].down) return;
+        const int* col = ranksT.data() + (size_t)sIdx * N;
         for (int l = 1; l < L; ++l) {
           Blk wb = levelBlock(sIdx ^ (1 << (l - 1)), l);
-          rr.clear();
-          for (int r = wb.base; r < wb.base + wb.size; ++r) rr.push_back({ranks[(size_t)r * N + sIdx], r});
-          std::stable_sort(rr.begin(), rr.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+          keys.resize((size_t)wb.size);
+          for (int i = 0; i < wb.size; ++i)  // unique keys: (rank, receiver) — ascending receiver inside a tie == stable order
+            keys[(size_t)i] = ((unsigned long long)(uint32_t)col[wb.base + i] << 32) | (unsigned long long)(uint32_t)(wb.base + i);
+          std::sort(keys.begin(), keys.end());
           uint32_t* out = peers.data() + (size_t)sIdx * (size_t)(N - 1) + (size_t)((1 << (l - 1)) - 1);
-          size_t o = 0;
-          for (size_t i = 0; i < rr.size();) {
-            size_t j = i;
-            while (j < rr.size() && rr[j].first == rr[i].first) ++j;
-            if (j - i > 1) {
-              group.clear();
-              for (size_t k = i; k < j; ++k) group.push_back(rr[k].second);
-              for (int m = (int)group.size(); m > 1; --m) std::swap(group[(size_t)m - 1], group[(size_t)hm.rd.nextInt(m)]);
-              for (int g : group) out[o++] = (uint32_t)g;
-            } else {
-              out[o++] = (uint32_t)rr[i].second;
-            }
+          for (int i = 0; i < wb.size; ++i) out[i] = (uint32_t)(keys[(size_t)i] & 0xFFFFFFFFULL);
+        }
+      };
+      unsigned hw = std::thread::hardware_concurrency();
+      int T = (int)std::max(1u, std::min(hw ? hw : 1u, 64u));
+      if (N < 2048) T = 1;
+      auto parallelFor = [&](int n, const std::function<void(int, int)>& body) {  // body(begin, end), contiguous chunks
+        if (T == 1) {
+          body(0, n);
+          return;
+        }
+        std::vector<std::thread> th;
+        int per = (n + T - 1) / T;
+        for (int t = 0; t < T; ++t) {
+          int b0 = t * per, b1 = std::min(n, b0 + per);
+          if (b0 < b1) th.emplace_back(body, b0, b1);
+        }
+        for (auto& x : th) x.join();
+      };
+      parallelFor(N, [&](int r0, int r1) { transposeRows(r0, r1); });
+      lap_("rank table transpose");
+      parallelFor(N, [&](int s0, int s1) {
+        std::vector<unsigned long long> keys;
+        for (int sIdx = s0; sIdx < s1; ++sIdx) sortSender(sIdx, keys);
+      });
+      lap_("emission lists: sort");
+      for (int sIdx = 0; sIdx < N; ++sIdx) {  // Collections.shuffle of every run of equal ranks, in the reference's order
+        if (hm.nodes[(size_t)sIdx].down) continue;
+        const int* col = ranksT.data() + (size_t)sIdx * N;
+        for (int l = 1; l < L; ++l) {
+          const int size = 1 << (l - 1);
+          uint32_t* out = peers.data() + (size_t)sIdx * (size_t)(N - 1) + (size_t)(size - 1);
+          for (int i = 0; i < size;) {
+            int j = i + 1;
+            const int rk = col[out[i]];
+            while (j < size && col[out[j]] == rk) ++j;
+            for (int m = j - i; m > 1; --m) std::swap(out[i + m - 1], out[i + hm.rd.nextInt(m)]);
             i = j;
           }
         }
       }
     }
+    lap_("emission lists");
     d.hRanks = dupload(ranks);
     d.peerBits = 32;
     d.peers = dupload(peers);
+    lap_("upload");
     Ctl c;
     std::memset(&c, 0, sizeof(c));
     long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
