@@ -80,3 +80,38 @@ def test_run_multiple_times_concurrent_equals_sequential_and_oracle():
         done.append(get_stats_on(c[4][live]))
         recv.append(get_stats_on(c[0][live]))
     assert avg(done) == seq[0] and avg(recv) == seq[1]
+
+
+@pytest.mark.gpu
+def test_progress_per_time_rounds():
+    """ProgressPerTime (C/ProgressPerTime.java:52-129): per-round series sampled every 10 ms and the averaged counters, concurrent
+    rounds equal to sequential ones and to the oracle's runs of the same seeds."""
+    from tests.oracle_lib import OracleGSF
+    from wittgenstein_b200 import DoneAtStatGetter, GSFSignature, GSFSignatureParameters, ProgressPerTime
+    from wittgenstein_b200.run_multiple import get_stats_on
+
+    args = (128, 100, 3, 20, 10, 10, 8, "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter")
+    tmpl = GSFSignature(GSFSignatureParameters(*args))
+    cont = lambda c: c.continue_if()  # noqa: E731
+    a = ProgressPerTime(tmpl, DoneAtStatGetter(), 3)
+    sa = a.run(cont, concurrency=1)
+    b = ProgressPerTime(tmpl, DoneAtStatGetter(), 3)
+    sb = b.run(cont, concurrency=3)
+    assert [[(t, s.min, s.max, s.avg) for t, s in r] for r in sa] == [[(t, s.min, s.max, s.avg) for t, s in r] for r in sb]
+    assert a.average == b.average
+    sums = {"msg_rcvd": 0, "done_at": 0}
+    for seed in range(3):
+        o = OracleGSF(*args, seed=seed)
+        o.init()
+        lines = []
+        while True:
+            o.run_ms(10)
+            live = o.attrs()["down"] == 0
+            st = get_stats_on(o.counters()[4][live])
+            lines.append((o.time, st.min, st.max, st.avg))
+            if not bool(((o.scalars()["card"] < args[1]) & live).any()):
+                break
+        assert lines == [(t, s.min, s.max, s.avg) for t, s in sa[seed]]
+        sums["msg_rcvd"] += get_stats_on(o.counters()[0][live]).avg
+        sums["done_at"] += get_stats_on(o.counters()[4][live]).avg
+    assert a.average["msg_rcvd"] == sums["msg_rcvd"] // 3 and a.average["done_at"] == sums["done_at"] // 3

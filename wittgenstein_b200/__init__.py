@@ -5,5 +5,5 @@ from .network import Network  # noqa: F401
 from .protocols import (CasperIMD, CasperParemeters, GSFSignature, GSFSignatureParameters, Handel, HandelParameters, PingPong,  # noqa: F401
                         PingPongParameters, SanFerminCappos, SanFerminCapposParameters, SanFerminSignature,
                         SanFerminSignatureParameters)
-from .run_multiple import (DoneAtStatGetter, MsgReceivedStatGetter, RunMultipleTimes, SimpleStats,  # noqa: F401
+from .run_multiple import (DoneAtStatGetter, MsgReceivedStatGetter, ProgressPerTime, RunMultipleTimes, SimpleStats,  # noqa: F401
                            cont_until_done)

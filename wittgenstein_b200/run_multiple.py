@@ -114,3 +114,51 @@ class RunMultipleTimes:
                 per = list(ex.map(lambda i: self._one(i, cont_if), range(self.run_count)))
         self.end_times = [t for _, t in per]
         return [avg([r[k] for r, _ in per]) for k in range(len(self.stats_getters))]
+
+
+class ProgressPerTime:
+    """ProgressPerTime (core/ProgressPerTime.java:16-140) without the graph output (tools/Graph is out of scope): `roundCount`
+    seeded rounds, a stat sampled every `statEachXms` ms of each round, the per-round and averaged node counters.  Rounds are
+    independent, so up to `concurrency` of them run at once, each on its own engine instance (see RunMultipleTimes above)."""
+
+    def __init__(self, template, stats_getter, round_count, end_callback=None, stat_each_x_ms=10):
+        if round_count <= 0:
+            raise ValueError(f"roundCount must be greater than 0. roundCount={round_count}")  # :36-39
+        self.protocol = template.copy()
+        self.stats_getter = stats_getter
+        self.round_count = round_count
+        self.end_callback = end_callback
+        self.stat_each_x_ms = stat_each_x_ms
+
+    def _round(self, r, cont_if):
+        p = self.protocol.copy()
+        p.network().set_seed(r)  # :71
+        p.init()
+        net = p.network()
+        series = []  # (time, Stat) lines of Graph.ReportLine
+        while True:
+            net.run_ms(self.stat_each_x_ms)
+            s = self.stats_getter.get(p)
+            series.append((net.time, s))
+            if not cont_if(p):
+                break
+        if self.end_callback is not None:
+            self.end_callback(p)
+        live = net.attrs()["down"] == 0
+        c = net.counters()
+        summary = {"bytes_sent": get_stats_on(c[2][live]), "bytes_rcvd": get_stats_on(c[3][live]), "msg_sent": get_stats_on(c[1][live]),
+                   "msg_rcvd": get_stats_on(c[0][live]), "done_at": get_stats_on(c[4][live])}
+        net.close()
+        return series, summary
+
+    def run(self, cont_if, concurrency=8):
+        if concurrency <= 1:
+            rounds = [self._round(r, cont_if) for r in range(self.round_count)]
+        else:
+            with ThreadPoolExecutor(max_workers=concurrency) as ex:
+                rounds = list(ex.map(lambda r: self._round(r, cont_if), range(self.round_count)))
+        self.series = [s for s, _ in rounds]
+        self.summaries = [m for _, m in rounds]
+        # "Average on the N rounds" (:122-129): truncating long division of the sums of the per-round averages
+        self.average = {k: sum(m[k].avg for m in self.summaries) // self.round_count for k in self.summaries[0]}
+        return self.series
