@@ -750,13 +750,16 @@ class CudaBackend : public Backend {
     profBegin(11);
     k_ms_scatter<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
     profEnd();
-    profBegin(12);
-    k_free<<<ARENA_STRIPES * 2, 256, 0, st>>>(d);
-    profEnd();
+    const bool pooled = d.proto == PROTO_GSF || d.proto == PROTO_HANDEL;  // only these protocols hold pooled payloads
+    if (pooled) {
+      profBegin(12);
+      k_free<<<ARENA_STRIPES * 2, 256, 0, st>>>(d);
+      profEnd();
+    }
     profBegin(13);
     k_end<<<1, 1, 0, st>>>(d, mode);
     profEnd();
-    launches += 9;
+    launches += pooled ? 9 : 8;
   }
   void configure(const Dev& d) {
     size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
