@@ -90,6 +90,14 @@ int wtg_casper_init(wtg_net* net, int byz_delay);
 /* .init(new ByzBlockProducer / SF / NS / WF (byz_delay, genesis)) — kind 3 / 4 / 5 / 6 (CasperIMD.java:511-707) */
 int wtg_casper_init_byz(wtg_net* net, int kind, int byz_delay);
 
+/* network.send(msg, from, to) / send(msg, from, dests) / sendAll(msg, from) called by the host between two runMs windows —
+ * Network.java:341-366: one rd.nextInt() per call, send time = time + 1.  `type` / `payload` name a message of the running
+ * protocol: PingPong 1 = Ping, 2 = Pong (payload unused); CasperIMD 2 = SendBlock(block id).  At most 16 destinations per
+ * wtg_send; wtg_send_all needs the sendAll path (CasperIMD).  Other protocols' messages carry device-resident payloads and are
+ * not offered. */
+int wtg_send(wtg_net* net, int type, unsigned long long payload, int from, const int* to, int n);
+int wtg_send_all(wtg_net* net, int type, unsigned long long payload, int from);
+
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);
 /* network.time — Network.java:49 */
@@ -103,7 +111,8 @@ int wtg_msgs_size_at(wtg_net* net, int t);
 /* node.stop() / node.start() — Node.java:120-127 */
 int wtg_stop_node(wtg_net* net, int node_id);
 int wtg_start_node(wtg_net* net, int node_id);
-/* network.partition(part) / network.endPartition() — Network.java:693-707 */
+/* network.partition(part) / network.endPartition() — Network.java:693-707.  For CasperIMD endPartition is
+ * BlockChainNetwork.endPartition (BlockChainNetwork.java:46-54): every node re-sends its head to all (needs rec_cap >= nodes + 64). */
 int wtg_partition(wtg_net* net, float part);
 int wtg_end_partition(wtg_net* net);
 

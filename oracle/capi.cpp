@@ -106,6 +106,7 @@ int wo_pp_run_ms(void* h, int ms) {
   WO_CATCH(-1)
 }
 int wo_pp_time(void* h) { return static_cast<PingPong*>(h)->network.time; }
+uint64_t wo_pp_rng_state(void* h) { return static_cast<PingPong*>(h)->network.rd.seed; }
 int wo_pp_msgs_size(void* h) { return static_cast<PingPong*>(h)->network.msgs.size(); }
 void wo_pp_pongs(void* h, int32_t* out) {
   auto* p = static_cast<PingPong*>(h);
@@ -670,5 +671,31 @@ void wo_cappos_node_scalars(void* h, int32_t* cpl, int32_t* sigs, int32_t* done,
     cacheMask[i] = m;
     thresholdAt[i] = n.thresholdAt;
   }
+}
+
+// PingPong: network.send(new Ping()/Pong(), from, dests) issued by the caller (type 1 = Ping, 2 = Pong)
+int wo_pp_send(void* h, int type, int from, const int32_t* to, int n) {
+  WO_TRY
+  auto* p = static_cast<PingPong*>(h);
+  std::vector<Node*> dests;
+  for (int i = 0; i < n; ++i) dests.push_back(&p->network.getNodeById(to[i]));
+  MessagePtr m;
+  if (type == 1)
+    m = std::make_shared<PingPong::Ping>();
+  else
+    m = std::make_shared<PingPong::Pong>();
+  p->network.send(m, p->network.getNodeById(from), dests);
+  return 0;
+  WO_CATCH(-1)
+}
+// CasperIMD: like the others, but endPartition is BlockChainNetwork.endPartition (every node re-sends its head)
+int wo_casper_net_ctl(void* h, int op, int arg) {
+  if (op == 3) {
+    WO_TRY
+    static_cast<CasperIMD*>(h)->endPartition();
+    return 0;
+    WO_CATCH(-1)
+  }
+  return netCtl(static_cast<CasperIMD*>(h)->network, op, arg);
 }
 }  // extern "C"

@@ -35,12 +35,14 @@ class HostBackend : public Backend {
   void tick(const Dev& d, int mode) override {
     CoopSerial c;
     std::vector<uint32_t> keep((size_t)std::max(1, d.qcap));
-    if (d.ffwd && mode == 1)
+    if (mode == 3) {
+      // host-injected sends: control block and descriptors are already in place (Engine::inject)
+    } else if (d.ffwd && mode == 1)
       tickBeginFfwd(d, c);
     else
       tickBegin(d, mode);
     if (d.ctl->error) return;
-    if (d.proto == PROTO_GSF) {
+    if (d.proto == PROTO_GSF && mode != 3) {
       for (int n = 0; n < d.N; ++n)
         if (gsfCondMark(d, n)) gsfCondScanQueue(d, c, n);
       int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
@@ -48,7 +50,7 @@ class HostBackend : public Backend {
       for (int n = 0; n < d.N; ++n)
         if (d.condDue[n]) gsfCondSelect(d, c, n, keep.data());
     }
-    if (d.proto == PROTO_HANDEL) {
+    if (d.proto == PROTO_HANDEL && mode != 3) {
       HScratch sc;
       for (int n = 0; n < d.N; ++n)
         if (hCondMark(d, n)) hCondScanQueue(d, c, n);
@@ -68,7 +70,7 @@ class HostBackend : public Backend {
         for (int n = 0; n < d.N; ++n) idx += (u64)hCondPick(d, n, idx, true);
       }
     }
-    if (mode != 2) {
+    if (mode != 2 && mode != 3) {
       int nEv = d.ctl->nEv;
       const bool coopDispatch = d.allCap > 0;
       for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchCountCoop(d, c, i) : dispatchCount(d, i);

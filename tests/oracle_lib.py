@@ -60,6 +60,7 @@ def load():
     for name in ("wo_pp_create", "wo_gsf_create"):
         getattr(lib, name).restype = C.c_void_p
     lib.wo_pp_create.argtypes = [C.c_int, C.c_char_p, C.c_char_p]
+    lib.wo_pp_rng_state.restype = C.c_uint64
     lib.wo_gsf_create.argtypes = [C.c_int] * 7 + [C.c_char_p, C.c_char_p]
     lib.wo_gsf_run_timed.restype = C.c_double
     lib.wo_gsf_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -134,6 +135,14 @@ class OraclePingPong(_NetCtl):
 
     def msgs_size(self):
         return self.lib.wo_pp_msgs_size(self.h)
+
+    def rng_state(self):
+        return int(self.lib.wo_pp_rng_state(self.h))
+
+    def send(self, msg_type, from_id, to):
+        dests = np.asarray([to] if np.isscalar(to) else list(to), np.int32)
+        if self.lib.wo_pp_send(self.h, int(msg_type), int(from_id), _p(dests, C.c_int32), len(dests)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
 
     def pongs(self):
         out = np.zeros(self.n, np.int32)
@@ -416,7 +425,9 @@ class OracleHandel(_NetCtl):
             self.h = None
 
 
-class OracleCasper:
+class OracleCasper(_NetCtl):
+    _ctl = "wo_casper_net_ctl"
+
     """protocols/CasperIMD.java through the oracle; init(byz_delay) = init(new ByzBlockProducerWF(byz_delay, genesis))."""
 
     def __init__(self, cycle_length, random_on_ties, block_producers_count, attesters_per_round, block_construction_time,
@@ -469,16 +480,6 @@ class OracleCasper:
 
     def deliveries(self):
         return int(self.lib.wo_casper_deliveries(self.h))
-
-    def stop_node(self, i):
-        self.lib.wo_casper_stop_node(self.h, i)
-
-    def start_node(self, i):
-        self.lib.wo_casper_start_node(self.h, i)
-
-    def partition(self, part):
-        if self.lib.wo_casper_partition(self.h, C.c_float(part)) != 0:
-            raise RuntimeError(self.lib.wo_last_error().decode())
 
     def counters(self):
         out = np.zeros((5, self.n), np.int64)

@@ -299,11 +299,12 @@ def test_casper_errors():
 
     with pytest.raises(WtgError):
         CasperIMD(CasperParemeters(0, False, 2, 2, 1000, 1))
-    p = CasperIMD(CasperParemeters(4, False, 3, 8, 1000, 1))
+    p = CasperIMD(CasperParemeters(4, False, 3, 200, 1000, 1))
+    p.network().set_tunable("rec_cap", 100)
     p.init(0)
     p.network().partition(0.5)
     with pytest.raises(WtgError):
-        p.network().end_partition()  # BlockChainNetwork.endPartition re-sends every head: not offered, and says so
+        p.network().end_partition()  # BlockChainNetwork.endPartition re-sends every head: needs one record slot per node
     p = CasperIMD(CasperParemeters(4, False, 3, 8, 1000, 1))
     p.init(8000)  # the Byzantine producer and producer 2 would both create a block in millisecond 16000
     with pytest.raises(WtgError):
@@ -553,3 +554,45 @@ def test_cappos_parity(n, k, nb, nl, seed, step, until, force):
         bad = _cappos_compare(p, o, f"t={o.time}")
         assert not bad, bad
     assert p.scalars()["done"].sum() > n // 2
+
+
+@pytest.mark.gpu
+def test_casper_end_partition_resends_heads():
+    """BlockChainNetwork.endPartition (C/BlockChainNetwork.java:46-54): after the partition every node sends its head to
+    everybody — N sendAll calls issued by the caller, one draw each, in node order."""
+    from tests.parity import compare_casper
+
+    p, o = _casper_pair(3, 3, 16, None, None, 2, 0, 160000)
+    for k in range(160):
+        if k == 30:
+            p.network().partition(0.45); o.partition(0.45)
+        if k == 70:
+            p.network().end_partition(); o.end_partition()
+        if k == 110:
+            p.network().partition(0.2); o.partition(0.2)
+        if k == 115:
+            p.network().end_partition(); o.end_partition()
+        assert p.network().run_ms(1000) == o.run_ms(1000)
+        bad = compare_casper(p, o, f"t={o.time}")
+        assert not bad, bad
+    assert not compare_casper(p, o, "end", atts=True)
+
+
+@pytest.mark.gpu
+def test_pingpong_sends_from_the_host():
+    """network.send(msg, from, to) / send(msg, from, dests) called between two windows (C/Network.java:353-366), like the
+    reference's NetworkTest drives its network: one draw per call, arrival through the latency model, LIFO insertion."""
+    p = PingPong(PingPongParameters(200, AWS_NB, AWS_NL))
+    o = OraclePingPong(200, AWS_NB, AWS_NL)
+    p.init(); o.init()
+    plan = {0: [(1, 5, [7])], 2: [(1, 9, [3, 4, 5, 150, 9]), (2, 11, [12])], 3: [(1, 0, list(range(20, 36)))], 7: [(2, 199, [0, 1])]}
+    for k in range(15):
+        for (typ, frm, to) in plan.get(k, []):
+            p.network().send(typ, frm, to if len(to) > 1 else to[0])
+            o.send(typ, frm, to)
+            assert p.network().rng_state() == o.rng_state()
+            assert p.network().msgs_size() == o.msgs_size()
+        assert p.network().run_ms(40) == o.run_ms(40)
+        assert (p.pongs() == o.pongs()).all()
+        assert (p.network().counters() == o.counters()).all()
+        assert p.network().msgs_size() == o.msgs_size()

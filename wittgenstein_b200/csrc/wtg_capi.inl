@@ -335,6 +335,23 @@ int WTG_API(handel_init)(void* h, const int* p) {
     return 0;
   });
 }
+// network.send(msg, from, to) / network.send(msg, from, dests) (Network.java:353-366) issued by the caller between two windows
+int WTG_API(send)(void* h, int type, unsigned long long payload, int from, const int* to, int n) {
+  return guard([&] {
+    if (n <= 0) return 0;  // send(m, from, emptyList) is a no-op (:354-356)
+    wtg::Engine::HostSend hs{from, (uint32_t)type, payload, std::vector<int>(to, to + n)};
+    ENG.inject({hs});
+    return 0;
+  });
+}
+// network.sendAll(msg, from) (Network.java:345-347)
+int WTG_API(send_all)(void* h, int type, unsigned long long payload, int from) {
+  return guard([&] {
+    wtg::Engine::HostSend hs{from, (uint32_t)type, payload, {}};
+    ENG.inject({hs});
+    return 0;
+  });
+}
 int WTG_API(run_ms)(void* h, int ms) {
   return guard([&] { return ENG.runMs(ms); });
 }

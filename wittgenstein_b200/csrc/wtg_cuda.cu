@@ -664,10 +664,14 @@ class CudaBackend : public Backend {
   void enqueueTick(const Dev& d, int mode) {
     const int wide = sms * 8;
     const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
-    profBegin(0);
-    k_begin<<<1, 32, 0, st>>>(d, mode);
-    profEnd();
-    if (d.proto == PROTO_HANDEL) {
+    // mode 3: the host prepared the control block and the descriptors of sends it injects at the current time
+    // (Engine::inject); only the emission half of the pipeline runs
+    if (mode != 3) {
+      profBegin(0);
+      k_begin<<<1, 32, 0, st>>>(d, mode);
+      profEnd();
+    }
+    if (d.proto == PROTO_HANDEL && mode != 3) {
       profBegin(1);
       k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
       k_cond_nodes<0><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
@@ -690,7 +694,7 @@ class CudaBackend : public Backend {
       profEnd();
       launches += 7;
     }
-    if (d.proto == PROTO_GSF) {
+    if (d.proto == PROTO_GSF && mode != 3) {
       size_t smem8 = (size_t)8 * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);
       k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
@@ -704,7 +708,7 @@ class CudaBackend : public Backend {
       profEnd();
       launches += 4;
     }
-    if (mode != 2) {
+    if (mode != 2 && mode != 3) {
       profBegin(2);
     k_dispatch_count<<<wide, 256, 0, st>>>(d);
     profEnd();

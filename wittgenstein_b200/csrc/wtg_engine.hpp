@@ -896,7 +896,8 @@ class Engine {
     hm.buildNodes(N - 1);  // byzantine producer, producers 1.., attesters — in this order (:479-507); registering tasks draws nothing
     ringExtra = std::max(cp.blockConstructionTime, cp.attestationConstructionTime);
     farEnabled = true;
-    const long long slots = 4LL * (cp.attestersPerRound + 2) + 64;  // sendAll envelopes alive at once, with margin
+    long long slots = 4LL * (cp.attestersPerRound + 2) + 64;  // sendAll envelopes alive at once, with margin
+    if (tun.recCap > slots) slots = tun.recCap;
     if (slots * N > 0x7fffffffLL) throw std::invalid_argument("attestersPerRound x nodes too large for the sendAll arena");
     recDestOverride = (int)(slots * N);
     if (!tun.recCap) tun.recCap = slots;
@@ -999,6 +1000,111 @@ class Engine {
     c.nextEvent = 0;  // unknown: the first window looks for itself
     writeCtl(c);
     inited = true;
+  }
+
+  // ---- sends issued by the caller between two runMs windows: network.send / sendAll (Network.java:341-366) and, for a
+  //      block-chain network, the re-send of BlockChainNetwork.endPartition (BlockChainNetwork.java:46-54).  The caller's
+  //      sends are descriptors like a handler's; only the emission half of the pipeline runs (backend mode 3). ----
+  struct HostSend {
+    int from;
+    uint32_t meta;
+    unsigned long long pl;
+    std::vector<int> to;  // empty: sendAll
+  };
+  int msgSizeOf(uint32_t) const {
+    if (d.proto == PROTO_PINGPONG || d.proto == PROTO_CASPER) return 1;  // Message.size() default (messages/Message.java:27-29)
+    throw std::logic_error("host-side sends are offered for PingPong and CasperIMD messages only");
+  }
+  void inject(const std::vector<HostSend>& sends) {
+    requireInited();
+    if (sends.empty()) return;
+    const int n = (int)sends.size();
+    if (n > d.descCap || n > d.itemCap) throw std::runtime_error("too many sends in one call");
+    Ctl c = readCtl();
+    if (c.error) throwDeviceError(c);
+    std::vector<Desc> descs((size_t)n);
+    std::vector<uint32_t> scratch;
+    std::vector<int> allList;
+    std::vector<long long> sent((size_t)d.N, 0), bytes((size_t)d.N, 0);
+    for (int i = 0; i < n; ++i) {
+      const HostSend& hs = sends[(size_t)i];
+      if (hs.from < 0 || hs.from >= d.N) throw std::invalid_argument("The from node is not in the network");  // Network.java:370-372
+      Desc ds;
+      std::memset(&ds, 0, sizeof(ds));
+      ds.item = (uint32_t)(d.N + i);
+      ds.sub = 0;
+      ds.from = (uint32_t)hs.from;
+      ds.evKind = EV_MSG;
+      ds.meta = hs.meta;
+      ds.pl = hs.pl;
+      int fan = 0;
+      if (hs.to.empty()) {
+        if (d.allCap <= 0) throw std::logic_error("sendAll from the host needs a protocol with the sendAll path (CasperIMD)");
+        ds.dkind = DK_SEND_ALL;
+        ds.evKind = EV_MULTI;
+        ds.nDest = (uint32_t)d.N;
+        ds.target = time + 1;
+        allList.push_back(i);
+        fan = d.N;
+      } else if (hs.to.size() == 1) {
+        if (hs.to[0] < 0 || hs.to[0] >= d.N) throw std::invalid_argument("The to node is not in the network");
+        ds.dkind = DK_SEND_SINGLE;
+        ds.to = (uint32_t)hs.to[0];
+        ds.nDest = 1;
+        fan = 1;
+      } else {
+        if ((int)hs.to.size() > MAX_ACC) throw std::invalid_argument("at most 16 destinations per send (or none: sendAll)");
+        ds.dkind = DK_SEND_MULTI;
+        ds.to = (uint32_t)scratch.size();
+        ds.nDest = (uint32_t)hs.to.size();
+        for (int t : hs.to) {
+          if (t < 0 || t >= d.N) throw std::invalid_argument("The to node is not in the network");
+          scratch.push_back((uint32_t)t);
+        }
+        fan = (int)hs.to.size();
+      }
+      descs[(size_t)i] = ds;
+      sent[(size_t)hs.from] += fan;
+      bytes[(size_t)hs.from] += (long long)fan * msgSizeOf(hs.meta);
+    }
+    if ((int)scratch.size() > d.destScratchCap / ARENA_STRIPES || (int)allList.size() > d.allCap) throw std::runtime_error("too many destinations in one call");
+    // control block of a "tick" at the current time with no bucket events, n items of one descriptor and one draw each
+    c.tick = time;
+    c.condMode = 0;
+    c.nEv = 0;
+    c.nItems = n;
+    c.totalSlots = c.totalDraws = 0;
+    c.hReject = 0;
+    c.shufReject = 0;
+    c.allCnt = (int)allList.size();
+    c.nextEvent = 0;  // fast-forward: the next window looks for the earliest arrival itself
+    const int per = d.descCap / ARENA_STRIPES;
+    for (int t = 0; t < ARENA_STRIPES; ++t) {
+      c.descCnt[t] = std::max(0, std::min(per, n - t * per));
+      c.destCnt[t] = c.workCnt[t] = c.dueCnt[t] = c.taskCnt[t] = 0;
+    }
+    be->upload(d.desc, descs.data(), descs.size() * sizeof(Desc));
+    std::vector<int> ones((size_t)n, 1), zerosN((size_t)d.N, 0);
+    be->upload(d.evSlots, ones.data(), ones.size() * sizeof(int));
+    be->upload(d.evDraws, ones.data(), ones.size() * sizeof(int));
+    be->upload(d.condFired, zerosN.data(), zerosN.size() * sizeof(int));
+    if (!scratch.empty()) be->upload(d.destScratch, scratch.data(), scratch.size() * sizeof(uint32_t));
+    if (!allList.empty()) be->upload(d.allList, allList.data(), allList.size() * sizeof(int));
+    {  // msgSent++ / bytesSent += size per destination (Network.java:476-477)
+      std::vector<long long> ms((size_t)d.N), bs((size_t)d.N);
+      be->download(ms.data(), d.msgSent, ms.size() * sizeof(long long));
+      be->download(bs.data(), d.bytesSent, bs.size() * sizeof(long long));
+      for (int i = 0; i < d.N; ++i) {
+        ms[(size_t)i] += sent[(size_t)i];
+        bs[(size_t)i] += bytes[(size_t)i];
+      }
+      be->upload(d.msgSent, ms.data(), ms.size() * sizeof(long long));
+      be->upload(d.bytesSent, bs.data(), bs.size() * sizeof(long long));
+    }
+    writeCtl(c);
+    be->tick(d, 3);
+    c = readCtl();
+    if (c.error) throwDeviceError(c);
   }
 
   // ---- runMs  (Network.java:318-338) ----
@@ -1121,10 +1227,16 @@ class Engine {
   }
   void endPartition() {
     requireInited();
-    if (d.proto == PROTO_CASPER)  // BlockChainNetwork.endPartition (BlockChainNetwork.java:46-54) also makes every node re-send its head
-      throw std::logic_error("endPartition of a block-chain network (full re-send of every node's head) is not supported by the B200 engine");
     partitionsInX.clear();
     uploadPartitions();
+    if (d.proto == PROTO_CASPER) {  // BlockChainNetwork.endPartition (BlockChainNetwork.java:46-54): every node re-sends its head to everybody
+      if (d.recSlots < d.N + 64) throw std::runtime_error("endPartition of a block-chain network keeps one sendAll per node in flight: raise rec_cap to nodes + 64 before init()");
+      std::vector<int> heads((size_t)d.N);
+      fetch(heads.data(), d.cHead, heads.size());
+      std::vector<HostSend> sends;
+      for (int i = 0; i < d.N; ++i) sends.push_back(HostSend{i, CM_BLOCK, (unsigned long long)(uint32_t)heads[(size_t)i], {}});
+      inject(sends);
+    }
   }
 
   // striped statistics summed (or max-ed) over the slots

@@ -1927,7 +1927,7 @@ WTG_HD void tickEnd(const Dev& d, int mode) {
     c.callId += 1;  // every processed message starts a new nextMessage() call
     c.didSomething = 1;
   }
-  if (mode != 2) d.bucketCount[c.tick & (d.ring - 1)] = 0;
+  if (mode != 2 && mode != 3) d.bucketCount[c.tick & (d.ring - 1)] = 0;  // 3: host-injected sends at the current time
   for (int t = 0; t < ARENA_STRIPES; ++t) c.freeCnt[t] = 0;
   if (d.proto == PROTO_CASPER && d.cg->createdThisTick > 1) setError(d, ERR_UNSUPPORTED, 4);
   if (d.proto == PROTO_GSF && (c.tick & 15) == 0)

@@ -59,6 +59,16 @@ class Network:
     def set_tunable(self, key, value):
         self.api.check(self.api.set_tunable(self.h, key.encode(), int(value)))
 
+    # ---- sends issued by the caller (Network.java:341-366) ----
+    def send(self, msg_type, from_id, to, payload=0):
+        """network.send(msg, from, to) / send(msg, from, dests): `to` is a node id or a list of at most 16 ids."""
+        dests = np.asarray([to] if np.isscalar(to) else list(to), np.int32)
+        self.api.check(self.api.send(self.h, int(msg_type), C.c_ulonglong(int(payload)), int(from_id), _p(dests, C.c_int), len(dests)))
+
+    def send_all(self, msg_type, from_id, payload=0):
+        """network.sendAll(msg, from)"""
+        self.api.check(self.api.send_all(self.h, int(msg_type), C.c_ulonglong(int(payload)), int(from_id)))
+
     # ---- run ----
     def run_ms(self, ms):
         return bool(self.api.check(self.api.run_ms(self.h, int(ms))))
