@@ -66,6 +66,13 @@ class Network {
     int sizeAt(int t) const { return check(wtg_msgs_size_at(net->h, t)); }
   } msgs{this};
 
+  // network.send(msg, from, to) / send(msg, from, dests) / sendAll(msg, from) issued by the caller (Network.java:341-366);
+  // msgType / payload name a message of the running protocol (see wtg.h)
+  void send(int msgType, int from, int to, unsigned long long payload = 0) { check(wtg_send(h, msgType, payload, from, &to, 1)); }
+  void send(int msgType, int from, const std::vector<int>& dests, unsigned long long payload = 0) {
+    check(wtg_send(h, msgType, payload, from, dests.data(), (int)dests.size()));
+  }
+  void sendAll(int msgType, int from, unsigned long long payload = 0) { check(wtg_send_all(h, msgType, payload, from)); }
   void stopNode(int id) { check(wtg_stop_node(h, id)); }    // node.stop()
   void startNode(int id) { check(wtg_start_node(h, id)); }  // node.start()
   void partition(float part) { check(wtg_partition(h, part)); }
