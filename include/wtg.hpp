@@ -12,7 +12,9 @@
 // Header-only; link with wittgenstein_b200/libwtg_b200.so.  tests/cpp/mirror_parity.cpp drives it against the CPU oracle.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -285,6 +287,93 @@ class CasperIMD {
 
  private:
   Network net;
+};
+
+// core/utils/StatsHelper.java:83-134
+struct SimpleStats {
+  long long min = 0, max = 0, avg = 0;
+};
+inline SimpleStats getStatsOn(const std::vector<long long>& values) {  // Java long arithmetic: avg = total / count, truncating
+  if (values.empty()) throw WtgError("no live node");
+  SimpleStats s;
+  s.min = s.max = values[0];
+  long long tot = 0;
+  for (long long v : values) {
+    tot += v;
+    if (v < s.min) s.min = v;
+    if (v > s.max) s.max = v;
+  }
+  s.avg = tot / (long long)values.size();
+  return s;
+}
+inline SimpleStats avg(const std::vector<SimpleStats>& stats) {  // StatsHelper.avg :32-52
+  if (stats.empty()) throw WtgError("no stats");
+  if (stats.size() == 1) return stats[0];
+  SimpleStats s;
+  for (const SimpleStats& x : stats) {
+    s.min += x.min;
+    s.max += x.max;
+    s.avg += x.avg;
+  }
+  s.min /= (long long)stats.size();
+  s.max /= (long long)stats.size();
+  s.avg /= (long long)stats.size();
+  return s;
+}
+
+// core/RunMultipleTimes.java:41-85 for a protocol mirror P (constructible from its parameter struct, with network(), init()):
+// runCount seeded runs of `runMs(10) while (maxTime == 0 || time < maxTime) && (!didSomething || contIf(p))`, the doneAt and
+// msgReceived stats of the live nodes averaged over the runs.  Up to `concurrency` runs are in flight at once, each on its own
+// engine instance and CUDA stream.
+template <class P, class Params>
+struct RunMultipleTimes {
+  Params params;
+  int runCount, maxTime;
+  std::vector<int> endTimes;
+  struct Result {
+    SimpleStats doneAt, msgReceived;
+  };
+  Result run(const std::function<bool(P&)>& contIf, int concurrency = 8) {
+    std::vector<Result> per((size_t)runCount);
+    endTimes.assign((size_t)runCount, 0);
+    std::vector<std::string> errors((size_t)runCount);
+    auto one = [&](int i) {
+      try {
+        P c(params);
+        c.network().rd.setSeed(i);  // :47
+        c.init();
+        bool did;
+        do {
+          did = c.network().runMs(10);
+        } while ((maxTime == 0 || c.network().time() < maxTime) && (!did || (contIf && contIf(c))));
+        NodeCounters cnt = c.network().counters();
+        std::vector<unsigned char> down = c.network().down();
+        std::vector<long long> d, m;
+        for (size_t n = 0; n < down.size(); ++n)
+          if (!down[n]) {
+            d.push_back(cnt.doneAt[n]);
+            m.push_back(cnt.msgReceived[n]);
+          }
+        per[(size_t)i] = Result{getStatsOn(d), getStatsOn(m)};
+        endTimes[(size_t)i] = c.network().time();
+      } catch (const std::exception& e) {
+        errors[(size_t)i] = e.what();
+      }
+    };
+    for (int i0 = 0; i0 < runCount; i0 += concurrency) {
+      std::vector<std::thread> th;
+      for (int i = i0; i < runCount && i < i0 + concurrency; ++i) th.emplace_back(one, i);
+      for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < runCount; ++i)
+      if (!errors[(size_t)i].empty()) throw WtgError("Failed execution for random seed of " + std::to_string(i) + ": " + errors[(size_t)i]);
+    std::vector<SimpleStats> d, m;
+    for (const Result& r : per) {
+      d.push_back(r.doneAt);
+      m.push_back(r.msgReceived);
+    }
+    return Result{avg(d), avg(m)};
+  }
 };
 
 }  // namespace wtg_b200

@@ -187,6 +187,24 @@ static void testCappos() {
   ASSERT_TRUE(done > 500);
 }
 
+// CT/StatsTest.java:10-22 and RunMultipleTimes: concurrent seeds give the sequential result
+static void testStatsAndRunMultipleTimes() {
+  SimpleStats a = avg({SimpleStats{10, 20, 30}, SimpleStats{16, 26, 36}});
+  ASSERT_EQ(a.min, 13);
+  ASSERT_EQ(a.max, 23);
+  ASSERT_EQ(a.avg, 33);
+  GSFSignatureParameters prm{128, 100, 3, 20, 10, 10, 8, "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"};
+  RunMultipleTimes<GSFSignature, GSFSignatureParameters> seq{prm, 4, 0, {}}, con{prm, 4, 0, {}};
+  auto cont = [](GSFSignature& p) { return p.continueIf(); };
+  auto r1 = seq.run(cont, 1);
+  auto r2 = con.run(cont, 4);
+  ASSERT_EQ(r1.doneAt.avg, r2.doneAt.avg);
+  ASSERT_EQ(r1.doneAt.max, r2.doneAt.max);
+  ASSERT_EQ(r1.msgReceived.avg, r2.msgReceived.avg);
+  for (int i = 0; i < 4; ++i) ASSERT_EQ(seq.endTimes[(size_t)i], con.endTimes[(size_t)i]);
+  ASSERT_TRUE(r1.doneAt.min > 0);
+}
+
 // error behaviour: the reference's unchecked exceptions surface as WtgError
 static void testErrors() {
   bool thrown = false;
@@ -215,6 +233,7 @@ int main() {
   testCasperForks();
   testHandel();
   testCappos();
+  testStatsAndRunMultipleTimes();
   testErrors();
   if (g_fail) {
     std::printf("MIRROR PARITY FAILED: %d\n", g_fail);
