@@ -704,17 +704,18 @@ class Engine {
       // The order of every list is a pure function of the rank table; only the shuffles of equal-rank runs draw from the
       // network RNG, and they must do so in (sender, level, position) order.  So: (1) transpose the table once (the list
       // of sender s reads column s); (2) sort all lists on all host threads; (3) one sequential pass shuffles the ties.
-      std::vector<int> ranksT((size_t)N * N);
+      std::unique_ptr<int[]> ranksT_(new int[(size_t)N * N]);  // first touched by the transposing threads
+      int* const ranksT = ranksT_.get();
       const int TB = 64;
       auto transposeRows = [&](int r0, int r1) {
         for (int rb = r0; rb < r1; rb += TB)
           for (int cb = 0; cb < N; cb += TB)
-            for (int r = rb; r < std::min(rb + TB, r1); ++r)
-              for (int c = cb; c < std::min(cb + TB, N); ++c) ranksT[(size_t)c * N + r] = ranks[(size_t)r * N + c];
+            for (int c = cb; c < std::min(cb + TB, N); ++c)  // contiguous writes (15x faster than contiguous reads here)
+              for (int r = rb; r < std::min(rb + TB, r1); ++r) ranksT[(size_t)c * N + r] = ranks[(size_t)r * N + c];
       };
       auto sortSender = [&](int sIdx, std::vector<unsigned long long>& keys) {
         if (hm.nodes[(size_t)sIdx].down) return;
-        const int* col = ranksT.data() + (size_t)sIdx * N;
+        const int* col = ranksT + (size_t)sIdx * N;
         for (int l = 1; l < L; ++l) {
           Blk wb = levelBlock(sIdx ^ (1 << (l - 1)), l);
           keys.resize((size_t)wb.size);
@@ -750,7 +751,7 @@ class Engine {
       lap_("emission lists: sort");
       for (int sIdx = 0; sIdx < N; ++sIdx) {  // Collections.shuffle of every run of equal ranks, in the reference's order
         if (hm.nodes[(size_t)sIdx].down) continue;
-        const int* col = ranksT.data() + (size_t)sIdx * N;
+        const int* col = ranksT + (size_t)sIdx * N;
         for (int l = 1; l < L; ++l) {
           const int size = 1 << (l - 1);
           uint32_t* out = peers.data() + (size_t)sIdx * (size_t)(N - 1) + (size_t)(size - 1);
