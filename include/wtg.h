@@ -28,6 +28,9 @@ const char* wtg_last_error(void);
 
 /* new Network<>()  — Network.java:13-49: rd = new Random(0), time = 0, IC3NetworkLatency */
 wtg_net* wtg_create(void);
+/* the same on CUDA device `device` (default: LOCAL_RANK / WTG_DEVICE / 0).  Independent networks — e.g. the seeds of a
+ * RunMultipleTimes sweep — can live on different GPUs of one process, one caller thread per network. */
+wtg_net* wtg_create_on(int device);
 void wtg_destroy(wtg_net* net);
 
 /* network.rd.setSeed(seed) before Protocol.init() — RunMultipleTimes.java:47, ProgressPerTime.java:71 */

@@ -140,7 +140,7 @@ class HostBackend : public Backend {
   }
 };
 
-Backend* makeBackend() { return new HostBackend(); }
+Backend* makeBackend(int) { return new HostBackend(); }
 long long backendLaunches(Backend* b) { return static_cast<HostBackend*>(b)->launches; }
 
 }  // namespace wtg

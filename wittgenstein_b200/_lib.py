@@ -22,6 +22,7 @@ class Api:
     _SIGS = {
         "last_error": (C.c_char_p, []),
         "create": (C.c_void_p, []),
+        "create_on": (C.c_void_p, [C.c_int]),
         "destroy": (None, [C.c_void_p]),
         "set_seed": (C.c_int, [C.c_void_p, C.c_longlong]),
         "set_network_latency": (C.c_int, [C.c_void_p, C.c_char_p]),

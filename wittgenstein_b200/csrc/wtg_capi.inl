@@ -5,7 +5,7 @@
 #include <string>
 
 namespace wtg {
-Backend* makeBackend();
+Backend* makeBackend(int device);
 long long backendLaunches(Backend* b);
 }  // namespace wtg
 
@@ -13,7 +13,7 @@ namespace {
 thread_local std::string g_lastError;
 struct NetHandle {
   wtg::Engine eng;
-  NetHandle() : eng(wtg::makeBackend()) {}
+  explicit NetHandle(int device = -1) : eng(wtg::makeBackend(device)) {}
 };
 template <class F>
 int guard(F f) {
@@ -36,6 +36,15 @@ const char* WTG_API(last_error)(void) { return g_lastError.c_str(); }
 void* WTG_API(create)(void) {
   try {
     return new NetHandle();
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return nullptr;
+  }
+}
+// a network on a given CUDA device (several networks, one per GPU, may be driven from one process: one caller thread each)
+void* WTG_API(create_on)(int device) {
+  try {
+    return new NetHandle(device);
   } catch (const std::exception& e) {
     g_lastError = e.what();
     return nullptr;

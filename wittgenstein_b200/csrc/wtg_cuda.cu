@@ -547,7 +547,7 @@ class CudaBackend : public Backend {
                                "k_dispatch_scatter", "k_node", "k_emit", "k_ms_count", "k_ms_scan", "k_ms_scatter", "k_free",
                                "k_end", "k_cond_score", "k_cond_select"};
 
-  CudaBackend() {
+  explicit CudaBackend(int requested = -1) {
     int dev = 0;
     const char* e = std::getenv("LOCAL_RANK");
     int cnt = 0;
@@ -556,6 +556,10 @@ class CudaBackend : public Backend {
     if (e) dev = std::atoi(e) % cnt;
     const char* e2 = std::getenv("WTG_DEVICE");
     if (e2) dev = std::atoi(e2) % cnt;
+    if (requested >= 0) {  // wtg_create_on: the caller places this network itself
+      if (requested >= cnt) throw std::invalid_argument("CUDA device " + std::to_string(requested) + " does not exist");
+      dev = requested;
+    }
     CUDA_OK(cudaSetDevice(dev));
     devId = dev;
     cudaDeviceProp p;
@@ -843,7 +847,7 @@ class CudaBackend : public Backend {
   }
 };
 
-Backend* makeBackend() { return new CudaBackend(); }
+Backend* makeBackend(int device) { return new CudaBackend(device); }
 long long backendLaunches(Backend* b) { return static_cast<CudaBackend*>(b)->launches; }
 
 }  // namespace wtg

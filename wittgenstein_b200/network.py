@@ -7,6 +7,7 @@ Reference: core/src/main/java/net/consensys/wittgenstein/core/Network.java — `
 Every method is a thin call through the C ABI declared in include/wtg.h.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -18,10 +19,21 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+_tls = threading.local()
+
+
+def set_thread_device(device):
+    """Networks created by this thread from now on live on CUDA device `device` (None: the library's default).  Lets one
+    process spread independent runs — RunMultipleTimes / ProgressPerTime seeds — over several GPUs, one thread per run."""
+    _tls.device = device
+
+
 class Network:
-    def __init__(self, _api=None):
+    def __init__(self, _api=None, device=None):
         self.api = _api or _lib.api()
-        self.h = C.c_void_p(self.api.create())
+        if device is None:
+            device = getattr(_tls, "device", None)
+        self.h = C.c_void_p(self.api.create() if device is None else self.api.create_on(int(device)))
         if not self.h:
             raise WtgError(self.api.last_error().decode())
 

@@ -9,6 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
+from .network import set_thread_device
+
 
 class SimpleStats:
     """StatsHelper.SimpleStats (:83-120): min / max / avg as Java longs (avg = total / count, truncating)."""
@@ -88,6 +90,8 @@ class RunMultipleTimes:
         self.final_check = final_check
 
     def _one(self, i, cont_if):
+        if self.devices:
+            set_thread_device(self.devices[i % len(self.devices)])
         c = self.p.copy()
         c.network().set_seed(i)  # :47
         c.init()
@@ -106,7 +110,9 @@ class RunMultipleTimes:
         net.close()
         return res, t
 
-    def run(self, cont_if, concurrency=8):
+    def run(self, cont_if, concurrency=8, devices=None):
+        """`devices`: CUDA device ids to spread the runs over (run i goes to devices[i % len]); None = the default device."""
+        self.devices = list(devices) if devices else None
         if concurrency <= 1:
             per = [self._one(i, cont_if) for i in range(self.run_count)]
         else:
