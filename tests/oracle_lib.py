@@ -66,8 +66,6 @@ def load():
     lib.wo_gsf_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.wo_gsf_rng_state.restype = C.c_uint64
     lib.wo_gsf_msgs_live.restype = C.c_int64
-    for name in dir(lib):
-        pass
     _lib = lib
     return lib
 
