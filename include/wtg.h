@@ -100,6 +100,9 @@ int wtg_casper_init_byz(wtg_net* net, int kind, int byz_delay);
  * not offered. */
 int wtg_send(wtg_net* net, int type, unsigned long long payload, int from, const int* to, int n);
 int wtg_send_all(wtg_net* net, int type, unsigned long long payload, int from);
+/* network.send(msg, sendTime, from, to) and send(msg, sendTime, from, dests, delaysBetweenMessage) — Network.java:369-382, 420-447:
+ * explicit send time (> time) and, for several destinations, `delay_between` ms between the sends (MultipleDestWithDelayEnvelope) */
+int wtg_send_at(wtg_net* net, int type, unsigned long long payload, int from, const int* to, int n, int send_time, int delay_between);
 
 /* network.runMs(ms) — Network.java:318-338.  Returns 1/0 like the reference's boolean. */
 int wtg_run_ms(wtg_net* net, int ms);

@@ -75,6 +75,10 @@ class Network {
     check(wtg_send(h, msgType, payload, from, dests.data(), (int)dests.size()));
   }
   void sendAll(int msgType, int from, unsigned long long payload = 0) { check(wtg_send_all(h, msgType, payload, from)); }
+  // send(msg, sendTime, from, dests, delaysBetweenMessage) (Network.java:420-447)
+  void send(int msgType, int sendTime, int from, const std::vector<int>& dests, int delayBetweenMessages, unsigned long long payload = 0) {
+    check(wtg_send_at(h, msgType, payload, from, dests.data(), (int)dests.size(), sendTime, delayBetweenMessages));
+  }
   void stopNode(int id) { check(wtg_stop_node(h, id)); }    // node.stop()
   void startNode(int id) { check(wtg_start_node(h, id)); }  // node.start()
   void partition(float part) { check(wtg_partition(h, part)); }

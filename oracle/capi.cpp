@@ -688,6 +688,24 @@ int wo_pp_send(void* h, int type, int from, const int32_t* to, int n) {
   return 0;
   WO_CATCH(-1)
 }
+int wo_pp_send_at(void* h, int type, int from, const int32_t* to, int n, int sendTime, int delay) {
+  WO_TRY
+  auto* p = static_cast<PingPong*>(h);
+  MessagePtr m;
+  if (type == 1)
+    m = std::make_shared<PingPong::Ping>();
+  else
+    m = std::make_shared<PingPong::Pong>();
+  if (n == 1) {
+    p->network.send(m, sendTime, p->network.getNodeById(from), p->network.getNodeById(to[0]));
+  } else {
+    std::vector<Node*> dests;
+    for (int i = 0; i < n; ++i) dests.push_back(&p->network.getNodeById(to[i]));
+    p->network.send(m, sendTime, p->network.getNodeById(from), dests, delay);
+  }
+  return 0;
+  WO_CATCH(-1)
+}
 // CasperIMD: like the others, but endPartition is BlockChainNetwork.endPartition (every node re-sends its head)
 int wo_casper_net_ctl(void* h, int op, int arg) {
   if (op == 3) {

@@ -137,9 +137,13 @@ class OraclePingPong(_NetCtl):
     def rng_state(self):
         return int(self.lib.wo_pp_rng_state(self.h))
 
-    def send(self, msg_type, from_id, to):
+    def send(self, msg_type, from_id, to, send_time=None, delay_between=0):
         dests = np.asarray([to] if np.isscalar(to) else list(to), np.int32)
-        if self.lib.wo_pp_send(self.h, int(msg_type), int(from_id), _p(dests, C.c_int32), len(dests)) != 0:
+        if send_time is None:
+            rc = self.lib.wo_pp_send(self.h, int(msg_type), int(from_id), _p(dests, C.c_int32), len(dests))
+        else:
+            rc = self.lib.wo_pp_send_at(self.h, int(msg_type), int(from_id), _p(dests, C.c_int32), len(dests), int(send_time), int(delay_between))
+        if rc != 0:
             raise RuntimeError(self.lib.wo_last_error().decode())
 
     def pongs(self):

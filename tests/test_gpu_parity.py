@@ -596,3 +596,30 @@ def test_pingpong_sends_from_the_host():
         assert (p.pongs() == o.pongs()).all()
         assert (p.network().counters() == o.counters()).all()
         assert p.network().msgs_size() == o.msgs_size()
+
+
+@pytest.mark.gpu
+def test_pingpong_delayed_multi_sends_from_the_host():
+    """send(msg, sendTime, from, dests, delaysBetweenMessage) — C/Network.java:420-467, the MultipleDestWithDelayEnvelope case of
+    CT/NetworkTest.java:122-188: destination i is sent delay + 1 ms after destination i - 1, arrivals sorted stably."""
+    p = PingPong(PingPongParameters(300, None, None))
+    o = OraclePingPong(300, None, None)
+    p.init(); o.init()
+    for k in range(12):
+        if k == 1:
+            for tgt in (p.network(), o):
+                tgt.send(1, 4, [10, 11, 12, 13, 200, 7], send_time=tgt.time + 5, delay_between=10)
+        if k == 2:
+            for tgt in (p.network(), o):
+                tgt.send(2, 9, [1, 2, 3], send_time=tgt.time + 1, delay_between=49)   # crosses several windows
+                tgt.send(1, 17, 18, send_time=tgt.time + 30)
+        if k == 4:
+            for tgt in (p.network(), o):
+                tgt.send(1, 0, list(range(100, 116)), send_time=tgt.time + 2, delay_between=3)
+        assert p.network().rng_state() == o.rng_state()
+        assert p.network().run_ms(50) == o.run_ms(50)
+        assert (p.pongs() == o.pongs()).all()
+        assert (p.network().counters() == o.counters()).all()
+        assert p.network().msgs_size() == o.msgs_size()
+    with pytest.raises(Exception):
+        p.network().send(1, 0, [1, 2], send_time=p.network().time)  # sendTime <= time (Network.java:470-473)

@@ -56,6 +56,7 @@ class Api:
         "handel_levels": (C.c_int, [C.c_void_p]),
         "send": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.POINTER(C.c_int), C.c_int]),
         "send_all": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int]),
+        "send_at": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),
         "run_ms": (C.c_int, [C.c_void_p, C.c_int]),
         "time": (C.c_int, [C.c_void_p]),
         "node_count": (C.c_int, [C.c_void_p]),

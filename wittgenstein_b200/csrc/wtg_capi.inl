@@ -353,6 +353,16 @@ int WTG_API(send)(void* h, int type, unsigned long long payload, int from, const
     return 0;
   });
 }
+// network.send(msg, sendTime, from, to) / send(msg, sendTime, from, dests, delaysBetweenMessage) (Network.java:369-382, 420-447)
+int WTG_API(send_at)(void* h, int type, unsigned long long payload, int from, const int* to, int n, int sendTime, int delayBetween) {
+  return guard([&] {
+    if (n <= 0) return 0;
+    if (sendTime <= 0) throw std::invalid_argument("sendTime <= time");
+    wtg::Engine::HostSend hs{from, (uint32_t)type, payload, std::vector<int>(to, to + n), sendTime, delayBetween};
+    ENG.inject({hs});
+    return 0;
+  });
+}
 // network.sendAll(msg, from) (Network.java:345-347)
 int WTG_API(send_all)(void* h, int type, unsigned long long payload, int from) {
   return guard([&] {

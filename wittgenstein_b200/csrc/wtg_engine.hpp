@@ -1011,6 +1011,8 @@ class Engine {
     uint32_t meta;
     unsigned long long pl;
     std::vector<int> to;  // empty: sendAll
+    int sendTime = 0;     // 0: time + 1
+    int delay = 0;        // delaysBetweenMessage of a multi-destination send
   };
   int msgSizeOf(uint32_t) const {
     if (d.proto == PROTO_PINGPONG || d.proto == PROTO_CASPER) return 1;  // Message.size() default (messages/Message.java:27-29)
@@ -1039,12 +1041,21 @@ class Engine {
       ds.meta = hs.meta;
       ds.pl = hs.pl;
       int fan = 0;
+      if (hs.sendTime != 0) {
+        if (hs.sendTime <= time) throw std::invalid_argument("sendTime <= time");  // Network.java:470-473
+        ds.aux |= DESC_SENDTIME;
+        ds.target = hs.sendTime;
+      }
+      if (hs.delay < 0 || hs.delay >= (1 << 20)) throw std::invalid_argument("delaysBetweenMessage");
+      if (hs.delay > 0 && hs.to.size() < 2) throw std::invalid_argument("a delay between messages needs several destinations");
+      ds.aux |= (uint32_t)hs.delay << DESC_DELAY_SHIFT;
       if (hs.to.empty()) {
         if (d.allCap <= 0) throw std::logic_error("sendAll from the host needs a protocol with the sendAll path (CasperIMD)");
         ds.dkind = DK_SEND_ALL;
         ds.evKind = EV_MULTI;
         ds.nDest = (uint32_t)d.N;
-        ds.target = time + 1;
+        ds.target = hs.sendTime != 0 ? hs.sendTime : time + 1;
+        ds.aux = 0;
         allList.push_back(i);
         fan = d.N;
       } else if (hs.to.size() == 1) {

@@ -1793,6 +1793,9 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     }
     int32_t seed = lcgNextIntAt(d, ctl.rng, drawIdx);
     int from = (int)ds.from;
+    if (ds.aux & DESC_SENDTIME) sendTime = ds.target;
+    const int delay = (int)(ds.aux >> DESC_DELAY_SHIFT);
+    const int step = delay > 0 ? delay + 1 : 0;  // sendTime += delaysBetweenMessage + 1 after every destination (:455-459)
     if (ds.dkind == DK_SEND_SINGLE) {
       int to = (int)ds.to;
       // createMessageArrival :478-484
@@ -1810,7 +1813,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
         if (d.npart[from] == d.npart[to] && !d.ndown[from] && !d.ndown[to]) {
           int nt = latency(d, from, to, pseudoRandom(to, seed));
           if (nt < d.msgDiscardTime) {
-            int a = sendTime + nt;
+            int a = sendTime + i * step + nt;
             int j = cnt++;  // stable insertion sort by arrival (Collections.sort is stable)
             while (j > 0 && arr[j - 1] > a) {
               arr[j] = arr[j - 1];

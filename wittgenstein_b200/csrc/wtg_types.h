@@ -64,6 +64,8 @@ constexpr int CASPER_MAX_BLKWORDS = 8;  // at most 512 blocks per run on the dev
 enum : uint32_t { CP_SWAP_REPLY = 1, CP_SWAP = 2, CP_T_GO = 4, CP_T_TIMEOUT = 5, CP_T_TRANSITION = 6 };
 constexpr int SHUFFLE_MAX = 64;          // longest destination list shuffled before a send (candidateCount + 1)
 constexpr uint32_t DESC_SHUFFLEK = 2u;   // Desc.aux: Collections.shuffle of the nDest destinations before the send (nDest - 1 draws + rejections)
+constexpr uint32_t DESC_SENDTIME = 4u;   // Desc.aux: Desc.target holds the explicit send time (send(m, sendTime, from, ...), Network.java:369-447)
+constexpr int DESC_DELAY_SHIFT = 8;      // Desc.aux >> 8: delaysBetweenMessage of a multi-destination send (Network.java:420-467)
 constexpr uint32_t DESC_SHUFFLE2 = 1u;  // Desc.aux: Collections.shuffle of the 2 destinations before the send (one extra draw)
 
 struct Ev {  // 32 bytes: one in-flight envelope / task

@@ -72,10 +72,15 @@ class Network:
         self.api.check(self.api.set_tunable(self.h, key.encode(), int(value)))
 
     # ---- sends issued by the caller (Network.java:341-366) ----
-    def send(self, msg_type, from_id, to, payload=0):
-        """network.send(msg, from, to) / send(msg, from, dests): `to` is a node id or a list of at most 16 ids."""
+    def send(self, msg_type, from_id, to, payload=0, send_time=None, delay_between=0):
+        """network.send(msg, from, to) / send(msg, from, dests): `to` is a node id or a list of at most 16 ids.  With
+        `send_time` (> time): send(msg, sendTime, from, to) / send(msg, sendTime, from, dests, delaysBetweenMessage)."""
         dests = np.asarray([to] if np.isscalar(to) else list(to), np.int32)
-        self.api.check(self.api.send(self.h, int(msg_type), C.c_ulonglong(int(payload)), int(from_id), _p(dests, C.c_int), len(dests)))
+        if send_time is None:
+            self.api.check(self.api.send(self.h, int(msg_type), C.c_ulonglong(int(payload)), int(from_id), _p(dests, C.c_int), len(dests)))
+        else:
+            self.api.check(self.api.send_at(self.h, int(msg_type), C.c_ulonglong(int(payload)), int(from_id), _p(dests, C.c_int), len(dests),
+                                            int(send_time), int(delay_between)))
 
     def send_all(self, msg_type, from_id, payload=0):
         """network.sendAll(msg, from)"""
