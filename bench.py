@@ -70,6 +70,27 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def metric_name(n):
+    return f"simulated-ms/sec, GSFSignature {n:,} nodes"
+
+
+def workload_name(n):
+    return (f"GSFSignature {n} nodes, threshold {int(.85*n)}, {int(.1*n)} dead, pairing 4, level timeout 50, period 20, "
+            f"10 accelerated calls, {AWS_NB}, {AWS_NL}, seed 0")
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "cores_total": os.cpu_count()}
+
+
 def make_gsf(n, seed):
     from wittgenstein_b200 import GSFSignature, GSFSignatureParameters
 
@@ -99,27 +120,58 @@ def algorithmic_bytes(ev):
     return b
 
 
-def cpu_baseline(n_cpu, step_ms, budget_s, threads=1):
-    """Oracle (C++ port of the reference engine, single thread like the reference) on a bounded sample:
-    the first runMs windows of the same GSF workload at n_cpu nodes, until ~budget_s of CPU time."""
+def cpu_baseline_and_parity(n, args):
+    """Oracle over the first windows of the run (bounded CPU time), then the GPU over exactly the same windows with
+    the same runMs slicing, then a bit-exact comparison of the two states (time, rd state, msgs.size(), the 5 node
+    counters, per-node scalars, verifiedSignatures and the per-level rows and scalars)."""
+    from tests import parity as par
     from tests.oracle_lib import OracleGSF
 
+    n_cpu = feasible_cpu_nodes(min(args.cpu_nodes, n), args.cpu_max_nodes)
     g = gsf_params(n_cpu)
     o = OracleGSF(n_cpu, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
     t0 = time.time()
     o.init_fast(min(64, os.cpu_count() or 1))  # init is threaded (and untimed); runMs below is single-threaded
     init_s = time.time() - t0
-    sim = 0
-    wall = 0.0
+    sim, wall, step = 0, 0.0, 10
     st0 = o.stats()
-    while wall < budget_s and sim < 4000:
-        wall += o.run_timed(step_ms, 1)
-        sim += step_ms
+    while wall < args.cpu_budget_s and sim < 4000:
+        wall += o.run_timed(step, 1)
+        sim += step
     st1 = o.stats()
     msgs = (st1["deliveries"] - st0["deliveries"]) + (st1["tasks"] - st0["tasks"]) + (st1["cond_runs"] - st0["cond_runs"])
-    return {"value": sim / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
-            "sample": f"oracle (C++ restatement, 1 thread), GSFSignature {n_cpu} nodes, first {sim} simulated ms in {wall:.1f} s "
-                      f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim}
+    cpu = {"value": sim / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
+           "sample": f"oracle (C++ restatement, 1 thread), GSFSignature {n_cpu} nodes, first {sim} simulated ms in {wall:.1f} s "
+                     f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim, "host": host_info()}
+    parity = None
+    if n_cpu == n:
+        p, _ = make_gsf(n, 0)
+        net = p.network()
+        net.timer_start()
+        for _ in range(sim // step):
+            net.run_ms(step)
+        pm = net.timer_stop_ms()
+        cpu["gpu_same_window"] = {"value": sim / (pm / 1000.0), "unit": "simulated-ms/s",
+                                  "window": f"[0,{sim}] ms, runMs({step}) slicing, device-timed"}
+        bad = par.compare_gsf(p, o, f"t={sim}", full=True)
+        parity = {"nodes": n, "t": sim, "slicing": f"runMs({step})", "status": "bit-exact" if not bad else "MISMATCH",
+                  "compared": "time, rd state, msgs.size(), 5 node counters, node scalars, verifiedSignatures, level rows + scalars"}
+        if bad:
+            parity["mismatches"] = bad[:8]
+        del p, net
+    else:
+        cpu["note"] = f"host memory too small for the oracle at {n} nodes: ran {n_cpu}; no parity check at the metric size"
+    return cpu, parity
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+    (profiles/r02_traffic.json, written by scripts/ncu_traffic.py from an `ncu --set full` page); None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t.get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def feasible_cpu_nodes(n, cap):
@@ -150,12 +202,14 @@ def run_reference(args):
     del w
     wall = o.run_timed(step_ms, args.steps)
     val = args.steps * step_ms / wall
-    line = {"impl": "reference", "metric": "simulated-ms/sec, GSFSignature", "value": val, "unit": "simulated-ms/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args.nodes), "value": val, "unit": "simulated-ms/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitmaps / int32", "data": "synthetic",
-            "config": {"workload": f"GSFSignature {n} nodes (target {args.nodes}), AWS regions, 33% Tor, 10% dead; step = runMs({step_ms}) "
-                                   f"of one run, timed window [0,{args.steps*step_ms}] ms "
-                                   "(the cheapest part of the run for the CPU engine: its cost per tick grows with the queues)",
+            "config": {"workload": workload_name(args.nodes),
+                       "sample": f"{n} nodes; step = runMs({step_ms}) of one run from t=0, timed window [0,{args.steps*step_ms}] ms "
+                                 "(the cheapest part of the run for the CPU engine: its cost per tick grows with the queues); the b200 "
+                                 "arm reports the same window as e2e_same_window_as_reference",
+                       "host": host_info(),
                        "note": "reference = C++ oracle port, 1 thread (the reference engine is single-threaded: Network.java:10); "
                                "Java reference not runnable here (no JVM)"},
             "cpu_baseline": {"value": val, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
@@ -324,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nodes", type=int, default=131072)
-    ap.add_argument("--step-ms", type=int, default=100)
+    ap.add_argument("--step-ms", type=int, default=0, help="0: ceil(run length / steps)")
     ap.add_argument("--ref-step-ms", type=int, default=20)
     ap.add_argument("--cpu-nodes", type=int, default=131072)
     ap.add_argument("--cpu-max-nodes", type=int, default=131072)
@@ -358,17 +412,24 @@ def main():
         run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks)
         return
 
-    n, K, W, S = args.nodes, args.steps, args.warmup, args.step_ms
+    n, K, W = args.nodes, args.steps, args.warmup
     seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)
 
-    # ---- warm-up: W untimed steps on a throw-away network of the same configuration (module load, graph
-    #      instantiation, clocks); the timed passes below each start a fresh, identically seeded network at t=0 so
-    #      that the timed window is the whole run [0, K*S] ----
+    # ---- warm-up: the whole run on a throw-away network of the same configuration (module load, graph
+    #      instantiation, clocks) — at least W steps; it also tells how long the run is: the timed passes below each
+    #      start a fresh, identically seeded network at t=0 and cover the run to completion (every live node has
+    #      reached the threshold: GSFSignature.newContIf, GSFSignature.java:670-682) in exactly K steps ----
     p, _ = make_gsf(n, seed)
-    for _ in range(W):
-        p.network().run_ms(S)
+    t_done = 0
+    warm_steps = 0
+    while warm_steps < W or (p.continue_if() and t_done < 60000):
+        p.network().run_ms(50)
+        t_done += 50
+        warm_steps += 1
     p.network().msgs_size()
     del p
+    t_done = int(max_over_ranks(t_done))
+    S = args.step_ms if args.step_ms > 0 else max(10, -(-t_done // K))  # K steps of runMs(S) cover [0, t_done]
 
     # ---- pass 1: device-timed (value) ----
     p, init_s = make_gsf(n, seed)
@@ -411,6 +472,22 @@ def main():
     ctl_bytes = 6000
     del p, net
 
+    # ---- pass 2b: the reference arm's window, end to end: [0, K*ref_step_ms] with runMs(ref_step_ms) slicing and the
+    #      same read-backs (what `bench.py --impl reference --steps K` times on the CPU) ----
+    R = args.ref_step_ms
+    p, _ = make_gsf(n, seed)
+    net = p.network()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        net.run_ms(R)
+        p.scalars()["card"]
+        net.counters()
+    torch.cuda.synchronize()
+    same_s = max_over_ranks(time.perf_counter() - t0)
+    del p, net
+
     # ---- pass 3: per-kernel CUDA-event timing of the same window (roofline of the dominant kernel) ----
     prof = {}
     if not args.no_profile:
@@ -423,23 +500,15 @@ def main():
         net.profile_enable(False)
         del p, net
 
-    # ---- CPU baseline on a bounded sample (prefix of the same run), and the GPU over the same prefix ----
+    # ---- CPU baseline on a bounded sample (prefix of the same run), the GPU over the same prefix, and the bit-exact
+    #      comparison of the two end states at the metric size ----
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu:
-        try:
-            cpu = cpu_baseline(feasible_cpu_nodes(min(args.cpu_nodes, n), args.cpu_max_nodes), 10, args.cpu_budget_s)
-            if cpu["nodes"] == n:
-                p, _ = make_gsf(n, seed)
-                net = p.network()
-                net.timer_start()
-                for _ in range(cpu["sim_ms"] // 10):
-                    net.run_ms(10)
-                pm = net.timer_stop_ms()
-                cpu["gpu_same_window"] = {"value": cpu["sim_ms"] / (pm / 1000.0), "unit": "simulated-ms/s",
-                                          "window": f"[0,{cpu['sim_ms']}] ms, runMs(10) slicing, device-timed"}
-                del p, net
-        except Exception as e:  # noqa: BLE001
-            cpu = {"error": str(e)}
+        cpu, parity = cpu_baseline_and_parity(n, args)
+        if parity is not None and parity.get("status") != "bit-exact":
+            print(json.dumps({"error": "GPU and oracle states differ", "parity": parity}))
+            sys.exit(3)
 
     value = sum_over_ranks(K * S) / (dev_ms / 1000.0)
     e2e = sum_over_ranks(K * S) / e2e_s
@@ -460,28 +529,33 @@ def main():
         if kname in ab and kcnt:
             achieved = ab[kname] / (kms / 1000.0) / 1e9
             roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                    "traffic": ncu_traffic(kname), "peak_source": "measured" if peaks else "fallback",
                     "avg_launch_us": 1000.0 * kms / kcnt, "algorithmic_bytes_per_launch": ab[kname] / kcnt,
                     "share_of_step": kms / total_ms,
                     "kernel_ms": {k: round(v[0], 3) for k, v in prof.items()},
                     "kernel_gbs": {k: round(ab[k] / (v[0] / 1000.0) / 1e9, 1) for k, v in prof.items() if k in ab and v[0] > 0}}
 
-    line = {"metric": "simulated-ms/sec, GSFSignature 131,072 nodes", "value": value, "unit": "simulated-ms/s", "n_gpus": world,
+    line = {"metric": metric_name(n), "value": value, "unit": "simulated-ms/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bitmaps / int32", "data": "synthetic",
-            "config": {"workload": f"GSFSignature {n} nodes, threshold {int(.85*n)}, {int(.1*n)} dead, pairing 4, level timeout 50, period 20, "
-                                   f"10 accelerated calls, {AWS_NB}, {AWS_NL}; step = runMs({S}) of one run, timed window "
-                                   f"[0,{K*S}] ms (fresh network; {W} warm-up steps ran on a throw-away network of the same config)",
+            "config": {"workload": workload_name(n),
+                       "window": f"step = runMs({S}) of one run; timed window [0,{K*S}] ms = the whole run of a fresh network (every live "
+                                 f"node reaches the threshold by {t_done} ms); warm-up = the same run on a throw-away network ({warm_steps} x runMs(50))",
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas (no data-path collective)",
                        "l2": "per-step working set (node rows + queues + ring) exceeds L2 at this size",
-                       "all_nodes_done_at_end": bool(done)},
+                       "all_nodes_done_at_end": bool(done), "host": host_info()},
             "msgs_per_s": sum_over_ranks(msgs) / (dev_ms / 1000.0),
             "e2e": {"value": e2e, "unit": "simulated-ms/s", "h2d_bytes_per_step": ctl_bytes, "d2h_bytes_per_step": int(d2h + ctl_bytes * 3)},
+            "e2e_same_window_as_reference": {"value": sum_over_ranks(K * R) / same_s, "unit": "simulated-ms/s",
+                                             "window": f"[0,{K*R}] ms, {K} x runMs({R}) with the per-step read-backs, wall clock"},
             "gpu_launches": int(launches), "init_s": init_s, "events": ev, "clocks": sampler.summary()}
     if roof:
         line["roofline"] = roof
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity"] = parity
+        line[f"parity_{n}"] = f"{parity['status']}@{parity['t']}"
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -115,3 +115,27 @@ def test_progress_per_time_rounds():
         sums["msg_rcvd"] += get_stats_on(o.counters()[0][live]).avg
         sums["done_at"] += get_stats_on(o.counters()[4][live]).avg
     assert a.average["msg_rcvd"] == sums["msg_rcvd"] // 3 and a.average["done_at"] == sums["done_at"] // 3
+
+
+def test_gsf_131072_prefix_vs_oracle():
+    """The metric configuration itself (BASELINE.json: GSFSignature, 131 072 nodes) against the oracle: bit-exact state
+    after [0, 300] ms with runMs(10) slicing — pooled payload levels up to 18 (8 KiB blocks), 3N-entry buckets.  Needs
+    ~80 GB of host memory for the oracle's peer tables; skipped on smaller hosts."""
+    import os
+
+    import psutil
+
+    from tests import parity
+    from tests.oracle_lib import OracleGSF
+
+    n = 131072
+    if psutil.virtual_memory().available < 110 * 2**30:
+        pytest.skip("host memory too small for the oracle at 131072 nodes")
+    o = OracleGSF(n, int(0.85 * n), 4, 50, 20, 10, int(0.10 * n), AWS_NB, AWS_NL)
+    o.init_fast(min(64, os.cpu_count() or 1))
+    p = make(n)
+    for _ in range(30):
+        p.network().run_ms(10)
+        o.run_ms(10)
+    bad = parity.compare_gsf(p, o, "t=300", full=True)
+    assert not bad, bad
