@@ -43,11 +43,11 @@ class HostBackend : public Backend {
       tickBegin(d, mode);
     if (d.ctl->error) return;
     if (d.proto == PROTO_GSF && mode != 3) {
-      for (int n = 0; n < d.N; ++n)
+      for (int n = d.n0; n < d.n0 + d.nLoc; ++n)
         if (gsfCondMark(d, n)) gsfCondScanQueue(d, c, n);
       int per = d.workCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->workCnt, per);
       for (int t = 0; t < tot; ++t) gsfScoreItem(d, c, d.workList[stripedIndex(d.ctl->workCnt, per, t)]);
-      for (int n = 0; n < d.N; ++n)
+      for (int n = d.n0; n < d.n0 + d.nLoc; ++n)
         if (d.condDue[n]) gsfCondSelect(d, c, n, keep.data());
     }
     if (d.proto == PROTO_HANDEL && mode != 3) {
@@ -77,11 +77,21 @@ class HostBackend : public Backend {
       pairScan(d, 0);
       if (d.ctl->error) return;
       for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchScatterCoop(d, c, i) : dispatchScatter(d, i);
-      for (int n = 0; n < d.N; ++n) nodeProcess(d, c, n, 0);
+      for (int n = d.n0; n < d.n0 + d.nLoc; ++n) nodeProcess(d, c, n, 0);
     }
     pairScan(d, 1);
-    if (d.ctl->error) return;
-    for (int n = 0; n < d.N; ++n) emitCond(d, n);
+    if (d.G > 1) {  // node-sharded: exchange 1 (items -> global creation / draw offsets)
+      for (int i = 0; i <= d.ctl->nItems; ++i) xPublishItem(d, i);
+      xPublishHeader(d);
+      xSignal(d, 0);
+      for (int q = 0; q < d.G; ++q) xWaitOne(d, 0, q);
+      if (!d.ctl->error) {
+        for (int i = 0; i < d.ctl->nItems; ++i) xOffsets(d, i);
+        xTotals(d);
+      }
+    }
+    if (!d.ctl->error) {
+    for (int n = d.n0; n < d.n0 + d.nLoc; ++n) emitCond(d, n);
     if (d.shufCap > 0) {
       int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
       for (int t = 0; t < tot; ++t) shuffleCheck(d, stripedIndex(d.ctl->descCnt, per, t));
@@ -96,11 +106,21 @@ class HostBackend : public Backend {
       int cnt = std::min(d.ctl->allCnt, d.allCap);
       for (int j = 0; j < cnt; ++j) emitAll(d, c, d.allList[j], tmp.data(), hist.data());
     }
+    }
+    if (d.G > 1) {  // exchange 2: every shard has stored its envelopes into the destination shards' arrays
+      xSignal(d, 1);
+      for (int q = 0; q < d.G; ++q) xWaitOne(d, 1, q);
+      if (d.ctl->error) return;
+      for (int g = 0; g < d.ctl->totalSlots; ++g)
+        if (xNeedsIngest(d, g)) xIngest(d, c, g);
+    }
+    if (d.ctl->error) return;
     // multisplit: stable append into the ring in creation order
     int G = d.ctl->totalSlots;
     for (int g = 0; g < G; ++g) {
       int t = d.newTarget[g];
       if (t < 0) continue;
+      if (d.G > 1) d.newTarget[g] = -1;  // the array is indexed by the global creation index: clean for the next pass
       int slot = t & (d.ring - 1);
       int pos = d.bucketCount[slot];
       if (pos >= d.bcap) {
@@ -108,6 +128,7 @@ class HostBackend : public Backend {
         continue;
       }
       d.buckets[(size_t)slot * d.bcap + pos] = d.newEv[g];
+      if (d.G > 1) d.bucketKey[(size_t)slot * d.bcap + pos] = orderKey((unsigned)d.ctl->tick, (unsigned)g);
       d.bucketCount[slot] = pos + 1;
     }
     {
@@ -118,7 +139,7 @@ class HostBackend : public Backend {
     launches += 1;
   }
   void gsfInitNodes(const Dev& d) override {
-    for (int n = 0; n < d.N; ++n) gsfInitNodeBody(d, n);
+    for (int n = d.n0; n < d.n0 + d.nLoc; ++n) gsfInitNodeBody(d, n);
   }
   void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
                      std::vector<unsigned long long>& out) override {
@@ -131,7 +152,7 @@ class HostBackend : public Backend {
   }
   void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) override {
     for (int l = d.L - 1; l >= 1; --l)
-      for (int n = 0; n < d.N; ++n) {
+      for (int n = d.n0; n < d.n0 + d.nLoc; ++n) {
         if (d.peerBits == 16)
           gsfShuffleLevel<uint16_t>(d, n, l, s0, liveRank, rejOrd, nRej);
         else

@@ -219,7 +219,7 @@ WTG_HD void cpHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   if (base < 0) return;
   int sub = 0;
   auto fill = [&](Desc& ds) {
-    ds.item = (uint32_t)(d.N + item);
+    ds.item = (uint32_t)(d.nLoc + item);
     ds.sub = (uint32_t)sub;
     ds.from = (uint32_t)n;
     ds.target = 0;

@@ -188,7 +188,7 @@ WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
 WTG_HD void cWriteSendAll(const Dev& d, int di, int n, int item, int sub, uint32_t meta, u64 pl, int sendTime) {
   Desc ds;
   ds.dkind = DK_SEND_ALL;
-  ds.item = (uint32_t)(d.N + item);
+  ds.item = (uint32_t)(d.nLoc + item);
   ds.sub = (uint32_t)sub;
   ds.from = (uint32_t)n;
   ds.to = 0;
@@ -211,7 +211,7 @@ WTG_HD void cWriteSendAll(const Dev& d, int di, int n, int item, int sub, uint32
 WTG_HD void cWriteInsert(const Dev& d, int di, int n, int item, int sub, uint32_t evKind, uint32_t meta, u64 pl, int target) {
   Desc ds;
   ds.dkind = DK_INSERT_AT;
-  ds.item = (uint32_t)(d.N + item);
+  ds.item = (uint32_t)(d.nLoc + item);
   ds.sub = (uint32_t)sub;
   ds.from = (uint32_t)n;
   ds.to = (uint32_t)n;

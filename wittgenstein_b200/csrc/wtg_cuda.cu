@@ -73,9 +73,9 @@ __device__ __forceinline__ void listAppendW(const Dev& d, bool active, int n, u6
 // conditional-task bookkeeping, one thread per node -> list of due nodes
 __global__ void __launch_bounds__(256) k_cond_mark(Dev d) {
   if (d.ctl->error) return;
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x;
   bool due = false;
-  if (n < d.N) due = d.proto == PROTO_HANDEL ? hCondMark(d, n) : gsfCondMark(d, n);
+  if (n < d.n0 + d.nLoc) due = d.proto == PROTO_HANDEL ? hCondMark(d, n) : gsfCondMark(d, n);
   listAppend(d, due, n, d.ctl->dueCnt, d.dueList);
 }
 // one warp per due node, blocks assigned to list stripes
@@ -130,16 +130,16 @@ __global__ void __launch_bounds__(256) k_cond_score(Dev d) {
 // does any nextInt(k) of this pass hit java.util.Random's rejection loop?  (probability ~ k / 2^31 per draw)
 __global__ void k_hpick_check(Dev d) {
   if (d.ctl->error) return;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x)
+  for (int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x; n < d.n0 + d.nLoc; n += gridDim.x * blockDim.x)
     if (d.hCandK[n] > 0 && hCondPick(d, n, (u64)d.hDrawBase[n], false) > d.condDraws[n]) d.ctl->hReject = 1;
 }
 __global__ void k_hpick_apply(Dev d) {
   if (d.ctl->error) return;
   if (!d.ctl->hReject) {
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x) hCondPick(d, n, (u64)d.hDrawBase[n], true);
+    for (int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x; n < d.n0 + d.nLoc; n += gridDim.x * blockDim.x) hCondPick(d, n, (u64)d.hDrawBase[n], true);
   } else if (blockIdx.x == 0 && threadIdx.x == 0) {  // a rejection shifts every later draw: redo the picks in node order
     u64 idx = 0;
-    for (int n = 0; n < d.N; ++n) idx += (u64)hCondPick(d, n, idx, true);
+    for (int n = d.n0; n < d.n0 + d.nLoc; ++n) idx += (u64)hCondPick(d, n, idx, true);
   }
 }
 
@@ -172,10 +172,10 @@ __global__ void k_dispatch_scatter(Dev d) {
 // nodeProcess); SanFermin: everything (all handlers are scalar).  Leaves nodeTasks[n] = 1 when a warp is needed.
 __global__ void __launch_bounds__(256) k_node_msgs(Dev d) {
   if (d.ctl->error) return;
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x;
   int flag = 0;
   u64 word = ~0ULL;
-  if (n < d.N && d.inboxFill[n] > 0) {
+  if (n < d.n0 + d.nLoc && d.inboxFill[n] > 0) {
     CoopSerial cs;
     if (d.proto == PROTO_SANFERMIN || d.proto == PROTO_CAPPOS)
       nodeProcess(d, cs, n, 0);
@@ -367,7 +367,7 @@ __global__ void k_shuffle_serial(Dev d) {
 __global__ void k_emit(Dev d) {
   if (d.ctl->error) return;
   // conditional-task inserts (one per node) ...
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) emitCond(d, i);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.nLoc; i += gridDim.x * blockDim.x) emitCond(d, d.n0 + i);
   // ... then the handlers' descriptors, blocks assigned to arena stripes
   const int per = d.descCap / ARENA_STRIPES;
   const int stripe = blockIdx.x & (ARENA_STRIPES - 1);
@@ -506,8 +506,8 @@ __global__ void k_free(Dev d) {
 
 // ---- init kernels ---------------------------------------------------------------------------
 __global__ void k_gsf_init_nodes(Dev d) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < d.N) gsfInitNodeBody(d, n);
+  int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < d.n0 + d.nLoc) gsfInitNodeBody(d, n);
 }
 __global__ void k_rng_candidates(Dev d, u64 s0, u64 count, u64 chunk, int maxBound, u64* out, int* outCount, int cap) {
   u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -518,8 +518,8 @@ __global__ void k_rng_candidates(Dev d, u64 s0, u64 count, u64 chunk, int maxBou
 }
 template <class PeerT>
 __global__ void k_gsf_shuffle(Dev d, int l, u64 s0, const int* liveRank, const u64* rejOrd, int nRej) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < d.N) gsfShuffleLevel<PeerT>(d, n, l, s0, liveRank, rejOrd, nRej);
+  int n = d.n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < d.n0 + d.nLoc) gsfShuffleLevel<PeerT>(d, n, l, s0, liveRank, rejOrd, nRej);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,7 +677,7 @@ class CudaBackend : public Backend {
     }
     if (d.proto == PROTO_HANDEL && mode != 3) {
       profBegin(1);
-      k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+      k_cond_mark<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
       k_cond_nodes<0><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(14);
@@ -701,7 +701,7 @@ class CudaBackend : public Backend {
     if (d.proto == PROTO_GSF && mode != 3) {
       size_t smem8 = (size_t)8 * (size_t)(d.qcap / 32) * sizeof(uint32_t);
       profBegin(1);
-      k_cond_mark<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+      k_cond_mark<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
       k_cond_nodes<0><<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
       profEnd();
       profBegin(14);
@@ -726,7 +726,7 @@ class CudaBackend : public Backend {
     k_dispatch_scatter<<<wide, 256, 0, st>>>(d);
     profEnd();
       profBegin(7);
-    k_node_msgs<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+    k_node_msgs<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
     k_node_tasks<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
     profEnd();
       launches += 6;
@@ -805,7 +805,7 @@ class CudaBackend : public Backend {
     launches += graphKernels * count;
   }
   void gsfInitNodes(const Dev& d) override {
-    k_gsf_init_nodes<<<(d.N + 255) / 256, 256, 0, st>>>(d);
+    k_gsf_init_nodes<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
     CUDA_OK(cudaGetLastError());
   }
   void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
@@ -838,9 +838,9 @@ class CudaBackend : public Backend {
   void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) override {
     for (int l = d.L - 1; l >= 1; --l) {
       if (d.peerBits == 16)
-        k_gsf_shuffle<uint16_t><<<(d.N + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
+        k_gsf_shuffle<uint16_t><<<(d.nLoc + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
       else
-        k_gsf_shuffle<uint32_t><<<(d.N + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
+        k_gsf_shuffle<uint32_t><<<(d.nLoc + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(st));

@@ -47,6 +47,7 @@ struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
   long long casperVotes = 0;   // CasperIMD: attestations one attester may publish in a run (default 6)
   long long casperBlocks = 0;  // CasperIMD: blocks of a run (default from casperVotes)
+  long long stageWords = 0;    // node-sharded GSF: staging capacity per (sending shard, pass parity) in 64-bit words
 };
 
 struct Backend {
@@ -68,6 +69,14 @@ struct Backend {
   virtual double timerStopMs() { return 0.0; }
   virtual void profileEnable(bool) {}
   virtual int profileRead(double* ms, long long* launches, const char** names, int cap) { (void)ms; (void)launches; (void)names; (void)cap; return 0; }
+  // node-sharded runs: one exchange region per shard that the other shards' kernels write into.  `allocShared` returns
+  // zero-initialised memory that can be mapped by other processes; exportShared / importShared carry the 64-byte handle
+  // (CUDA IPC); backends whose shards live in one address space never need them.
+  virtual void* allocShared(size_t bytes) { return alloc(bytes); }
+  virtual void exportShared(void* p, unsigned char* handle64) { std::memset(handle64, 0, 64); std::memcpy(handle64, &p, sizeof(p)); }
+  virtual void* importShared(const unsigned char* handle64) { void* p; std::memcpy(&p, handle64, sizeof(p)); return p; }
+  virtual void enablePeer(int /*device*/) {}
+  virtual int deviceId() const { return 0; }
   virtual void gsfInitNodes(const Dev& d) = 0;
   // scan `count` stream positions after state s0 for values that nextInt(bound<=maxBound) could reject
   virtual void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
@@ -93,7 +102,97 @@ class Engine {
   std::vector<int> liveRank;  // GSF: rank among live nodes, -1 when down
   unsigned long long initDraws = 0;
 
+  // ---- node-sharded simulation: this engine is shard `shardRank` of `shardWorld` (set before init) ----
+  int shardRank = 0, shardWorld = 1;
+  bool linked = false;          // peers' exchange regions are mapped
+  void* xRegion = nullptr;      // this shard's exchange region
+  size_t xBytes = 0;
+  long long stageWordsWanted = 0;  // protocol-specific staging capacity per (sender, parity), in 64-bit words
+  struct XLayout {
+    size_t hdr, flags, items, newEv, newTarget, stage, rec, recDest, recArrival, total;
+  } xl{};
+
   explicit Engine(Backend* b) : be(b) { std::memset(&d, 0, sizeof(d)); }
+  void setShard(int rank, int world) {
+    requireNotInited();
+    if (world < 1 || world > MAX_SHARDS || (world & (world - 1)) != 0) throw std::invalid_argument("the number of shards must be a power of two <= 8");
+    if (rank < 0 || rank >= world) throw std::invalid_argument("shard rank");
+    shardRank = rank;
+    shardWorld = world;
+  }
+  bool sharded() const { return shardWorld > 1; }
+  void requireUnsharded(const char* what) const {
+    if (sharded()) throw std::logic_error(std::string(what) + " is not available on a node-sharded network");
+  }
+  // per-node arrays of a shard hold nLoc rows and are addressed by global id: the base is biased by -n0 rows
+  template <class T>
+  T* dallocNodes(size_t perNode = 1) {
+    T* p = dalloc<T>((size_t)d.nLoc * perNode);
+    return p - (size_t)d.n0 * perNode;
+  }
+  template <class T>
+  T* duploadNodes(const std::vector<T>& full, size_t perNode = 1) {  // `full` holds all N rows; the shard keeps its own
+    T* p = dalloc<T>((size_t)d.nLoc * perNode);
+    be->upload(p, full.data() + (size_t)d.n0 * perNode, (size_t)d.nLoc * perNode * sizeof(T));
+    return p - (size_t)d.n0 * perNode;
+  }
+  Peer peerView(void* base) const {
+    char* b = (char*)base;
+    Peer q;
+    q.hdr = (XHdr*)(b + xl.hdr);
+    q.flags = (int*)(b + xl.flags);
+    q.items = (XItem*)(b + xl.items);
+    q.newEv = (Ev*)(b + xl.newEv);
+    q.newTarget = (int*)(b + xl.newTarget);
+    q.stage = (unsigned long long*)(b + xl.stage);
+    q.rec = (MultiRec*)(b + xl.rec);
+    q.recDest = (uint32_t*)(b + xl.recDest);
+    q.recArrival = (int*)(b + xl.recArrival);
+    return q;
+  }
+  // exchange region: everything another shard's kernels write (one allocation = one IPC handle)
+  void allocExchange() {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t o = 0;
+    xl.hdr = o;        o += al(sizeof(XHdr) * MAX_SHARDS);
+    xl.flags = o;      o += al(sizeof(int) * 2 * MAX_SHARDS);
+    xl.items = o;      o += al(sizeof(XItem) * (size_t)d.G * d.xItemCap);
+    xl.newEv = o;      o += al(sizeof(Ev) * (size_t)d.newEvCap);
+    xl.newTarget = o;  o += al(sizeof(int) * (size_t)d.newEvCap);
+    xl.stage = o;      o += al(sizeof(unsigned long long) * 2 * (size_t)d.G * (size_t)d.stageCapWords);
+    xl.rec = o;        o += al(sizeof(MultiRec) * (size_t)d.recCap);
+    xl.recDest = o;    o += al(sizeof(uint32_t) * (size_t)d.recDestCap);
+    xl.recArrival = o; o += al(sizeof(int) * (size_t)d.recDestCap);
+    xl.total = o;
+    xBytes = o;
+    xRegion = be->allocShared(o);
+    allocs.push_back(xRegion);
+    for (int q = 0; q < MAX_SHARDS; ++q) std::memset(&d.peer[q], 0, sizeof(Peer));
+    d.peer[d.rank] = peerView(xRegion);
+    d.newEv = d.peer[d.rank].newEv;
+    d.newTarget = d.peer[d.rank].newTarget;
+    d.rec = d.peer[d.rank].rec;
+    d.recDest = d.peer[d.rank].recDest;
+    d.recArrival = d.peer[d.rank].recArrival;
+    std::vector<int> m1((size_t)d.newEvCap, -1);  // "nothing for this shard"
+    be->upload(d.newTarget, m1.data(), m1.size() * sizeof(int));
+  }
+  void exportExchange(unsigned char* handle64) {
+    requireInited();
+    if (!sharded()) throw std::logic_error("not a node-sharded network");
+    be->exportShared(xRegion, handle64);
+  }
+  // handles: world x 64 bytes, in rank order (the own entry is ignored)
+  void linkExchange(const unsigned char* handles, const int* devices) {
+    requireInited();
+    if (!sharded()) throw std::logic_error("not a node-sharded network");
+    for (int q = 0; q < shardWorld; ++q) {
+      if (q == shardRank) continue;
+      if (devices && devices[q] != be->deviceId()) be->enablePeer(devices[q]);
+      d.peer[q] = peerView(be->importShared(handles + (size_t)q * 64));
+    }
+    linked = true;
+  }
   ~Engine() { freeAll(); }
 
   void freeAll() {
@@ -129,22 +228,37 @@ class Engine {
   void allocCommon(int N, int proto) {
     d.N = N;
     d.proto = proto;
+    d.G = shardWorld;
+    d.rank = shardRank;
+    if (N % shardWorld != 0) throw std::invalid_argument("the node count must be a multiple of the number of shards");
+    d.nLoc = N / shardWorld;
+    d.n0 = shardRank * d.nLoc;
+    d.ownShift = 0;
+    if (sharded()) {
+      if ((d.nLoc & (d.nLoc - 1)) != 0) throw std::invalid_argument("a node-sharded network needs a power-of-two number of nodes per shard");
+      while ((1 << d.ownShift) < d.nLoc) ++d.ownShift;
+    }
+    const int NL = d.nLoc;
     d.msgDiscardTime = msgDiscardTime;
     int ring = 2048;
     int need = hm.latMax + 64 + ringExtra;
     if (farEnabled) need *= 2;  // envelopes are "near" up to ring/2 ms ahead
     while (ring < need) ring <<= 1;
-    if (tun.ring) ring = (int)tun.ring;
+    if (tun.ring) {
+      if (tun.ring < need || (tun.ring & (tun.ring - 1)) != 0) throw std::invalid_argument("tunable ring must be a power of two >= " + std::to_string(need));
+      ring = (int)tun.ring;
+    }
     d.ring = ring;
     ringMask = ring - 1;
-    long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 3LL * N);
+    long long bcap = tun.bcap ? tun.bcap : std::max<long long>(16384, 3LL * NL);
     d.bcap = (int)bcap;
     d.itemCap = (int)(2 * bcap + 1024);
-    d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 32LL * N));
+    d.descCap = (int)(tun.descCap ? tun.descCap : std::max<long long>(65536, 32LL * NL));
     d.descCap = (d.descCap + ARENA_STRIPES - 1) / ARENA_STRIPES * ARENA_STRIPES;
     d.destScratchCap = destScratchOverride ? destScratchOverride : d.descCap;
-    d.newEvCap = d.descCap + N;
-    d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * N));
+    // sharded: the new-envelope arrays are indexed by the creation index over all shards
+    d.newEvCap = sharded() ? (int)std::min<long long>(0x7fffffffLL, (long long)shardWorld * (d.descCap + NL)) : d.descCap + N;
+    d.recCap = (int)(tun.recCap ? tun.recCap : std::max<long long>(65536, 32LL * NL));
     d.recDestCap = recDestOverride ? recDestOverride : d.recCap * 4 + N + 1024;
     d.freeCap = d.descCap;
     d.latKind = hm.latKind;
@@ -161,17 +275,17 @@ class Engine {
       city[i] = (uint8_t)hm.nodes[i].city;
       down[i] = hm.nodes[i].down ? 1 : 0;
     }
-    d.nx = dupload(x);
+    d.nx = dupload(x);  // node attributes are replicated on every shard (latency needs both ends)
     d.ny = dupload(y);
     d.nextra = dupload(ex);
     d.ncity = dupload(city);
     d.ndown = dupload(down);
     d.npart = dupload(part);
-    d.msgReceived = dalloc<long long>(N);
-    d.msgSent = dalloc<long long>(N);
-    d.bytesSent = dalloc<long long>(N);
-    d.bytesReceived = dalloc<long long>(N);
-    d.doneAt = dalloc<long long>(N);
+    d.msgReceived = dallocNodes<long long>();
+    d.msgSent = dallocNodes<long long>();
+    d.bytesSent = dallocNodes<long long>();
+    d.bytesReceived = dallocNodes<long long>();
+    d.doneAt = dallocNodes<long long>();
     d.latTab = dupload(hm.latTab);
     d.latBase = dupload(hm.latBase);
     d.latJit = dupload(hm.latJit);
@@ -181,11 +295,11 @@ class Engine {
     d.jumpC = dupload(jc);
     d.buckets = dalloc<Ev>((size_t)ring * (size_t)d.bcap);
     d.bucketCount = dalloc<int>(ring);
-    d.inboxCnt = dalloc<int>(N);
-    d.inboxOff = dalloc<int>(N);
-    d.inboxFill = dalloc<int>(N);
-    d.nodeTasks = dalloc<int>(N);
-    d.listStripeCap = ((N + 31) / 32 + ARENA_STRIPES - 1) / ARENA_STRIPES * 32 + 32;
+    d.inboxCnt = dallocNodes<int>();
+    d.inboxOff = dallocNodes<int>();
+    d.inboxFill = dallocNodes<int>();
+    d.nodeTasks = dallocNodes<int>();
+    d.listStripeCap = ((NL + 31) / 32 + ARENA_STRIPES - 1) / ARENA_STRIPES * 32 + 32;
     d.dueList = dalloc<int>((size_t)ARENA_STRIPES * d.listStripeCap);
     d.taskList = dalloc<int>((size_t)ARENA_STRIPES * d.listStripeCap);
     d.taskWord = dalloc<unsigned long long>((size_t)ARENA_STRIPES * d.listStripeCap);
@@ -194,26 +308,41 @@ class Engine {
     d.itemBase = dalloc<int>(d.bcap);
     d.evSlots = dalloc<int>(d.itemCap);
     d.evDraws = dalloc<int>(d.itemCap);
-    d.condFired = dalloc<int>(N);
-    d.condDraws = dalloc<int>(N);
-    d.condDue = dalloc<int>(N);
-    d.workCap = (int)std::max<long long>(1 << 16, 64LL * N) / ARENA_STRIPES * ARENA_STRIPES;
+    d.condFired = dallocNodes<int>();
+    d.condDraws = dallocNodes<int>();
+    d.condDue = dallocNodes<int>();
+    d.workCap = (int)std::max<long long>(1 << 16, 64LL * NL) / ARENA_STRIPES * ARENA_STRIPES;
     d.workList = dalloc<uint32_t>(d.workCap);
-    d.condEv = dalloc<Ev>(N);
-    d.condTarget = dalloc<int>(N);
-    d.slotBase = dalloc<int>((size_t)N + d.itemCap);
-    d.drawBase = dalloc<int>((size_t)N + d.itemCap);
+    d.condEv = dallocNodes<Ev>();
+    d.condTarget = dallocNodes<int>();
+    d.slotBase = dalloc<int>((size_t)NL + d.itemCap);
+    d.drawBase = dalloc<int>((size_t)NL + d.itemCap);
     d.scanPartial = dalloc<int>(2 * 8192);
     d.desc = dalloc<Desc>(d.descCap);
     d.destScratch = dalloc<uint32_t>(d.destScratchCap);
-    d.newEv = dalloc<Ev>(d.newEvCap);
-    d.newTarget = dalloc<int>(d.newEvCap);
     d.msChunks = (d.newEvCap + MS_CHUNK - 1) / MS_CHUNK;
     d.msCount = dalloc<int>((size_t)d.msChunks * (size_t)ring);
-    d.rec = dalloc<MultiRec>(d.recCap);
-    d.recDest = dalloc<uint32_t>(d.recDestCap);
-    d.recArrival = dalloc<int>(d.recDestCap);
     d.freeList = dalloc<uint32_t>(d.freeCap);
+    if (sharded()) {
+      if (farEnabled) throw std::logic_error("this protocol cannot run node-sharded yet (far-future calendar)");
+      d.xItemCap = d.itemCap + 1;
+      d.stageCapWords = (int)std::min<long long>(0x7fffffffLL, stageWordsWanted);
+      d.recCap = d.recCap / shardWorld * shardWorld;
+      d.recDestCap = d.recDestCap / shardWorld * shardWorld;
+      d.xRecCap = d.recCap / shardWorld;
+      d.xRecDestCap = d.recDestCap / shardWorld;
+      allocExchange();
+      d.bucketKey = dalloc<unsigned long long>((size_t)ring * (size_t)d.bcap);
+      d.itemKey = dalloc<unsigned long long>((size_t)d.itemCap);
+      d.xoffS = dalloc<uint32_t>((size_t)d.itemCap);
+      d.xoffD = dalloc<uint32_t>((size_t)d.itemCap);
+    } else {
+      d.newEv = dalloc<Ev>(d.newEvCap);
+      d.newTarget = dalloc<int>(d.newEvCap);
+      d.rec = dalloc<MultiRec>(d.recCap);
+      d.recDest = dalloc<uint32_t>(d.recDestCap);
+      d.recArrival = dalloc<int>(d.recDestCap);
+    }
     if (farEnabled) {
       d.ffwd = 1;
       d.farCap = 2 * N + 1024;
@@ -363,7 +492,15 @@ class Engine {
     }
     int L = 1;
     while ((1 << L) <= N) ++L;  // levels 0..log2(N)   (:186)
+    if (sharded()) {
+      // pooled payloads that cross shards are staged on the receiving shard (one area per sender and pass parity): in one
+      // pass a shard receives from one sender at most about one level block per sending node
+      const long long nl = N / shardWorld;
+      stageWordsWanted = std::max<long long>(65536, nl * std::max<long long>(1, nl / 64) * 5 / 4 + 8192);
+      if (tun.stageWords) stageWordsWanted = tun.stageWords;
+    }
     allocCommon(N, PROTO_GSF);
+    const int NL = d.nLoc;
     d.L = L;
     d.W64 = std::max(1, N / 64);
     d.threshold = p.threshold;
@@ -372,36 +509,40 @@ class Engine {
     d.accel = p.acceleratedCallsCount;
     d.qcap = (int)(tun.qcap ? tun.qcap : std::min<long long>(4096, std::max<long long>(64, 2LL * N)));
     d.qcap = (d.qcap + 31) / 32 * 32;
-    d.verified = dalloc<unsigned long long>((size_t)N * d.W64);
-    d.indivSeen = dalloc<unsigned long long>((size_t)N * d.W64);
-    d.indivVer = dalloc<unsigned long long>((size_t)N * d.W64);
-    d.pos = dalloc<int>((size_t)N * L);
-    d.remaining = dalloc<int>((size_t)N * L);
-    d.cntVer = dalloc<int>((size_t)N * L);
-    d.cntIndiv = dalloc<int>((size_t)N * L);
-    d.cntUnion = dalloc<int>((size_t)N * L);
-    d.totalCard = dalloc<int>(N);
-    d.minStart = dalloc<int>(N);
-    d.stamp = dalloc<uint32_t>(N);
-    d.qLen = dalloc<int>(N);
-    d.sigChecked = dalloc<int>(N);
-    d.sigQueueSize = dalloc<int>(N);
-    d.queue = dalloc<QEntry>((size_t)N * d.qcap);
-    d.qScore = dalloc<int>((size_t)N * d.qcap);
-    d.qStamp = dalloc<uint32_t>((size_t)N * d.qcap);
-    d.lvVer = dalloc<uint32_t>((size_t)N * L);
+    d.verified = dallocNodes<unsigned long long>(d.W64);
+    d.indivSeen = dallocNodes<unsigned long long>(d.W64);
+    d.indivVer = dallocNodes<unsigned long long>(d.W64);
+    d.pos = dallocNodes<int>(L);
+    d.remaining = dallocNodes<int>(L);
+    d.cntVer = dallocNodes<int>(L);
+    d.cntIndiv = dallocNodes<int>(L);
+    d.cntUnion = dallocNodes<int>(L);
+    d.totalCard = dallocNodes<int>();
+    d.minStart = dallocNodes<int>();
+    d.stamp = dallocNodes<uint32_t>();
+    d.qLen = dallocNodes<int>();
+    d.sigChecked = dallocNodes<int>();
+    d.sigQueueSize = dallocNodes<int>();
+    d.queue = dallocNodes<QEntry>(d.qcap);
+    d.qScore = dallocNodes<int>(d.qcap);
+    d.qStamp = dallocNodes<uint32_t>(d.qcap);
+    d.lvVer = dallocNodes<uint32_t>(L);
     std::vector<int> pairing(N);
     for (int i = 0; i < N; ++i) pairing[i] = (int)std::max(1.0, p.pairingTime * hm.nodes[i].speed);  // :170
-    d.pairing = dupload(pairing);
+    d.pairing = duploadNodes(pairing);
     d.peerBits = (N / 2 <= 65536) ? 16 : 32;
-    d.peers = be->alloc((size_t)N * (size_t)(N - 1) * (size_t)(d.peerBits / 8));
-    allocs.push_back(d.peers);
+    {
+      const size_t rowBytes = (size_t)(N - 1) * (size_t)(d.peerBits / 8);
+      void* pp = be->alloc((size_t)NL * rowBytes);
+      allocs.push_back(pp);
+      d.peers = (char*)pp - (size_t)d.n0 * rowBytes;
+    }
     // payload pools for levels whose block is wider than one word
     Ctl c;
     std::memset(&c, 0, sizeof(c));
     long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
     for (int l = INLINE_MAX_LEVEL + 1; l < L; ++l) {
-      long long slots = std::max<long long>(1024, perNode * N);
+      long long slots = std::max<long long>(1024, perNode * NL);
       slots = (slots + POOL_STRIPES - 1) / POOL_STRIPES * POOL_STRIPES;
       d.poolCap[l] = (int)slots;
       d.pool[l] = dalloc<unsigned long long>((size_t)slots * (size_t)poolWords(l));
@@ -464,7 +605,8 @@ class Engine {
 
     // registerPeriodicTask(doCycle, 1, period) for live nodes in id order (:630) -> bucket of ms 1
     std::vector<Ev> per;
-    for (int i = 0; i < N; ++i)
+    std::vector<unsigned long long> keys;
+    for (int i = d.n0; i < d.n0 + d.nLoc; ++i)
       if (!hm.nodes[i].down) {
         Ev ev;
         std::memset(&ev, 0, sizeof(ev));
@@ -472,9 +614,11 @@ class Engine {
         ev.to = (uint32_t)i;
         ev.from = (uint32_t)i;
         per.push_back(ev);
+        keys.push_back(orderKey(0, (unsigned)i));
       }
     if ((int)per.size() > d.bcap) throw std::runtime_error("bucket capacity too small");
     be->upload(d.buckets + (size_t)1 * d.bcap, per.data(), per.size() * sizeof(Ev));
+    if (sharded() && !keys.empty()) be->upload(d.bucketKey + (size_t)1 * d.bcap, keys.data(), keys.size() * sizeof(unsigned long long));
     int cnt = (int)per.size();
     be->upload(d.bucketCount + 1, &cnt, sizeof(int));
     c = readCtl();

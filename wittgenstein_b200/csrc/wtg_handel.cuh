@@ -249,7 +249,7 @@ WTG_HD void hDissemination(const Dev& d, C& c, int n, int item, int& outSlots, i
     if (base >= 0 && c.lane() == 0) {
       Desc ds;
       ds.dkind = DK_SEND_SINGLE;
-      ds.item = (uint32_t)(d.N + item);
+      ds.item = (uint32_t)(d.nLoc + item);
       ds.sub = (uint32_t)sub;
       ds.from = (uint32_t)n;
       ds.to = dest[l];
@@ -267,7 +267,7 @@ WTG_HD void hDissemination(const Dev& d, C& c, int n, int item, int& outSlots, i
     if (base >= 0) {
       Desc ds;
       ds.dkind = DK_INSERT_AT;
-      ds.item = (uint32_t)(d.N + item);
+      ds.item = (uint32_t)(d.nLoc + item);
       ds.sub = (uint32_t)sub;
       ds.from = (uint32_t)n;
       ds.to = (uint32_t)n;
@@ -465,7 +465,7 @@ WTG_HD void hUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u64
           int base = descAlloc(d, c, n, 1);
           if (base >= 0 && c.lane() == 0) {
             Desc ds;
-            ds.item = (uint32_t)(d.N + item);
+            ds.item = (uint32_t)(d.nLoc + item);
             ds.sub = (uint32_t)sub;
             ds.from = (uint32_t)n;
             ds.evKind = EV_MSG;

@@ -262,6 +262,42 @@ WTG_HD bool poolAlloc(const Dev& d, int level, int n, uint32_t& slot) {
   return false;
 }
 
+}  // namespace wtg
+#include "wtg_shard.cuh"
+namespace wtg {
+
+// node-sharded runs: a pooled payload that arrived from another shard sits in this shard's staging area; move it
+// into a pool slab of this shard and make the envelope an ordinary PK_POOL one (one coop per envelope)
+template <class C>
+WTG_HD void xIngest(const Dev& d, C& c, int g) {
+  Ev* ev = &d.newEv[g];
+  const uint32_t meta = ev->meta;
+  const int l = (int)metaLevel(meta);
+  const int src = (int)((meta >> META_SRC_SHIFT) & 7u);
+  const int nw = poolWords(l);
+  const u64 pl = ev->pl;
+  uint32_t slot = 0;
+  int ok = 1;
+  if (c.lane() == 0) ok = poolAlloc(d, l, (int)ev->to, slot) ? 1 : 0;
+  slot = (uint32_t)c.bcast((int)slot, 0);
+  ok = c.bcast(ok, 0);
+  if (ok) {
+    const u64* from = xStagePtr(d, d.rank, src, (int)(uint32_t)pl);
+    u64* dst = d.pool[l] + (size_t)slot * (size_t)nw;
+    for (int w = c.lane(); w < nw; w += C::LANES) dst[w] = from[w];
+  }
+  c.sync();
+  if (c.lane() == 0) {
+    ev->meta = meta & ~(META_STAGED | (7u << META_SRC_SHIFT));
+    ev->pl = (pl & 0xFFFFFFFF00000000ULL) | (u64)slot;
+    if (!ok) d.newTarget[g] = -1;
+  }
+  c.sync();
+}
+WTG_HD bool xNeedsIngest(const Dev& d, int g) {
+  return d.newTarget[g] >= 0 && d.newEv[g].kind == EV_MSG && (d.newEv[g].meta & META_STAGED) != 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // evaluateSig  (GSFSignature.java:482-534) on range-compressed operands
 // ------------------------------------------------------------------------------------------
@@ -905,7 +941,7 @@ WTG_HD void gsfUpdate(const Dev& d, C& c, int n, uint32_t from, uint32_t meta, u
         sentBytes += (long long)cnt * msgSize(cur);
         if (base >= 0 && c.lane() == 0) {
           Desc ds;
-          ds.item = (uint32_t)(d.N + item);
+          ds.item = (uint32_t)(d.nLoc + item);
           ds.sub = (uint32_t)sub;
           ds.from = (uint32_t)n;
           ds.evKind = EV_MSG;
@@ -992,11 +1028,23 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
           meta = metaMake(PK_POOL, (uint32_t)l, 0);
           uint32_t slot = 0;
           int ok = 1;
-          if (c.lane() == 0) ok = poolAlloc(d, l, n, slot) ? 1 : 0;
-          slot = (uint32_t)c.bcast((int)slot, 0);
-          ok = c.bcast(ok, 0);
+          const int q = ownerOf(d, (int)dest);
+          u64* dst = nullptr;
+          if (q != d.rank) {  // the receiver lives on another shard: the snapshot goes into its staging area
+            int off = 0;
+            if (c.lane() == 0) off = xStageAlloc(d, q, ob.nw);
+            off = c.bcast(off, 0);
+            ok = off >= 0;
+            slot = (uint32_t)(ok ? off : 0);
+            meta |= META_STAGED | ((uint32_t)d.rank << META_SRC_SHIFT);
+            if (ok) dst = xStagePtr(d, q, d.rank, off);
+          } else {
+            if (c.lane() == 0) ok = poolAlloc(d, l, n, slot) ? 1 : 0;
+            slot = (uint32_t)c.bcast((int)slot, 0);
+            ok = c.bcast(ok, 0);
+            if (ok) dst = d.pool[l] + (size_t)slot * (size_t)ob.nw;
+          }
           if (ok) {
-            u64* dst = d.pool[l] + (size_t)slot * (size_t)ob.nw;
             for (int w = c.lane(); w < ob.nw; w += C::LANES) dst[w] = rowV[ob.w0 + w];
             words += (unsigned long long)(2 * ob.nw);
           }
@@ -1007,7 +1055,7 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
       if (base >= 0 && c.lane() == 0) {
         Desc ds;
         ds.dkind = DK_SEND_SINGLE;
-        ds.item = (uint32_t)(d.N + item);
+        ds.item = (uint32_t)(d.nLoc + item);
         ds.sub = (uint32_t)sub;
         ds.from = (uint32_t)n;
         ds.to = dest;
@@ -1027,7 +1075,7 @@ WTG_HD void gsfCycle(const Dev& d, C& c, int n, int item, int& outSlots, int& ou
     if (base >= 0) {  // re-arm: network.sendArriveAt(this, time + period, sender, sender)
       Desc ds;
       ds.dkind = DK_INSERT_AT;
-      ds.item = (uint32_t)(d.N + item);
+      ds.item = (uint32_t)(d.nLoc + item);
       ds.sub = (uint32_t)sub;
       ds.from = (uint32_t)n;
       ds.to = (uint32_t)n;
@@ -1111,6 +1159,7 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
   uint32_t dest = 0, meta = 0, slot = 0;
   u64 pl = 0;
   bool pooled = false;
+  int stagedOn = -1;
   if (snd) {
     dest = peerAt(d, n, l, p);  // getRemainingPeers(1) :325-349
     int p2 = p + 1 >= size ? 0 : p + 1;
@@ -1124,7 +1173,16 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
       pl = rowV[ob.w0] & ob.mask;
     } else {
       meta = metaMake(PK_POOL, (uint32_t)l, 0);
-      pooled = poolAlloc(d, l, n, slot);
+      const int q = ownerOf(d, (int)dest);
+      if (q != d.rank) {  // the receiver lives on another shard: the snapshot goes into its staging area
+        int off = xStageAlloc(d, q, poolWords(l));
+        pooled = off >= 0;
+        slot = (uint32_t)(pooled ? off : 0);
+        meta |= META_STAGED | ((uint32_t)d.rank << META_SRC_SHIFT);
+        stagedOn = q;
+      } else {
+        pooled = poolAlloc(d, l, n, slot);
+      }
       pl = (u64)slot | ((u64)(uint32_t)prefix << 32);
     }
   }
@@ -1134,14 +1192,16 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
     int src = __ffs(pm) - 1;
     pm &= pm - 1;
     uint32_t sl = __shfl_sync(FULLM, slot, src);
+    int so = __shfl_sync(FULLM, stagedOn, src);
     Blk ob = levelBlock(n, src);  // our own half of level `src`: what the receiver waits for at its level
-    warpCopyWords(d.pool[src] + (size_t)sl * (size_t)ob.nw, rowV + ob.w0, ob.nw, lane);
+    u64* dstp = so >= 0 ? xStagePtr(d, so, d.rank, (int)sl) : d.pool[src] + (size_t)sl * (size_t)ob.nw;
+    warpCopyWords(dstp, rowV + ob.w0, ob.nw, lane);
     words += (unsigned long long)(2 * ob.nw);
   }
   if (snd && base >= 0) {
     Desc ds;
     ds.dkind = DK_SEND_SINGLE;
-    ds.item = (uint32_t)(d.N + item);
+    ds.item = (uint32_t)(d.nLoc + item);
     ds.sub = (uint32_t)sub;
     ds.from = (uint32_t)n;
     ds.to = dest;
@@ -1159,7 +1219,7 @@ __device__ __forceinline__ void gsfCycleWarp(const Dev& d, int n, int item, int&
     if (base >= 0) {  // re-arm: network.sendArriveAt(this, time + period, sender, sender)
       Desc ds;
       ds.dkind = DK_INSERT_AT;
-      ds.item = (uint32_t)(d.N + item);
+      ds.item = (uint32_t)(d.nLoc + item);
       ds.sub = (uint32_t)nSend;
       ds.from = (uint32_t)n;
       ds.to = (uint32_t)n;
@@ -1367,7 +1427,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   int sub = 0;
   if (em.nSend > 0) {
     Desc ds;
-    ds.item = (uint32_t)(d.N + item);
+    ds.item = (uint32_t)(d.nLoc + item);
     ds.sub = 0;
     ds.from = (uint32_t)n;
     ds.evKind = EV_MSG;
@@ -1396,7 +1456,7 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   if (em.task) {
     Desc ds;
     ds.dkind = DK_INSERT_AT;
-    ds.item = (uint32_t)(d.N + item);
+    ds.item = (uint32_t)(d.nLoc + item);
     ds.sub = (uint32_t)sub;
     ds.from = (uint32_t)n;
     ds.to = (uint32_t)n;
@@ -1493,7 +1553,7 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
         if (base >= 0) {
           Desc ds;
           ds.dkind = DK_SEND_SINGLE;
-          ds.item = (uint32_t)(d.N + item);
+          ds.item = (uint32_t)(d.nLoc + item);
           ds.sub = 0;
           ds.from = (uint32_t)n;
           ds.to = from;
@@ -1609,12 +1669,17 @@ WTG_HD void dispatchCount(const Dev& d, int i) {
     const MultiRec& rc = d.rec[ev.aux];
     int j = (int)rc.cur;
     m = 0;
+    int lastOwner = d.rank;
     while (j < (int)rc.n && d.recArrival[rc.off + j] == ctl.tick) {
-      WTG_ATOMIC_ADD(&d.inboxCnt[d.recDest[rc.off + j]], 1);
+      const int to = (int)d.recDest[rc.off + j];
+      lastOwner = ownerOf(d, to);
+      if (lastOwner == d.rank) {  // node-sharded: the other shards holding this envelope deliver their own destinations
+        WTG_ATOMIC_ADD(&d.inboxCnt[to], 1);
+        ++m;
+      }
       ++j;
-      ++m;
     }
-    rep = j < (int)rc.n ? 1 : 0;
+    rep = (j < (int)rc.n && lastOwner == d.rank) ? 1 : 0;  // the shard of the group's last destination re-pushes
   } else {
     WTG_ATOMIC_ADD(&d.inboxCnt[ev.to], 1);
   }
@@ -1625,19 +1690,26 @@ WTG_HD void dispatchCount(const Dev& d, int i) {
 WTG_HD void dispatchScatter(const Dev& d, int i) {
   const Ctl& ctl = *d.ctl;
   int p = ctl.nEv - 1 - i;
-  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  const size_t be = (size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i;
+  const Ev& ev = d.buckets[be];
   int item0 = d.itemBase[p];
+  const u64 bkey = d.G > 1 ? d.bucketKey[be] : 0;
   if (ev.kind == EV_MULTI) {
     MultiRec& rc = d.rec[ev.aux];
     int j = (int)rc.cur, m = 0;
+    int lastOwner = d.rank;
     while (j < (int)rc.n && d.recArrival[rc.off + j] == ctl.tick) {
       int to = (int)d.recDest[rc.off + j];
-      int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
-      d.inbox[s] = inboxMake(item0 + m, i);
+      lastOwner = ownerOf(d, to);
+      if (lastOwner == d.rank) {
+        int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+        d.inbox[s] = inboxMake(item0 + m, i);
+        if (d.G > 1) d.itemKey[item0 + m] = bkey | (u64)(255 - j);
+        ++m;
+      }
       ++j;
-      ++m;
     }
-    if (j < (int)rc.n) {  // Network.java:629-632: re-push for the next destination, after the handler ran
+    if (j < (int)rc.n && lastOwner == d.rank) {  // Network.java:629-632: re-push for the next destination, after the handler ran
       int dst_ = i & (ARENA_STRIPES - 1), dper_ = d.descCap / ARENA_STRIPES;
       int di = WTG_ATOMIC_ADD(&d.ctl->descCnt[dst_], 1);
       bool dok_ = di < dper_;
@@ -1645,7 +1717,7 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
       if (dok_) {
         Desc ds;
         ds.dkind = DK_INSERT_AT;
-        ds.item = (uint32_t)(d.N + item0 + m);
+        ds.item = (uint32_t)(d.nLoc + item0 + m);
         ds.sub = 0;
         ds.from = rc.from;
         ds.to = d.recDest[rc.off + j];
@@ -1661,12 +1733,14 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
       }
       d.evSlots[item0 + m] = 1;
       d.evDraws[item0 + m] = 0;
+      if (d.G > 1) d.itemKey[item0 + m] = bkey | (u64)(255 - j);
     }
     rc.cur = (uint32_t)j;
   } else {
     int to = (int)ev.to;
     int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
     d.inbox[s] = inboxMake(item0, i);
+    if (d.G > 1) d.itemKey[item0] = bkey | 255ULL;
   }
 }
 
@@ -1728,7 +1802,7 @@ WTG_HD void dispatchScatterCoop(const Dev& d, C& c, int i) {
       if (di < dper_) {
         Desc ds;
         ds.dkind = DK_INSERT_AT;
-        ds.item = (uint32_t)(d.N + item0 + m);
+        ds.item = (uint32_t)(d.nLoc + item0 + m);
         ds.sub = 0;
         ds.from = rc.from;
         ds.to = d.recDest[rc.off + up];
@@ -1757,7 +1831,9 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   const Ctl& ctl = *d.ctl;
   const Desc& ds = d.desc[di];
   if (ds.dkind == DK_SEND_ALL) return;  // built by emitAll
+  const bool shard = d.G > 1;
   int g = d.slotBase[ds.item] + (int)ds.sub;
+  if (shard) g += (int)d.xoffS[ds.item - d.nLoc];  // creation indices of the other shards that come first
   if (g >= d.newEvCap) {
     setError(d, ERR_DESC_OVERFLOW, g);
     return;
@@ -1774,8 +1850,14 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   int sendTime = ctl.tick + 1;  // send(m, from, to) == send(m, time + 1, from, to)   Network.java:364-366
   if (ds.dkind == DK_INSERT_AT) {
     target = ds.target;
+    if (shard && ds.evKind == EV_MULTI) {  // re-push of a multi-destination envelope: its next arrivals may lie on other shards
+      const MultiRec& rc = d.rec[ds.aux];
+      xPlaceMulti(d, g, rc.from, rc.meta, rc.pl, (int)rc.n, (int)rc.cur, d.recDest + rc.off, d.recArrival + rc.off, (int)ds.aux);
+      return;
+    }
   } else {
     u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
+    if (shard) drawIdx += (u64)d.xoffD[ds.item - d.nLoc];
     if (d.shufCap > 0) {  // protocols with k-element shuffles: draws per descriptor vary (wtg_cappos.cuh)
       drawIdx = ctl.shufReject ? (u64)d.descDraw[di] : descDrawOptimistic(d, di);
       if (ds.dkind == DK_SEND_MULTI && (ds.aux & DESC_SHUFFLEK)) {
@@ -1828,6 +1910,13 @@ WTG_HD void emitDesc(const Dev& d, int di) {
       if (cnt == 1) {
         ev.to = dst[0];
         target = arr[0];
+      } else if (cnt > 1 && shard) {
+        if (arr[cnt - 1] - ctl.tick >= d.ring) {
+          setError(d, ERR_FAR_FUTURE, arr[cnt - 1]);
+          return;
+        }
+        xPlaceMulti(d, g, ds.from, ds.meta, ds.pl, cnt, 0, dst, arr, -1);
+        return;
       } else if (cnt > 1) {
         ev.aux = 0;
         int ri = WTG_ATOMIC_ADD(&d.ctl->recTop, 1);
@@ -1855,7 +1944,8 @@ WTG_HD void emitDesc(const Dev& d, int di) {
         }
       }
     }
-    if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL) freeDirect(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
+    if (target < 0 && d.proto == PROTO_GSF && metaKind(ds.meta) == PK_POOL && !(ds.meta & META_STAGED))
+      freeDirect(d, (int)metaLevel(ds.meta), (uint32_t)ds.pl);
   }
   if (d.farCap > 0) {
     if (target >= 0 && target - ctl.tick >= farHorizon(d)) {
@@ -1866,6 +1956,10 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     setError(d, ERR_FAR_FUTURE, target);
     target = -1;
   }
+  if (shard) {  // straight into the arrays of the shard that owns the destination; dropped envelopes leave no trace
+    if (target >= 0) xStoreEnvelope(d, ownerOf(d, (int)ev.to), g, ev, target);
+    return;
+  }
   d.newEv[g] = ev;
   d.newTarget[g] = target;
 }
@@ -1873,7 +1967,8 @@ WTG_HD void emitDesc(const Dev& d, int di) {
 // conditional-task inserts come first in creation order (slot = scan over nodes)
 WTG_HD void emitCond(const Dev& d, int n) {
   if (!d.condFired[n]) return;
-  int g = d.slotBase[n];
+  int g = d.slotBase[n - d.n0];
+  if (d.G > 1) g += d.ctl->condXoffS;  // the lower shards' nodes come first
   if (g >= d.newEvCap) {
     setError(d, ERR_DESC_OVERFLOW, g);
     return;
@@ -1883,6 +1978,7 @@ WTG_HD void emitCond(const Dev& d, int n) {
     setError(d, ERR_FAR_FUTURE, target);
     target = -1;
   }
+  if (d.G > 1 && target < 0) return;
   d.newEv[g] = d.condEv[n];
   d.newTarget[g] = target;
 }
@@ -1920,13 +2016,18 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
   c.allCnt = 0;
   c.shufReject = 0;
   if (c.nEv > c.maxBucket) c.maxBucket = c.nEv;
+  if (d.G > 1) {
+    c.xseq += 1;
+    c.nEvGlobal = 0;
+    for (int q = 0; q < MAX_SHARDS; ++q) c.stageTop[q] = 0;
+  }
 }
 WTG_HD void tickEnd(const Dev& d, int mode) {
   Ctl& c = *d.ctl;
   c.rng = lcgAdvance(d.jumpA, d.jumpC, c.rng, (u64)c.totalDraws);
   c.statDraws += (unsigned long long)c.totalDraws;
   c.statEvents += (unsigned long long)c.nItems;
-  if (c.nEv > 0) {
+  if ((d.G > 1 ? c.nEvGlobal : c.nEv) > 0) {
     c.callId += 1;  // every processed message starts a new nextMessage() call
     c.didSomething = 1;
   }
@@ -2043,7 +2144,7 @@ struct Pair {
 WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
   Pair p;
   if (which == 2) {  // Handel: draws of the conditional pass, over nodes
-    p.a = d.condDraws[j];
+    p.a = d.condDraws[d.n0 + j];
     p.b = 0;
     return p;
   }
@@ -2054,23 +2155,23 @@ WTG_HD Pair scanLoad(const Dev& d, int which, int j) {
       p.b = 0;
     } else {
       p.a = 0;
-      p.b = d.inboxCnt[j - nEv];
+      p.b = d.inboxCnt[d.n0 + j - nEv];
     }
   } else {
-    if (j < d.N) {
-      p.a = d.condFired[j];
-      p.b = d.condDraws[j];
+    if (j < d.nLoc) {
+      p.a = d.condFired[d.n0 + j];
+      p.b = d.condDraws[d.n0 + j];
     } else {
-      p.a = d.evSlots[j - d.N];
-      p.b = d.evDraws[j - d.N];
+      p.a = d.evSlots[j - d.nLoc];
+      p.b = d.evDraws[j - d.nLoc];
     }
   }
   return p;
 }
-WTG_HD int scanCount(const Dev& d, int which) { return which == 2 ? d.N : which == 0 ? d.ctl->nEv + d.N : d.N + d.ctl->nItems; }
+WTG_HD int scanCount(const Dev& d, int which) { return which == 2 ? d.nLoc : which == 0 ? d.ctl->nEv + d.nLoc : d.nLoc + d.ctl->nItems; }
 WTG_HD void scanStore(const Dev& d, int which, int j, Pair ex) {
   if (which == 2) {
-    d.hDrawBase[j] = ex.a;
+    d.hDrawBase[d.n0 + j] = ex.a;
     return;
   }
   if (which == 0) {
@@ -2078,8 +2179,8 @@ WTG_HD void scanStore(const Dev& d, int which, int j, Pair ex) {
     if (j < nEv)
       d.itemBase[j] = ex.a;
     else {
-      d.inboxOff[j - nEv] = ex.b;
-      d.inboxCnt[j - nEv] = 0;
+      d.inboxOff[d.n0 + j - nEv] = ex.b;
+      d.inboxCnt[d.n0 + j - nEv] = 0;
     }
   } else {
     d.slotBase[j] = ex.a;

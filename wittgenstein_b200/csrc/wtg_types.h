@@ -27,6 +27,7 @@ constexpr int MAX_LEVELS = 24;
 constexpr int MAX_ACC = 16;          // max destinations of a protocol multi-send handled on device
 constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bits for l <= 7
 constexpr int MAX_DIST = 1144;       // core/Node.java:17-18
+constexpr int MAX_SHARDS = 8;        // node-id shards of one simulation (one GPU each); power of two
 
 // protocols
 enum : int { PROTO_NONE = 0, PROTO_PINGPONG = 1, PROTO_GSF = 2, PROTO_SANFERMIN = 3, PROTO_HANDEL = 4, PROTO_CASPER = 5, PROTO_CAPPOS = 6 };
@@ -142,6 +143,33 @@ struct FarEv {  // an envelope whose arrival lies beyond the time ring's horizon
   unsigned long long key;  // (creation tick << 32) | creation index: insertion order among far envelopes
 };
 
+// ---- node-sharded simulation: what the shards exchange every pipeline pass ----
+// Shard r owns the ids [r * nLoc, (r + 1) * nLoc).  Every bucket entry carries an ordering key
+//   (creation tick << 36) | (creation index << 8) | (255 - j)       j = position inside a multi-destination record
+// so that "processed earlier" (LIFO by insertion, Network.java:145-147) == larger key on every shard.
+struct XItem {  // one scan item of a shard, in its local processing order
+  unsigned long long key;
+  uint32_t ps, pd;  // exclusive prefix of (slots, draws) over the shard's items
+};
+struct XHdr {  // per pass and shard
+  int seq, nEv, nItems, condSlots, condDraws, itemSlots, itemDraws, error;
+};
+constexpr uint32_t META_STAGED = 1u << 15;  // GSF: the pooled payload still sits in the staging area written by shard (meta >> 16) & 7
+constexpr int META_SRC_SHIFT = 16;
+struct MultiRec;
+struct Ev;
+struct Peer {  // exchange region of one shard as mapped into this process (own region included: peer[rank])
+  XHdr* hdr;            // [G]            written by shard q at [q]
+  XItem* items;         // [G][xItemCap]  written by shard q at [q][*]
+  int* flags;           // [2][G]         pass sequence number of the last completed publication (0: items, 1: envelopes)
+  Ev* newEv;            // [newEvCap]     this tick's new envelopes, indexed by global creation index
+  int* newTarget;       // [newEvCap]     arrival tick, -1 = nothing for this shard
+  unsigned long long* stage;  // [2][G][stageCapWords] pooled payloads of envelopes addressed to this shard
+  MultiRec* rec;        // [G][recCap / G] multi-destination records, one sub-arena per sending shard
+  uint32_t* recDest;    // [G][recDestCap / G]
+  int* recArrival;      // [G][recDestCap / G]
+};
+
 struct CasperG {  // CasperIMD: block counter and the Byzantine producer's scalars (CasperIMD.java:511-518, 648-649)
   int nBlocks;    // blocks created so far, genesis included (Block.blockId, per engine)
   int byzToSend, byzH, byzLate, byzOnTime;
@@ -180,6 +208,14 @@ struct Ctl {  // device-resident control block (one per engine)
   int workCnt[ARENA_STRIPES];   // stale pooled queue entries to re-score this tick, per stripe
   int dueCnt[ARENA_STRIPES];    // nodes whose conditional task runs this tick, per stripe
   int taskCnt[ARENA_STRIPES];   // nodes with task events this tick, per stripe
+  // ---- node-sharded simulation ----
+  int xseq;                      // pipeline passes so far (identical on every shard): sequence number of the exchanges
+  int nEvGlobal;                 // bucket entries of this tick over all shards
+  int condXoffS, condXoffD;      // creation / draw index of this shard's first conditional-task insert
+  int allCondS, allCondD;        // conditional-task inserts / draws of all shards
+  int stageTop[MAX_SHARDS];      // words staged for shard q in this pass
+  int xRecTop[MAX_SHARDS];       // records / destinations allocated in this shard's sub-arena of shard q
+  int xRecDestTop[MAX_SHARDS];
   int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
   int poolFreeCnt[MAX_LEVELS][POOL_STRIPES];   // free slots per (level, stripe)
 };
@@ -204,7 +240,10 @@ enum : int {
   ERR_INBOX_OVERFLOW = 9,
   ERR_FAR_OVERFLOW = 10,
   ERR_PROTO_STATE = 11,   // the reference would have thrown IllegalStateException / IllegalArgumentException in a handler
-  ERR_UNSUPPORTED = 12    // a situation the device path does not implement (detail says which)
+  ERR_UNSUPPORTED = 12,   // a situation the device path does not implement (detail says which)
+  ERR_PEER_TIMEOUT = 13,  // a shard did not publish its part of the exchange in time
+  ERR_PEER_ERROR = 14,    // another shard reported an error
+  ERR_STAGE_OVERFLOW = 15 // staging area for cross-shard payloads exceeded
 };
 
 // All device pointers + sizes; passed by value to kernels.
@@ -220,6 +259,15 @@ struct Dev {
   int descCap, destScratchCap, recCap, recDestCap, freeCap, newEvCap, itemCap, workCap;
   int latKind, latParam;
   int peerBits;  // 16 or 32
+  // ---- node-sharded simulation: this engine owns the ids [n0, n0 + nLoc); per-node arrays hold nLoc rows and are
+  //      addressed by global id (their base pointers are biased by -n0 rows); node attributes are replicated ----
+  int n0, nLoc, G, rank, ownShift;
+  int xItemCap, stageCapWords, xRecCap, xRecDestCap;
+  Peer peer[MAX_SHARDS];
+  unsigned long long* bucketKey;  // [ring][bcap] ordering key of every bucket entry (sharded runs only)
+  unsigned long long* itemKey;    // [itemCap]
+  uint32_t* xoffS;                // [itemCap] creation indices / draws of the other shards that precede the item
+  uint32_t* xoffD;
   // ---- control ----
   Ctl* ctl;
   unsigned long long* stats;  // [STAT_SLOTS][ST_COUNT]
