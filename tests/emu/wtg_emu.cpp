@@ -32,6 +32,19 @@ class HostBackend : public Backend {
     }
     scanTotals(d, which, run);
   }
+  // a shard that hit an error still publishes its header (which carries the error) and both signals of the pass, so the
+  // other shards stop at once instead of waiting for their time-out
+  bool bail(const Dev& d, int phasesDone) {
+    if (!d.ctl->error) return false;
+    if (d.G > 1) {
+      if (phasesDone < 1) {
+        xPublishHeader(d);
+        xSignal(d, 0);
+      }
+      if (phasesDone < 2) xSignal(d, 1);
+    }
+    return true;
+  }
   void tick(const Dev& d, int mode) override {
     CoopSerial c;
     std::vector<uint32_t> keep((size_t)std::max(1, d.qcap));
@@ -41,7 +54,7 @@ class HostBackend : public Backend {
       tickBeginFfwd(d, c);
     else
       tickBegin(d, mode);
-    if (d.ctl->error) return;
+    if (bail(d, 0)) return;
     if (d.proto == PROTO_GSF && mode != 3) {
       for (int n = d.n0; n < d.n0 + d.nLoc; ++n)
         if (gsfCondMark(d, n)) gsfCondScanQueue(d, c, n);
@@ -75,7 +88,7 @@ class HostBackend : public Backend {
       const bool coopDispatch = d.allCap > 0;
       for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchCountCoop(d, c, i) : dispatchCount(d, i);
       pairScan(d, 0);
-      if (d.ctl->error) return;
+      if (bail(d, 0)) return;
       for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchScatterCoop(d, c, i) : dispatchScatter(d, i);
       for (int n = d.n0; n < d.n0 + d.nLoc; ++n) nodeProcess(d, c, n, 0);
     }
@@ -89,8 +102,10 @@ class HostBackend : public Backend {
         for (int i = 0; i < d.ctl->nItems; ++i) xOffsets(d, i);
         xTotals(d);
       }
+      if (bail(d, 1)) return;
     }
-    if (!d.ctl->error) {
+    if (d.ctl->error) return;
+    {
     for (int n = d.n0; n < d.n0 + d.nLoc; ++n) emitCond(d, n);
     if (d.shufCap > 0) {
       int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);

@@ -24,6 +24,11 @@ class Api:
         "create": (C.c_void_p, []),
         "create_on": (C.c_void_p, [C.c_int]),
         "destroy": (None, [C.c_void_p]),
+        "shard_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
+        "shard_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
+        "shard_link": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]),
+        "shard_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "device": (C.c_int, [C.c_void_p]),
         "set_seed": (C.c_int, [C.c_void_p, C.c_longlong]),
         "set_network_latency": (C.c_int, [C.c_void_p, C.c_char_p]),
         "set_network_latency_measured": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),

@@ -54,6 +54,48 @@ void WTG_API(destroy)(void* h) { delete static_cast<NetHandle*>(h); }
 
 #define ENG (static_cast<NetHandle*>(h)->eng)
 
+// ---- node-sharded simulation: shard `rank` of `world` (a power of two <= 8) of ONE network.  Every shard is configured and
+//      initialised with identical calls (same seed, builder, latency, protocol parameters), from its own thread or process;
+//      after init() the shards exchange the 64-byte handles of their exchange regions and link; then every shard calls
+//      run_ms with the same arguments.  Node-indexed read-backs of a shard cover its own ids [n0, n0 + nLoc). ----
+void* WTG_API(shard_create)(int rank, int world, int device) {
+  try {
+    NetHandle* nh = new NetHandle(device);
+    try {
+      nh->eng.setShard(rank, world);
+    } catch (...) {
+      delete nh;
+      throw;
+    }
+    return nh;
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return nullptr;
+  }
+}
+int WTG_API(shard_export)(void* h, unsigned char* handle64) {
+  return guard([&] {
+    ENG.exportExchange(handle64);
+    return 0;
+  });
+}
+// handles: world x 64 bytes in rank order; devices: CUDA device of every shard (NULL: all shards are other processes)
+int WTG_API(shard_link)(void* h, const unsigned char* handles, const int* devices) {
+  return guard([&] {
+    ENG.linkExchange(handles, devices);
+    return 0;
+  });
+}
+int WTG_API(shard_range)(void* h, int* n0, int* nLoc) {
+  return guard([&] {
+    ENG.requireInited();
+    *n0 = ENG.d.n0;
+    *nLoc = ENG.d.nLoc;
+    return 0;
+  });
+}
+int WTG_API(device)(void* h) { return ENG.be->deviceId(); }
+
 int WTG_API(set_seed)(void* h, long long seed) {
   return guard([&] {
     ENG.setSeed(seed);
@@ -102,6 +144,7 @@ int WTG_API(set_tunable)(void* h, const char* key, long long v) {
     else if (k == "casper_votes") ENG.tun.casperVotes = v;
     else if (k == "force_shuffle_serial") ENG.forceShufSerial = v != 0;
     else if (k == "casper_blocks") ENG.tun.casperBlocks = v;
+    else if (k == "stage_words") ENG.tun.stageWords = v;
     else throw std::invalid_argument("unknown tunable " + k);
     return 0;
   });
@@ -420,12 +463,12 @@ unsigned long long WTG_API(rng_state)(void* h) {
 int WTG_API(node_counters)(void* h, long long* out5N) {
   return guard([&] {
     ENG.requireInited();
-    size_t n = (size_t)ENG.d.N;
-    ENG.fetch(out5N + 0 * n, ENG.d.msgReceived, n);
-    ENG.fetch(out5N + 1 * n, ENG.d.msgSent, n);
-    ENG.fetch(out5N + 2 * n, ENG.d.bytesSent, n);
-    ENG.fetch(out5N + 3 * n, ENG.d.bytesReceived, n);
-    ENG.fetch(out5N + 4 * n, ENG.d.doneAt, n);
+    size_t n = (size_t)ENG.d.nLoc, o = (size_t)ENG.d.n0;  // a shard reports its own nodes: out5N holds 5 x nLoc values
+    ENG.fetch(out5N + 0 * n, ENG.d.msgReceived + o, n);
+    ENG.fetch(out5N + 1 * n, ENG.d.msgSent + o, n);
+    ENG.fetch(out5N + 2 * n, ENG.d.bytesSent + o, n);
+    ENG.fetch(out5N + 3 * n, ENG.d.bytesReceived + o, n);
+    ENG.fetch(out5N + 4 * n, ENG.d.doneAt + o, n);
     return 0;
   });
 }
@@ -546,7 +589,7 @@ int WTG_API(handel_levels)(void* h) { return ENG.d.L; }
 int WTG_API(gsf_verified)(void* h, unsigned long long* outNW) {
   return guard([&] {
     requireGsf(ENG);
-    ENG.fetch(outNW, ENG.d.verified, (size_t)ENG.d.N * ENG.d.W64);
+    ENG.fetch(outNW, ENG.d.verified + (size_t)ENG.d.n0 * ENG.d.W64, (size_t)ENG.d.nLoc * ENG.d.W64);
     return 0;
   });
 }
@@ -555,19 +598,19 @@ int WTG_API(gsf_rows)(void* h, int which, unsigned long long* outNW) {
   return guard([&] {
     requireGsf(ENG);
     const unsigned long long* src = which == 0 ? ENG.d.verified : which == 1 ? ENG.d.indivSeen : ENG.d.indivVer;
-    ENG.fetch(outNW, src, (size_t)ENG.d.N * ENG.d.W64);
+    ENG.fetch(outNW, src + (size_t)ENG.d.n0 * ENG.d.W64, (size_t)ENG.d.nLoc * ENG.d.W64);
     return 0;
   });
 }
 int WTG_API(gsf_node_scalars)(void* h, int* pairing, int* sigChecked, int* sigQueueSize, int* toVerifySize, int* card) {
   return guard([&] {
     requireGsf(ENG);
-    size_t n = (size_t)ENG.d.N;
-    if (pairing) ENG.fetch(pairing, ENG.d.pairing, n);
-    if (sigChecked) ENG.fetch(sigChecked, ENG.d.sigChecked, n);
-    if (sigQueueSize) ENG.fetch(sigQueueSize, ENG.d.sigQueueSize, n);
-    if (toVerifySize) ENG.fetch(toVerifySize, ENG.d.qLen, n);
-    if (card) ENG.fetch(card, ENG.d.totalCard, n);
+    size_t n = (size_t)ENG.d.nLoc, o = (size_t)ENG.d.n0;
+    if (pairing) ENG.fetch(pairing, ENG.d.pairing + o, n);
+    if (sigChecked) ENG.fetch(sigChecked, ENG.d.sigChecked + o, n);
+    if (sigQueueSize) ENG.fetch(sigQueueSize, ENG.d.sigQueueSize + o, n);
+    if (toVerifySize) ENG.fetch(toVerifySize, ENG.d.qLen + o, n);
+    if (card) ENG.fetch(card, ENG.d.totalCard + o, n);
     return 0;
   });
 }
@@ -575,10 +618,10 @@ int WTG_API(gsf_node_scalars)(void* h, int* pairing, int* sigChecked, int* sigQu
 int WTG_API(gsf_level_scalars)(void* h, int* pos, int* remaining, int* card) {
   return guard([&] {
     requireGsf(ENG);
-    size_t n = (size_t)ENG.d.N * ENG.d.L;
-    if (pos) ENG.fetch(pos, ENG.d.pos, n);
-    if (remaining) ENG.fetch(remaining, ENG.d.remaining, n);
-    if (card) ENG.fetch(card, ENG.d.cntVer, n);
+    size_t n = (size_t)ENG.d.nLoc * ENG.d.L, o = (size_t)ENG.d.n0 * ENG.d.L;
+    if (pos) ENG.fetch(pos, ENG.d.pos + o, n);
+    if (remaining) ENG.fetch(remaining, ENG.d.remaining + o, n);
+    if (card) ENG.fetch(card, ENG.d.cntVer + o, n);
     return 0;
   });
 }
@@ -586,6 +629,7 @@ int WTG_API(gsf_peers)(void* h, int node, int level, int* out, int cap) {
   return guard([&] {
     requireGsf(ENG);
     if (node < 0 || node >= ENG.d.N || level < 0 || level >= ENG.d.L) throw std::invalid_argument("node/level");
+    if (node < ENG.d.n0 || node >= ENG.d.n0 + ENG.d.nLoc) throw std::invalid_argument("node belongs to another shard");
     if (level == 0 || ENG.hm.nodes[(size_t)node].down) return 0;
     int size = 1 << (level - 1);
     size_t off = (size_t)node * (size_t)(ENG.d.N - 1) + (size_t)(size - 1);

@@ -372,6 +372,7 @@ class Engine {
   // ---- PingPong.init()  (protocols/PingPong.java:82-87) ----
   void pingpongInit(int nodeCt) {
     requireNotInited();
+    requireUnsharded("this protocol");
     if (nodeCt <= 0) throw std::invalid_argument("nodeCt");
     checkLatencyBuilder();
     hm.buildNodes(nodeCt);
@@ -657,6 +658,7 @@ class Engine {
   }
   void sanferminInit() {
     requireNotInited();
+    requireUnsharded("this protocol");
     if (!sfConstructed) throw std::logic_error("SanFerminSignature not constructed");
     const int N = sp.nodeCount;
     {
@@ -723,6 +725,7 @@ class Engine {
   HandelParams hp{};
   void handelInit(const HandelParams& p) {
     requireNotInited();
+    requireUnsharded("this protocol");
     const int N = p.nodeCount;
     if (p.nodesDown >= N || p.nodesDown < 0 || p.threshold > N || (p.nodesDown + p.threshold > N))  // :112-117
       throw std::invalid_argument("nodeCount=" + std::to_string(N) + ", threshold=" + std::to_string(p.threshold));
@@ -960,6 +963,7 @@ class Engine {
   CapposParams qp{};
   void capposInit(const CapposParams& p) {
     requireNotInited();
+    requireUnsharded("this protocol");
     const int N = p.nodeCount;
     if (N < 2 || (N & (N - 1)) != 0) throw std::invalid_argument("the B200 engine needs a power-of-two nodeCount >= 2 for SanFerminCappos");
     if (p.candidateCount < 1 || p.candidateCount + 1 > SHUFFLE_MAX) throw std::invalid_argument("candidateCount must be in [1, 63]");
@@ -1033,6 +1037,7 @@ class Engine {
   }
   void casperInit(int byzDelay, int byzKind = CK_BYZ_WF) {
     requireNotInited();
+    requireUnsharded("this protocol");
     if (!casperConstructed) throw std::logic_error("CasperIMD not constructed");
     const int attCount = cp.attestersPerRound * cp.cycleLength;
     const int N = 1 + cp.blockProducersCount + attCount;
@@ -1164,6 +1169,7 @@ class Engine {
   }
   void inject(const std::vector<HostSend>& sends) {
     requireInited();
+    requireUnsharded("a send issued by the caller");
     if (sends.empty()) return;
     const int n = (int)sends.size();
     if (n > d.descCap || n > d.itemCap) throw std::runtime_error("too many sends in one call");
@@ -1266,6 +1272,7 @@ class Engine {
   // ---- runMs  (Network.java:318-338) ----
   int runMs(int ms) {
     requireInited();
+    if (sharded() && !linked) throw std::logic_error("node-sharded network: link the shards' exchange regions before runMs");
     if (ms <= 0) throw std::invalid_argument("Should be greater than 0. ms=" + std::to_string(ms));
     long long endAt = (long long)time + ms;
     if (endAt > 0x7fffffffLL) throw std::runtime_error("Maximum time reached!");

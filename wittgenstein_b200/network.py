@@ -29,13 +29,45 @@ def set_thread_device(device):
 
 
 class Network:
-    def __init__(self, _api=None, device=None):
+    def __init__(self, _api=None, device=None, shard=None):
+        """shard = (rank, world): this object is one node-id shard of a network spread over `world` engines (sharded.py)."""
         self.api = _api or _lib.api()
         if device is None:
             device = getattr(_tls, "device", None)
-        self.h = C.c_void_p(self.api.create() if device is None else self.api.create_on(int(device)))
+        self.shard = shard
+        if shard is not None:
+            self.h = C.c_void_p(self.api.shard_create(int(shard[0]), int(shard[1]), -1 if device is None else int(device)))
+        else:
+            self.h = C.c_void_p(self.api.create() if device is None else self.api.create_on(int(device)))
         if not self.h:
             raise WtgError(self.api.last_error().decode())
+
+    # ---- node-sharded networks ----
+    def shard_range(self):
+        """(first id, count) of the nodes this engine owns; node-indexed read-backs cover exactly these."""
+        a, b = C.c_int(0), C.c_int(0)
+        self.api.check(self.api.shard_range(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard_export(self):
+        buf = (C.c_ubyte * 64)()
+        self.api.check(self.api.shard_export(self.h, buf))
+        return bytes(buf)
+
+    def shard_link(self, handles, devices=None):
+        """handles: the 64-byte exports of all shards in rank order; devices: their CUDA devices when they live in this
+        process (None: every other shard is another process, mapped through CUDA IPC)."""
+        blob = (C.c_ubyte * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        dev = None if devices is None else (C.c_int * len(devices))(*[int(x) for x in devices])
+        self.api.check(self.api.shard_link(self.h, blob, dev))
+
+    @property
+    def device(self):
+        return self.api.device(self.h)
+
+    @property
+    def local_count(self):
+        return self.shard_range()[1] if self.shard is not None else self.node_count
 
     def close(self):
         if getattr(self, "h", None):
@@ -125,7 +157,7 @@ class Network:
     # ---- read-back ----
     def counters(self):
         """rows: msgReceived, msgSent, bytesSent, bytesReceived, doneAt (int64, [5, N])."""
-        out = np.zeros((5, self.node_count), np.int64)
+        out = np.zeros((5, self.local_count), np.int64)
         self.api.check(self.api.node_counters(self.h, _p(out, C.c_longlong)))
         return out
 

@@ -70,11 +70,11 @@ class GSFSignatureParameters:
 
 
 class GSFSignature:
-    def __init__(self, params, _api=None, tunables=None):
+    def __init__(self, params, _api=None, tunables=None, shard=None, device=None):
         self.params = params
         self._api = _api
         self._tunables = dict(tunables or {})
-        self._net = Network(_api)
+        self._net = Network(_api, device=device, shard=shard)
         self._net.set_node_builder(params.node_builder_name)  # GSFSignature.java:111
         self._net.set_network_latency(params.network_latency_name)  # :112-113
         for k, v in self._tunables.items():
@@ -93,28 +93,29 @@ class GSFSignature:
         self._net.api.check(self._net.api.gsf_init(self._net.h, _p(arr, C.c_int)))
         self.levels = self._net.api.gsf_levels(self._net.h)
         self.words = max(1, p.node_count // 64)
+        self.rows_local = self._net.local_count  # a shard reads back its own nodes
 
     # ---- read-back of node state (GSFNode fields) ----
     def verified(self):
         """verifiedSignatures of every node: uint64 [N, N/64]; bit i of the set = bit i%64 of word i//64."""
-        out = np.zeros((self.params.node_count, self.words), np.uint64)
+        out = np.zeros((self.rows_local, self.words), np.uint64)
         self._net.api.check(self._net.api.gsf_verified(self._net.h, _p(out, C.c_ulonglong)))
         return out
 
     def rows(self, which):
         """0 verified, 1 individualSignatures (union over levels), 2 indivVerifiedSig (union over levels)."""
-        out = np.zeros((self.params.node_count, self.words), np.uint64)
+        out = np.zeros((self.rows_local, self.words), np.uint64)
         self._net.api.check(self._net.api.gsf_rows(self._net.h, int(which), _p(out, C.c_ulonglong)))
         return out
 
     def scalars(self):
-        n = self.params.node_count
+        n = self.rows_local
         a = [np.zeros(n, np.int32) for _ in range(5)]
         self._net.api.check(self._net.api.gsf_node_scalars(self._net.h, *[_p(v, C.c_int) for v in a]))
         return dict(pairing=a[0], sig_checked=a[1], sig_queue_size=a[2], to_verify=a[3], card=a[4])
 
     def level_scalars(self):
-        n, L = self.params.node_count, self.levels
+        n, L = self.rows_local, self.levels
         a = [np.zeros((n, L), np.int32) for _ in range(3)]
         self._net.api.check(self._net.api.gsf_level_scalars(self._net.h, *[_p(v, C.c_int) for v in a]))
         return dict(pos=a[0], remaining=a[1], card=a[2])
@@ -129,6 +130,9 @@ class GSFSignature:
         """GSFSignature.newConfIf (:670-682): some live node is still below the threshold."""
         card = self.scalars()["card"]
         down = self._net.attrs()["down"]
+        if self._net.shard is not None:
+            n0, nl = self._net.shard_range()
+            down = down[n0:n0 + nl]
         return bool(((card < self.params.threshold) & (down == 0)).any())
 
 

@@ -1,0 +1,168 @@
+"""One simulation spread over several engines by node id: shard r owns the ids [r*N/G, (r+1)*N/G).
+
+Two ways to drive the same C ABI (include/wtg.h, `wtg_shard_*`):
+
+* `ShardedGSFSignature` — all shards in this process, one host thread per shard (the engines may sit on different GPUs
+  of the box, or share one): what a single-process caller such as the reference's JVM would do through JNI.
+* `DistributedGSFSignature` — one shard per process (torchrun: one rank per GPU); the 64-byte CUDA-IPC handles of the
+  exchange regions travel through `torch.distributed`, after that the data path is peer stores between the GPUs'
+  kernels — no collective call per tick.
+
+Every shard is configured with identical calls; node-indexed read-backs are concatenated in rank order, so the result
+has the layout of the unsharded protocol object (and is compared with it / the oracle by the tests).
+"""
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from .protocols import GSFSignature
+
+
+class _ShardedNetwork:
+    def __init__(self, owner):
+        self._o = owner
+
+    def _each(self, fn):
+        return self._o._each(fn)
+
+    def set_seed(self, seed):
+        self._each(lambda s: s.network().set_seed(seed))
+
+    def set_tunable(self, k, v):
+        self._each(lambda s: s.network().set_tunable(k, v))
+
+    def run_ms(self, ms):
+        return any(self._each(lambda s: s.network().run_ms(ms)))
+
+    @property
+    def time(self):
+        return self._o.shards[0].network().time
+
+    @property
+    def node_count(self):
+        return self._o.params.node_count
+
+    def rng_state(self):
+        st = set(self._each(lambda s: s.network().rng_state()))
+        assert len(st) == 1, "shards disagree on the rd state"
+        return st.pop()
+
+    def msgs_size(self):
+        return sum(self._each(lambda s: s.network().msgs_size()))
+
+    def counters(self):
+        return np.concatenate(self._each(lambda s: s.network().counters()), axis=1)
+
+    def attrs(self):
+        return self._o.shards[0].network().attrs()
+
+    def stop_node(self, i):
+        self._each(lambda s: s.network().stop_node(i))
+
+    def start_node(self, i):
+        self._each(lambda s: s.network().start_node(i))
+
+    def partition(self, part):
+        self._each(lambda s: s.network().partition(part))
+
+    def end_partition(self):
+        self._each(lambda s: s.network().end_partition())
+
+    def stats(self):
+        sts = self._each(lambda s: s.network().stats())
+        out = dict(sts[0])
+        for k in ("deliveries", "tasks", "cond_runs", "eval_entries", "eval_words", "updates", "cycles", "sends", "multi_sends",
+                  "send_words", "update_words", "reevaluated", "kernel_launches"):
+            out[k] = sum(st[k] for st in sts)
+        for k in ("max_queue", "max_bucket", "max_inbox"):
+            out[k] = max(st[k] for st in sts)
+        return out
+
+    def timer_start(self):
+        self._each(lambda s: s.network().timer_start())
+
+    def timer_stop_ms(self):
+        return max(self._each(lambda s: s.network().timer_stop_ms()))
+
+
+class ShardedGSFSignature:
+    """GSFSignature over `world` node-id shards driven from this process (one thread per shard)."""
+
+    def __init__(self, params, world, devices=None, _api=None, tunables=None):
+        self.params = params
+        self.world = world
+        self.devices = list(devices) if devices is not None else [None] * world
+        self.shards = [GSFSignature(params, _api, tunables, shard=(r, world), device=self.devices[r]) for r in range(world)]
+        self._pool = ThreadPoolExecutor(max_workers=world)
+        self._net = _ShardedNetwork(self)
+
+    def _each(self, fn):
+        return list(self._pool.map(fn, self.shards))
+
+    def network(self):
+        return self._net
+
+    def init(self):
+        self._each(lambda s: s.init())
+        handles = [s.network().shard_export() for s in self.shards]
+        devs = [s.network().device for s in self.shards]
+        self._each(lambda s: s.network().shard_link(handles, devs))
+        self.levels = self.shards[0].levels
+        self.words = self.shards[0].words
+
+    def verified(self):
+        return np.concatenate(self._each(lambda s: s.verified()), axis=0)
+
+    def rows(self, which):
+        return np.concatenate(self._each(lambda s: s.rows(which)), axis=0)
+
+    def scalars(self):
+        parts = self._each(lambda s: s.scalars())
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+    def level_scalars(self):
+        parts = self._each(lambda s: s.level_scalars())
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+    def peers(self, node, level):
+        nl = self.params.node_count // self.world
+        return self.shards[node // nl].peers(node, level)
+
+    def continue_if(self):
+        return any(self._each(lambda s: s.continue_if()))
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for s in self.shards:
+            s.network().close()
+
+
+class DistributedGSFSignature:
+    """This process's shard of a GSFSignature network spread over the ranks of a torch.distributed group (one GPU each)."""
+
+    def __init__(self, params, dist, rank, world, device, tunables=None):
+        self.params, self.dist, self.rank, self.world = params, dist, rank, world
+        self.local = GSFSignature(params, None, tunables, shard=(rank, world), device=device)
+
+    def network(self):
+        return self.local.network()
+
+    def init(self):
+        self.local.init()
+        mine = self.local.network().shard_export()
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine)
+        self.local.network().shard_link(handles, None)
+        self.dist.barrier()
+        self.levels, self.words = self.local.levels, self.local.words
+
+    def scalars(self):
+        return self.local.scalars()
+
+    def continue_if(self):
+        """some live node of some shard is still below the threshold"""
+        import torch
+
+        t = torch.tensor([1 if self.local.continue_if() else 0], dtype=torch.int32, device=f"cuda:{self.local.network().device}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return bool(t.item())
