@@ -33,6 +33,23 @@ wtg_net* wtg_create(void);
 wtg_net* wtg_create_on(int device);
 void wtg_destroy(wtg_net* net);
 
+/* ---- node-sharded simulation (the reference has no counterpart: core/Network.java is one thread) ----
+ * ONE network spread over `world` engines (a power of two <= 8, one GPU each): shard `rank` owns the node ids
+ * [rank * N / world, (rank + 1) * N / world).  Every shard is configured and initialised with IDENTICAL calls (seed,
+ * builder, latency, protocol parameters) from its own thread (all shards in one process: the JNI case) or its own
+ * process (one rank per GPU); after the protocol's init each shard exports the 128-byte handle of its exchange region,
+ * all handles are handed to wtg_shard_link of every shard (same-process shards are mapped directly with peer access,
+ * other processes through CUDA IPC), and from then on every shard calls wtg_run_ms with the same arguments.  The data
+ * path between shards is device-to-device stores inside the tick kernels (no host call, no collective per tick).
+ * Node-indexed read-backs of a shard (counters, GSF rows / scalars) cover its own ids only: wtg_shard_range.
+ * Available for GSFSignature; the other protocols refuse to initialise on a sharded network. */
+wtg_net* wtg_shard_create(int rank, int world, int device /* -1: default */);
+int wtg_shard_export(wtg_net* net, unsigned char* handle128);
+int wtg_shard_link(wtg_net* net, const unsigned char* handles /* world x 128 bytes, rank order */);
+int wtg_shard_range(wtg_net* net, int* first_id, int* count);
+/* CUDA device the network lives on */
+int wtg_device(wtg_net* net);
+
 /* network.rd.setSeed(seed) before Protocol.init() — RunMultipleTimes.java:47, ProgressPerTime.java:71 */
 int wtg_set_seed(wtg_net* net, long long seed);
 

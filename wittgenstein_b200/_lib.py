@@ -26,7 +26,7 @@ class Api:
         "destroy": (None, [C.c_void_p]),
         "shard_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
         "shard_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
-        "shard_link": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]),
+        "shard_link": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
         "shard_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "device": (C.c_int, [C.c_void_p]),
         "set_seed": (C.c_int, [C.c_void_p, C.c_longlong]),

@@ -56,7 +56,7 @@ void WTG_API(destroy)(void* h) { delete static_cast<NetHandle*>(h); }
 
 // ---- node-sharded simulation: shard `rank` of `world` (a power of two <= 8) of ONE network.  Every shard is configured and
 //      initialised with identical calls (same seed, builder, latency, protocol parameters), from its own thread or process;
-//      after init() the shards exchange the 64-byte handles of their exchange regions and link; then every shard calls
+//      after init() the shards exchange the 128-byte handles of their exchange regions and link; then every shard calls
 //      run_ms with the same arguments.  Node-indexed read-backs of a shard cover its own ids [n0, n0 + nLoc). ----
 void* WTG_API(shard_create)(int rank, int world, int device) {
   try {
@@ -73,16 +73,16 @@ void* WTG_API(shard_create)(int rank, int world, int device) {
     return nullptr;
   }
 }
-int WTG_API(shard_export)(void* h, unsigned char* handle64) {
+int WTG_API(shard_export)(void* h, unsigned char* handle128) {
   return guard([&] {
-    ENG.exportExchange(handle64);
+    ENG.exportExchange(handle128);
     return 0;
   });
 }
-// handles: world x 64 bytes in rank order; devices: CUDA device of every shard (NULL: all shards are other processes)
-int WTG_API(shard_link)(void* h, const unsigned char* handles, const int* devices) {
+// handles: world x 128 bytes in rank order (shards of the same process are mapped directly, the others through CUDA IPC)
+int WTG_API(shard_link)(void* h, const unsigned char* handles) {
   return guard([&] {
-    ENG.linkExchange(handles, devices);
+    ENG.linkExchange(handles);
     return 0;
   });
 }

@@ -8,6 +8,7 @@
 // All sizes are read from the device control block, so a whole runMs window is enqueued without
 // a host round trip.  See DESIGN.md §4 for why this reproduces the reference's sequential order.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -363,6 +364,51 @@ __global__ void k_shuffle_serial(Dev d) {
   shuffleSerial(d);
 }
 
+// ---- node-sharded runs: the two exchanges of a pass (wtg_shard.cuh) --------------------------------------------
+// exchange 1, publication: every item of this shard (key, prefix of slots / draws) into every shard's copy of this shard's
+// list — peer stores over NVLink; a shard in error still publishes its header (which carries the error) so that the
+// others stop at once
+__global__ void __launch_bounds__(256) k_x1_publish(Dev d) {
+  const int n = d.ctl->error ? -1 : d.ctl->nItems;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) xPublishItem(d, i);
+  if (blockIdx.x == 0 && threadIdx.x == 0) xPublishHeader(d);
+}
+// signal the end of this shard's publication of `phase` to every shard, then wait for all of theirs (one block:
+// spinning must not occupy the machine — shards may share a GPU in the tests)
+__global__ void k_x_sync(Dev d, int phase) {
+  if (threadIdx.x == 0) xSignal(d, phase);  // stream order: the publishing kernel has completed
+  __syncthreads();
+  if (threadIdx.x < d.G && threadIdx.x != d.rank) xWaitOne(d, phase, threadIdx.x);
+}
+// exchange 1, evaluation: global totals, and for every local item that created something the creation indices / draws
+// of the other shards that come first
+__global__ void __launch_bounds__(256) k_x1_offsets(Dev d) {
+  if (d.ctl->error) return;
+  const int n = d.ctl->nItems;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xOffsets(d, i);
+}
+__global__ void k_x1_totals(Dev d) {
+  if (d.ctl->error) return;
+  xTotals(d);
+}
+// exchange 2, after the wait: pooled payloads that arrived in the staging area move into pool slabs (warp per envelope)
+__global__ void __launch_bounds__(256) k_x2_ingest(Dev d) {
+  if (d.ctl->error) return;
+  const int G = d.ctl->totalSlots;
+  CoopWarp c;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int g0 = gw * 32; g0 < G; g0 += nw * 32) {
+    int g = g0 + lane;
+    unsigned m = __ballot_sync(0xffffffffu, g < G && xNeedsIngest(d, g));
+    while (m) {
+      int src = __ffs(m) - 1;
+      m &= m - 1;
+      xIngest(d, c, g0 + src);
+    }
+  }
+}
+
 // ---- emit ------------------------------------------------------------------------------------
 __global__ void k_emit(Dev d) {
   if (d.ctl->error) return;
@@ -486,7 +532,9 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
           int4 x = src[0], y = src[1];
           dst[0] = x;
           dst[1] = y;
+          if (d.G > 1) d.bucketKey[(size_t)(t & (ring - 1)) * (size_t)d.bcap + pos] = orderKey((unsigned)tick, (unsigned)g);
         }
+        if (d.G > 1) d.newTarget[g] = -1;  // the array is indexed by the global creation index: clean for the next pass
       }
       __syncwarp();
     }
@@ -543,7 +591,7 @@ class CudaBackend : public Backend {
   size_t evUsed = 0;
   double profMs[NK] = {};
   long long profCnt[NK] = {};
-  const char* profNames[NK] = {"k_begin", "k_cond_scan", "k_dispatch_count", "k_scan_partial", "k_scan_tiles", "k_scan_final",
+  const char* profNames[NK] = {"k_begin", "k_cond_scan", "k_dispatch_count", "k_scan_partial", "k_exchange", "k_scan_final",
                                "k_dispatch_scatter", "k_node", "k_emit", "k_ms_count", "k_ms_scan", "k_ms_scatter", "k_free",
                                "k_end", "k_cond_score", "k_cond_select"};
 
@@ -570,6 +618,7 @@ class CudaBackend : public Backend {
     if (g && g[0] == '1') useGraph = false;
   }
   ~CudaBackend() override {
+    for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
     if (tickGraph) cudaGraphExecDestroy(tickGraph);
     if (st) cudaStreamDestroy(st);
   }
@@ -582,6 +631,47 @@ class CudaBackend : public Backend {
     return p;
   }
   void release(void* p) override { cudaFree(p); }
+  int deviceId() const override { return devId; }
+  // exchange region of a shard: plain cudaMalloc memory (CUDA IPC cannot export pool allocations)
+  void exportShared(void* p, unsigned char* handle) override {
+    bind();
+    std::memset(handle, 0, 128);
+    cudaIpcMemHandle_t ih;
+    CUDA_OK(cudaIpcGetMemHandle(&ih, p));
+    static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t");
+    std::memcpy(handle, &ih, 64);
+    long long pid = (long long)getpid();
+    std::memcpy(handle + 64, &pid, 8);
+    std::memcpy(handle + 72, &p, sizeof(p));
+    std::memcpy(handle + 80, &devId, 4);
+  }
+  std::vector<void*> ipcOpened;
+  void* importShared(const unsigned char* handle) override {
+    bind();
+    long long pid;
+    void* p;
+    int dev;
+    std::memcpy(&pid, handle + 64, 8);
+    std::memcpy(&p, handle + 72, sizeof(p));
+    std::memcpy(&dev, handle + 80, 4);
+    if (pid == (long long)getpid()) {  // a shard of this process: same address space
+      if (dev != devId) {
+        int can = 0;
+        CUDA_OK(cudaDeviceCanAccessPeer(&can, devId, dev));
+        if (!can) throw std::runtime_error("GPU " + std::to_string(devId) + " cannot access GPU " + std::to_string(dev) + " (peer access)");
+        cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(e);
+        cudaGetLastError();
+      }
+      return p;
+    }
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, handle, 64);
+    void* q = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&q, ih, cudaIpcMemLazyEnablePeerAccess));
+    ipcOpened.push_back(q);
+    return q;
+  }
   void upload(void* dst, const void* src, size_t bytes) override {
     bind();
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
@@ -737,6 +827,15 @@ class CudaBackend : public Backend {
     profBegin(5);
     k_scan_final<<<wide, SCAN_THREADS, 0, st>>>(d, 1);
     profEnd();
+    if (d.G > 1) {  // node-sharded: exchange 1 (items -> creation / draw offsets over all shards)
+      profBegin(4);
+      k_x1_publish<<<sms * 2, 256, 0, st>>>(d);
+      k_x_sync<<<1, 32, 0, st>>>(d, 0);
+      k_x1_totals<<<1, 1, 0, st>>>(d);
+      k_x1_offsets<<<sms * 2, 256, 0, st>>>(d);
+      profEnd();
+      launches += 4;
+    }
     profBegin(8);
     if (d.shufCap > 0) {
       k_shuffle_check<<<ARENA_STRIPES * 4, 256, 0, st>>>(d);
@@ -749,6 +848,13 @@ class CudaBackend : public Backend {
       launches += 1;
     }
     profEnd();
+    if (d.G > 1) {  // exchange 2: the envelopes were stored into their destination shards' arrays by k_emit
+      profBegin(4);
+      k_x_sync<<<1, 32, 0, st>>>(d, 1);
+      k_x2_ingest<<<sms * 4, 256, 0, st>>>(d);
+      profEnd();
+      launches += 2;
+    }
     profBegin(9);
     k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
     profEnd();

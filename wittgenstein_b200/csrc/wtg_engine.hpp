@@ -73,9 +73,16 @@ struct Backend {
   // zero-initialised memory that can be mapped by other processes; exportShared / importShared carry the 64-byte handle
   // (CUDA IPC); backends whose shards live in one address space never need them.
   virtual void* allocShared(size_t bytes) { return alloc(bytes); }
-  virtual void exportShared(void* p, unsigned char* handle64) { std::memset(handle64, 0, 64); std::memcpy(handle64, &p, sizeof(p)); }
-  virtual void* importShared(const unsigned char* handle64) { void* p; std::memcpy(&p, handle64, sizeof(p)); return p; }
-  virtual void enablePeer(int /*device*/) {}
+  // handle: SHARD_HANDLE_BYTES = 128 bytes: [0,64) interprocess handle, [64,72) process id, [72,80) address, [80,84) device
+  virtual void exportShared(void* p, unsigned char* handle) {
+    std::memset(handle, 0, 128);
+    std::memcpy(handle + 72, &p, sizeof(p));
+  }
+  virtual void* importShared(const unsigned char* handle) {
+    void* p;
+    std::memcpy(&p, handle + 72, sizeof(p));
+    return p;
+  }
   virtual int deviceId() const { return 0; }
   virtual void gsfInitNodes(const Dev& d) = 0;
   // scan `count` stream positions after state s0 for values that nextInt(bound<=maxBound) could reject
@@ -177,19 +184,18 @@ class Engine {
     std::vector<int> m1((size_t)d.newEvCap, -1);  // "nothing for this shard"
     be->upload(d.newTarget, m1.data(), m1.size() * sizeof(int));
   }
-  void exportExchange(unsigned char* handle64) {
+  void exportExchange(unsigned char* handle128) {
     requireInited();
     if (!sharded()) throw std::logic_error("not a node-sharded network");
-    be->exportShared(xRegion, handle64);
+    be->exportShared(xRegion, handle128);
   }
-  // handles: world x 64 bytes, in rank order (the own entry is ignored)
-  void linkExchange(const unsigned char* handles, const int* devices) {
+  // handles: world x 128 bytes, in rank order (the own entry is ignored)
+  void linkExchange(const unsigned char* handles) {
     requireInited();
     if (!sharded()) throw std::logic_error("not a node-sharded network");
     for (int q = 0; q < shardWorld; ++q) {
       if (q == shardRank) continue;
-      if (devices && devices[q] != be->deviceId()) be->enablePeer(devices[q]);
-      d.peer[q] = peerView(be->importShared(handles + (size_t)q * 64));
+      d.peer[q] = peerView(be->importShared(handles + (size_t)q * 128));
     }
     linked = true;
   }

@@ -50,16 +50,15 @@ class Network:
         return a.value, b.value
 
     def shard_export(self):
-        buf = (C.c_ubyte * 64)()
+        buf = (C.c_ubyte * 128)()
         self.api.check(self.api.shard_export(self.h, buf))
         return bytes(buf)
 
-    def shard_link(self, handles, devices=None):
-        """handles: the 64-byte exports of all shards in rank order; devices: their CUDA devices when they live in this
-        process (None: every other shard is another process, mapped through CUDA IPC)."""
-        blob = (C.c_ubyte * (64 * len(handles))).from_buffer_copy(b"".join(handles))
-        dev = None if devices is None else (C.c_int * len(devices))(*[int(x) for x in devices])
-        self.api.check(self.api.shard_link(self.h, blob, dev))
+    def shard_link(self, handles):
+        """handles: the 128-byte exports of all shards in rank order (shards of this process are mapped directly, shards of
+        other processes through CUDA IPC)."""
+        blob = (C.c_ubyte * (128 * len(handles))).from_buffer_copy(b"".join(handles))
+        self.api.check(self.api.shard_link(self.h, blob))
 
     @property
     def device(self):

@@ -4,7 +4,7 @@ Two ways to drive the same C ABI (include/wtg.h, `wtg_shard_*`):
 
 * `ShardedGSFSignature` — all shards in this process, one host thread per shard (the engines may sit on different GPUs
   of the box, or share one): what a single-process caller such as the reference's JVM would do through JNI.
-* `DistributedGSFSignature` — one shard per process (torchrun: one rank per GPU); the 64-byte CUDA-IPC handles of the
+* `DistributedGSFSignature` — one shard per process (torchrun: one rank per GPU); the 128-byte handles (CUDA IPC) of the
   exchange regions travel through `torch.distributed`, after that the data path is peer stores between the GPUs'
   kernels — no collective call per tick.
 
@@ -105,8 +105,7 @@ class ShardedGSFSignature:
     def init(self):
         self._each(lambda s: s.init())
         handles = [s.network().shard_export() for s in self.shards]
-        devs = [s.network().device for s in self.shards]
-        self._each(lambda s: s.network().shard_link(handles, devs))
+        self._each(lambda s: s.network().shard_link(handles))
         self.levels = self.shards[0].levels
         self.words = self.shards[0].words
 
@@ -152,7 +151,7 @@ class DistributedGSFSignature:
         mine = self.local.network().shard_export()
         handles = [None] * self.world
         self.dist.all_gather_object(handles, mine)
-        self.local.network().shard_link(handles, None)
+        self.local.network().shard_link(handles)
         self.dist.barrier()
         self.levels, self.words = self.local.levels, self.local.words
 
