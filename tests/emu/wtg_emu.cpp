@@ -143,7 +143,7 @@ class HostBackend : public Backend {
         continue;
       }
       d.buckets[(size_t)slot * d.bcap + pos] = d.newEv[g];
-      if (d.G > 1) d.bucketKey[(size_t)slot * d.bcap + pos] = orderKey((unsigned)d.ctl->tick, (unsigned)g);
+      if (d.G > 1) d.bucketKey[(size_t)slot * d.bcap + pos] = orderKey((unsigned)d.ctl->xseq, (unsigned)g);
       d.bucketCount[slot] = pos + 1;
     }
     {
@@ -183,3 +183,35 @@ long long backendLaunches(Backend* b) { return static_cast<HostBackend*>(b)->lau
 
 #define WTG_API(name) wtgemu_##name
 #include "../../wittgenstein_b200/csrc/wtg_capi.inl"
+
+// debugging aid of the host build only: the entries of the bucket of millisecond t (kind, to, from, meta per entry)
+extern "C" int wtgemu_debug_bucket(void* h, int t, unsigned* out, int cap) {
+  wtg::Engine& e = static_cast<NetHandle*>(h)->eng;
+  int slot = t & (e.d.ring - 1);
+  int n = e.d.bucketCount[slot];
+  for (int i = 0; i < n && i < cap; ++i) {
+    const wtg::Ev& ev = e.d.buckets[(size_t)slot * e.d.bcap + i];
+    out[4 * i] = ev.kind;
+    out[4 * i + 1] = ev.to;
+    out[4 * i + 2] = ev.from;
+    out[4 * i + 3] = ev.meta;
+  }
+  return n;
+}
+extern "C" int wtgemu_debug_recs(void* h, unsigned from, int* out, int cap) {  // records sent by `from`: idx, n, cur, then (dest, arrival) pairs
+  wtg::Engine& e = static_cast<NetHandle*>(h)->eng;
+  int k = 0;
+  for (int r = 0; r < e.d.recCap && k + 40 < cap; ++r) {
+    const wtg::MultiRec& rc = e.d.rec[r];
+    if (rc.n == 0 || rc.from != from) continue;
+    out[k++] = r;
+    out[k++] = (int)rc.n;
+    out[k++] = (int)rc.cur;
+    for (unsigned i = 0; i < rc.n; ++i) {
+      out[k++] = (int)e.d.recDest[rc.off + i];
+      out[k++] = e.d.recArrival[rc.off + i];
+    }
+    out[k++] = -1;
+  }
+  return k;
+}

@@ -34,7 +34,7 @@ def run_pair(n, world, until, step, seed=None, nb=AWS_NB, nl=AWS_NL, accel=10, d
 
 
 @pytest.mark.parametrize("n,world,until,step,seed", [(64, 2, 300, 1, None), (256, 2, 600, 10, None), (256, 4, 600, 7, 3),
-                                                     (512, 8, 400, 10, 1), (1024, 4, 700, 10, None)])
+                                                     (512, 8, 400, 10, 1), (1024, 4, 700, 10, None), (1024, 2, 200, 1, 4), (4096, 2, 150, 10, None)])
 def test_gsf_sharded_vs_oracle(n, world, until, step, seed):
     run_pair(n, world, until, step, seed, full_every=3)
 

@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) {
           int4 x = src[0], y = src[1];
           dst[0] = x;
           dst[1] = y;
-          if (d.G > 1) d.bucketKey[(size_t)(t & (ring - 1)) * (size_t)d.bcap + pos] = orderKey((unsigned)tick, (unsigned)g);
+          if (d.G > 1) d.bucketKey[(size_t)(t & (ring - 1)) * (size_t)d.bcap + pos] = orderKey((unsigned)d.ctl->xseq, (unsigned)g);
         }
         if (d.G > 1) d.newTarget[g] = -1;  // the array is indexed by the global creation index: clean for the next pass
       }

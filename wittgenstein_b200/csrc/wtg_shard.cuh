@@ -21,7 +21,9 @@
 
 namespace wtg {
 
-WTG_HD u64 orderKey(unsigned tick, unsigned g) { return ((u64)tick << 36) | ((u64)g << 8); }
+// `pass` = Ctl.xseq of the pipeline pass that created the envelope (a millisecond can have two passes: the reference's extra
+// time++ at the end of a runMs window creates tasks too)
+WTG_HD u64 orderKey(unsigned pass, unsigned g) { return ((u64)pass << 36) | ((u64)g << 8); }
 WTG_HD int ownerOf(const Dev& d, int n) { return d.G > 1 ? (n >> d.ownShift) : 0; }
 
 WTG_HD void xFence() {

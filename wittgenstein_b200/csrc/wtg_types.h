@@ -145,7 +145,7 @@ struct FarEv {  // an envelope whose arrival lies beyond the time ring's horizon
 
 // ---- node-sharded simulation: what the shards exchange every pipeline pass ----
 // Shard r owns the ids [r * nLoc, (r + 1) * nLoc).  Every bucket entry carries an ordering key
-//   (creation tick << 36) | (creation index << 8) | (255 - j)       j = position inside a multi-destination record
+//   (creating pass << 36) | (creation index << 8) | (255 - j)       j = position inside a multi-destination record
 // so that "processed earlier" (LIFO by insertion, Network.java:145-147) == larger key on every shard.
 struct XItem {  // one scan item of a shard, in its local processing order
   unsigned long long key;
