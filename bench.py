@@ -91,15 +91,48 @@ def host_info():
     return {"cpu_model": model, "cores_total": os.cpu_count()}
 
 
+SHARD = None  # (dist, rank, world, local) when the ranks of this job are node-id shards of ONE simulation
+
+
 def make_gsf(n, seed):
     from wittgenstein_b200 import GSFSignature, GSFSignatureParameters
 
-    p = GSFSignature(GSFSignatureParameters(**gsf_params(n)))
+    if SHARD is not None:
+        from wittgenstein_b200.sharded import DistributedGSFSignature
+
+        dist, rank, world, local = SHARD
+        p = DistributedGSFSignature(GSFSignatureParameters(**gsf_params(n)), dist, rank, world, local)
+    else:
+        p = GSFSignature(GSFSignatureParameters(**gsf_params(n)))
     p.network().set_seed(seed)
     t0 = time.time()
     p.init()
     p.network().msgs_size()  # sync
     return p, time.time() - t0
+
+
+def state_digests(p, lo=None, hi=None):
+    """blake2b digests of a protocol object's state (rows [lo, hi) of an oracle / unsharded object; all rows of a shard)"""
+    import hashlib
+
+    import numpy as np
+
+    def dg(a):
+        a = np.ascontiguousarray(a if lo is None else a[lo:hi])
+        return hashlib.blake2b(a.tobytes(), digest_size=16).hexdigest()
+
+    net = p if hasattr(p, "counters") else p.network()
+    cnt = net.counters()
+    out = {"counters": dg(cnt.T)}
+    for k, v in p.scalars().items():
+        out["scalar_" + k] = dg(v)
+    out["verified"] = dg(p.verified())
+    rows = p.level_rows if hasattr(p, "level_rows") else p.rows
+    out["rows1"] = dg(rows(1))
+    out["rows2"] = dg(rows(2))
+    for k, v in p.level_scalars().items():
+        out["level_" + k] = dg(v)
+    return out
 
 
 def event_counts(st0, st1):
@@ -123,44 +156,77 @@ def algorithmic_bytes(ev):
 def cpu_baseline_and_parity(n, args):
     """Oracle over the first windows of the run (bounded CPU time), then the GPU over exactly the same windows with
     the same runMs slicing, then a bit-exact comparison of the two states (time, rd state, msgs.size(), the 5 node
-    counters, per-node scalars, verifiedSignatures and the per-level rows and scalars)."""
+    counters, per-node scalars, verifiedSignatures and the per-level rows and scalars).  Node-sharded job: rank 0 runs the
+    oracle, every rank runs its shard over the window and reports digests of its rows; rank 0 compares them with the
+    digests of the oracle's corresponding rows."""
     from tests import parity as par
-    from tests.oracle_lib import OracleGSF
 
-    n_cpu = feasible_cpu_nodes(min(args.cpu_nodes, n), args.cpu_max_nodes)
-    g = gsf_params(n_cpu)
-    o = OracleGSF(n_cpu, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
-    t0 = time.time()
-    o.init_fast(min(64, os.cpu_count() or 1))  # init is threaded (and untimed); runMs below is single-threaded
-    init_s = time.time() - t0
-    sim, wall, step = 0, 0.0, 10
-    st0 = o.stats()
-    while wall < args.cpu_budget_s and sim < 4000:
-        wall += o.run_timed(step, 1)
-        sim += step
-    st1 = o.stats()
-    msgs = (st1["deliveries"] - st0["deliveries"]) + (st1["tasks"] - st0["tasks"]) + (st1["cond_runs"] - st0["cond_runs"])
-    cpu = {"value": sim / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
-           "sample": f"oracle (C++ restatement, 1 thread), GSFSignature {n_cpu} nodes, first {sim} simulated ms in {wall:.1f} s "
-                     f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim, "host": host_info()}
+    rank = SHARD[1] if SHARD is not None else 0
+    o, cpu, sim, step = None, None, 0, 10
+    if rank == 0:
+        from tests.oracle_lib import OracleGSF
+
+        n_cpu = feasible_cpu_nodes(min(args.cpu_nodes, n), args.cpu_max_nodes)
+        g = gsf_params(n_cpu)
+        o = OracleGSF(n_cpu, g["threshold"], 4, 50, 20, 10, g["nodes_down"], AWS_NB, AWS_NL)
+        t0 = time.time()
+        o.init_fast(min(64, os.cpu_count() or 1))  # init is threaded (and untimed); runMs below is single-threaded
+        init_s = time.time() - t0
+        wall = 0.0
+        st0 = o.stats()
+        while wall < args.cpu_budget_s and sim < 4000:
+            wall += o.run_timed(step, 1)
+            sim += step
+        st1 = o.stats()
+        msgs = (st1["deliveries"] - st0["deliveries"]) + (st1["tasks"] - st0["tasks"]) + (st1["cond_runs"] - st0["cond_runs"])
+        cpu = {"value": sim / wall, "unit": "simulated-ms/s", "cores": 1, "kind": "port",
+               "sample": f"oracle (C++ restatement, 1 thread), GSFSignature {n_cpu} nodes, first {sim} simulated ms in {wall:.1f} s "
+                         f"(init {init_s:.1f} s excluded)", "msgs_per_s": msgs / wall, "nodes": n_cpu, "sim_ms": sim, "host": host_info()}
+        if n_cpu != n:
+            cpu["note"] = f"host memory too small for the oracle at {n} nodes: ran {n_cpu}; no parity check at the metric size"
+            sim = 0
+    if SHARD is not None:
+        box = [sim]
+        SHARD[0].broadcast_object_list(box, src=0)
+        sim = box[0]
+    if sim == 0:
+        return cpu, None
+    p, _ = make_gsf(n, 0)
+    net = p.network()
+    net.timer_start()
+    for _ in range(sim // step):
+        net.run_ms(step)
+    pm = net.timer_stop_ms()
     parity = None
-    if n_cpu == n:
-        p, _ = make_gsf(n, 0)
-        net = p.network()
-        net.timer_start()
-        for _ in range(sim // step):
-            net.run_ms(step)
-        pm = net.timer_stop_ms()
+    if SHARD is None:
         cpu["gpu_same_window"] = {"value": sim / (pm / 1000.0), "unit": "simulated-ms/s",
                                   "window": f"[0,{sim}] ms, runMs({step}) slicing, device-timed"}
         bad = par.compare_gsf(p, o, f"t={sim}", full=True)
+    else:
+        dist, _, world, _ = SHARD
+        mine = {"range": net.shard_range(), "time": net.time, "rng": net.rng_state(), "msgs": net.msgs_size(), "ms": pm,
+                "digests": state_digests(p.local)}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        bad = []
+        if rank == 0:
+            cpu["gpu_same_window"] = {"value": sim / (max(r["ms"] for r in allr) / 1000.0), "unit": "simulated-ms/s",
+                                      "window": f"[0,{sim}] ms, runMs({step}) slicing, device-timed, max over shards"}
+            if sum(r["msgs"] for r in allr) != o.msgs_live():
+                bad.append(f"msgs.size() {sum(r['msgs'] for r in allr)} vs {o.msgs_live()}")
+            for q, r in enumerate(allr):
+                if r["time"] != o.time or r["rng"] != o.rng_state():
+                    bad.append(f"shard {q}: time / rd state differ")
+                n0, nl = r["range"]
+                want = state_digests(o, n0, n0 + nl)
+                bad += [f"shard {q}: {k} differs" for k in want if want[k] != r["digests"][k]]
+    if rank == 0:
         parity = {"nodes": n, "t": sim, "slicing": f"runMs({step})", "status": "bit-exact" if not bad else "MISMATCH",
-                  "compared": "time, rd state, msgs.size(), 5 node counters, node scalars, verifiedSignatures, level rows + scalars"}
+                  "compared": "time, rd state, msgs.size(), 5 node counters, node scalars, verifiedSignatures, level rows + scalars"
+                              + (" (per shard, as digests)" if SHARD is not None else "")}
         if bad:
             parity["mismatches"] = bad[:8]
-        del p, net
-    else:
-        cpu["note"] = f"host memory too small for the oracle at {n} nodes: ran {n_cpu}; no parity check at the metric size"
+    del p, net
     return cpu, parity
 
 
@@ -383,6 +449,10 @@ def main():
     ap.add_argument("--cpu-nodes", type=int, default=131072)
     ap.add_argument("--cpu-max-nodes", type=int, default=131072)
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "weak", "replicas"],
+                    help="N > 1: sharded = ONE simulation of --nodes nodes, node ids sharded over the GPUs (default; strong scaling); "
+                         "weak = one sharded simulation of --weak-nodes-per-gpu x N nodes (BASELINE config #5); replicas = N independent seeds")
+    ap.add_argument("--weak-nodes-per-gpu", type=int, default=32768)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
@@ -412,8 +482,24 @@ def main():
         run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks)
         return
 
+    global SHARD
     n, K, W = args.nodes, args.steps, args.warmup
-    seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)
+    mode = args.mode if args.mode != "auto" else ("sharded" if world > 1 else "replicas")
+    if world == 1:
+        mode = "single" if args.mode != "weak" else "weak"
+    sharded = world > 1 and mode in ("sharded", "weak")
+    if mode == "weak":
+        n = args.weak_nodes_per_gpu * world
+    if sharded:
+        SHARD = (dist, rank, world, local)
+        seed = 0  # one simulation: every shard is configured identically
+        jobs = 1
+    else:
+        seed = rank  # replicas: rank r simulates seed r (RunMultipleTimes.java:44-48 runs seeds one after the other)
+        jobs = world
+
+    def total(x):  # whole-job count of something every rank holds a share of
+        return sum_over_ranks(x) if world > 1 else x
 
     # ---- warm-up: the whole run on a throw-away network of the same configuration (module load, graph
     #      instantiation, clocks) — at least W steps; it also tells how long the run is: the timed passes below each
@@ -452,6 +538,8 @@ def main():
     card_end = p.scalars()["card"]
     done = not p.continue_if()
     dev_ms = max_over_ranks(dev_ms)
+    ev_all = {k: int(total(v)) for k, v in ev.items()} if sharded else ev
+    launches_all = int(total(launches)) if sharded else launches
     del p, net
 
     # ---- pass 2: end to end through the public API with host read-backs every step ----
@@ -506,12 +594,15 @@ def main():
     parity = None
     if rank == 0 and not args.no_cpu:
         cpu, parity = cpu_baseline_and_parity(n, args)
-        if parity is not None and parity.get("status") != "bit-exact":
-            print(json.dumps({"error": "GPU and oracle states differ", "parity": parity}))
-            sys.exit(3)
+    elif sharded and not args.no_cpu:
+        cpu_baseline_and_parity(n, args)  # the other shards run their part of the same window and report their digests
+    if rank == 0 and parity is not None and parity.get("status") != "bit-exact":
+        print(json.dumps({"error": "GPU and oracle states differ", "parity": parity}))
+        sys.stdout.flush()
+        os._exit(3)
 
-    value = sum_over_ranks(K * S) / (dev_ms / 1000.0)
-    e2e = sum_over_ranks(K * S) / e2e_s
+    value = jobs * K * S / (dev_ms / 1000.0)
+    e2e = jobs * K * S / e2e_s
     msgs = ev["deliveries"] + ev["tasks"] + ev["cond_runs"]
 
     peaks = {}
@@ -536,19 +627,25 @@ def main():
                     "kernel_gbs": {k: round(ab[k] / (v[0] / 1000.0) / 1e9, 1) for k, v in prof.items() if k in ab and v[0] > 0}}
 
     line = {"metric": metric_name(n), "value": value, "unit": "simulated-ms/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "strong" if (sharded and mode == "sharded") else "weak", "vs_baseline": None,
             "dtype": "u64 bitmaps / int32", "data": "synthetic",
             "config": {"workload": workload_name(n),
                        "window": f"step = runMs({S}) of one run; timed window [0,{K*S}] ms = the whole run of a fresh network (every live "
                                  f"node reaches the threshold by {t_done} ms); warm-up = the same run on a throw-away network ({warm_steps} x runMs(50))",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas (no data-path collective)",
+                       "parallelism": "1 GPU" if world == 1 else (
+                           f"node-sharded: ONE simulation, node ids split over {world} GPUs ({n // world} nodes each); per pass two "
+                           "device-side exchanges through peer stores over NVLink (items -> global creation / draw offsets; envelopes "
+                           "and pooled payloads into the destination shard), no host call or collective per tick"
+                           if sharded else f"{world} independent seeded replicas (no data-path collective)"),
+                       "mode": mode,
                        "l2": "per-step working set (node rows + queues + ring) exceeds L2 at this size",
                        "all_nodes_done_at_end": bool(done), "host": host_info()},
             "msgs_per_s": sum_over_ranks(msgs) / (dev_ms / 1000.0),
             "e2e": {"value": e2e, "unit": "simulated-ms/s", "h2d_bytes_per_step": ctl_bytes, "d2h_bytes_per_step": int(d2h + ctl_bytes * 3)},
-            "e2e_same_window_as_reference": {"value": sum_over_ranks(K * R) / same_s, "unit": "simulated-ms/s",
+            "e2e_same_window_as_reference": {"value": jobs * K * R / same_s, "unit": "simulated-ms/s",
                                              "window": f"[0,{K*R}] ms, {K} x runMs({R}) with the per-step read-backs, wall clock"},
-            "gpu_launches": int(launches), "init_s": init_s, "events": ev, "clocks": sampler.summary()}
+            "gpu_launches": int(launches_all), "init_s": init_s, "events": ev_all, "clocks": sampler.summary()}
     if roof:
         line["roofline"] = roof
     if cpu is not None:

@@ -19,7 +19,7 @@ def devices_for(world):
     return [r % n for r in range(world)]
 
 
-def run_pair(n, world, until, step, seed=None, full_every=1, devices=None):
+def run_pair(n, world, until, step, seed=None, full_every=1, devices=None, to_completion=False):
     from wittgenstein_b200 import GSFSignatureParameters
     from wittgenstein_b200.sharded import ShardedGSFSignature
 
@@ -32,12 +32,14 @@ def run_pair(n, world, until, step, seed=None, full_every=1, devices=None):
     o.init()
     assert not parity.compare_init(p, o)
     i = 0
-    while o.time < until:
+    while o.time < until and (not to_completion or o.continue_if()):
         assert p.network().run_ms(step) == o.run_ms(step)
         i += 1
         bad = parity.compare_gsf(p, o, f"t={o.time}", full=(i % full_every == 0))
         assert not bad, bad
     done = not p.continue_if()
+    bad = parity.compare_gsf(p, o, "end", full=True)
+    assert not bad, bad
     p.close()
     return done
 
@@ -50,7 +52,7 @@ def test_gsf_sharded_small(n, world, until, step, seed):
 @pytest.mark.parametrize("world", [2, 4])
 def test_gsf_4096_sharded_to_completion(world):
     """config #2 (GSFSignature 4 096 nodes) on 2 and 4 shards, to completion, every 10 ms against the oracle"""
-    assert run_pair(4096, world, 1300, 10, None, full_every=10)
+    assert run_pair(4096, world, 4000, 10, None, full_every=10, to_completion=True)
 
 
 def test_gsf_sharded_on_one_gpu_equals_unsharded_engine():
