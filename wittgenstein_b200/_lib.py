@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwtg_b200.so")
+LIB_PATH = os.environ.get("WTG_LIB") or os.path.join(_HERE, "libwtg_b200.so")  # WTG_LIB: a differently built copy of the same library (kernel experiments)
 
 
 class WtgError(RuntimeError):

@@ -242,7 +242,8 @@ __device__ __forceinline__ void b_node_tasks(const Dev& d, const int VB, const i
       nodeProcess(d, c, n, split ? 2 : 0);
   }
 }
-__global__ void __launch_bounds__(256) k_node_tasks(Dev d) { b_node_tasks(d, blockIdx.x, gridDim.x); }
+// three blocks per SM = 80 registers: measured best (profiles/README.md, round 2: 64 / 80 / 128 registers -> 258 / 251 / 382 ms)
+__global__ void __launch_bounds__(256, 3) k_node_tasks(Dev d) { b_node_tasks(d, blockIdx.x, gridDim.x); }
 // ---- pair scans ---------------------------------------------------------------------------
 __device__ __forceinline__ Pair pairAdd(Pair x, Pair y) {
   Pair r;
