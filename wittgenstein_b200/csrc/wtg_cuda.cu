@@ -30,6 +30,12 @@ namespace wtg {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int NODE_BLOCK = WARPS_PER_BLOCK * 32;
+#if defined(WTG_TMA_SNAPSHOT)
+constexpr int NODE_TMA_SMEM = 8 * TMA_TILES * TMA_TILE_BYTES;
+#else
+constexpr int NODE_TMA_SMEM = 0;
+#endif
+//  // dynamic shared memory of k_node_tasks (GSF): bulk-copy tiles
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -224,6 +230,17 @@ __global__ void __launch_bounds__(256) k_node_msgs(Dev d) { b_node_msgs(d, block
 // pass 2: one warp per node that has tasks (updateVerifiedSignatures / doCycle / ...), or, for protocols whose
 // events do not commute (Handel), all of the node's events in reference order; blocks assigned to list stripes.
 __device__ __forceinline__ void b_node_tasks(const Dev& d, const int VB, const int VG) {
+  // bulk-copy tiles and their mbarriers, one set per warp (wtg_tma.cuh): payload snapshots of doCycle
+  CoopWarp c;
+#if defined(WTG_TMA_SNAPSHOT)
+  extern __shared__ __align__(128) unsigned long long tmaTiles[];  // [8 warps][TMA_TILES * TMA_TILE_BYTES / 8] (dynamic: NODE_TMA_SMEM)
+  __shared__ __align__(8) unsigned long long tmaBars[8][TMA_TILES];
+  if (d.proto == PROTO_GSF) {  // the mbarriers are initialised by the first snapshot of the warp (most launches have none)
+    const int warp = threadIdx.x >> 5;
+    c.tma.buf = tmaTiles + (size_t)warp * (TMA_TILES * TMA_TILE_BYTES / 8);
+    c.tma.bar = &tmaBars[warp][0];
+  }
+#endif
   if (d.ctl->error) return;
   const bool split = d.proto == PROTO_GSF || d.proto == PROTO_PINGPONG;
   const int stripe = VB & (ARENA_STRIPES - 1);
@@ -232,7 +249,6 @@ __device__ __forceinline__ void b_node_tasks(const Dev& d, const int VB, const i
   const int nsub = (VG >> 6) * 8;
   const int* list = d.taskList + (size_t)stripe * d.listStripeCap;
   const u64* words = d.taskWord + (size_t)stripe * d.listStripeCap;
-  CoopWarp c;
   for (int t = sub; t < cnt; t += nsub) {
     const int n = list[t];
     const u64 w = words[t];
@@ -241,6 +257,9 @@ __device__ __forceinline__ void b_node_tasks(const Dev& d, const int VB, const i
     else
       nodeProcess(d, c, n, split ? 2 : 0);
   }
+#if defined(WTG_TMA_SNAPSHOT)
+  if (c.tma.ready && (threadIdx.x & 31) == 0) bulkWaitAll();
+#endif  // this lane's bulk stores are complete before the kernel ends
 }
 // three blocks per SM = 80 registers: measured best (profiles/README.md, round 2: 64 / 80 / 128 registers -> 258 / 251 / 382 ms)
 __global__ void __launch_bounds__(256, 3) k_node_tasks(Dev d) { b_node_tasks(d, blockIdx.x, gridDim.x); }
@@ -977,7 +996,7 @@ class CudaBackend : public Backend {
     profEnd();
       profBegin(7);
     k_node_msgs<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
-    k_node_tasks<<<ARENA_STRIPES * 19, 256, 0, st>>>(d);
+    k_node_tasks<<<ARENA_STRIPES * 19, 256, NODE_TMA_SMEM, st>>>(d);
     profEnd();
       launches += 6;
     }
@@ -1082,6 +1101,7 @@ class CudaBackend : public Backend {
     size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
     CUDA_OK(cudaFuncSetAttribute(k_ms_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
     CUDA_OK(cudaFuncSetAttribute(k_ms_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
+    if (NODE_TMA_SMEM > 0) CUDA_OK(cudaFuncSetAttribute(k_node_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_TMA_SMEM));
   }
   void tick(const Dev& d, int mode) override {
     bind();
