@@ -612,6 +612,15 @@ static int netCtl(Network& net, int op, int arg) {
   return 0;
   WO_CATCH(-1)
 }
+// network.setNetworkLatency(distribProp, distribVal) — MeasuredNetworkLatency (Network.java:665-667), after construction, before init()
+static int setMeasured(Network& net, const int* props, const int* vals, int n) {
+  WO_TRY
+  net.setNetworkLatency(NetworkLatency::measured(std::vector<int>(props, props + n), std::vector<int>(vals, vals + n)));
+  return 0;
+  WO_CATCH(-1)
+}
+int wo_pp_set_latency_measured(void* h, const int* p, const int* v, int n) { return setMeasured(static_cast<PingPong*>(h)->network, p, v, n); }
+int wo_gsf_set_latency_measured(void* h, const int* p, const int* v, int n) { return setMeasured(static_cast<GSFSignature*>(h)->network, p, v, n); }
 int wo_pp_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<PingPong*>(h)->network, op, arg); }
 int wo_gsf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<GSFSignature*>(h)->network, op, arg); }
 int wo_sf_net_ctl(void* h, int op, int arg) { return netCtl(static_cast<SanFerminSignature*>(h)->network, op, arg); }

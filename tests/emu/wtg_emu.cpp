@@ -52,6 +52,8 @@ class HostBackend : public Backend {
       // host-injected sends: control block and descriptors are already in place (Engine::inject)
     } else if (d.ffwd && mode == 1)
       tickBeginFfwd(d, c);
+    else if (d.farCap > 0 && !d.ffwd)
+      tickBeginFar(d, c, mode);
     else
       tickBegin(d, mode);
     if (bail(d, 0)) return;

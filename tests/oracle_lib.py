@@ -83,6 +83,14 @@ class _NetCtl:
 
     _ctl = None
 
+    def set_network_latency_measured(self, proportions, values):
+        """network.setNetworkLatency(int[] distribProp, int[] distribVal) (Network.java:665-667), before init()"""
+        p = np.asarray(proportions, np.int32)
+        v = np.asarray(values, np.int32)
+        fn = getattr(self.lib, self._ctl.replace("net_ctl", "set_latency_measured"))
+        if fn(self.h, _p(p, C.c_int), _p(v, C.c_int), len(p)) != 0:
+            raise RuntimeError(self.lib.wo_last_error().decode())
+
     def _c(self, op, arg=0):
         if getattr(self.lib, self._ctl)(self.h, op, int(arg)) != 0:
             raise RuntimeError(self.lib.wo_last_error().decode())

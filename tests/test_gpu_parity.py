@@ -623,3 +623,34 @@ def test_pingpong_delayed_multi_sends_from_the_host():
         assert p.network().msgs_size() == o.msgs_size()
     with pytest.raises(Exception):
         p.network().send(1, 0, [1, 2], send_time=p.network().time)  # sendTime <= time (Network.java:470-473)
+
+
+@pytest.mark.parametrize("latency,measured", [("EthScanNetworkLatency", False), (None, True), ("NetworkFixedLatency(8000)", False),
+                                              ("NetworkUniformLatency(8000)", False)])
+def test_pingpong_far_latencies(latency, measured):
+    """NetworkLatency.java:277-383 (Measured, EthScan with its doubled extraLatency) and Fixed / Uniform(8000) on the device:
+    arrivals >= 2 048 ms ahead go through the far-future calendar (time ring fixed at 4 096 buckets)."""
+    from tests.test_far_latency_emu import check_pingpong, pingpong_pair
+
+    p, o = pingpong_pair(latency, measured, None)
+    assert p.network().stats()["ring"] == 4096
+    check_pingpong(p, o, 30, 1000)
+    assert o.pongs()[0] > 0
+
+
+def test_gsf_256_ethscan_and_measured():
+    """GSFSignature (conditional tasks: ticks every millisecond) over EthScan / Measured latencies: far-future calendar under GSF"""
+    from tests.test_far_latency_emu import MEASURED
+
+    for latency, measured in (("EthScanNetworkLatency", False), (None, True)):
+        args = (256, 204, 4, 50, 20, 10, 25, "RANDOM_SPEED=CONSTANT_TOR=0.00", latency)
+        p = GSFSignature(GSFSignatureParameters(*args))
+        o = OracleGSF(*args)
+        if measured:
+            p.network().set_network_latency_measured(*MEASURED)
+            o.set_network_latency_measured(*MEASURED)
+        p.init(); o.init()
+        for i in range(80):
+            assert p.network().run_ms(100) == o.run_ms(100)
+            bad = compare_gsf(p, o, f"t={o.time}", full=(i % 8 == 0))
+            assert not bad, bad

@@ -45,6 +45,9 @@ __device__ __forceinline__ void b_begin(const Dev& d, int mode, const int VB, co
   if (d.ffwd && mode == 1) {
     CoopWarp c;
     tickBeginFfwd(d, c);
+  } else if (d.farCap > 0 && !d.ffwd) {
+    CoopWarp c;
+    tickBeginFar(d, c, mode);
   } else if (threadIdx.x == 0) {
     tickBegin(d, mode);
   }

@@ -47,6 +47,7 @@ struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
   long long casperVotes = 0;   // CasperIMD: attestations one attester may publish in a run (default 6)
   long long casperBlocks = 0;  // CasperIMD: blocks of a run (default from casperVotes)
+  long long farCap = 0;        // far-future calendar entries (latency models with multi-second arrivals)
   long long stageWords = 0;    // node-sharded GSF: staging capacity per (sending shard, pass parity) in 64-bit words
 };
 
@@ -255,6 +256,15 @@ class Engine {
     d.msgDiscardTime = msgDiscardTime;
     int ring = 2048;
     int need = hm.latMax + 64 + ringExtra;
+    if (!farEnabled && need > 4096) {
+      // latency models with multi-second arrivals (EthScan 12 000 ms, Fixed / Uniform(8000)): the ring stays at 4 096
+      // buckets (the multisplit keeps a histogram of the ring in shared memory) and arrivals 2 048 ms or more ahead go
+      // through the far-future calendar; the protocol still ticks every millisecond
+      if (sharded()) throw std::logic_error("this latency model needs the far-future calendar, which node-sharded networks do not have yet");
+      farEnabled = true;
+      farTicking = true;
+      need = std::min(need, 2048 - 64 + ringExtra);
+    }
     if (farEnabled) need *= 2;  // envelopes are "near" up to ring/2 ms ahead
     while (ring < need) ring <<= 1;
     if (tun.ring) {
@@ -357,8 +367,8 @@ class Engine {
       d.recArrival = dalloc<int>(d.recDestCap);
     }
     if (farEnabled) {
-      d.ffwd = 1;
-      d.farCap = 2 * N + 1024;
+      d.ffwd = farTicking ? 0 : 1;
+      d.farCap = tun.farCap ? (int)tun.farCap : (farTicking ? (int)std::min<long long>(0x3fffffffLL, 64LL * N + 4096) : 2 * N + 1024);
       d.far = dalloc<FarEv>(d.farCap);
       d.farSel = dalloc<int>(d.farCap);
     }
@@ -367,7 +377,8 @@ class Engine {
   int destScratchOverride = 0;
   bool forceShufSerial = false;  // tunable force_shuffle_serial (test hook)
   int ringExtra = 0;        // longest handler-chosen delay of a near envelope (e.g. blockConstructionTime)
-  bool farEnabled = false;  // far-future calendar + fast-forward (protocols without conditional tasks)
+  bool farEnabled = false;  // far-future calendar (+ fast-forward for protocols without conditional tasks)
+  bool farTicking = false;  // calendar without fast-forward: the latency model, not the protocol, asked for it
 
   Ctl readCtl() {
     Ctl c;
@@ -443,7 +454,7 @@ class Engine {
         c.recDestTop = (int)da.size();
       }
       int tgt = da[0].arrival;
-      if (tgt >= d.ring) throw std::runtime_error("latency exceeds the time ring");
+      if (tgt >= (farEnabled ? d.ring / 2 : d.ring)) throw std::runtime_error("latency exceeds the time ring");
       be->upload(d.buckets + (size_t)(tgt & ringMask) * d.bcap, &ev, sizeof(ev));
       int one = 1;
       be->upload(d.bucketCount + (tgt & ringMask), &one, sizeof(int));

@@ -2077,6 +2077,15 @@ WTG_HD void tickBegin(const Dev& d, int mode) {
     for (int q = 0; q < MAX_SHARDS; ++q) c.stageTop[q] = 0;
   }
 }
+// tickBegin for protocols that keep the far-future calendar but tick every millisecond (conditional tasks): the calendar
+// entries that come within the horizon of this tick move to the head of their buckets first (one coop)
+template <class C>
+WTG_HD void tickBeginFar(const Dev& d, C& c, int mode) {
+  if (mode != 2) farMigrate(d, c, mode == 1 ? d.ctl->time + 1 : d.ctl->time);
+  c.sync();
+  if (c.lane() == 0) tickBegin(d, mode);
+  c.sync();
+}
 WTG_HD void tickEnd(const Dev& d, int mode) {
   Ctl& c = *d.ctl;
   c.rng = lcgAdvance(d.jumpA, d.jumpC, c.rng, (u64)c.totalDraws);
