@@ -752,6 +752,7 @@ class CudaBackend : public Backend {
   int devId = 0;  // every entry point binds it: callers may drive different networks from different host threads
   void bind() const { cudaSetDevice(devId); }
   int sms = 148;
+  int smemOptin = 0;
   cudaGraphExec_t tickGraph = nullptr;
   const void* graphFor = nullptr;
   bool useGraph = true;
@@ -789,6 +790,10 @@ class CudaBackend : public Backend {
     CUDA_OK(cudaGetDeviceProperties(&p, dev));
     sms = p.multiProcessorCount;
     CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CUDA_OK(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_OK(cudaFuncSetAttribute(k_ms_count, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+    CUDA_OK(cudaFuncSetAttribute(k_ms_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+    if (NODE_TMA_SMEM > 0) CUDA_OK(cudaFuncSetAttribute(k_node_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_TMA_SMEM));
     const char* g = std::getenv("WTG_NO_GRAPH");
     if (g && g[0] == '1') useGraph = false;
 #if defined(WTG_PERSISTENT_WINDOW)
@@ -878,6 +883,7 @@ class CudaBackend : public Backend {
     CUDA_OK(cudaEventRecord(tm0, st));
   }
   double timerStopMs() override {
+    bind();
     CUDA_OK(cudaEventRecord(tm1, st));
     CUDA_OK(cudaEventSynchronize(tm1));
     float ms = 0;
@@ -1100,11 +1106,11 @@ class CudaBackend : public Backend {
     windows += 1;
   }
 #endif
+  // dynamic shared memory of the multisplit kernels: the attribute is per device and shared by every engine on it (several
+  // engines may be driven from concurrent host threads), so it is set once, to the device's opt-in maximum
   void configure(const Dev& d) {
-    size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
-    CUDA_OK(cudaFuncSetAttribute(k_ms_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
-    CUDA_OK(cudaFuncSetAttribute(k_ms_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msSmem));
-    if (NODE_TMA_SMEM > 0) CUDA_OK(cudaFuncSetAttribute(k_node_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_TMA_SMEM));
+    const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    if (msSmem > (size_t)smemOptin) throw std::runtime_error("time ring too large for the multisplit's shared-memory histogram");
   }
   void tick(const Dev& d, int mode) override {
     bind();
@@ -1137,11 +1143,13 @@ class CudaBackend : public Backend {
     launches += graphKernels * count;
   }
   void gsfInitNodes(const Dev& d) override {
+    bind();
     k_gsf_init_nodes<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
     CUDA_OK(cudaGetLastError());
   }
   void rngCandidates(const Dev& d, unsigned long long s0, unsigned long long count, int maxBound,
                      std::vector<unsigned long long>& out) override {
+    bind();
     const u64 chunk = 16384;
     u64 threads = (count + chunk - 1) / chunk;
     int cap = (int)std::min<u64>((u64)1 << 26, count / 1024 + (1 << 16));
@@ -1168,6 +1176,7 @@ class CudaBackend : public Backend {
     cudaFree(dCnt);
   }
   void gsfShufflePeers(const Dev& d, unsigned long long s0, const int* liveRank, const unsigned long long* rejOrd, int nRej) override {
+    bind();
     for (int l = d.L - 1; l >= 1; --l) {
       if (d.peerBits == 16)
         k_gsf_shuffle<uint16_t><<<(d.nLoc + 127) / 128, 128, 0, st>>>(d, l, s0, liveRank, rejOrd, nRej);
