@@ -38,8 +38,9 @@ def test_pingpong_far_latencies_host_build(latency, measured):
     assert o.pongs()[0] > 0
 
 
-def test_gsf_ethscan_host_build():
-    args = (128, 100, 3, 20, 10, 10, 8, "RANDOM_SPEED=CONSTANT_TOR=0.00", "EthScanNetworkLatency")
+@pytest.mark.parametrize("n", [128, 256])
+def test_gsf_ethscan_host_build(n):
+    args = (n, int(0.8 * n), 3, 20, 10, 10, n // 16, "RANDOM_SPEED=CONSTANT_TOR=0.00", "EthScanNetworkLatency")
     p = GSFSignature(GSFSignatureParameters(*args), _api=emu_lib.api())
     o = OracleGSF(*args)
     p.init(); o.init()

@@ -566,6 +566,8 @@ class Engine {
     Ctl c;
     std::memset(&c, 0, sizeof(c));
     long long perNode = tun.poolSlotsPerNode ? tun.poolSlotsPerNode : 24;
+    // multi-second latency models keep a payload in flight for latMax / period cycles of its sender
+    if (!tun.poolSlotsPerNode && farTicking) perNode = std::max<long long>(perNode, 2LL * hm.latMax / std::max(1, p.periodDurationMs) + 24);
     for (int l = INLINE_MAX_LEVEL + 1; l < L; ++l) {
       long long slots = std::max<long long>(1024, perNode * NL);
       slots = (slots + POOL_STRIPES - 1) / POOL_STRIPES * POOL_STRIPES;
