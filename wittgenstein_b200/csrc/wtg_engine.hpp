@@ -123,6 +123,7 @@ class Engine {
   void* xRegion = nullptr;      // this shard's exchange region
   size_t xBytes = 0;
   long long stageWordsWanted = 0;  // protocol-specific staging capacity per (sender, parity), in 64-bit words
+  long long farWanted = 0;         // protocol-specific size of the far-future calendar when the latency model needs one
   struct XLayout {
     size_t hdr, flags, items, newEv, newTarget, stage, rec, recDest, recArrival, total;
   } xl{};
@@ -368,7 +369,7 @@ class Engine {
     }
     if (farEnabled) {
       d.ffwd = farTicking ? 0 : 1;
-      d.farCap = tun.farCap ? (int)tun.farCap : (farTicking ? (int)std::min<long long>(0x3fffffffLL, 64LL * N + 4096) : 2 * N + 1024);
+      d.farCap = tun.farCap ? (int)tun.farCap : (farTicking ? (int)std::min<long long>(1LL << 26, std::max<long long>(64LL * N + 4096, farWanted)) : 2 * N + 1024);
       d.far = dalloc<FarEv>(d.farCap);
       d.farSel = dalloc<int>(d.farCap);
     }
@@ -517,6 +518,9 @@ class Engine {
     }
     int L = 1;
     while ((1 << L) <= N) ++L;  // levels 0..log2(N)   (:186)
+    // envelopes in flight beyond the ring's horizon under a multi-second latency model: every node sends at most once per
+    // level and period, and keeps it in flight for at most latMax
+    farWanted = (long long)N * L * (hm.latMax / std::max(1, p.periodDurationMs) + 1) / 2 + 4096;
     if (sharded()) {
       // pooled payloads that cross shards are staged on the receiving shard (one area per sender and pass parity): in one
       // pass a shard receives from one sender at most about one level block per sending node
