@@ -49,3 +49,22 @@ def test_create_without_gpu_fails_loudly():
 
     with pytest.raises(WtgError):
         Network()
+
+
+def test_jni_shim_compiles_against_the_header():
+    """bindings/jni/wtg_jni.c (the reference-side binding) type-checks against include/wtg.h; without a JDK
+    the check uses a minimal stub of <jni.h> (tests/cpp/jni_stub)."""
+    import subprocess
+
+    jni = None
+    jh = os.environ.get("JAVA_HOME")
+    if jh and os.path.exists(os.path.join(jh, "include", "jni.h")):
+        jni = ["-I" + os.path.join(jh, "include"), "-I" + os.path.join(jh, "include", "linux")]
+    inc = jni or ["-I" + os.path.join(ROOT, "tests", "cpp", "jni_stub")]
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror"] + inc + ["-I" + os.path.join(ROOT, "include"),
+                                                                                os.path.join(ROOT, "bindings", "jni", "wtg_jni.c")])
+    # every native method of NativeNetwork.java has its wrapper
+    java = open(os.path.join(ROOT, "bindings", "jni", "NativeNetwork.java")).read()
+    c = open(os.path.join(ROOT, "bindings", "jni", "wtg_jni.c")).read()
+    for name in re.findall(r"native\s+[\w\[\]]+\s+(\w+)\(", java):
+        assert f"NN({name})" in c, name
