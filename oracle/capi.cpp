@@ -128,7 +128,13 @@ static void nodeAttrs(const std::vector<Node*>& nodes, int32_t* x, int32_t* y, i
     if (x) x[i] = nodes[i]->x;
     if (y) y[i] = nodes[i]->y;
     if (extra) extra[i] = nodes[i]->extraLatency;
-    if (city) city[i] = nodes[i]->cityIdx < 0 ? -1 : awsRegionOf(nodes[i]->cityName);
+    if (city) {  // AWS builder: region index; CITIES builder: 100 + index of the latency table (cf. wtg_node_attrs)
+      int reg = nodes[i]->cityIdx < 0 ? -1 : awsRegionOf(nodes[i]->cityName);
+      bool aws = false;
+      if (reg >= 0)
+        for (auto& c : awsCitiesPutOrder()) aws |= c.region == reg && c.mercX == nodes[i]->x && c.mercY == nodes[i]->y;
+      city[i] = nodes[i]->cityIdx < 0 ? -1 : aws ? reg : 100 + latencyCityIndex(nodes[i]->cityName);
+    }
     if (speed) speed[i] = nodes[i]->speedRatio;
     if (down) down[i] = nodes[i]->down ? 1 : 0;
   }

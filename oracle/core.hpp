@@ -234,6 +234,78 @@ inline NodeBuilder makeAwsCityBuilder() {
   return nb;
 }
 
+// ----------------------------------------------------------------------------------------
+// geoinfo/GeoAllCities.java + NodeBuilder.NodeBuilderWithCity over CSVLatencyReader.cities()
+// (RegistryNodeBuilders.java:50-52).  The tables come from the reference's resources through
+// scripts/make_city_data.py (text parsing only); everything order- or rounding-sensitive is here.
+// ----------------------------------------------------------------------------------------
+namespace citydata {
+#include "city_data.inc"
+}
+// GeoAllCities.convertToMercatorX / Y (:54-75); mapWidth = MAX_X, mapHeight = MAX_Y
+inline int mercatorX(double longitude) {
+  const double mapWidth = MAX_X;
+  int posX = static_cast<int>((longitude + 180) * (mapWidth / 360));
+  if (posX < mapWidth / 2)
+    posX = posX - 45;
+  else
+    posX = posX - 70;
+  return posX;
+}
+inline int mercatorY(float latitude) {
+  const double mapHeight = MAX_Y;
+  // (int) Math.round(double): floor(x + 0.5)
+  double v = (mapHeight / 2) - (latitude * mapHeight / 180);  // float * double -> double
+  int posY = static_cast<int>(std::floor(v + 0.5));
+  if (posY < 0.2 * mapHeight) posY = posY - 35;
+  return posY;
+}
+inline int latencyCityIndex(const std::string& name) {
+  for (int i = 0; i < citydata::kLatCityCount; ++i)
+    if (name == citydata::kLatCities[i]) return i;
+  return -1;
+}
+inline NodeBuilder makeAllCitiesBuilder() {
+  NodeBuilder nb;
+  nb.kind = NodeBuilder::CITY;
+  // readCityInfo (:29-52): HashMap<String,int[]> filled in file order; population += 200000; int total
+  std::vector<std::string> keys;
+  int totalPopulation = 0;
+  for (int i = 0; i < citydata::kGeoCityCount; ++i) {
+    keys.push_back(citydata::kGeoCities[i].name);
+    totalPopulation += citydata::kGeoCities[i].population + 200000;
+  }
+  // Geo.cityInfoMap (Geo.java:10-19): cumulative probability in the HashMap's iteration order, float arithmetic
+  std::vector<int> order = javaHashMapOrder(keys);
+  std::vector<CityInfo> all;
+  float cumulativeProbability = 0.f;
+  for (int i : order) {
+    const auto& c = citydata::kGeoCities[i];
+    cumulativeProbability = cumulativeProbability + static_cast<float>(c.population + 200000) * 1.f / static_cast<float>(totalPopulation);
+    all.push_back({c.name, mercatorX(static_cast<double>(c.longitude)), mercatorY(c.latitude), cumulativeProbability});
+  }
+  // citiesInfo map -> copy (citiesPosition()) -> filter by the latency reader's cities (case-insensitive) -> Collectors.toMap:
+  // every step is a HashMap over (a subset of) the same keys filled in the previous one's iteration order
+  std::vector<CityInfo> kept;
+  std::vector<std::string> keptKeys;
+  for (const CityInfo& ci : all) {
+    bool in = false;
+    for (int k = 0; k < citydata::kLatCityCount && !in; ++k) {
+      std::string a = ci.name, b = citydata::kLatCities[k];
+      for (auto& ch : a) ch = static_cast<char>(std::toupper(static_cast<unsigned char>(ch)));
+      for (auto& ch : b) ch = static_cast<char>(std::toupper(static_cast<unsigned char>(ch)));
+      in = a == b;
+    }
+    if (in) {
+      kept.push_back(ci);
+      keptKeys.push_back(ci.name);
+    }
+  }
+  for (int i : javaHashMapOrder(keptKeys)) nb.citiesInfo.push_back(kept[static_cast<size_t>(i)]);
+  nb.citiesListSize = citydata::kLatCityCount;  // cities.size(): the reader's key set, whether or not cities.csv knows the city
+  return nb;
+}
+
 // RegistryNodeBuilders.name / getByName (RegistryNodeBuilders.java:21-25, 71-81)
 inline NodeBuilder nodeBuilderByName(const std::string& nameIn) {
   std::string name = nameIn;
@@ -260,7 +332,7 @@ inline NodeBuilder nodeBuilderByName(const std::string& nameIn) {
   else if (site == "RANDOM")
     nb.kind = NodeBuilder::RANDOM_POSITION;
   else if (site == "CITIES")
-    throw IllegalArgument("CITIES builder needs the WonderNetwork CSV data: out of scope (SURVEY.md §8f rank 2)");
+    nb = makeAllCitiesBuilder();
   else
     throw IllegalArgument(name + " not in the registry");
   if (speed == "GAUSSIAN")
@@ -310,7 +382,9 @@ struct NetworkLatency {
     NO_LATENCY = 4,
     MEASURED = 5,
     ETHSCAN = 6,
-    IC3 = 7
+    IC3 = 7,
+    BY_CITY = 8,
+    BY_CITY_W_JITTER = 9
   } kind = IC3;
   int param = 0;             // FIXED / UNIFORM
   int longDistrib[100] = {};  // MEASURED / ETHSCAN
@@ -345,8 +419,32 @@ struct NetworkLatency {
     if (li != 100) throw IllegalArgument("li");
   }
 
+  // NetworkLatencyByCity.getLatency(cityFrom, cityTo) :188-198 (the converter resolved the "other direction" fallback)
+  static float cityLatency(const Node& from, const Node& to) {
+    if (from.cityIdx < 0 || to.cityIdx < 0) throw IllegalState("Can't use NetworkLatencyByCity model with default city location");
+    int a = latencyCityIndex(from.cityName), b = latencyCityIndex(to.cityName);
+    if (a < 0) throw IllegalArgument("Can't find latencies for " + from.cityName);
+    if (b < 0) throw IllegalArgument("Can't find latencies for " + to.cityName);
+    return citydata::kCityLatency[a][b];
+  }
   int getExtendedLatency(const Node& from, const Node& to, int delta) const {
     switch (kind) {
+      case BY_CITY: {  // :168-185
+        if (from.nodeId == to.nodeId) return 1;
+        float h = 0.5f * cityLatency(from, to);
+        int r = static_cast<int>(std::floor(static_cast<double>(h) + 0.5));  // Math.round(float): floor(x + 1/2), exact
+        return std::max(1, r);
+      }
+      case BY_CITY_W_JITTER: {  // :204-232
+        if (from.nodeId == to.nodeId) return 1;
+        float lat = cityLatency(from, to);
+        double raw = getJitter(delta);
+        if (from.cityName == to.cityName)
+          raw += 10;
+        else
+          raw += lat;  // float widened to double
+        return std::max(1, static_cast<int>(std::floor(0.5 * raw + 0.5)));  // (int) Math.round(double)
+      }
       case BY_DISTANCE_W_JITTER: {  // :67-72
         checkDelta(delta);
         double raw = getFixedLatency(from.dist(to)) + getJitter(delta);
@@ -446,8 +544,10 @@ inline NetworkLatency networkLatencyByName(const std::string& nameIn, bool isNul
   if (name == "AwsRegionNetworkLatency") return NetworkLatency::ofKind(NetworkLatency::AWS_REGION);
   if (name == "NetworkNoLatency") return NetworkLatency::ofKind(NetworkLatency::NO_LATENCY);
   if (name == "EthScanNetworkLatency") return NetworkLatency::ethScan();
+  if (name == "NetworkLatencyByCity") return NetworkLatency::ofKind(NetworkLatency::BY_CITY);
+  if (name == "NetworkLatencyByCityWJitter") return NetworkLatency::ofKind(NetworkLatency::BY_CITY_W_JITTER);
   if (name == "IC3NetworkLatency") return NetworkLatency::ofKind(NetworkLatency::IC3);
-  throw IllegalArgument("latency '" + name + "' not available (ByCity* need CSV data: out of scope)");
+  throw IllegalArgument("latency '" + name + "' not in the registry");
 }
 
 // ----------------------------------------------------------------------------------------

@@ -654,3 +654,39 @@ def test_gsf_256_ethscan_and_measured():
             assert p.network().run_ms(100) == o.run_ms(100)
             bad = compare_gsf(p, o, f"t={o.time}", full=(i % 8 == 0))
             assert not bad, bad
+
+
+@pytest.mark.parametrize("nb,nl", [("CITIES_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByCityWJitter"), ("CITIES_SPEED=GAUSSIAN_TOR=0.33", "NetworkLatencyByCity")])
+def test_pingpong_cities(nb, nl):
+    """CITIES node builder + NetworkLatencyByCity[WJitter] (NetworkLatency.java:159-233, NodeBuilder.java:98-148) on the device"""
+    from wittgenstein_b200 import PingPong, PingPongParameters
+
+    p = PingPong(PingPongParameters(1000, nb, nl))
+    o = OraclePingPong(1000, nb, nl)
+    p.init(); o.init()
+    a, b = p.network().attrs(), o.attrs()
+    for k in ("x", "y", "extra", "city", "down"):
+        assert (a[k] == b[k]).all(), k
+    for _ in range(20):
+        assert p.network().run_ms(100) == o.run_ms(100)
+        assert (p.pongs() == o.pongs()).all()
+        assert (p.network().counters() == o.counters()).all()
+        assert p.network().msgs_size() == o.msgs_size()
+    assert p.pongs()[0] > 0
+
+
+def test_handel_2048_default_scenario_cities():
+    """HandelScenarios.defaultParams (HandelScenarios.java:65-120): 2 048 nodes, CITIES builder, NetworkLatencyByCityWJitter —
+    to completion (Handel.newContIf), every 10 ms against the oracle"""
+    from tests.test_cities_emu import handel_default_params
+
+    args = handel_default_params(2048)
+    p, o = _handel_pair(*args)
+    steps = 0
+    while o.continue_if() and steps < 600:
+        assert p.network().run_ms(10) == o.run_ms(10)
+        steps += 1
+        bad = _handel_compare(p, o, f"t={o.time}", full=(steps % 20 == 0))
+        assert not bad, bad
+    assert not o.continue_if()
+    assert not _handel_compare(p, o, "end")

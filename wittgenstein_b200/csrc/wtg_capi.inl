@@ -481,7 +481,7 @@ int WTG_API(node_attrs)(void* h, int* x, int* y, int* extra, int* city, double* 
       if (x) x[i] = n.x;
       if (y) y[i] = n.y;
       if (extra) extra[i] = n.extra;
-      if (city) city[i] = ENG.hm.builder == wtg::HostModel::B_AWS ? n.city : -1;
+      if (city) city[i] = ENG.hm.builder == wtg::HostModel::B_AWS ? n.city : ENG.hm.builder == wtg::HostModel::B_CITIES ? 100 + n.city : -1;  // AWS: region; CITIES: 100 + index of the latency table
       if (speed) speed[i] = n.speed;
       if (down) down[i] = n.down ? 1 : 0;
     }

@@ -392,6 +392,8 @@ class Engine {
   void checkLatencyBuilder() const {
     if (hm.latKind == LAT_CITY && hm.builder != HostModel::B_AWS)
       throw std::invalid_argument("AwsRegionNetworkLatency needs nodes built by an AWS_* node builder");  // NetworkLatency.java:146-148
+    if (hm.latKind == LAT_CITY_MAT && hm.builder != HostModel::B_CITIES)
+      throw std::logic_error("Can't use NetworkLatencyByCity model with default city location");  // NetworkLatency.java:178-181
   }
 
   // ---- PingPong.init()  (protocols/PingPong.java:82-87) ----

@@ -181,6 +181,12 @@ WTG_HD int latency(const Dev& d, int from, int to, int delta) {
       ext = inner < 1 ? 1 : inner;
       break;
     }
+    case LAT_CITY_MAT: {
+      const int K = d.latParam & 0xffff;
+      const int cell = (int)d.ncity[from] * K + (int)d.ncity[to];
+      ext = (d.latParam >> 16) ? d.latTab[cell * 100 + delta] : d.latTab[cell];
+      break;
+    }
     default:  // LAT_DIST
       ext = d.latTab[nodeDist(d, from, to)];
       break;

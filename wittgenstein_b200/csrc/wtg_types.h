@@ -133,7 +133,9 @@ enum : int {
   LAT_CONST = 2,       // param                          NetworkFixedLatency / NetworkNoLatency
   LAT_DELTA = 3,       // tab[delta]                     NetworkUniformLatency / MeasuredNetworkLatency
   LAT_DELTA_2X = 4,    // max(1, extra+extra+tab[delta]) then extras again (EthScanNetworkLatency quirk)
-  LAT_DIST = 5         // tab[dist]                      IC3NetworkLatency
+  LAT_DIST = 5,        // tab[dist]                      IC3NetworkLatency
+  LAT_CITY_MAT = 6     // tab[(cityFrom * K + cityTo) * stride + (stride == 100 ? delta : 0)]; K = param & 0xffff, stride = param >> 16 ? 100 : 1
+                       //                                NetworkLatencyByCity / NetworkLatencyByCityWJitter
 };
 
 struct FarEv {  // an envelope whose arrival lies beyond the time ring's horizon (periodic tasks with long periods)
