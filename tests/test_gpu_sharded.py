@@ -70,3 +70,20 @@ def test_gsf_sharded_on_one_gpu_equals_unsharded_engine():
     assert a.network().rng_state() == b.network().rng_state()
     assert a.network().msgs_size() == b.network().msgs_size()
     b.close()
+
+
+def test_gsf_wide_peer_ids():
+    """32-bit absolute peer ids (the layout of runs with more than 131 072 nodes, config #5) forced at 1 024 nodes, 2 shards"""
+    from wittgenstein_b200 import GSFSignatureParameters
+    from wittgenstein_b200.sharded import ShardedGSFSignature
+
+    prm = GSFSignatureParameters(1024, 0.85, 4, 50, 20, 10, 0.1, AWS_NB, AWS_NL)
+    p = ShardedGSFSignature(prm, 2, devices=devices_for(2), tunables={"peer_bits_32": 1})
+    o = OracleGSF(1024, prm.threshold, 4, 50, 20, 10, prm.nodes_down, AWS_NB, AWS_NL)
+    p.init(); o.init()
+    assert p.network().stats()["peer_bits"] == 32
+    for i in range(50):
+        assert p.network().run_ms(10) == o.run_ms(10)
+        bad = parity.compare_gsf(p, o, f"t={o.time}", full=(i % 10 == 0))
+        assert not bad, bad
+    p.close()

@@ -60,3 +60,24 @@ def test_gsf_sharded_stop_start_partition():
             p.network().start_node(hook.a); o.start_node(hook.a)
 
     run_pair(256, 4, 500, 10, 2, hook=hook, full_every=5)
+
+
+def test_gsf_wide_peer_ids_host_build():
+    """the 32-bit absolute peer-id layout (used when N / 2 > 65 536, i.e. from 262 144 nodes on: BASELINE config #5) forced at a
+    size the oracle reaches, unsharded and on 2 shards"""
+    from wittgenstein_b200 import GSFSignature
+
+    prm = GSFSignatureParameters(512, 0.8, 4, 50, 20, 10, 0.1, AWS_NB, AWS_NL)
+    for world in (1, 2):
+        if world == 1:
+            p = GSFSignature(prm, _api=emu_lib.api(), tunables={"peer_bits_32": 1})
+        else:
+            p = ShardedGSFSignature(prm, world, _api=emu_lib.api(), tunables={"peer_bits_32": 1})
+        o = OracleGSF(512, prm.threshold, 4, 50, 20, 10, prm.nodes_down, AWS_NB, AWS_NL)
+        p.init(); o.init()
+        assert p.network().stats()["peer_bits"] == 32
+        assert not parity.compare_init(p, o)
+        for i in range(40):
+            p.network().run_ms(10); o.run_ms(10)
+            bad = parity.compare_gsf(p, o, f"t={o.time}", full=(i % 8 == 0))
+            assert not bad, bad

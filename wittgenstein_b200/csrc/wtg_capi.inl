@@ -146,6 +146,7 @@ int WTG_API(set_tunable)(void* h, const char* key, long long v) {
     else if (k == "casper_blocks") ENG.tun.casperBlocks = v;
     else if (k == "stage_words") ENG.tun.stageWords = v;
     else if (k == "far_cap") ENG.tun.farCap = v;
+    else if (k == "peer_bits_32") ENG.tun.peerBits32 = v;
     else throw std::invalid_argument("unknown tunable " + k);
     return 0;
   });

@@ -28,8 +28,6 @@ namespace wtg {
     if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
   } while (0)
 
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int NODE_BLOCK = WARPS_PER_BLOCK * 32;
 #if defined(WTG_TMA_SNAPSHOT)
 constexpr int NODE_TMA_SMEM = 8 * TMA_TILES * TMA_TILE_BYTES;
 #else
@@ -489,41 +487,56 @@ __device__ __forceinline__ void b_emit_all(const Dev& d, const int VB, const int
 __global__ void __launch_bounds__(128) k_emit_all(Dev d) { b_emit_all(d, blockIdx.x, gridDim.x); }
 
 // ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
-// chunk = MS_CHUNK consecutive envelopes in creation order, one warp per chunk
-constexpr int MS_ROUNDS = MS_CHUNK / 32;
+// A block of Dev.msWarps warps handles a chunk of msWarps * MS_SUB consecutive envelopes (creation order); warp w owns the w-th
+// sub-chunk of MS_SUB envelopes.  count: per-warp histograms over the ring bins in shared memory -> one row of totals per
+// chunk.  scan: running offset per bin over the chunks.  scatter: the histograms again, turned into each warp's first
+// position per bin (chunk offset + the lower warps' counts); then MS_SUB / 32 rounds of match-any ranked placement per warp.
+constexpr int MS_SUB = 256;  // envelopes per warp
+constexpr int MS_ROUNDS = MS_SUB / 32;
+// warps per block = Dev.msWarps (8 unless the ring is so long that 8 histograms do not fit in shared memory); chunk = msWarps * MS_SUB
+__device__ __forceinline__ void msZero(int* hist, int ring, int warps) {
+  for (int i = threadIdx.x * 4; i < warps * ring; i += blockDim.x * 4) *reinterpret_cast<int4*>(hist + i) = make_int4(0, 0, 0, 0);
+}
+// this warp's targets of the chunk (kept in registers) and their histogram
+__device__ __forceinline__ void msWarpHistogram(const Dev& d, int* hw, int g0, int G, int tick, int lane, int (&tg)[MS_ROUNDS]) {
+#pragma unroll
+  for (int r = 0; r < MS_ROUNDS; ++r) {  // all targets are in flight before the first one is used
+    int g = g0 + r * 32 + lane;
+    tg[r] = g < G ? d.newTarget[g] : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < MS_ROUNDS; ++r)
+    if (tg[r] >= 0) atomicAdd(&hw[tg[r] - tick], 1);
+}
 __device__ __forceinline__ void b_ms_count(const Dev& d, const int VB, const int VG) {
-  extern __shared__ int msHist[];  // [WARPS_PER_BLOCK][ring]
+  extern __shared__ int msHist[];  // [msWarps][ring]
   if (d.ctl->error) return;
-  int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
-  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int WPB = blockDim.x >> 5;
-  int* hist = msHist + warp * ring;
-  for (int ch = VB * WPB + warp; ch < nChunks; ch += VG * WPB) {
-    int g0 = ch * MS_CHUNK;
-    int tg[MS_ROUNDS];  // all targets of the chunk are in flight before the first one is used
-#pragma unroll
-    for (int r = 0; r < MS_ROUNDS; ++r) {
-      int g = g0 + r * 32 + lane;
-      tg[r] = g < G ? d.newTarget[g] : -1;
-    }
-    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(hist + b) = make_int4(0, 0, 0, 0);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < MS_ROUNDS; ++r)
-      if (tg[r] >= 0) atomicAdd(&hist[tg[r] - tick], 1);
-    __syncwarp();
+  const int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
+  const int W = d.msWarps, CH = W * MS_SUB;
+  const int nChunks = (G + CH - 1) / CH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ch = VB; ch < nChunks; ch += VG) {
+    msZero(msHist, ring, W);
+    __syncthreads();
+    int tg[MS_ROUNDS];
+    msWarpHistogram(d, msHist + warp * ring, ch * CH + warp * MS_SUB, G, tick, lane, tg);
+    __syncthreads();
     int* row = d.msCount + (size_t)ch * ring;
-    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(row + b) = *reinterpret_cast<const int4*>(hist + b);
-    __syncwarp();
+    for (int b = threadIdx.x; b < ring; b += blockDim.x) {
+      int tot = 0;
+      for (int w = 0; w < W; ++w) tot += msHist[w * ring + b];
+      row[b] = tot;
+    }
+    __syncthreads();
   }
 }
-__global__ void __launch_bounds__(NODE_BLOCK) k_ms_count(Dev d) { b_ms_count(d, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_ms_count(Dev d) { b_ms_count(d, blockIdx.x, gridDim.x); }
 // per ring bin: running offset over chunks, starting at the bucket's current fill
 __device__ __forceinline__ void b_ms_scan(const Dev& d, const int VB, const int VG) {
   if (d.ctl->error) return;
   int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
-  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
+  const int CH = d.msWarps * MS_SUB;
+  int nChunks = (G + CH - 1) / CH;
   if (nChunks == 0) return;
   for (int b = VB * blockDim.x + threadIdx.x; b < ring; b += VG * blockDim.x) {
     int slot = (tick + b) & (ring - 1);
@@ -550,22 +563,28 @@ __global__ void k_ms_scan(Dev d) { b_ms_scan(d, blockIdx.x, gridDim.x); }
 __device__ __forceinline__ void b_ms_scatter(const Dev& d, const int VB, const int VG) {
   extern __shared__ int msHist[];
   if (d.ctl->error) return;
-  int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
-  int nChunks = (G + MS_CHUNK - 1) / MS_CHUNK;
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int WPB = blockDim.x >> 5;
+  const int G = d.ctl->totalSlots, tick = d.ctl->tick, ring = d.ring;
+  const int W = d.msWarps, CH = W * MS_SUB;
+  const int nChunks = (G + CH - 1) / CH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* base = msHist + warp * ring;
-  for (int ch = VB * WPB + warp; ch < nChunks; ch += VG * WPB) {
-    int g0 = ch * MS_CHUNK;
+  for (int ch = VB; ch < nChunks; ch += VG) {
+    msZero(msHist, ring, W);
+    __syncthreads();
+    const int g0 = ch * CH + warp * MS_SUB;
     int tg[MS_ROUNDS];
-#pragma unroll
-    for (int r = 0; r < MS_ROUNDS; ++r) {
-      int g = g0 + r * 32 + lane;
-      tg[r] = g < G ? d.newTarget[g] : -1;
+    msWarpHistogram(d, base, g0, G, tick, lane, tg);
+    __syncthreads();
+    const int* row = d.msCount + (size_t)ch * ring;  // first position of this chunk in every bin (after the scan)
+    for (int b = threadIdx.x; b < ring; b += blockDim.x) {
+      int run = row[b];
+      for (int w = 0; w < W; ++w) {
+        int c = msHist[w * ring + b];
+        msHist[w * ring + b] = run;
+        run += c;
+      }
     }
-    const int* row = d.msCount + (size_t)ch * ring;
-    for (int b = lane * 4; b < ring; b += 128) *reinterpret_cast<int4*>(base + b) = *reinterpret_cast<const int4*>(row + b);
-    __syncwarp();
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < MS_ROUNDS; ++r) {
       int g = g0 + r * 32 + lane;
@@ -594,9 +613,10 @@ __device__ __forceinline__ void b_ms_scatter(const Dev& d, const int VB, const i
       }
       __syncwarp();
     }
+    __syncthreads();
   }
 }
-__global__ void __launch_bounds__(NODE_BLOCK) k_ms_scatter(Dev d) { b_ms_scatter(d, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_ms_scatter(Dev d) { b_ms_scatter(d, blockIdx.x, gridDim.x); }
 
 __device__ __forceinline__ void b_free(const Dev& d, const int VB, const int VG) {
   if (d.ctl->error) return;
@@ -945,7 +965,7 @@ class CudaBackend : public Backend {
 
   void enqueueTick(const Dev& d, int mode) {
     const int wide = sms * 8;
-    const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    const size_t msSmem = (size_t)d.msWarps * d.ring * sizeof(int);
     // mode 3: the host prepared the control block and the descriptors of sends it injects at the current time
     // (Engine::inject); only the emission half of the pipeline runs
     if (mode != 3) {
@@ -1044,13 +1064,13 @@ class CudaBackend : public Backend {
       launches += 2;
     }
     profBegin(9);
-    k_ms_count<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    k_ms_count<<<sms * 2, d.msWarps * 32, msSmem, st>>>(d);
     profEnd();
     profBegin(10);
     k_ms_scan<<<(d.ring + 127) / 128, 128, 0, st>>>(d);
     profEnd();
     profBegin(11);
-    k_ms_scatter<<<sms * 4, NODE_BLOCK, msSmem, st>>>(d);
+    k_ms_scatter<<<sms * 2, d.msWarps * 32, msSmem, st>>>(d);
     profEnd();
     const bool pooled = d.proto == PROTO_GSF || d.proto == PROTO_HANDEL;  // only these protocols hold pooled payloads
     if (pooled) {
@@ -1109,7 +1129,7 @@ class CudaBackend : public Backend {
   // dynamic shared memory of the multisplit kernels: the attribute is per device and shared by every engine on it (several
   // engines may be driven from concurrent host threads), so it is set once, to the device's opt-in maximum
   void configure(const Dev& d) {
-    const size_t msSmem = (size_t)WARPS_PER_BLOCK * d.ring * sizeof(int);
+    const size_t msSmem = (size_t)d.msWarps * d.ring * sizeof(int);
     if (msSmem > (size_t)smemOptin) throw std::runtime_error("time ring too large for the multisplit's shared-memory histogram");
   }
   void tick(const Dev& d, int mode) override {

@@ -47,6 +47,7 @@ struct Tunables {  // capacities; 0 = derive from N
   long long bcap = 0, qcap = 0, poolSlotsPerNode = 0, descCap = 0, recCap = 0, ring = 0;
   long long casperVotes = 0;   // CasperIMD: attestations one attester may publish in a run (default 6)
   long long casperBlocks = 0;  // CasperIMD: blocks of a run (default from casperVotes)
+  long long peerBits32 = 0;    // GSF: absolute 32-bit peer ids even when 16-bit block-relative ones would do
   long long farCap = 0;        // far-future calendar entries (latency models with multi-second arrivals)
   long long stageWords = 0;    // node-sharded GSF: staging capacity per (sending shard, pass parity) in 64-bit words
 };
@@ -344,7 +345,9 @@ class Engine {
     d.scanPartial = dalloc<int>(2 * 8192);
     d.desc = dalloc<Desc>(d.descCap);
     d.destScratch = dalloc<uint32_t>(d.destScratchCap);
-    d.msChunks = (d.newEvCap + MS_CHUNK - 1) / MS_CHUNK;
+    d.msWarps = 8;
+    while (d.msWarps > 1 && (size_t)d.msWarps * ring * sizeof(int) > 200 * 1024) d.msWarps >>= 1;  // shared-memory histograms
+    d.msChunks = (d.newEvCap + d.msWarps * MS_SUB_ENVELOPES - 1) / (d.msWarps * MS_SUB_ENVELOPES);
     d.msCount = dalloc<int>((size_t)d.msChunks * (size_t)ring);
     d.freeList = dalloc<uint32_t>(d.freeCap);
     if (sharded()) {
@@ -561,7 +564,7 @@ class Engine {
     std::vector<int> pairing(N);
     for (int i = 0; i < N; ++i) pairing[i] = (int)std::max(1.0, p.pairingTime * hm.nodes[i].speed);  // :170
     d.pairing = duploadNodes(pairing);
-    d.peerBits = (N / 2 <= 65536) ? 16 : 32;
+    d.peerBits = (N / 2 <= 65536 && !tun.peerBits32) ? 16 : 32;  // 16-bit entries are block-relative; tunable peer_bits_32 forces the wide layout at small N (tests)
     {
       const size_t rowBytes = (size_t)(N - 1) * (size_t)(d.peerBits / 8);
       void* pp = be->alloc((size_t)NL * rowBytes);

@@ -22,7 +22,7 @@ namespace wtg {
 
 constexpr int POOL_STRIPES = 64;     // independent free stacks per pool level (allocation contention / 64)
 constexpr int ARENA_STRIPES = 64;    // per-tick arenas are striped by node id for the same reason
-constexpr int MS_CHUNK = 1024;       // new envelopes per multisplit chunk (one warp)
+constexpr int MS_SUB_ENVELOPES = 256; // new envelopes per warp of a multisplit block (chunk = Dev.msWarps * 256)
 constexpr int MAX_LEVELS = 24;
 constexpr int MAX_ACC = 16;          // max destinations of a protocol multi-send handled on device
 constexpr int INLINE_MAX_LEVEL = 7;  // level-l block has 2^(l-1) bits: <= 64 bits for l <= 7
@@ -256,6 +256,7 @@ struct Dev {
   int N, L, W64;
   int ring;      // buckets in the time ring (power of two > largest latency + period)
   int msChunks;  // rows of msCount
+  int msWarps;   // warps (histograms over the ring) per multisplit block: 8, fewer for very long rings
   int proto;
   int threshold, timeoutPerLevel, period, accel;
   int qcap, bcap;
