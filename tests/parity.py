@@ -86,3 +86,28 @@ def compare_casper(p, o, tag, atts=False):
             if p.block_attestations(i) != o.block_attestations(i):
                 bad.append(f"{tag}: attestations of block {i} differ")
     return bad
+
+
+def state_digest(arrays):
+    """blake2b over a list of numpy arrays (shape, dtype and bytes)"""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.shape).encode() + str(a.dtype).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def handel_digests(x, is_oracle):
+    """digests of a Handel run's state: x is wittgenstein_b200.Handel or tests.oracle_lib.OracleHandel"""
+    net = x if is_oracle else x.network()
+    out = {"rng": int(net.rng_state()), "msgs": int(net.msgs_live() if is_oracle else net.msgs_size()),
+           "counters": state_digest([net.counters()])}
+    sc = x.scalars()
+    out["scalars"] = state_digest([sc[k] for k in sorted(sc)])
+    out["rows"] = state_digest([x.rows(w) for w in range(6)])
+    lv = x.level_scalars()
+    out["levels"] = state_digest([lv[k] for k in ("pos", "outgoing_finished", "suicide_biz_after")])
+    return out

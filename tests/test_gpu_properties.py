@@ -139,3 +139,47 @@ def test_gsf_131072_prefix_vs_oracle():
         o.run_ms(10)
     bad = parity.compare_gsf(p, o, "t=300", full=True)
     assert not bad, bad
+
+
+def test_handel_32768_config3_against_offline_oracle_digests():
+    """BASELINE config #3 (Handel 32 768 nodes, 8 192 suicide-Byzantine, AWS latencies): the device run against digests of the
+    oracle's state produced offline (tests/golden/make_handel32768.py; the oracle needs minutes per simulated second here),
+    every 100 ms up to the last committed checkpoint — past the start of the Byzantine phase."""
+    import json
+    import os
+
+    from tests.parity import handel_digests
+    from wittgenstein_b200 import Handel, HandelParameters
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handel32768_config3.json")
+    if not os.path.exists(path):
+        pytest.skip("no offline digests committed")
+    fx = json.load(open(path))
+    prm = fx["params"]
+    p = Handel(HandelParameters(*prm[:8], prm[8], prm[9], prm[10], prm[11], prm[12]))
+    p.init()
+    last = max(int(t) for t in fx["checkpoints"])
+    assert last >= 300
+    while p.network().time < last:
+        p.network().run_ms(100)
+        want = fx["checkpoints"].get(str(p.network().time))
+        if want is not None:
+            got = handel_digests(p, False)
+            assert got == want, (p.network().time, {k: (got[k], want[k]) for k in got if got[k] != want[k]})
+
+
+def test_casper_16390_config4_prefix_vs_oracle():
+    """BASELINE config #4 (CasperIMD 64-slot cycles, 5 producers, 256 attesters per slot = 16 390 nodes) against the oracle
+    through the first 40 000 ms (5 slots: 1 280 votes x 16 390 destinations), every 4 000 ms"""
+    from tests.oracle_lib import OracleCasper
+    from tests.parity import compare_casper
+    from wittgenstein_b200 import CasperIMD, CasperParemeters
+
+    nb, nl = "RANDOM_SPEED=CONSTANT_TOR=0.00", "NetworkLatencyByDistanceWJitter"
+    p = CasperIMD(CasperParemeters(64, False, 5, 256, 1000, 1, nb, nl))
+    o = OracleCasper(64, False, 5, 256, 1000, 1, nb, nl)
+    p.init(0); o.init(0)
+    while o.time < 40000:
+        assert p.network().run_ms(4000) == o.run_ms(4000)
+        bad = compare_casper(p, o, f"t={o.time}")
+        assert not bad, bad
