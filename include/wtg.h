@@ -130,6 +130,13 @@ int wtg_node_count(wtg_net* net);
 /* network.msgs.size() / network.msgs.sizeAt(t) — Network.java:204-220 */
 int wtg_msgs_size(wtg_net* net);
 int wtg_msgs_size_at(wtg_net* net, int t);
+/* network.msgs.peekMessages() — Network.java:279-286 (EnvelopeInfo.java:8-14; the call behind the REST façade's
+ * GET /w/network/messages, wserver/.../ws/WServer.java:71-75): one row per pending arrival — every remaining destination of a
+ * multi-destination envelope is a row — sorted by arrival time.  from/to: node ids; sent_at: Envelope.sendTime (-1 when the
+ * engine did not record it: tasks registered by init()); kind: 0 message, 2 Task, 3 PeriodicTask; msg_type: the protocol's
+ * message type code (GSF/Handel: payload kind and level).  Returns the number of pending arrivals; at most `cap` rows are
+ * written (any output pointer may be NULL).  On a node-sharded network: the arrivals at this shard's nodes. */
+int wtg_peek_messages(wtg_net* net, int* from, int* to, int* sent_at, int* arriving_at, int* kind, int* msg_type, int cap);
 
 /* node.stop() / node.start() — Node.java:120-127 */
 int wtg_stop_node(wtg_net* net, int node_id);

@@ -112,6 +112,21 @@ void wo_pp_pongs(void* h, int32_t* out) {
   auto* p = static_cast<PingPong*>(h);
   for (size_t i = 0; i < p->nodes.size(); ++i) out[i] = p->nodes[i]->pong;
 }
+// network.msgs.peekMessages() (Network.java:279-286): rows sorted by (arrivingAt, from, to); returns the total
+static int peekRows(const Network& net, int32_t* from, int32_t* to, int32_t* sentAt, int32_t* arrivingAt, int32_t* isTask, int cap) {
+  std::vector<EnvelopeInfo> v = net.msgs.peekMessages();
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) {
+    from[i] = v[i].from;
+    to[i] = v[i].to;
+    sentAt[i] = v[i].sentAt;
+    arrivingAt[i] = v[i].arrivingAt;
+    isTask[i] = v[i].isTask ? 1 : 0;
+  }
+  return (int)v.size();
+}
+int wo_pp_peek_messages(void* h, int32_t* from, int32_t* to, int32_t* sentAt, int32_t* arrivingAt, int32_t* isTask, int cap) {
+  return peekRows(static_cast<PingPong*>(h)->network, from, to, sentAt, arrivingAt, isTask, cap);
+}
 static void nodeCounters(const std::vector<Node*>& nodes, int64_t* out5N) {
   size_t n = nodes.size();
   for (size_t i = 0; i < n; ++i) {
@@ -189,6 +204,9 @@ double wo_gsf_run_timed(void* h, int ms, int steps) {
 int wo_gsf_time(void* h) { return static_cast<GSFSignature*>(h)->network.time; }
 int wo_gsf_msgs_size(void* h) { return static_cast<GSFSignature*>(h)->network.msgs.size(); }
 int64_t wo_gsf_msgs_live(void* h) { return static_cast<GSFSignature*>(h)->network.msgs.live; }
+int wo_gsf_peek_messages(void* h, int32_t* from, int32_t* to, int32_t* sentAt, int32_t* arrivingAt, int32_t* isTask, int cap) {
+  return peekRows(static_cast<GSFSignature*>(h)->network, from, to, sentAt, arrivingAt, isTask, cap);
+}
 int wo_gsf_msgs_size_at(void* h, int t) {
   WO_TRY
   return static_cast<GSFSignature*>(h)->network.msgs.sizeAt(t);

@@ -594,6 +594,13 @@ struct Envelope {
   virtual int nextArrivalTime(const Network& network) const = 0;
   virtual void markRead() = 0;
   virtual bool hasNextReader() const = 0;
+  // Envelope.infos(network) (:39): (destination, arrival) of every destination not yet served
+  virtual void infos(const Network& network, std::vector<std::pair<int, int>>& out) const = 0;
+};
+
+struct EnvelopeInfo {  // core/EnvelopeInfo.java:8-14 (msg: the isTask flag is all the checker needs)
+  int from, to, sentAt, arrivingAt;
+  bool isTask;
 };
 
 struct MessageArrival {  // Network.java:392-410
@@ -609,6 +616,7 @@ struct SingleDestEnvelope : Envelope {  // Envelope.java:230-301
   int nextArrivalTime(const Network&) const override { return arrivalTime; }
   void markRead() override {}
   bool hasNextReader() const override { return false; }
+  void infos(const Network&, std::vector<std::pair<int, int>>& out) const override { out.emplace_back(toNodeId, arrivalTime); }  // :297-300
 };
 
 struct MultipleDestEnvelope : Envelope {  // Envelope.java:57-155
@@ -621,8 +629,12 @@ struct MultipleDestEnvelope : Envelope {  // Envelope.java:57-155
   }
   int getNextDestId() const override { return destIds[static_cast<size_t>(curPos)]; }
   int nextArrivalTime(const Network& network) const override;  // recomputed from the seed (:107-118)
+  int arrivalTime(const Network& network, int destId) const;    // :120-124
   void markRead() override { curPos++; }
   bool hasNextReader() const override { return curPos < static_cast<int>(destIds.size()); }
+  void infos(const Network& network, std::vector<std::pair<int, int>>& out) const override {  // :145-154
+    for (size_t i = static_cast<size_t>(curPos); i < destIds.size(); ++i) out.emplace_back(destIds[i], arrivalTime(network, destIds[i]));
+  }
 };
 
 struct MultipleDestWithDelayEnvelope : Envelope {  // Envelope.java:157-228
@@ -639,6 +651,9 @@ struct MultipleDestWithDelayEnvelope : Envelope {  // Envelope.java:157-228
   int nextArrivalTime(const Network&) const override { return arrivalTime[static_cast<size_t>(curPos)]; }
   void markRead() override { curPos++; }
   bool hasNextReader() const override { return curPos < static_cast<int>(destIds.size()); }
+  void infos(const Network&, std::vector<std::pair<int, int>>& out) const override {  // :219-227
+    for (size_t i = static_cast<size_t>(curPos); i < destIds.size(); ++i) out.emplace_back(destIds[i], arrivalTime[i]);
+  }
 };
 
 // ----------------------------------------------------------------------------------------
@@ -743,6 +758,7 @@ struct Network {
       clearAll();
       cleanup();
     }
+    std::vector<EnvelopeInfo> peekMessages() const;  // :279-286 (defined after Message)
     Envelope* peekFirst() {  // :271-277
       for (auto& ms : msgsBySlot)
         for (Envelope* m : ms->msgsByMs)
@@ -1020,6 +1036,33 @@ struct Network {
   std::vector<ConditionalTask*> snapshot_;
 };
 
+inline int MultipleDestEnvelope::arrivalTime(const Network& network, int destId) const {  // Envelope.java:120-124
+  int rd = Network::getPseudoRandom(destId, randomSeed);
+  const Node& f = *network.allNodes[static_cast<size_t>(fromNodeId)];
+  const Node& t = *network.allNodes[static_cast<size_t>(destId)];
+  return sendTime + network.networkLatency.getLatency(f, t, rd);
+}
+// Network.MessageStorage.peekMessages :279-286 — all slots, MsgsSlot.infos (:178-187: per ms, the list from its head), sorted
+// with EnvelopeInfo.compareTo (EnvelopeInfo.java:33-48: arrivingAt, then from; its remaining keys compare arrivingAt again or
+// identity hashes, i.e. no defined order) — the checker sorts by (arrivingAt, from, to, sentAt)
+inline std::vector<EnvelopeInfo> Network::MessageStorage::peekMessages() const {
+  std::vector<EnvelopeInfo> res;
+  std::vector<std::pair<int, int>> tmp;
+  for (auto& ms : msgsBySlot)
+    for (Envelope* m : ms->msgsByMs)
+      for (; m != nullptr; m = m->nextSameTime) {
+        tmp.clear();
+        m->infos(net, tmp);
+        for (auto& da : tmp) res.push_back(EnvelopeInfo{m->fromNodeId, da.first, m->sendTime, da.second, m->message->isTask()});
+      }
+  std::stable_sort(res.begin(), res.end(), [](const EnvelopeInfo& a, const EnvelopeInfo& b) {
+    if (a.arrivingAt != b.arrivingAt) return a.arrivingAt < b.arrivingAt;
+    if (a.from != b.from) return a.from < b.from;
+    if (a.to != b.to) return a.to < b.to;
+    return a.sentAt < b.sentAt;
+  });
+  return res;
+}
 inline int MultipleDestEnvelope::nextArrivalTime(const Network& network) const {  // Envelope.java:107-118
   int destId = getNextDestId();
   int rd = Network::getPseudoRandom(destId, randomSeed);

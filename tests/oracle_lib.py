@@ -95,6 +95,14 @@ class _NetCtl:
         if getattr(self.lib, self._ctl)(self.h, op, int(arg)) != 0:
             raise RuntimeError(self.lib.wo_last_error().decode())
 
+    def peek_messages(self, cap=1 << 16):
+        """network.msgs.peekMessages() (Network.java:279-286): (total, dict of arrays), rows sorted by (arrivingAt, from, to)"""
+        a = [np.zeros(cap, np.int32) for _ in range(5)]
+        fn = getattr(self.lib, self._ctl.replace("net_ctl", "peek_messages"))
+        total = fn(self.h, *[_p(x, C.c_int32) for x in a], int(cap))
+        k = min(total, cap)
+        return total, dict(zip(["from", "to", "sent_at", "arriving_at", "is_task"], [x[:k] for x in a]))
+
     def stop_node(self, i):
         self._c(0, i)
 

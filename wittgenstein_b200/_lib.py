@@ -67,6 +67,7 @@ class Api:
         "node_count": (C.c_int, [C.c_void_p]),
         "msgs_size": (C.c_int, [C.c_void_p]),
         "msgs_size_at": (C.c_int, [C.c_void_p, C.c_int]),
+        "peek_messages": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6 + [C.c_int]),
         "stop_node": (C.c_int, [C.c_void_p, C.c_int]),
         "start_node": (C.c_int, [C.c_void_p, C.c_int]),
         "partition": (C.c_int, [C.c_void_p, C.c_float]),

@@ -427,6 +427,21 @@ int WTG_API(msgs_size)(void* h) {
 int WTG_API(msgs_size_at)(void* h, int t) {
   return guard([&] { return ENG.msgsSizeAt(t); });
 }
+int WTG_API(peek_messages)(void* h, int* from, int* to, int* sentAt, int* arrivingAt, int* kind, int* msgType, int cap) {
+  return guard([&] {
+    std::vector<wtg::Engine::PeekRow> rows;
+    long long total = ENG.peekMessages(rows, cap < 0 ? 0 : cap);
+    for (size_t i = 0; i < rows.size(); ++i) {
+      if (from) from[i] = rows[i].from;
+      if (to) to[i] = rows[i].to;
+      if (sentAt) sentAt[i] = rows[i].sentAt;
+      if (arrivingAt) arrivingAt[i] = rows[i].arrivingAt;
+      if (kind) kind[i] = rows[i].kind;
+      if (msgType) msgType[i] = (int)rows[i].meta;
+    }
+    return (int)std::min<long long>(total, 0x7fffffffLL);
+  });
+}
 int WTG_API(stop_node)(void* h, int id) {
   return guard([&] {
     ENG.setDown(id, true);

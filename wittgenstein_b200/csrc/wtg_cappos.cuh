@@ -365,7 +365,7 @@ WTG_HD void emitShuffled(const Dev& d, int di, int g, u64 drawIdx) {
   ev.meta = ds.meta;
   ev.pl = ds.pl;
   ev.aux = 0;
-  ev.pad = 0;
+  ev.pad = (uint32_t)sendTime + 1u;  // EnvelopeInfo.sentAt + 1
   int target = -1;
   if (cnt == 1) {
     ev.to = list[0];
@@ -383,7 +383,7 @@ WTG_HD void emitShuffled(const Dev& d, int di, int g, u64 drawIdx) {
       rc.n = (uint32_t)cnt;
       rc.cur = 0;
       rc.off = (uint32_t)off;
-      rc.pad = 0;
+      rc.pad = (uint32_t)sendTime + 1u;
       d.rec[ri] = rc;
       for (int i = 0; i < cnt; ++i) {
         d.recDest[off + i] = list[i];

@@ -511,7 +511,7 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
   ev.meta = ds.meta;
   ev.pl = ds.pl;
   ev.aux = 0;
-  ev.pad = 0;
+  ev.pad = (uint32_t)ds.target + 1u;  // sendAll(msg, sendTime, from): EnvelopeInfo.sentAt + 1
   int target = -1;
   if (cnt == 1) {  // SingleDestEnvelope
     for (int to = c.lane(); to < N; to += C::LANES)
@@ -606,7 +606,7 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
         rc.n = (uint32_t)cnt;
         rc.cur = 0;
         rc.off = (uint32_t)off;
-        rc.pad = 0;
+        rc.pad = (uint32_t)ds.target + 1u;
         d.rec[ri] = rc;
       }
       c.sync();

@@ -432,6 +432,7 @@ class Engine {
       if ((int)da.size() > d.recDestCap) throw std::runtime_error("record arena too small");
       Ev ev;
       std::memset(&ev, 0, sizeof(ev));
+      ev.pad = 2;  // sendAll at time 0: sendTime 1 (+1)
       ev.from = 0;
       ev.meta = PP_PING;
       ev.to = da[0].dest;
@@ -442,6 +443,7 @@ class Engine {
         ev.aux = 0;
         MultiRec rc;
         std::memset(&rc, 0, sizeof(rc));
+        rc.pad = 2;
         rc.from = 0;
         rc.meta = PP_PING;
         rc.n = (uint32_t)da.size();
@@ -646,6 +648,7 @@ class Engine {
       if (!hm.nodes[i].down) {
         Ev ev;
         std::memset(&ev, 0, sizeof(ev));
+        ev.pad = 1;  // registered at time 0 (Envelope.sendTime + 1)
         ev.kind = EV_PERIODIC;
         ev.to = (uint32_t)i;
         ev.from = (uint32_t)i;
@@ -737,6 +740,7 @@ class Engine {
     for (int i = 0; i < N; ++i) {
       Ev ev;
       std::memset(&ev, 0, sizeof(ev));
+      ev.pad = 1;  // registered at time 0 (Envelope.sendTime + 1)
       ev.kind = EV_TASK;
       ev.to = (uint32_t)i;
       ev.from = (uint32_t)i;
@@ -976,6 +980,7 @@ class Engine {
       if (!hm.nodes[(size_t)i].down) {
         Ev ev;
         std::memset(&ev, 0, sizeof(ev));
+        ev.pad = 1;  // registered at time 0 (Envelope.sendTime + 1)
         ev.kind = EV_PERIODIC;
         ev.to = (uint32_t)i;
         ev.from = (uint32_t)i;
@@ -1039,6 +1044,7 @@ class Engine {
     for (int i = 0; i < N; ++i) {
       Ev ev;
       std::memset(&ev, 0, sizeof(ev));
+      ev.pad = 1;  // registered at time 0 (Envelope.sendTime + 1)
       ev.kind = EV_TASK;
       ev.to = (uint32_t)i;
       ev.from = (uint32_t)i;
@@ -1151,6 +1157,7 @@ class Engine {
     for (const Reg& r : regs) {
       Ev ev;
       std::memset(&ev, 0, sizeof(ev));
+      ev.pad = 1;  // registered at time 0 (Envelope.sendTime + 1)
       ev.kind = EV_PERIODIC;
       ev.to = (uint32_t)r.node;
       ev.from = (uint32_t)r.node;
@@ -1382,6 +1389,76 @@ class Engine {
         if (f.target == t) ++v;
     }
     return v;
+  }
+
+  // network.msgs.peekMessages() (Network.java:279-286, Envelope.infos :34-37, :145-154, :219-227, :297-300): one
+  // EnvelopeInfo {from, to, sentAt, arrivingAt, message} per pending arrival — every remaining destination of a
+  // multi-destination envelope counts — sorted by arrival time (EnvelopeInfo.compareTo; ties here by from, to, sentAt).
+  // Host-side read-back of the time ring (and of the far-future calendar); rows: from, to, sentAt (-1: not recorded),
+  // arrivingAt, event kind (EV_*), message type (Ev.meta).  Returns the number of pending arrivals; at most `cap` are written.
+  struct PeekRow {
+    int from, to, sentAt, arrivingAt, kind;
+    uint32_t meta;
+  };
+  long long peekMessages(std::vector<PeekRow>& out, long long cap) {
+    requireInited();
+    out.clear();
+    long long total = 0;
+    std::vector<int> bc(d.ring);
+    be->sync();
+    be->download(bc.data(), d.bucketCount, sizeof(int) * d.ring);
+    std::vector<Ev> evs;
+    std::vector<uint32_t> rd;
+    std::vector<int> ra;
+    auto addOne = [&](const Ev& e, int arrival) {
+      if (e.kind == EV_MULTI) {
+        MultiRec rc;
+        be->download(&rc, d.rec + e.aux, sizeof(MultiRec));
+        const int m = (int)rc.n - (int)rc.cur;
+        if (m <= 0) return;
+        total += m;
+        long long room = cap - (long long)out.size();
+        int take = (int)std::max<long long>(0, std::min<long long>(room, m));
+        if (take > 0) {
+          rd.resize((size_t)take);
+          ra.resize((size_t)take);
+          be->download(rd.data(), d.recDest + rc.off + rc.cur, sizeof(uint32_t) * (size_t)take);
+          be->download(ra.data(), d.recArrival + rc.off + rc.cur, sizeof(int) * (size_t)take);
+          for (int i = 0; i < take; ++i) {
+            if (sharded() && ((int)rd[(size_t)i] >> d.ownShift) != d.rank) {  // the owner's shard reports this destination
+              --total;
+              continue;
+            }
+            out.push_back(PeekRow{(int)rc.from, (int)rd[(size_t)i], (int)rc.pad - 1, ra[(size_t)i], (int)EV_MSG, rc.meta});
+          }
+        }
+      } else {
+        total += 1;
+        // tasks are self-addressed envelopes (Network.java:505-519); Ev.from of a task is protocol payload (e.g. the signer)
+        const int from = (e.kind == EV_TASK || e.kind == EV_PERIODIC) ? (int)e.to : (int)e.from;
+        if ((long long)out.size() < cap) out.push_back(PeekRow{from, (int)e.to, (int)e.pad - 1, arrival, (int)e.kind, e.meta});
+      }
+    };
+    for (int b = 0; b < d.ring; ++b) {
+      if (bc[(size_t)b] <= 0) continue;
+      const int arrival = time + ((b - time) & ringMask);
+      evs.resize((size_t)bc[(size_t)b]);
+      be->download(evs.data(), d.buckets + (size_t)b * (size_t)d.bcap, evs.size() * sizeof(Ev));
+      for (const Ev& e : evs) addOne(e, arrival);
+    }
+    if (d.farCap > 0) {
+      Ctl c = readCtl();
+      std::vector<FarEv> far((size_t)c.farCnt);
+      if (c.farCnt) be->download(far.data(), d.far, far.size() * sizeof(FarEv));
+      for (const FarEv& f : far) addOne(f.ev, f.target);
+    }
+    std::stable_sort(out.begin(), out.end(), [](const PeekRow& a, const PeekRow& b) {
+      if (a.arrivingAt != b.arrivingAt) return a.arrivingAt < b.arrivingAt;
+      if (a.from != b.from) return a.from < b.from;
+      if (a.to != b.to) return a.to < b.to;
+      return a.sentAt < b.sentAt;
+    });
+    return total;
   }
 
   void setDown(int id, bool down) {

@@ -1012,7 +1012,7 @@ WTG_HD int hCondPick(const Dev& d, int n, u64 drawIdx, bool apply) {
   ev.meta = e.meta;
   ev.pl = e.pl;
   ev.aux = e.id;
-  ev.pad = 0;
+  ev.pad = (uint32_t)d.ctl->tick + 1u;  // registerTask at network.time: EnvelopeInfo.sentAt + 1
   d.condEv[n] = ev;
   d.condTarget[n] = d.ctl->tick + d.pairing[n];
   d.condFired[n] = 1;

@@ -660,7 +660,7 @@ WTG_HD void gsfCondSelect(const Dev& d, C& c, int n, uint32_t* keepBits) {  // n
       ev.meta = best.meta;
       ev.pl = best.pl;
       ev.aux = 0;
-      ev.pad = 0;
+      ev.pad = (uint32_t)d.ctl->tick + 1u;  // Envelope.sendTime + 1 (EnvelopeInfo.sentAt for peekMessages; 0 = not recorded)
       d.condEv[n] = ev;
       d.condTarget[n] = ctl.tick + pairing;
     }
@@ -1906,7 +1906,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   ev.meta = ds.meta;
   ev.pl = ds.pl;
   ev.aux = ds.dkind == DK_INSERT_AT ? ds.aux : 0;
-  ev.pad = 0;
+  ev.pad = (uint32_t)ctl.tick + 1u;  // sendTime + 1 of sendArriveAt / registerTask (Network.java:390, 509): EnvelopeInfo.sentAt
   int target = -1;
   int sendTime = ctl.tick + 1;  // send(m, from, to) == send(m, time + 1, from, to)   Network.java:364-366
   if (ds.dkind == DK_INSERT_AT) {
@@ -1937,6 +1937,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     int32_t seed = lcgNextIntAt(d, ctl.rng, drawIdx);
     int from = (int)ds.from;
     if (ds.aux & DESC_SENDTIME) sendTime = ds.target;
+    ev.pad = (uint32_t)sendTime + 1u;
     const int delay = (int)(ds.aux >> DESC_DELAY_SHIFT);
     const int step = delay > 0 ? delay + 1 : 0;  // sendTime += delaysBetweenMessage + 1 after every destination (:455-459)
     if (ds.dkind == DK_SEND_SINGLE) {
@@ -1992,7 +1993,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
           rc.n = (uint32_t)cnt;
           rc.cur = 0;
           rc.off = (uint32_t)off;
-          rc.pad = 0;
+          rc.pad = (uint32_t)sendTime + 1u;
           d.rec[ri] = rc;
           for (int i = 0; i < cnt; ++i) {
             d.recDest[off + i] = dst[i];

@@ -138,6 +138,14 @@ class Network:
     def msgs_size_at(self, t):
         return self.api.check(self.api.msgs_size_at(self.h, int(t)))
 
+    def peek_messages(self, cap=1 << 16):
+        """network.msgs.peekMessages() (Network.java:279-286): (total, rows) with rows = dict of int32 arrays from, to, sent_at,
+        arriving_at, kind, msg_type, sorted by arrival; at most `cap` rows."""
+        a = [np.zeros(cap, np.int32) for _ in range(6)]
+        total = self.api.check(self.api.peek_messages(self.h, *[_p(x, C.c_int) for x in a], int(cap)))
+        k = min(total, cap)
+        return total, dict(zip(["from", "to", "sent_at", "arriving_at", "kind", "msg_type"], [x[:k] for x in a]))
+
     def stop_node(self, node_id):
         self.api.check(self.api.stop_node(self.h, int(node_id)))
 
