@@ -326,14 +326,25 @@ def run_casper_reference(args):
 
 
 def run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over_ranks):
-    """--workload casper: SURVEY.md §8d config #4 on the device engine (replicas with different seeds for N > 1)."""
+    """--workload casper: SURVEY.md §8d config #4 on the device engine.  N > 1: ONE simulation, node ids sharded over the ranks'
+    GPUs (BASELINE config #4: "node-sharded across 4xB200"; `--mode replicas`: independent seeds instead)."""
     import torch
 
     from wittgenstein_b200 import CasperIMD, CasperParemeters
 
     K, W = args.steps, args.warmup
+    sharded = world > 1 and args.mode != "replicas"
+    if sharded:
+        sum_over_ranks_job = sum_over_ranks
+        sum_over_ranks = lambda x: x  # noqa: E731  one run: its simulated time is not multiplied by the ranks
 
     def make():
+        if sharded:
+            from wittgenstein_b200.sharded import DistributedCasperIMD
+
+            p = DistributedCasperIMD(CasperParemeters(**casper_cfg()), dist, rank, world, local, tunables={"casper_votes": (K + W) // 64 + 3})
+            p.init(0)
+            return p
         p = CasperIMD(CasperParemeters(**casper_cfg()))
         p.network().set_seed(rank)
         p.network().set_tunable("casper_votes", (K + W) // 64 + 3)
@@ -403,6 +414,23 @@ def run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over
         del o
     deliveries = st1["deliveries"] - st0["deliveries"]
     tasks = st1["tasks"] - st0["tasks"]
+    parity_unsharded = None
+    if sharded:  # every shard's heads against the unsharded engine on the same slots (which the -m gpu tests pin on the oracle)
+        deliveries, tasks = sum_over_ranks_job(deliveries), sum_over_ranks_job(tasks)
+        ps = make()
+        for _ in range(W + K):
+            ps.network().run_ms(8000)
+        got = ps.all_heads()
+        nb_sh = len(ps.blocks()["height"])
+        del ps
+        if rank == 0:
+            pu = CasperIMD(CasperParemeters(**casper_cfg()))
+            pu.network().set_tunable("casper_votes", (K + W) // 64 + 3)
+            pu.init(0)
+            for _ in range(W + K):
+                pu.network().run_ms(8000)
+            parity_unsharded = bool((pu.heads() == got).all() and len(pu.blocks()["height"]) == nb_sh)
+            del pu
     value = sum_over_ranks(K * 8000) / (dev_ms / 1000.0)
     peaks = {}
     try:
@@ -411,9 +439,11 @@ def run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     line = {"metric": "simulated-ms/sec, CasperIMD 16,390 nodes", "value": value, "unit": "simulated-ms/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u64 bitmaps / int32", "data": "synthetic",
-            "config": {"workload": casper_workload(K, W), "parallelism": "1 GPU" if world == 1 else f"{world} independent seeded replicas",
+            "config": {"workload": casper_workload(K, W),
+                       "parallelism": "1 GPU" if world == 1 else (f"node-sharded: ONE simulation, {world} contiguous ranges of node ids, replicated block / attestation "
+                                                                  "tables, per-pass exchanges as peer stores over NVLink" if sharded else f"{world} independent seeded replicas"),
                        "l2": "launch-bound: ~340 non-empty milliseconds per slot, ~12 k deliveries each; working set (attestation bitmaps 200 MB) exceeds L2",
                        "blocks_at_end": nblocks},
             "msgs_per_s": sum_over_ranks(deliveries + tasks) / (dev_ms / 1000.0),
@@ -430,10 +460,14 @@ def run_casper(args, rank, world, local, dist, barrier, max_over_ranks, sum_over
                             "ticks": int(prof.get("k_begin", (0, 0))[1])}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity_unsharded is not None:
+        line["parity_sharded_vs_unsharded"] = "heads and block count identical" if parity_unsharded else "MISMATCH"
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    if parity_unsharded is False:
+        sys.exit(3)
 
 
 def main():

@@ -41,7 +41,10 @@ class HostBackend : public Backend {
         xPublishHeader(d);
         xSignal(d, 0);
       }
-      if (phasesDone < 2) xSignal(d, 1);
+      if (phasesDone < 2) {
+        if (d.allCap > 0) xPublishAllCount(d);
+        xSignal(d, 1);
+      }
     }
     return true;
   }
@@ -118,7 +121,11 @@ class HostBackend : public Backend {
       int per = d.descCap / ARENA_STRIPES, tot = stripedTotal(d.ctl->descCnt, per);
       for (int t = 0; t < tot; ++t) emitDesc(d, stripedIndex(d.ctl->descCnt, per, t));
     }
-    if (d.allCap > 0) {
+    if (d.allCap > 0 && d.G > 1) {  // node-sharded sendAll: publish the descriptors; built after the envelope exchange
+      int cnt = std::min(d.ctl->allCnt, d.xAllCap);
+      for (int j = 0; j < cnt; ++j) xPublishAll(d, j);
+      xPublishAllCount(d);
+    } else if (d.allCap > 0) {
       std::vector<int> tmp((size_t)d.N), hist((size_t)ALL_HIST);
       int cnt = std::min(d.ctl->allCnt, d.allCap);
       for (int j = 0; j < cnt; ++j) emitAll(d, c, d.allList[j], tmp.data(), hist.data());
@@ -130,6 +137,11 @@ class HostBackend : public Backend {
       if (d.ctl->error) return;
       for (int g = 0; g < d.ctl->totalSlots; ++g)
         if (xNeedsIngest(d, g)) xIngest(d, c, g);
+      if (d.allCap > 0) {
+        std::vector<int> tmp((size_t)d.N), hist((size_t)ALL_HIST);
+        int cnt = xAllTotal(d);
+        for (int k = 0; k < cnt; ++k) xBuildAll(d, c, k, tmp.data(), hist.data());
+      }
     }
     if (d.ctl->error) return;
     // multisplit: stable append into the ring in creation order

@@ -312,14 +312,14 @@ int WTG_API(casper_node_state)(void* h, int* head, int* attsReceived, int* heads
   return guard([&] {
     requireCasper(ENG);
     const wtg::Dev& d = ENG.d;
-    size_t n = (size_t)d.N;
-    ENG.fetch(head, d.cHead, n);
+    size_t n = (size_t)d.nLoc, o = (size_t)d.n0;  // a shard reports its own nodes
+    ENG.fetch(head, d.cHead + o, n);
     std::vector<int> ah((size_t)d.cMaxAtts), ahd((size_t)d.cMaxAtts);
     ENG.fetch(ah.data(), d.attHeight, ah.size());
     ENG.fetch(ahd.data(), d.attHead, ahd.size());
     std::vector<unsigned long long> br(n * (size_t)d.cBlkWords), tr(n * (size_t)d.cBlkWords);
-    ENG.fetch(br.data(), d.cBlkRecv, br.size());
-    ENG.fetch(tr.data(), d.cToReeval, tr.size());
+    ENG.fetch(br.data(), d.cBlkRecv + o * (size_t)d.cBlkWords, br.size());
+    ENG.fetch(tr.data(), d.cToReeval + o * (size_t)d.cBlkWords, tr.size());
     std::vector<unsigned long long> row((size_t)d.cAttWords);
     std::vector<unsigned char> seen((size_t)d.cMaxBlocks);
     for (size_t i = 0; i < n; ++i) {
@@ -330,7 +330,7 @@ int WTG_API(casper_node_state)(void* h, int* head, int* attsReceived, int* heads
       }
       blocksReceived[i] = b;
       toReevaluate[i] = t;
-      ENG.fetch(row.data(), d.cAttRecv + i * (size_t)d.cAttWords, row.size());
+      ENG.fetch(row.data(), d.cAttRecv + (o + i) * (size_t)d.cAttWords, row.size());
       std::fill(seen.begin(), seen.end(), 0);
       int cnt = 0, heads = 0;
       unsigned long long hs = 0;
@@ -358,7 +358,7 @@ int WTG_API(casper_node_state)(void* h, int* head, int* attsReceived, int* heads
 int WTG_API(casper_heads)(void* h, int* head) {
   return guard([&] {
     requireCasper(ENG);
-    ENG.fetch(head, ENG.d.cHead, (size_t)ENG.d.N);
+    ENG.fetch(head, ENG.d.cHead + ENG.d.n0, (size_t)ENG.d.nLoc);
     return 0;
   });
 }

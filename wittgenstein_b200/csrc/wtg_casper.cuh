@@ -172,6 +172,10 @@ WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
       if (cmaskHas(chain, d.attHead[a]) && d.attHeight[a] < height) out |= 1ULL << b;  // :414-423
     }
     inc[w] = out;
+    if (d.G > 1)  // the block table is replicated: the creator stores the row into every shard's copy (visible to the
+                  // receivers before the block can arrive: the exchange that follows the handlers is a system-scope release)
+      for (int q = 0; q < d.G; ++q)
+        if (q != d.rank) casperTabsOf(d, q).cbIncluded[(size_t)nb * W + w] = out;
   }
   if (c.lane() == 0) {
     d.cbHeight[nb] = height;
@@ -179,6 +183,17 @@ WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
     d.cbProducer[nb] = n;
     d.cbTime[nb] = tick;
     WTG_ATOMIC_ADD(&d.cg->createdThisTick, 1);  // see tickEnd
+    if (d.G > 1)
+      for (int q = 0; q < d.G; ++q)
+        if (q != d.rank) {
+          CasperTabs t = casperTabsOf(d, q);
+          t.cbHeight[nb] = height;
+          t.cbParent[nb] = base;
+          t.cbProducer[nb] = n;
+          t.cbTime[nb] = tick;
+          WTG_ATOMIC_ADD(&t.cg->nBlocks, 1);          // the same id everywhere: at most one block per pass (tickEnd checks)
+          WTG_ATOMIC_ADD(&t.cg->createdThisTick, 1);
+        }
   }
   c.sync();
   return nb;
@@ -317,6 +332,13 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
     if (c.lane() == 0 && base >= 0) {
       d.attHead[a] = d.cHead[n];
       d.attHeight[a] = tick / CASPER_SLOT;
+      if (d.G > 1)  // replicated attestation table
+        for (int q = 0; q < d.G; ++q)
+          if (q != d.rank) {
+            CasperTabs t = casperTabsOf(d, q);
+            t.attHead[a] = d.cHead[n];
+            t.attHeight[a] = tick / CASPER_SLOT;
+          }
       d.cVotes[n] = k + 1;
       cWriteSendAll(d, base, n, item, 0, CM_ATT, (u64)(uint32_t)a, tick + d.cAttTime);
       cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
@@ -472,19 +494,20 @@ WTG_HD void casperDeliver(const Dev& d, C& c, int n, uint32_t evKind, uint32_t m
 //   hist [ALL_HIST] counters private to the coop (shared memory on the device)
 // ------------------------------------------------------------------------------------------
 constexpr int ALL_HIST = 1024;
+// `seq` < 0: record slot from the engine's own counter (one engine = the whole network).  `seq` >= 0 (node-sharded run): the
+// sendAll's global sequence number — every shard builds the identical record in slot seq % recSlots and keeps the bucket
+// entry of the first group only when it owns one of that group's destinations.
 template <class C>
-WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
+WTG_HD void emitAllCore(const Dev& d, C& c, uint32_t fromU, uint32_t meta, u64 pl, int sendTime, int g, u64 drawIdx, int seq, int* tmp, int* hist) {
   const Ctl& ctl = *d.ctl;
-  const Desc ds = d.desc[di];
   const int N = d.N;
-  int g = d.slotBase[ds.item] + (int)ds.sub;
+  const bool shard = seq >= 0;
   if (g >= d.newEvCap) {
     setError(d, ERR_DESC_OVERFLOW, g);
     return;
   }
-  const u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
   const int32_t seed = lcgNextIntAt(d, ctl.rng, drawIdx);
-  const int from = (int)ds.from, sendTime = ds.target;
+  const int from = (int)fromU;
   const bool fromOk = !d.ndown[from];
   int mn = 0x7fffffff, mx = -1, cnt = 0;
   for (int to = c.lane(); to < N; to += C::LANES) {
@@ -507,15 +530,15 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
   Ev ev;
   ev.kind = EV_MULTI;
   ev.to = 0;
-  ev.from = ds.from;
-  ev.meta = ds.meta;
-  ev.pl = ds.pl;
+  ev.from = fromU;
+  ev.meta = meta;
+  ev.pl = pl;
   ev.aux = 0;
-  ev.pad = (uint32_t)ds.target + 1u;  // sendAll(msg, sendTime, from): EnvelopeInfo.sentAt + 1
+  ev.pad = (uint32_t)sendTime + 1u;  // sendAll(msg, sendTime, from): EnvelopeInfo.sentAt + 1
   int target = -1;
   if (cnt == 1) {  // SingleDestEnvelope
     for (int to = c.lane(); to < N; to += C::LANES)
-      if (tmp[to] >= 0) {
+      if (tmp[to] >= 0 && (!shard || ownerOf(d, to) == d.rank)) {
         ev.kind = EV_MSG;
         ev.to = (uint32_t)to;
         target = tmp[to];
@@ -525,12 +548,19 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
       }
     return;
   }
+  bool keep = true;  // this engine holds the bucket entry of the first group
   if (cnt > 1) {
     int ri = 0;
-    if (c.lane() == 0) ri = (int)((unsigned)WTG_ATOMIC_ADD(&d.ctl->recTop, 1) % (unsigned)d.recSlots);
+    if (shard)
+      ri = (int)((unsigned)seq % (unsigned)d.recSlots);
+    else if (c.lane() == 0)
+      ri = (int)((unsigned)WTG_ATOMIC_ADD(&d.ctl->recTop, 1) % (unsigned)d.recSlots);
     ri = c.bcast(ri, 0);
     MultiRec old = d.rec[ri];
-    if (old.cur < old.n) {  // the slot still holds a live envelope
+    // the slot still holds a live envelope?  (replicated records: the cursor lives in the bucket entries, so a slot is
+    // free once its last arrival has been processed)
+    const bool live = shard ? (old.n > 0 && d.recArrival[old.off + old.n - 1] > ctl.tick) : (old.cur < old.n);
+    if (live) {
       setError(d, ERR_REC_OVERFLOW, ri);
       cnt = 0;
     } else {
@@ -600,19 +630,33 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
       }
       if (c.lane() == 0) {
         MultiRec rc;
-        rc.from = ds.from;
-        rc.meta = ds.meta;
-        rc.pl = ds.pl;
+        rc.from = fromU;
+        rc.meta = meta;
+        rc.pl = pl;
         rc.n = (uint32_t)cnt;
         rc.cur = 0;
         rc.off = (uint32_t)off;
-        rc.pad = (uint32_t)ds.target + 1u;
+        rc.pad = (uint32_t)sendTime + 1u;
         d.rec[ri] = rc;
       }
       c.sync();
       ev.to = d.recDest[off];
       ev.aux = (uint32_t)ri;
       target = mn;
+      if (shard) {  // first destination of the first group that this shard owns (none: another shard holds the entry)
+        int first = 0x7fffffff;
+        for (int j0 = 0; j0 < cnt; j0 += C::LANES) {
+          int j = j0 + c.lane();
+          bool inGroup = j < cnt && d.recArrival[off + j] == mn;
+          if (inGroup && ownerOf(d, (int)d.recDest[off + j]) == d.rank && j < first) first = j;
+          if (!c.any(inGroup)) break;
+        }
+        first = c.minv(first);
+        keep = first != 0x7fffffff;
+        if (keep) ev.to = d.recDest[off + first];
+        ev.meta = 0;
+        ev.pl = 0;  // index of the group's first destination (multiCur)
+      }
     }
   }
   if (c.lane() == 0) {
@@ -620,9 +664,58 @@ WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
       setError(d, ERR_FAR_FUTURE, target);
       target = -1;
     }
-    d.newEv[g] = ev;
-    d.newTarget[g] = target;
+    if (!shard) {
+      d.newEv[g] = ev;
+      d.newTarget[g] = target;
+    } else if (keep && target >= 0) {
+      d.newEv[g] = ev;
+      d.newTarget[g] = target;
+    }
   }
+}
+template <class C>
+WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
+  const Desc ds = d.desc[di];
+  const int g = d.slotBase[ds.item] + (int)ds.sub;
+  const u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
+  emitAllCore(d, c, ds.from, ds.meta, ds.pl, ds.target, g, drawIdx, -1, tmp, hist);
+}
+// node-sharded: publish this shard's j-th sendAll of the pass (global creation / draw index) into every shard's list ...
+WTG_HD void xPublishAll(const Dev& d, int j) {
+  const Desc ds = d.desc[d.allList[j]];
+  XAll a;
+  a.from = ds.from;
+  a.meta = ds.meta;
+  a.pl = ds.pl;
+  a.sendTime = ds.target;
+  a.g = d.slotBase[ds.item] + (int)ds.sub + (int)d.xoffS[ds.item - d.nLoc];
+  a.draw = (u64)(d.drawBase[ds.item] + (int)ds.sub) + (u64)d.xoffD[ds.item - d.nLoc];
+  for (int q = 0; q < d.G; ++q) d.peer[q].all[(size_t)d.rank * d.xAllCap + j] = a;
+}
+WTG_HD void xPublishAllCount(const Dev& d) {
+  int cnt = d.ctl->error ? 0 : d.ctl->allCnt;
+  if (cnt > d.xAllCap) {
+    setError(d, ERR_DESC_OVERFLOW, cnt);
+    cnt = 0;
+  }
+  for (int q = 0; q < d.G; ++q) d.peer[q].allCnt[d.rank] = cnt;
+}
+// ... and, after the envelope exchange, build the k-th sendAll of the pass over all shards (shard-major order)
+WTG_HD int xAllTotal(const Dev& d) {
+  int tot = 0;
+  for (int q = 0; q < d.G; ++q) tot += d.peer[d.rank].allCnt[q];
+  return tot;
+}
+template <class C>
+WTG_HD void xBuildAll(const Dev& d, C& c, int k, int* tmp, int* hist) {
+  int q = 0, i = k;
+  while (q < d.G && i >= d.peer[d.rank].allCnt[q]) {
+    i -= d.peer[d.rank].allCnt[q];
+    ++q;
+  }
+  if (q >= d.G) return;
+  const XAll a = d.peer[d.rank].all[(size_t)q * d.xAllCap + i];
+  emitAllCore(d, c, a.from, a.meta, a.pl, a.sendTime, a.g, a.draw, (int)(((unsigned)d.ctl->allSeq + (unsigned)k) & 0x3fffffffu), tmp, hist);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -639,7 +732,8 @@ WTG_HD bool farAppend(const Dev& d, const Ev& ev, int target, int g) {
   f.ev = ev;
   f.target = target;
   f.pad = 0;
-  f.key = ((u64)(uint32_t)d.ctl->tick << 32) | (u64)(uint32_t)g;
+  // insertion order among far envelopes; node-sharded: the ordering key of the bucket entry it becomes (wtg_shard.cuh)
+  f.key = d.G > 1 ? orderKey((unsigned)d.ctl->xseq, (unsigned)g) : (((u64)(uint32_t)d.ctl->tick << 32) | (u64)(uint32_t)g);
   d.far[fi] = f;
   WTG_ATOMIC_MIN(&d.ctl->farMin, target);
   return true;
@@ -682,9 +776,10 @@ WTG_HD void farMigrate(const Dev& d, C& c, int t) {
     }
     int slot = e.target & (d.ring - 1);
     int pos = d.bucketCount[slot] + rank;
-    if (pos < d.bcap)
+    if (pos < d.bcap) {
       d.buckets[(size_t)slot * (size_t)d.bcap + pos] = e.ev;
-    else
+      if (d.G > 1) d.bucketKey[(size_t)slot * (size_t)d.bcap + pos] = e.key;
+    } else
       setError(d, ERR_BUCKET_OVERFLOW, e.target);
   }
   c.sync();
@@ -749,15 +844,55 @@ WTG_HD void tickBeginFfwd(const Dev& d, C& c) {
   Ctl& ctl = *d.ctl;
   const int time = ctl.time, until = ctl.until;
   const int H = farHorizon(d);
+  if (c.lane() == 0) {  // per-pass counters first: in a node-sharded run the other shards' handlers of this pass (which start
+                        // after the begin exchange below) store into some of them
+    for (int t = 0; t < ARENA_STRIPES; ++t) {
+      ctl.descCnt[t] = 0;
+      ctl.destCnt[t] = 0;
+      ctl.workCnt[t] = 0;
+      ctl.dueCnt[t] = 0;
+      ctl.taskCnt[t] = 0;
+    }
+    ctl.nItems = 0;
+    ctl.totalSlots = 0;
+    ctl.totalDraws = 0;
+    ctl.hReject = 0;
+    ctl.allCnt = 0;
+    ctl.shufReject = 0;
+    if (d.cg) d.cg->createdThisTick = 0;
+    if (d.G > 1) {
+      ctl.xseq += 1;
+      ctl.nEvGlobal = 0;
+      for (int q = 0; q < MAX_SHARDS; ++q) ctl.stageTop[q] = 0;
+    }
+  }
+  c.sync();
   int span = until - time;
   if (span > H - 1) span = H - 1;
   int next = 0x7fffffff;
   if (!ctl.idle && span > 0) next = ringNextNonEmpty(d, c, time, span);
   if (!ctl.idle && ctl.farMin <= until && ctl.farMin < next) next = ctl.farMin;
   c.sync();
+  int after = 0x7fffffff;
+  if (d.G > 1) {  // the next event of the whole network: minimum over the shards (every shard takes the same decision)
+    if (!ctl.idle && next > until) {
+      after = ringNextNonEmpty(d, c, time, H - 1);
+      if (ctl.farMin < after) after = ctl.farMin;
+    }
+    c.sync();
+    if (c.lane() == 0) {
+      int gn = next, ga = after;
+      xBeginExchange(d, next, after, gn, ga);
+      ctl.xNext = gn;
+      ctl.xAfter = ga;
+    }
+    c.sync();
+    next = ctl.xNext;
+    after = ctl.xAfter;
+    if (ctl.error) return;
+  }
   if (next > until) {  // nothing before the end of the window
-    int after = 0x7fffffff;
-    if (!ctl.idle) {
+    if (d.G == 1 && !ctl.idle) {
       after = ringNextNonEmpty(d, c, time, H - 1);
       if (ctl.farMin < after) after = ctl.farMin;
     }
@@ -779,22 +914,6 @@ WTG_HD void tickBeginFfwd(const Dev& d, C& c) {
       ctl.nEv = d.bucketCount[next & (d.ring - 1)];
       if (ctl.nEv > ctl.maxBucket) ctl.maxBucket = ctl.nEv;
     }
-  }
-  if (c.lane() == 0) {
-    for (int t = 0; t < ARENA_STRIPES; ++t) {
-      ctl.descCnt[t] = 0;
-      ctl.destCnt[t] = 0;
-      ctl.workCnt[t] = 0;
-      ctl.dueCnt[t] = 0;
-      ctl.taskCnt[t] = 0;
-    }
-    ctl.nItems = 0;
-    ctl.totalSlots = 0;
-    ctl.totalDraws = 0;
-    ctl.hReject = 0;
-    ctl.allCnt = 0;
-    ctl.shufReject = 0;
-    if (d.cg) d.cg->createdThisTick = 0;
   }
   c.sync();
 }

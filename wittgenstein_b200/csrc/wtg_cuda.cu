@@ -485,6 +485,26 @@ __device__ __forceinline__ void b_emit_all(const Dev& d, const int VB, const int
   for (int j = gw; j < cnt; j += nw) emitAll(d, c, d.allList[j], d.allTmp + (size_t)gw * d.N, hist[warp]);
 }
 __global__ void __launch_bounds__(128) k_emit_all(Dev d) { b_emit_all(d, blockIdx.x, gridDim.x); }
+// node-sharded sendAll (CasperIMD): the descriptors are published to every shard before the envelope exchange ...
+__device__ __forceinline__ void b_x_all_publish(const Dev& d, const int VB, const int VG) {
+  int cnt = d.ctl->error ? 0 : d.ctl->allCnt;
+  if (cnt > d.xAllCap) cnt = 0;  // xPublishAllCount reports the overflow
+  for (int j = VB * blockDim.x + threadIdx.x; j < cnt; j += VG * blockDim.x) xPublishAll(d, j);
+  if (VB == 0 && threadIdx.x == 0) xPublishAllCount(d);
+}
+__global__ void __launch_bounds__(128) k_x_all_publish(Dev d) { b_x_all_publish(d, blockIdx.x, gridDim.x); }
+// ... and after it every shard builds every sendAll of the pass: the same sorted record in the same slot (replicated records)
+__device__ __forceinline__ void b_x_all_build(const Dev& d, const int VB, const int VG) {
+  __shared__ int hist[4][ALL_HIST];
+  if (d.ctl->error) return;
+  const int cnt = xAllTotal(d);
+  const int warp = threadIdx.x >> 5;
+  if (warp >= 4) return;
+  const int gw = VB * 4 + warp, nw = VG * 4;
+  CoopWarp c;
+  for (int k = gw; k < cnt; k += nw) xBuildAll(d, c, k, d.allTmp + (size_t)gw * d.N, hist[warp]);
+}
+__global__ void __launch_bounds__(128) k_x_all_build(Dev d) { b_x_all_build(d, blockIdx.x, gridDim.x); }
 
 // ---- multisplit: stable distribution of the new envelopes into the time ring -----------------
 // A block of Dev.msWarps warps handles a chunk of msWarps * MS_SUB consecutive envelopes (creation order); warp w owns the w-th
@@ -1052,7 +1072,10 @@ class CudaBackend : public Backend {
     }
     k_emit<<<ARENA_STRIPES * 16, 256, 0, st>>>(d);
     if (d.allCap > 0) {
-      k_emit_all<<<d.allWarps / 4, 128, 0, st>>>(d);
+      if (d.G > 1)
+        k_x_all_publish<<<8, 128, 0, st>>>(d);
+      else
+        k_emit_all<<<d.allWarps / 4, 128, 0, st>>>(d);
       launches += 1;
     }
     profEnd();
@@ -1060,8 +1083,12 @@ class CudaBackend : public Backend {
       profBegin(4);
       k_x_sync<<<1, 32, 0, st>>>(d, 1);
       k_x2_ingest<<<sms * 4, 256, 0, st>>>(d);
-      profEnd();
       launches += 2;
+      if (d.allCap > 0) {
+        k_x_all_build<<<d.allWarps / 4, 128, 0, st>>>(d);
+        launches += 1;
+      }
+      profEnd();
     }
     profBegin(9);
     k_ms_count<<<sms * 2, d.msWarps * 32, msSmem, st>>>(d);

@@ -126,8 +126,14 @@ class Engine {
   long long stageWordsWanted = 0;  // protocol-specific staging capacity per (sender, parity), in 64-bit words
   long long farWanted = 0;         // protocol-specific size of the far-future calendar when the latency model needs one
   struct XLayout {
-    size_t hdr, flags, items, newEv, newTarget, stage, rec, recDest, recArrival, total;
+    size_t hdr, flags, items, newEv, newTarget, stage, rec, recDest, recArrival, beg, all, allCnt, casper, total;
   } xl{};
+  // protocol-specific parts of the exchange region, set before allocCommon (CasperIMD: replicated block / attestation tables,
+  // sendAll descriptors of a pass); unevenShards: the protocol's node count need not split into power-of-two shards
+  size_t xCasperBytes = 0;
+  int xAllCapWanted = 0;
+  bool unevenShards = false;
+  bool shardFarOk = false;  // the protocol's far-future envelopes are tasks of the shard's own nodes
 
   explicit Engine(Backend* b) : be(b) { std::memset(&d, 0, sizeof(d)); }
   void setShard(int rank, int world) {
@@ -165,6 +171,10 @@ class Engine {
     q.rec = (MultiRec*)(b + xl.rec);
     q.recDest = (uint32_t*)(b + xl.recDest);
     q.recArrival = (int*)(b + xl.recArrival);
+    q.beg = (XBegin*)(b + xl.beg);
+    q.all = (XAll*)(b + xl.all);
+    q.allCnt = (int*)(b + xl.allCnt);
+    q.casper = b + xl.casper;
     return q;
   }
   // exchange region: everything another shard's kernels write (one allocation = one IPC handle)
@@ -172,7 +182,7 @@ class Engine {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t o = 0;
     xl.hdr = o;        o += al(sizeof(XHdr) * MAX_SHARDS);
-    xl.flags = o;      o += al(sizeof(int) * 2 * MAX_SHARDS);
+    xl.flags = o;      o += al(sizeof(int) * 3 * MAX_SHARDS);
     xl.items = o;      o += al(sizeof(XItem) * (size_t)d.G * d.xItemCap);
     xl.newEv = o;      o += al(sizeof(Ev) * (size_t)d.newEvCap);
     xl.newTarget = o;  o += al(sizeof(int) * (size_t)d.newEvCap);
@@ -180,6 +190,10 @@ class Engine {
     xl.rec = o;        o += al(sizeof(MultiRec) * (size_t)d.recCap);
     xl.recDest = o;    o += al(sizeof(uint32_t) * (size_t)d.recDestCap);
     xl.recArrival = o; o += al(sizeof(int) * (size_t)d.recDestCap);
+    xl.beg = o;        o += al(sizeof(XBegin) * MAX_SHARDS);
+    xl.all = o;        o += al(sizeof(XAll) * (size_t)d.G * (size_t)std::max(1, d.xAllCap));
+    xl.allCnt = o;     o += al(sizeof(int) * MAX_SHARDS);
+    xl.casper = o;     o += al(xCasperBytes);
     xl.total = o;
     xBytes = o;
     xRegion = be->allocShared(o);
@@ -246,15 +260,22 @@ class Engine {
     d.proto = proto;
     d.G = shardWorld;
     d.rank = shardRank;
-    if (N % shardWorld != 0) throw std::invalid_argument("the node count must be a multiple of the number of shards");
-    d.nLoc = N / shardWorld;
-    d.n0 = shardRank * d.nLoc;
+    if (N % shardWorld != 0 && !unevenShards) throw std::invalid_argument("the node count must be a multiple of the number of shards");
+    d.perShard = (N + shardWorld - 1) / shardWorld;
+    d.n0 = shardRank * d.perShard;
+    d.nLoc = std::min(d.perShard, N - d.n0);
+    if (d.nLoc <= 0) throw std::invalid_argument("more shards than the node count can fill");
     d.ownShift = 0;
+    d.xAllCap = xAllCapWanted;
     if (sharded()) {
-      if ((d.nLoc & (d.nLoc - 1)) != 0) throw std::invalid_argument("a node-sharded network needs a power-of-two number of nodes per shard");
-      while ((1 << d.ownShift) < d.nLoc) ++d.ownShift;
+      if ((d.perShard & (d.perShard - 1)) != 0) {
+        if (!unevenShards) throw std::invalid_argument("a node-sharded network needs a power-of-two number of nodes per shard");
+        d.ownShift = -1;  // ownerOf divides
+      } else {
+        while ((1 << d.ownShift) < d.perShard) ++d.ownShift;
+      }
     }
-    const int NL = d.nLoc;
+    const int NL = d.perShard;  // capacities are those of a full shard: every shard lays its exchange region out identically
     d.msgDiscardTime = msgDiscardTime;
     int ring = 2048;
     int need = hm.latMax + 64 + ringExtra;
@@ -262,7 +283,7 @@ class Engine {
       // latency models with multi-second arrivals (EthScan 12 000 ms, Fixed / Uniform(8000)): the ring stays at 4 096
       // buckets (the multisplit keeps a histogram of the ring in shared memory) and arrivals 2 048 ms or more ahead go
       // through the far-future calendar; the protocol still ticks every millisecond
-      if (sharded()) throw std::logic_error("this latency model needs the far-future calendar, which node-sharded networks do not have yet");
+      if (sharded()) throw std::logic_error("this latency model needs the far-future calendar for messages, which node-sharded networks do not have");
       farEnabled = true;
       farTicking = true;
       need = std::min(need, 2048 - 64 + ringExtra);
@@ -351,7 +372,7 @@ class Engine {
     d.msCount = dalloc<int>((size_t)d.msChunks * (size_t)ring);
     d.freeList = dalloc<uint32_t>(d.freeCap);
     if (sharded()) {
-      if (farEnabled) throw std::logic_error("this protocol cannot run node-sharded yet (far-future calendar)");
+      if (farEnabled && !shardFarOk) throw std::logic_error("this protocol cannot run node-sharded yet (far-future calendar)");
       d.xItemCap = d.itemCap + 1;
       d.stageCapWords = (int)std::min<long long>(0x7fffffffLL, stageWordsWanted);
       d.recCap = d.recCap / shardWorld * shardWorld;
@@ -1078,12 +1099,12 @@ class Engine {
   }
   void casperInit(int byzDelay, int byzKind = CK_BYZ_WF) {
     requireNotInited();
-    requireUnsharded("this protocol");
     if (!casperConstructed) throw std::logic_error("CasperIMD not constructed");
     const int attCount = cp.attestersPerRound * cp.cycleLength;
     const int N = 1 + cp.blockProducersCount + attCount;
     if (CASPER_SLOT + byzDelay <= 0) throw std::invalid_argument("the Byzantine producer's first slot would start in the past");
     if (byzKind != CK_BYZ && byzKind != CK_BYZ_SF && byzKind != CK_BYZ_NS && byzKind != CK_BYZ_WF) throw std::invalid_argument("unknown Byzantine producer kind");
+    if (sharded() && N > (int)KEY_SUB_MAX) throw std::invalid_argument("a node-sharded sendAll protocol holds at most 65535 nodes (ordering-key layout)");
     hm.buildNodes(N - 1);  // byzantine producer, producers 1.., attesters — in this order (:479-507); registering tasks draws nothing
     ringExtra = std::max(cp.blockConstructionTime, cp.attestationConstructionTime);
     farEnabled = true;
@@ -1092,11 +1113,19 @@ class Engine {
     if (slots * N > 0x7fffffffLL) throw std::invalid_argument("attestersPerRound x nodes too large for the sendAll arena");
     recDestOverride = (int)(slots * N);
     if (!tun.recCap) tun.recCap = slots;
-    allocCommon(N, PROTO_CASPER);
     const int maxVotes = (int)(tun.casperVotes ? tun.casperVotes : 6);
     long long maxBlocks = tun.casperBlocks ? tun.casperBlocks : (long long)cp.cycleLength * (maxVotes + 1) + 64;
     maxBlocks = (maxBlocks + 63) / 64 * 64;
     if (maxBlocks > 64 * CASPER_MAX_BLKWORDS) maxBlocks = 64 * CASPER_MAX_BLKWORDS;
+    const int maxAtts = (attCount * maxVotes + 63) / 64 * 64;
+    if (sharded()) {  // node ids split into G contiguous ranges (1 + producers + attesters is no power of two); the block /
+                      // attestation tables are replicated inside the exchange region; periodic tasks are the only far envelopes
+      unevenShards = true;
+      shardFarOk = true;
+      xCasperBytes = casperTabsBytes((int)maxBlocks, maxAtts, maxAtts / 64);
+      xAllCapWanted = N / shardWorld + 64;
+    }
+    allocCommon(N, PROTO_CASPER);
     d.cCycle = cp.cycleLength;
     d.cBpCount = cp.blockProducersCount;
     d.cAttPerRound = cp.attestersPerRound;
@@ -1107,7 +1136,7 @@ class Engine {
     d.cByzDelay = byzDelay;
     d.cMaxBlocks = (int)maxBlocks;
     d.cBlkWords = (int)(maxBlocks / 64);
-    d.cMaxAtts = (attCount * maxVotes + 63) / 64 * 64;
+    d.cMaxAtts = maxAtts;
     d.cAttWords = d.cMaxAtts / 64;
     d.cFirstAtt = 1 + cp.blockProducersCount;
     std::vector<uint8_t> kind((size_t)N, CK_ATTESTER);
@@ -1115,29 +1144,46 @@ class Engine {
     kind[1] = (uint8_t)byzKind;
     for (int i = 1; i < cp.blockProducersCount; ++i) kind[(size_t)(1 + i)] = CK_PRODUCER;
     d.cKind = dupload(kind);
-    d.cHead = dalloc<int>(N);
-    d.cVotes = dalloc<int>(N);
-    d.cAttRecv = dalloc<unsigned long long>((size_t)N * d.cAttWords);
+    d.cHead = dallocNodes<int>();
+    d.cVotes = dallocNodes<int>();
+    d.cAttRecv = dallocNodes<unsigned long long>((size_t)d.cAttWords);
     std::vector<unsigned long long> br((size_t)N * d.cBlkWords, 0);
     for (int i = 0; i < N; ++i) br[(size_t)i * d.cBlkWords] = 1ULL;  // blocksReceivedByBlockId.put(genesis.id, genesis)
-    d.cBlkRecv = dupload(br);
-    d.cToReeval = dalloc<unsigned long long>((size_t)N * d.cBlkWords);
+    d.cBlkRecv = duploadNodes(br, (size_t)d.cBlkWords);
+    d.cToReeval = dallocNodes<unsigned long long>((size_t)d.cBlkWords);
     std::vector<int> minus1((size_t)d.cMaxBlocks, -1);
-    d.cbHeight = dalloc<int>(d.cMaxBlocks);
-    d.cbParent = dupload(minus1);
-    d.cbProducer = dupload(minus1);
-    d.cbTime = dalloc<int>(d.cMaxBlocks);
-    d.cbIncluded = dalloc<unsigned long long>((size_t)d.cMaxBlocks * d.cAttWords);
-    d.attHead = dalloc<int>(d.cMaxAtts);
-    d.attHeight = dalloc<int>(d.cMaxAtts);
     CasperG g;
     std::memset(&g, 0, sizeof(g));
     g.nBlocks = 1;
     g.byzToSend = 1;
-    d.cg = dalloc<CasperG>(1);
+    if (sharded()) {
+      std::vector<char> zero(xCasperBytes, 0);
+      be->upload(d.peer[d.rank].casper, zero.data(), zero.size());
+      CasperTabs t = casperTabsAt(d.peer[d.rank].casper, d.cMaxBlocks, d.cMaxAtts);
+      d.cg = t.cg;
+      d.cbHeight = t.cbHeight;
+      d.cbParent = t.cbParent;
+      d.cbProducer = t.cbProducer;
+      d.cbTime = t.cbTime;
+      d.cbIncluded = t.cbIncluded;
+      d.attHead = t.attHead;
+      d.attHeight = t.attHeight;
+      be->upload(d.cbParent, minus1.data(), minus1.size() * sizeof(int));
+      be->upload(d.cbProducer, minus1.data(), minus1.size() * sizeof(int));
+    } else {
+      d.cbHeight = dalloc<int>(d.cMaxBlocks);
+      d.cbParent = dupload(minus1);
+      d.cbProducer = dupload(minus1);
+      d.cbTime = dalloc<int>(d.cMaxBlocks);
+      d.cbIncluded = dalloc<unsigned long long>((size_t)d.cMaxBlocks * d.cAttWords);
+      d.attHead = dalloc<int>(d.cMaxAtts);
+      d.attHeight = dalloc<int>(d.cMaxAtts);
+      d.cg = dalloc<CasperG>(1);
+    }
     be->upload(d.cg, &g, sizeof(g));
     // sendAll machinery: records recycled over recSlots slots of N destinations
     d.allCap = N + 64;
+    if (sharded()) d.allCap = d.xAllCap;
     d.allList = dalloc<int>(d.allCap);
     d.allWarps = 512;
     d.allTmp = dalloc<int>((size_t)d.allWarps * N);
@@ -1152,6 +1198,7 @@ class Engine {
     for (int i = 0; i < attCount; ++i) regs.push_back({d.cFirstAtt + i, CASPER_SLOT * (1 + i % cp.cycleLength) + 4000});
     std::vector<FarEv> far;
     std::vector<std::vector<Ev>> near((size_t)d.ring);
+    std::vector<std::vector<unsigned long long>> nearKey((size_t)d.ring);
     int farMin = 0x7fffffff;
     unsigned long long seq = 0;
     for (const Reg& r : regs) {
@@ -1161,14 +1208,19 @@ class Engine {
       ev.kind = EV_PERIODIC;
       ev.to = (uint32_t)r.node;
       ev.from = (uint32_t)r.node;
-      if (r.startAt < d.ring / 2) {
+      const bool mine = r.node >= d.n0 && r.node < d.n0 + d.nLoc;  // a shard keeps the tasks of its own nodes
+      // insertion order = registration order; node-sharded: as the ordering key of "pass 0" (wtg_shard.cuh)
+      const unsigned long long key = sharded() ? orderKey(0, (unsigned)seq) : seq;
+      if (!mine) {
+      } else if (r.startAt < d.ring / 2) {
         near[(size_t)r.startAt].push_back(ev);
+        nearKey[(size_t)r.startAt].push_back(key);
       } else {
         FarEv f;
         std::memset(&f, 0, sizeof(f));
         f.ev = ev;
         f.target = r.startAt;
-        f.key = seq;
+        f.key = key;
         far.push_back(f);
         farMin = std::min(farMin, r.startAt);
       }
@@ -1180,6 +1232,7 @@ class Engine {
       if (!near[(size_t)t].empty()) {
         if ((int)near[(size_t)t].size() > d.bcap) throw std::runtime_error("bucket capacity too small");
         be->upload(d.buckets + (size_t)t * d.bcap, near[(size_t)t].data(), near[(size_t)t].size() * sizeof(Ev));
+        if (sharded()) be->upload(d.bucketKey + (size_t)t * d.bcap, nearKey[(size_t)t].data(), nearKey[(size_t)t].size() * sizeof(unsigned long long));
         int cnt = (int)near[(size_t)t].size();
         be->upload(d.bucketCount + t, &cnt, sizeof(int));
       }
@@ -1365,13 +1418,34 @@ class Engine {
     throw std::runtime_error(std::string("device engine error: ") + names[c.error < 13 ? c.error : 8] + " (detail " + std::to_string(c.errorDetail) + ")");
   }
 
+  // node-sharded sendAll protocols: a multi-destination envelope has one bucket entry on every shard that owns a destination
+  // of its next group; msgs.size() counts it once — on the shard that owns the group's first destination
+  int countBucket(int slot, int cnt) {
+    if (!(sharded() && d.allCap > 0)) return cnt;
+    std::vector<Ev> evs((size_t)cnt);
+    be->download(evs.data(), d.buckets + (size_t)slot * (size_t)d.bcap, evs.size() * sizeof(Ev));
+    int c = 0;
+    for (const Ev& e : evs) {
+      if (e.kind != EV_MULTI) {
+        ++c;
+        continue;
+      }
+      MultiRec rc;
+      be->download(&rc, d.rec + e.aux, sizeof(MultiRec));
+      uint32_t first = 0;
+      be->download(&first, d.recDest + rc.off + (uint32_t)e.pl, sizeof(uint32_t));
+      if (ownerOf(d, (int)first) == d.rank) ++c;
+    }
+    return c;
+  }
   int msgsSize() {
     requireInited();
     std::vector<int> bc(d.ring);
     be->sync();
     be->download(bc.data(), d.bucketCount, sizeof(int) * d.ring);
     long long s = 0;
-    for (int v : bc) s += v;
+    for (int b = 0; b < d.ring; ++b)
+      if (bc[(size_t)b] > 0) s += countBucket(b, bc[(size_t)b]);
     if (d.farCap > 0) s += readCtl().farCnt;
     return (int)s;
   }
@@ -1381,6 +1455,7 @@ class Engine {
     int v = 0;
     be->sync();
     if (t < time + d.ring) be->download(&v, d.bucketCount + (t & ringMask), sizeof(int));
+    if (v > 0) v = countBucket(t & ringMask, v);
     if (d.farCap > 0) {
       Ctl c = readCtl();
       std::vector<FarEv> far((size_t)c.farCnt);
@@ -1425,7 +1500,7 @@ class Engine {
           be->download(rd.data(), d.recDest + rc.off + rc.cur, sizeof(uint32_t) * (size_t)take);
           be->download(ra.data(), d.recArrival + rc.off + rc.cur, sizeof(int) * (size_t)take);
           for (int i = 0; i < take; ++i) {
-            if (sharded() && ((int)rd[(size_t)i] >> d.ownShift) != d.rank) {  // the owner's shard reports this destination
+            if (sharded() && ownerOf(d, (int)rd[(size_t)i]) != d.rank) {  // the owner's shard reports this destination
               --total;
               continue;
             }

@@ -303,7 +303,7 @@ WTG_HD void xIngest(const Dev& d, C& c, int g) {
   c.sync();
 }
 WTG_HD bool xNeedsIngest(const Dev& d, int g) {
-  return d.newTarget[g] >= 0 && d.newEv[g].kind == EV_MSG && (d.newEv[g].meta & META_STAGED) != 0;
+  return d.proto == PROTO_GSF && d.newTarget[g] >= 0 && d.newEv[g].kind == EV_MSG && (d.newEv[g].meta & META_STAGED) != 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1765,7 +1765,7 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
       if (lastOwner == d.rank) {
         int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
         d.inbox[s] = inboxMake(item0 + m, i);
-        if (d.G > 1) d.itemKey[item0 + m] = bkey | (u64)(255 - j);
+        if (d.G > 1) d.itemKey[item0 + m] = bkey | keySub(j);
         ++m;
       }
       ++j;
@@ -1794,14 +1794,14 @@ WTG_HD void dispatchScatter(const Dev& d, int i) {
       }
       d.evSlots[item0 + m] = 1;
       d.evDraws[item0 + m] = 0;
-      if (d.G > 1) d.itemKey[item0 + m] = bkey | (u64)(255 - j);
+      if (d.G > 1) d.itemKey[item0 + m] = bkey | keySub(j);
     }
     rc.cur = (uint32_t)j;
   } else {
     int to = (int)ev.to;
     int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
     d.inbox[s] = inboxMake(item0, i);
-    if (d.G > 1) d.itemKey[item0] = bkey | 255ULL;
+    if (d.G > 1) d.itemKey[item0] = bkey | keySub(0);
   }
 }
 
@@ -1819,6 +1819,33 @@ WTG_HD int multiUpper(const Dev& d, const MultiRec& rc, int tick) {  // first in
   }
   return lo;
 }
+// rank of this lane among the lanes with `flag` set, and their number (warp ballot; the 1-lane host coop is trivial)
+template <class C>
+WTG_HD int coopRank(C& c, bool flag, int& total) {
+  uint32_t m = c.ballot(flag);
+#if defined(__CUDA_ARCH__)
+  if (C::LANES == 32) {
+    total = __popc(m);
+    return __popc(m & ((1u << c.lane()) - 1u));
+  }
+#endif
+  total = (int)(m & 1u);
+  return 0;
+}
+// first destination index of the group a bucket entry stands for: the record's own cursor, or — replicated sendAll records
+// of a node-sharded run, where every shard walks its own copy — the index carried by the entry
+WTG_HD int multiCur(const Dev& d, const Ev& ev, const MultiRec& rc) { return d.G > 1 ? (int)(uint32_t)ev.pl : (int)rc.cur; }
+WTG_HD int multiUpperFrom(const Dev& d, const MultiRec& rc, int cur, int tick) {
+  int lo = cur, hi = (int)rc.n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (d.recArrival[rc.off + mid] <= tick)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
 template <class C>
 WTG_HD void dispatchCountCoop(const Dev& d, C& c, int i) {
   const Ctl& ctl = *d.ctl;
@@ -1826,6 +1853,21 @@ WTG_HD void dispatchCountCoop(const Dev& d, C& c, int i) {
   const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
   if (ev.kind == EV_MULTI) {
     const MultiRec& rc = d.rec[ev.aux];
+    if (d.G > 1) {  // node-sharded: this shard delivers its own destinations of the group; the shard of the last one re-pushes
+      const int cur = multiCur(d, ev, rc), up = multiUpperFrom(d, rc, cur, ctl.tick);
+      int m = 0;
+      for (int j0 = cur; j0 < up; j0 += C::LANES) {
+        int j = j0 + c.lane();
+        bool mine = j < up && ownerOf(d, (int)d.recDest[rc.off + j]) == d.rank;
+        if (mine) WTG_ATOMIC_ADD(&d.inboxCnt[d.recDest[rc.off + j]], 1);
+        int tot;
+        coopRank(c, mine, tot);
+        m += tot;
+      }
+      const bool rep = up < (int)rc.n && up > cur && ownerOf(d, (int)d.recDest[rc.off + up - 1]) == d.rank;
+      if (c.lane() == 0) d.subCount[p] = m + (rep ? 1 : 0);
+      return;
+    }
     int cur = (int)rc.cur, up = multiUpper(d, rc, ctl.tick);
     for (int j = cur + c.lane(); j < up; j += C::LANES) WTG_ATOMIC_ADD(&d.inboxCnt[d.recDest[rc.off + j]], 1);
     if (c.lane() == 0) d.subCount[p] = (up - cur) + (up < (int)rc.n ? 1 : 0);
@@ -1834,21 +1876,72 @@ WTG_HD void dispatchCountCoop(const Dev& d, C& c, int i) {
     d.subCount[p] = 1;
   }
 }
+// re-push descriptor of a multi-destination envelope whose next group starts at index `up` (Network.java:629-632)
+WTG_HD void writeRepush(const Dev& d, int i, int item, const MultiRec& rc, uint32_t rec, int up) {
+  int dst_ = i & (ARENA_STRIPES - 1), dper_ = d.descCap / ARENA_STRIPES;
+  int di = WTG_ATOMIC_ADD(&d.ctl->descCnt[dst_], 1);
+  if (di < dper_) {
+    Desc ds;
+    ds.dkind = DK_INSERT_AT;
+    ds.item = (uint32_t)(d.nLoc + item);
+    ds.sub = 0;
+    ds.from = rc.from;
+    ds.to = d.recDest[rc.off + up];
+    ds.nDest = 0;
+    ds.evKind = EV_MULTI;
+    ds.meta = 0;
+    ds.pl = (u64)(uint32_t)up;  // replicated records: the index the next group starts at
+    ds.target = d.recArrival[rc.off + up];
+    ds.aux = rec;
+    d.desc[dst_ * dper_ + di] = ds;
+  } else {
+    setError(d, ERR_DESC_OVERFLOW, di);
+  }
+  d.evSlots[item] = 1;
+  d.evDraws[item] = 0;
+}
 template <class C>
 WTG_HD void dispatchScatterCoop(const Dev& d, C& c, int i) {
   const Ctl& ctl = *d.ctl;
   int p = ctl.nEv - 1 - i;
-  const Ev& ev = d.buckets[(size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i];
+  const size_t be = (size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap + i;
+  const Ev& ev = d.buckets[be];
   int item0 = d.itemBase[p];
+  const u64 bkey = d.G > 1 ? d.bucketKey[be] : 0;
   if (ev.kind != EV_MULTI) {
     if (c.lane() == 0) {
       int to = (int)ev.to;
       int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
       d.inbox[s] = inboxMake(item0, i);
+      if (d.G > 1) d.itemKey[item0] = bkey | keySub(0);
     }
     return;
   }
   MultiRec& rc = d.rec[ev.aux];
+  if (d.G > 1) {
+    const int cur = multiCur(d, ev, rc), up = multiUpperFrom(d, rc, cur, ctl.tick);
+    int m = 0;
+    for (int j0 = cur; j0 < up; j0 += C::LANES) {
+      int j = j0 + c.lane();
+      int to = j < up ? (int)d.recDest[rc.off + j] : -1;
+      bool mine = j < up && ownerOf(d, to) == d.rank;
+      int tot;
+      int r = coopRank(c, mine, tot);
+      if (mine) {
+        int s = d.inboxOff[to] + WTG_ATOMIC_ADD(&d.inboxFill[to], 1);
+        d.inbox[s] = inboxMake(item0 + m + r, i);
+        d.itemKey[item0 + m + r] = bkey | keySub(j);
+      }
+      m += tot;
+    }
+    c.sync();
+    if (c.lane() == 0 && up < (int)rc.n && up > cur && ownerOf(d, (int)d.recDest[rc.off + up - 1]) == d.rank) {
+      writeRepush(d, i, item0 + m, rc, ev.aux, up);
+      d.itemKey[item0 + m] = bkey | keySub(up);
+    }
+    c.sync();
+    return;
+  }
   const int cur = (int)rc.cur, up = multiUpper(d, rc, ctl.tick), m = up - cur;
   for (int j = cur + c.lane(); j < up; j += C::LANES) {
     int to = (int)d.recDest[rc.off + j];
@@ -1857,29 +1950,7 @@ WTG_HD void dispatchScatterCoop(const Dev& d, C& c, int i) {
   }
   c.sync();
   if (c.lane() == 0) {
-    if (up < (int)rc.n) {  // Network.java:629-632: re-push for the next destination, after the handler ran
-      int dst_ = i & (ARENA_STRIPES - 1), dper_ = d.descCap / ARENA_STRIPES;
-      int di = WTG_ATOMIC_ADD(&d.ctl->descCnt[dst_], 1);
-      if (di < dper_) {
-        Desc ds;
-        ds.dkind = DK_INSERT_AT;
-        ds.item = (uint32_t)(d.nLoc + item0 + m);
-        ds.sub = 0;
-        ds.from = rc.from;
-        ds.to = d.recDest[rc.off + up];
-        ds.nDest = 0;
-        ds.evKind = EV_MULTI;
-        ds.meta = 0;
-        ds.pl = 0;
-        ds.target = d.recArrival[rc.off + up];
-        ds.aux = ev.aux;
-        d.desc[dst_ * dper_ + di] = ds;
-      } else {
-        setError(d, ERR_DESC_OVERFLOW, di);
-      }
-      d.evSlots[item0 + m] = 1;
-      d.evDraws[item0 + m] = 0;
-    }
+    if (up < (int)rc.n) writeRepush(d, i, item0 + m, rc, ev.aux, up);
     rc.cur = (uint32_t)up;
   }
   c.sync();
@@ -1911,6 +1982,10 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   int sendTime = ctl.tick + 1;  // send(m, from, to) == send(m, time + 1, from, to)   Network.java:364-366
   if (ds.dkind == DK_INSERT_AT) {
     target = ds.target;
+    if (shard && ds.evKind == EV_MULTI && d.allCap > 0) {  // sendAll record, replicated on every shard: entries only
+      xPlaceReplicated(d, g, (int)ds.aux, (int)(uint32_t)ds.pl);
+      return;
+    }
     if (shard && ds.evKind == EV_MULTI) {  // re-push of a multi-destination envelope: its next arrivals may lie on other shards
       const MultiRec& rc = d.rec[ds.aux];
       xPlaceMulti(d, g, rc.from, rc.meta, rc.pl, (int)rc.n, (int)rc.cur, d.recDest + rc.off, d.recArrival + rc.off, (int)ds.aux);
@@ -2011,7 +2086,10 @@ WTG_HD void emitDesc(const Dev& d, int di) {
   }
   if (d.farCap > 0) {
     if (target >= 0 && target - ctl.tick >= farHorizon(d)) {
-      farAppend(d, ev, target, g);
+      if (shard && ownerOf(d, (int)ev.to) != d.rank)  // the calendar is local: far-future envelopes are tasks of the shard's own nodes
+        setError(d, ERR_UNSUPPORTED, 7);
+      else
+        farAppend(d, ev, target, g);
       target = -1;
     }
   } else if (target >= 0 && target - ctl.tick >= d.ring) {
@@ -2105,6 +2183,7 @@ WTG_HD void tickEnd(const Dev& d, int mode) {
   if (mode != 2 && mode != 3) d.bucketCount[c.tick & (d.ring - 1)] = 0;  // 3: host-injected sends at the current time
   for (int t = 0; t < ARENA_STRIPES; ++t) c.freeCnt[t] = 0;
   if (d.proto == PROTO_CASPER && d.cg->createdThisTick > 1) setError(d, ERR_UNSUPPORTED, 4);
+  if (d.G > 1 && d.allCap > 0 && mode != 3) c.allSeq = (int)(((unsigned)c.allSeq + (unsigned)xAllTotal(d)) & 0x3fffffffu);  // record slots of the next pass
   if (d.proto == PROTO_GSF && (c.tick & 15) == 0)
     for (int l = INLINE_MAX_LEVEL + 1; l < d.L; ++l) {
       int f = 0;

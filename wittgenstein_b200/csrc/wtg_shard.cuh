@@ -23,8 +23,9 @@ namespace wtg {
 
 // `pass` = Ctl.xseq of the pipeline pass that created the envelope (a millisecond can have two passes: the reference's extra
 // time++ at the end of a runMs window creates tasks too)
-WTG_HD u64 orderKey(unsigned pass, unsigned g) { return ((u64)pass << 36) | ((u64)g << 8); }
-WTG_HD int ownerOf(const Dev& d, int n) { return d.G > 1 ? (n >> d.ownShift) : 0; }
+WTG_HD u64 orderKey(unsigned pass, unsigned g) { return ((u64)pass << KEY_PASS_SHIFT) | ((u64)g << KEY_G_SHIFT); }
+WTG_HD u64 keySub(int j) { return (u64)(KEY_SUB_MAX - (unsigned)j); }  // position j inside a multi-destination record
+WTG_HD int ownerOf(const Dev& d, int n) { return d.G > 1 ? (d.ownShift >= 0 ? (n >> d.ownShift) : n / d.perShard) : 0; }
 
 WTG_HD void xFence() {
 #if defined(__CUDA_ARCH__)
@@ -49,6 +50,37 @@ WTG_HD void xStoreRelease(int* p, int v) {
   __atomic_store_n(p, v, __ATOMIC_RELEASE);
 #endif
 }
+
+// ---- CasperIMD: block / attestation tables inside the exchange region, one copy per shard (layout from the Dev's sizes) ----
+struct CasperTabs {
+  CasperG* cg;
+  int* cbHeight;
+  int* cbParent;
+  int* cbProducer;
+  int* cbTime;
+  int* attHead;
+  int* attHeight;
+  unsigned long long* cbIncluded;
+};
+WTG_HD size_t casperTabsBytes(int maxBlocks, int maxAtts, int attWords) {
+  return 256 + sizeof(int) * (4 * (size_t)maxBlocks + 2 * (size_t)maxAtts) + 64 + sizeof(unsigned long long) * (size_t)maxBlocks * (size_t)attWords;
+}
+WTG_HD CasperTabs casperTabsAt(char* base, int maxBlocks, int maxAtts) {
+  CasperTabs t;
+  t.cg = reinterpret_cast<CasperG*>(base);
+  int* p = reinterpret_cast<int*>(base + 256);
+  t.cbHeight = p;
+  t.cbParent = p + maxBlocks;
+  t.cbProducer = p + 2 * (size_t)maxBlocks;
+  t.cbTime = p + 3 * (size_t)maxBlocks;
+  t.attHead = p + 4 * (size_t)maxBlocks;
+  t.attHeight = t.attHead + maxAtts;
+  size_t off = 256 + sizeof(int) * (4 * (size_t)maxBlocks + 2 * (size_t)maxAtts);
+  off = (off + 63) / 64 * 64;
+  t.cbIncluded = reinterpret_cast<unsigned long long*>(base + off);
+  return t;
+}
+WTG_HD CasperTabs casperTabsOf(const Dev& d, int q) { return casperTabsAt(d.peer[q].casper, d.cMaxBlocks, d.cMaxAtts); }
 
 // ---- exchange 1: items -------------------------------------------------------------------------------------------
 // local conditional-task totals: the scan over [cond | items] holds them at the first item position
@@ -151,6 +183,7 @@ WTG_HD void xTotals(const Dev& d) {
   c.totalDraws = totD;
   c.nEvGlobal = nEv;
   if (totS > d.newEvCap) setError(d, ERR_DESC_OVERFLOW, totS);
+  if (totS >= (1 << (KEY_PASS_SHIFT - KEY_G_SHIFT)) || (unsigned)c.xseq >= (1u << (64 - KEY_PASS_SHIFT))) setError(d, ERR_INTERNAL, 720);  // ordering-key fields
 }
 // creation indices / draws of the other shards that precede local item i.  Run after xTotals' inputs are complete but
 // independent of its outputs (reads the headers itself).
@@ -232,6 +265,62 @@ WTG_HD void xPlaceMulti(const Dev& d, int g, uint32_t from, uint32_t meta, u64 p
     ev.aux = (uint32_t)ri;
     ev.pad = 0;
     xStoreEnvelope(d, q, g, ev, arr[j0]);
+  }
+}
+
+// Replicated records (sendAll: every shard built the same sorted record in the same slot `ri`): the bucket entries of the
+// group that starts at index j0 — one per shard that owns one of its destinations, all with creation index g; the entry
+// carries j0 (Ev.pl) because the shards advance through their copies independently.
+WTG_HD void xPlaceReplicated(const Dev& d, int g, int ri, int j0) {
+  const MultiRec& rc = d.rec[ri];
+  const uint32_t* dst = d.recDest + rc.off;
+  const int* arr = d.recArrival + rc.off;
+  const int n = (int)rc.n;
+  uint32_t done = 0;
+  for (int j = j0; j < n && arr[j] == arr[j0]; ++j) {
+    int q = ownerOf(d, (int)dst[j]);
+    if (done & (1u << q)) continue;
+    done |= 1u << q;
+    Ev ev;
+    ev.kind = EV_MULTI;
+    ev.to = dst[j];
+    ev.from = rc.from;
+    ev.meta = 0;
+    ev.pl = (u64)(uint32_t)j0;
+    ev.aux = (uint32_t)ri;
+    ev.pad = rc.pad;
+    xStoreEnvelope(d, q, g, ev, arr[j0]);
+    if (done == (1u << d.G) - 1u) break;
+  }
+}
+
+// ---- begin exchange (fast-forwarding protocols): the next millisecond that holds an event, over all shards ----
+// one thread: publish (next, after) of this shard, signal, wait for the others, reduce
+WTG_HD void xBeginExchange(const Dev& d, int next, int after, int& gNext, int& gAfter) {
+  XBegin b;
+  b.seq = d.ctl->xseq;
+  b.next = next;
+  b.after = after;
+  b.error = d.ctl->error;
+  for (int q = 0; q < d.G; ++q) d.peer[q].beg[d.rank] = b;
+  xSignal(d, 2);
+  gNext = next;
+  gAfter = after;
+  for (int q = 0; q < d.G; ++q) {
+    if (q == d.rank) continue;
+    xWaitOne(d, 2, q);
+    if (d.ctl->error) return;
+    const XBegin o = d.peer[d.rank].beg[q];
+    if (o.error) {
+      setError(d, ERR_PEER_ERROR, q);
+      return;
+    }
+    if (o.seq != d.ctl->xseq) {
+      setError(d, ERR_INTERNAL, 710 + q);
+      return;
+    }
+    if (o.next < gNext) gNext = o.next;
+    if (o.after < gAfter) gAfter = o.after;
   }
 }
 

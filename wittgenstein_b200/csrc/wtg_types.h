@@ -146,15 +146,27 @@ struct FarEv {  // an envelope whose arrival lies beyond the time ring's horizon
 };
 
 // ---- node-sharded simulation: what the shards exchange every pipeline pass ----
-// Shard r owns the ids [r * nLoc, (r + 1) * nLoc).  Every bucket entry carries an ordering key
-//   (creating pass << 36) | (creation index << 8) | (255 - j)       j = position inside a multi-destination record
-// so that "processed earlier" (LIFO by insertion, Network.java:145-147) == larger key on every shard.
+// Shard r owns the ids [r * perShard, (r + 1) * perShard) (the last one may hold fewer).  Every bucket entry carries an ordering key
+//   (creating pass << 40) | (creation index << 16) | (65535 - j)    j = position inside a multi-destination record
+// so that "processed earlier" (LIFO by insertion, Network.java:145-147) == larger key on every shard.  (16 bits of position:
+// a sendAll record holds one destination per node.)
+constexpr unsigned KEY_SUB_MAX = 65535u;
+constexpr int KEY_G_SHIFT = 16, KEY_PASS_SHIFT = 40;
 struct XItem {  // one scan item of a shard, in its local processing order
   unsigned long long key;
   uint32_t ps, pd;  // exclusive prefix of (slots, draws) over the shard's items
 };
 struct XHdr {  // per pass and shard
   int seq, nEv, nItems, condSlots, condDraws, itemSlots, itemDraws, error;
+};
+struct XBegin {  // fast-forwarding protocols (CasperIMD): what a shard knows about the next millisecond that holds an event
+  int seq, next, after, error;
+};
+struct XAll {  // a sendAll of this pass: every shard builds the same sorted record from it (the record is replicated, not shipped)
+  uint32_t from, meta;
+  unsigned long long pl;
+  int sendTime, g;
+  unsigned long long draw;
 };
 constexpr uint32_t META_STAGED = 1u << 15;  // GSF: the pooled payload still sits in the staging area written by shard (meta >> 16) & 7
 constexpr int META_SRC_SHIFT = 16;
@@ -163,13 +175,17 @@ struct Ev;
 struct Peer {  // exchange region of one shard as mapped into this process (own region included: peer[rank])
   XHdr* hdr;            // [G]            written by shard q at [q]
   XItem* items;         // [G][xItemCap]  written by shard q at [q][*]
-  int* flags;           // [2][G]         pass sequence number of the last completed publication (0: items, 1: envelopes)
+  int* flags;           // [3][G]         pass sequence number of the last completed publication (0: items, 1: envelopes, 2: next event)
   Ev* newEv;            // [newEvCap]     this tick's new envelopes, indexed by global creation index
   int* newTarget;       // [newEvCap]     arrival tick, -1 = nothing for this shard
   unsigned long long* stage;  // [2][G][stageCapWords] pooled payloads of envelopes addressed to this shard
   MultiRec* rec;        // [G][recCap / G] multi-destination records, one sub-arena per sending shard
   uint32_t* recDest;    // [G][recDestCap / G]
   int* recArrival;      // [G][recDestCap / G]
+  XBegin* beg;          // [G]            written by shard q at [q] at the start of a pass (fast-forwarding protocols)
+  XAll* all;            // [G][xAllCap]   sendAll descriptors of the pass, written by shard q at [q][*]
+  int* allCnt;          // [G]
+  char* casper;         // CasperIMD: the block / attestation tables, replicated on every shard (writers store to all copies)
 };
 
 struct CasperG {  // CasperIMD: block counter and the Byzantine producer's scalars (CasperIMD.java:511-518, 648-649)
@@ -220,6 +236,8 @@ struct Ctl {  // device-resident control block (one per engine)
   int stageTop[MAX_SHARDS];      // words staged for shard q in this pass
   int xRecTop[MAX_SHARDS];       // records / destinations allocated in this shard's sub-arena of shard q
   int xRecDestTop[MAX_SHARDS];
+  int allSeq;                    // sendAll envelopes created so far over all shards: the next record slot (replicated records)
+  int xNext, xAfter;             // global results of the begin exchange of this pass
   int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
   int poolFreeCnt[MAX_LEVELS][POOL_STRIPES];   // free slots per (level, stripe)
 };
@@ -268,6 +286,8 @@ struct Dev {
   //      addressed by global id (their base pointers are biased by -n0 rows); node attributes are replicated ----
   int n0, nLoc, G, rank, ownShift;
   int xItemCap, stageCapWords, xRecCap, xRecDestCap;
+  int perShard;   // ids per shard (ceil(N / G)); ownShift = log2(perShard) when that is a power of two, else -1
+  int xAllCap;    // sendAll descriptors per pass and shard (node-sharded CasperIMD)
   Peer peer[MAX_SHARDS];
   unsigned long long* bucketKey;  // [ring][bcap] ordering key of every bucket entry (sharded runs only)
   unsigned long long* itemKey;    // [itemCap]

@@ -207,12 +207,14 @@ class CasperIMD:
     init(new ByzBlockProducerWF(byz_delay, genesis)) (:472-508): node 1 is the Byzantine producer, then the other
     producers, then the attesters.  Blocks are identified by their creation rank (genesis = 0)."""
 
-    def __init__(self, params, _api=None):
+    def __init__(self, params, _api=None, tunables=None, shard=None, device=None):
         self.params = params
         self._api = _api
-        self._net = Network(_api)
+        self._net = Network(_api, device=device, shard=shard)
         self._net.set_node_builder(params.node_builder_name)
         self._net.set_network_latency(params.network_latency_name)
+        for k, v in dict(tunables or {}).items():
+            self._net.set_tunable(k, v)
         arr = np.array([params.cycle_length, 1 if params.random_on_ties else 0, params.block_producers_count,
                         params.attesters_per_round, params.block_construction_time, params.attestation_construction_time], np.int32)
         self._net.api.check(self._net.api.casper_construct(self._net.h, _p(arr, C.c_int)))
@@ -249,7 +251,7 @@ class CasperIMD:
             cap = k
 
     def node_state(self):
-        n = self.node_count()
+        n = self._net.local_count  # a shard reads back its own nodes
         v = [np.zeros(n, np.int32) for _ in range(5)]
         hs = np.zeros(n, np.uint64)
         a = self._net.api
@@ -259,7 +261,7 @@ class CasperIMD:
         return d
 
     def heads(self):
-        out = np.zeros(self.node_count(), np.int32)
+        out = np.zeros(self._net.local_count, np.int32)
         self._net.api.check(self._net.api.casper_heads(self._net.h, _p(out, C.c_int)))
         return out
 

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from .protocols import GSFSignature
+from .protocols import CasperIMD, GSFSignature
 
 
 class _ShardedNetwork:
@@ -40,7 +40,7 @@ class _ShardedNetwork:
 
     @property
     def node_count(self):
-        return self._o.params.node_count
+        return self._o.shards[0].network().node_count
 
     def rng_state(self):
         st = set(self._each(lambda s: s.network().rng_state()))
@@ -134,6 +134,88 @@ class ShardedGSFSignature:
         self._pool.shutdown(wait=True)
         for s in self.shards:
             s.network().close()
+
+
+class ShardedCasperIMD:
+    """CasperIMD (BASELINE config #4) over `world` node-id shards driven from this process (one thread per shard): ids split
+    into `world` contiguous ranges; the block and attestation tables are replicated (their creator stores into every copy),
+    a sendAll is published once and every shard builds the same sorted record; the fast-forward over idle milliseconds takes the
+    minimum of the shards' next events at the start of every pass."""
+
+    def __init__(self, params, world, devices=None, _api=None, tunables=None):
+        self.params = params
+        self.world = world
+        self.devices = list(devices) if devices is not None else [None] * world
+        self.shards = [CasperIMD(params, _api, tunables, shard=(r, world), device=self.devices[r]) for r in range(world)]
+        self._pool = ThreadPoolExecutor(max_workers=world)
+        self._net = _ShardedNetwork(self)
+
+    def _each(self, fn):
+        return list(self._pool.map(fn, self.shards))
+
+    def network(self):
+        return self._net
+
+    def node_count(self):
+        return self.shards[0].node_count()
+
+    def init(self, byz_delay=0, byz_kind="WF"):
+        self._each(lambda s: s.init(byz_delay, byz_kind))
+        handles = [s.network().shard_export() for s in self.shards]
+        self._each(lambda s: s.network().shard_link(handles))
+
+    def blocks(self):
+        return self.shards[0].blocks()  # replicated table
+
+    def block_attestations(self, block):
+        return self.shards[0].block_attestations(block)
+
+    def node_state(self):
+        parts = self._each(lambda s: s.node_state())
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+    def heads(self):
+        return np.concatenate(self._each(lambda s: s.heads()))
+
+    def byz(self):
+        return self.shards[0].byz()  # node 1 (the Byzantine producer) lives on shard 0
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for s in self.shards:
+            s.network().close()
+
+
+class DistributedCasperIMD:
+    """This process's shard of a CasperIMD network spread over the ranks of a torch.distributed group (one GPU each): the
+    handles of the exchange regions travel once through `torch.distributed`; the data path is peer stores between kernels."""
+
+    def __init__(self, params, dist, rank, world, device, tunables=None):
+        self.params, self.dist, self.rank, self.world = params, dist, rank, world
+        self.local = CasperIMD(params, None, tunables, shard=(rank, world), device=device)
+
+    def network(self):
+        return self.local.network()
+
+    def init(self, byz_delay=0, byz_kind="WF"):
+        self.local.init(byz_delay, byz_kind)
+        mine = self.local.network().shard_export()
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine)
+        self.local.network().shard_link(handles)
+        self.dist.barrier()
+
+    def heads(self):
+        """heads of this shard's nodes"""
+        return self.local.heads()
+
+    def all_heads(self):
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, self.local.heads())
+        return np.concatenate(parts)
+
+    def blocks(self):
+        return self.local.blocks()
 
 
 class DistributedGSFSignature:
