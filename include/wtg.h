@@ -103,8 +103,10 @@ int wtg_handel_init(wtg_net* net, const int* params11);
  * .init(new ByzBlockProducerWF(byz_delay, genesis)) — :472-508 (init() itself uses byz_delay 0).
  * params6 = { cycleLength, randomOnTies, blockProducersCount, attestersPerRound, blockConstructionTime,
  *             attestationConstructionTime } (CasperParemeters :18-71).  Node ids: 0 observer, 1 the Byzantine producer,
- * 2.. the other producers, then the attesters.  Device engine: with randomOnTies a vote tie
- * between two branches is reported as an error (the tie-break draws from network.rd inside a handler, :250-253). */
+ * 2.. the other producers, then the attesters.  randomOnTies: a vote tie between two branches draws network.rd.nextBoolean()
+ * inside the handler (:250-253) at its exact position in the draw order (the node is suspended in the parallel pass and run
+ * by a tie pass in processing order); blocks created in the same millisecond get their ids in processing order.  Both are
+ * reported as errors on a node-sharded network only. */
 int wtg_casper_construct(wtg_net* net, const int* params6);
 int wtg_casper_init(wtg_net* net, int byz_delay);
 /* .init(new ByzBlockProducer / SF / NS / WF (byz_delay, genesis)) — kind 3 / 4 / 5 / 6 (CasperIMD.java:511-707) */

@@ -96,6 +96,8 @@ class HostBackend : public Backend {
       if (bail(d, 0)) return;
       for (int i = 0; i < nEv; ++i) coopDispatch ? dispatchScatterCoop(d, c, i) : dispatchScatter(d, i);
       for (int n = d.n0; n < d.n0 + d.nLoc; ++n) nodeProcess(d, c, n, 0);
+      if (d.proto == PROTO_CASPER && d.cRandomTies && d.ctl->tieCnt > 0 && !d.ctl->error) casperResolveTies(d, c);
+      if (d.proto == PROTO_CASPER && d.G == 1 && !d.ctl->error) casperRenumber(d, c);
     }
     pairScan(d, 1);
     if (d.G > 1) {  // node-sharded: exchange 1 (items -> global creation / draw offsets)

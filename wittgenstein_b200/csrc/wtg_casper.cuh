@@ -83,9 +83,21 @@ WTG_HD int cCountAttestations(const Dev& d, C& c, int n, int start, int h) {
   return c.sum(cnt);
 }
 
+// network.rd.nextBoolean() on a fork-choice tie (CasperIMD.java:250-253) is a draw from the network's one Random *inside* a
+// handler: its index is the number of draws of every event processed before this one in the millisecond, which the parallel
+// handler pass cannot know.  Every tie of a handler comes before the handler's first non-idempotent write (reevaluateHead
+// folds before it stores the head; onBlock compares before it records the block), so a handler that hits a tie can simply
+// stop: the node is suspended at that event, and the tie pass (casperResolveTies: one warp, after the parallel pass) runs the
+// suspended events in processing order, each with its exact draw index (all earlier events are complete by then).
+struct CTie {
+  int resolve;  // 0: parallel pass (a tie suspends the node); 1: tie pass (draws are taken at base + used)
+  u64 base;     // draws of all events processed before this one in the pass
+  int used;     // ties drawn by this event so far
+  bool hit;     // parallel pass: a tie was found, nothing may be written
+};
 // CasperNode.best (CasperIMD.java:205-257)
 template <class C>
-WTG_HD int cBest(const Dev& d, C& c, int n, int o1, int o2) {
+WTG_HD int cBest(const Dev& d, C& c, int n, int o1, int o2, CTie& tc) {
   if (o1 == o2) return o1;
   int h1 = d.cbHeight[o1], h2 = d.cbHeight[o2];
   if (h1 == h2) {  // two blocks for the same height: IllegalStateException (:208-212)
@@ -110,27 +122,37 @@ WTG_HD int cBest(const Dev& d, C& c, int n, int o1, int o2) {
   int v2 = cCountAttestations(d, c, n, o2, h);
   if (v1 > v2) return o1;
   if (v1 < v2) return o2;
-  if (d.cRandomTies) {  // network.rd.nextBoolean() inside a handler (:250-253) is not reproduced on the device
-    setError(d, ERR_UNSUPPORTED, 1);
-    return o1;
+  if (d.cRandomTies) {  // return network.rd.nextBoolean() ? o1 : o2  (:250-253)
+    if (d.G > 1) {  // node-sharded runs would need the draw prefix of the other shards' events here
+      setError(d, ERR_UNSUPPORTED, 1);
+      return o1;
+    }
+    if (!tc.resolve) {
+      tc.hit = true;
+      return o1;
+    }
+    u64 st = lcgAdvance(d.jumpA, d.jumpC, d.ctl->rng, tc.base + (u64)tc.used + 1);
+    tc.used += 1;
+    return ((st >> 47) & 1ULL) ? o1 : o2;  // Random.nextBoolean() = next(1) != 0
   }
   return b1 >= b2 ? o1 : o2;
 }
 
 // reevaluateHead (CasperIMD.java:348-353)
 template <class C>
-WTG_HD void cReevaluate(const Dev& d, C& c, int n) {
+WTG_HD void cReevaluate(const Dev& d, C& c, int n, CTie& tc) {
   u64* tr = d.cToReeval + (size_t)n * d.cBlkWords;
   int head = d.cHead[n];
-  for (int w = 0; w < d.cBlkWords; ++w) {
+  for (int w = 0; w < d.cBlkWords && !tc.hit; ++w) {
     u64 bits = tr[w];
-    while (bits) {
+    while (bits && !tc.hit) {
       int b = w * 64 + WTG_CTZ64(bits);
       bits &= bits - 1;
-      head = cBest(d, c, n, head, b);
+      head = cBest(d, c, n, head, b, tc);
     }
   }
   c.sync();
+  if (tc.hit) return;  // suspended: nothing written
   if (c.lane() == 0) {
     d.cHead[n] = head;
     for (int w = 0; w < d.cBlkWords; ++w) tr[w] = 0;
@@ -141,7 +163,7 @@ WTG_HD void cReevaluate(const Dev& d, C& c, int n) {
 // BlockProducer.buildBlock (CasperIMD.java:383-428) + the Block constructor checks (Block.java:38-47).
 // Returns the new block's index, -1 on error.
 template <class C>
-WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
+WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height, int item) {
   const int tick = d.ctl->tick;
   if (height <= 0 || tick < d.cbTime[base] || d.cbHeight[base] >= height) {  // IllegalArgumentException
     setError(d, ERR_PROTO_STATE, 2);
@@ -182,6 +204,7 @@ WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
     d.cbParent[nb] = base;
     d.cbProducer[nb] = n;
     d.cbTime[nb] = tick;
+    d.cbItem[nb] = item;                        // creating event: ids follow the processing order (casperRenumber)
     WTG_ATOMIC_ADD(&d.cg->createdThisTick, 1);  // see tickEnd
     if (d.G > 1)
       for (int q = 0; q < d.G; ++q)
@@ -200,13 +223,13 @@ WTG_HD int cBuildBlock(const Dev& d, C& c, int n, int base, int height) {
 }
 
 // network.sendAll(msg, sendTime, from): the descriptor; the envelope is built by emitAll
-WTG_HD void cWriteSendAll(const Dev& d, int di, int n, int item, int sub, uint32_t meta, u64 pl, int sendTime) {
+WTG_HD void cWriteSendAll(const Dev& d, int di, int n, int item, int sub, uint32_t meta, u64 pl, int sendTime, int tieDraws = 0) {
   Desc ds;
   ds.dkind = DK_SEND_ALL;
   ds.item = (uint32_t)(d.nLoc + item);
   ds.sub = (uint32_t)sub;
   ds.from = (uint32_t)n;
-  ds.to = 0;
+  ds.to = (uint32_t)tieDraws;  // fork-choice ties drawn by this handler before the send: they come first in the draw order
   ds.nDest = (uint32_t)d.N;
   ds.evKind = EV_MULTI;
   ds.meta = meta;
@@ -241,7 +264,7 @@ WTG_HD void cWriteInsert(const Dev& d, int di, int n, int item, int sub, uint32_
 
 // BlockChainNode.onBlock + CasperNode.onBlock + ByzBlockProducerWF.onBlock (BlockChainNode.java:33-49, CasperIMD.java:298-314, 667-701)
 template <class C>
-WTG_HD void cOnBlock(const Dev& d, C& c, int n, int b, int item, int& slots, int& draws) {
+WTG_HD void cOnBlock(const Dev& d, C& c, int n, int b, int item, int& slots, int& draws, CTie& tc) {
   const int tick = d.ctl->tick;
   u64* tr = d.cToReeval + (size_t)n * d.cBlkWords;
   u64* br = d.cBlkRecv + (size_t)n * d.cBlkWords;
@@ -256,7 +279,8 @@ WTG_HD void cOnBlock(const Dev& d, C& c, int n, int b, int item, int& slots, int
     c.sync();
     return;
   }
-  int nh = cBest(d, c, n, head, b);
+  int nh = cBest(d, c, n, head, b, tc);
+  if (tc.hit) return;  // suspended (the two marks above are idempotent)
   if (c.lane() == 0) {
     br[b >> 6] |= 1ULL << (b & 63);
     d.cHead[n] = nh;
@@ -268,13 +292,13 @@ WTG_HD void cOnBlock(const Dev& d, C& c, int n, int b, int item, int& slots, int
   const int perfectDate = CASPER_SLOT * toSend + d.cByzDelay;
   c.sync();
   if (tick >= perfectDate) {  // r.run(); late++ (:689-691)
-    int nb = cBuildBlock(d, c, n, b, toSend);
+    int nb = cBuildBlock(d, c, n, b, toSend, item);
     int base = descAlloc(d, c, n, 1);
     if (c.lane() == 0) {
       d.cg->byzToSend = toSend + d.cBpCount;
       d.cg->byzLate += 1;
       if (nb >= 0) d.cHead[n] = nb;
-      if (nb >= 0 && base >= 0) cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
+      if (nb >= 0 && base >= 0) cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime, tc.used);
     }
     slots = 1;
     draws = 1;
@@ -316,12 +340,13 @@ WTG_HD int cFirstAtHeight(const Dev& d, int n, int hh) {
 // periodic tasks: Attester.vote (:455-464), BlockProducer (:376-381, 430-436), ByzBlockProducerWF (:656-665, reevaluateH :529-542)
 // followed by the re-arm of PeriodicTask.action (messages/PeriodicTask.java:40-47)
 template <class C>
-WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draws) {
+WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draws, CTie& tc) {
   const int tick = d.ctl->tick;
   const int kind = d.cKind[n];
   const int period = casperPeriod(d, kind);
   if (kind == CK_ATTESTER) {
-    cReevaluate(d, c, n);
+    cReevaluate(d, c, n, tc);
+    if (tc.hit) return;
     int k = d.cVotes[n];
     int a = k * d.cAttCount + (n - d.cFirstAtt);
     if (a >= d.cMaxAtts) {
@@ -340,25 +365,27 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
             t.attHeight[a] = tick / CASPER_SLOT;
           }
       d.cVotes[n] = k + 1;
-      cWriteSendAll(d, base, n, item, 0, CM_ATT, (u64)(uint32_t)a, tick + d.cAttTime);
+      cWriteSendAll(d, base, n, item, 0, CM_ATT, (u64)(uint32_t)a, tick + d.cAttTime, tc.used);
       cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
     }
     slots = 2;
     draws = 1;
   } else if (kind == CK_PRODUCER) {
-    cReevaluate(d, c, n);
-    int nb = cBuildBlock(d, c, n, d.cHead[n], tick / CASPER_SLOT);
+    cReevaluate(d, c, n, tc);
+    if (tc.hit) return;
+    int nb = cBuildBlock(d, c, n, d.cHead[n], tick / CASPER_SLOT, item);
     int base = descAlloc(d, c, n, 2);
     if (c.lane() == 0 && base >= 0 && nb >= 0) {
       d.cHead[n] = nb;
-      cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
+      cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime, tc.used);
       cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
     }
     slots = 2;
     draws = 1;
   } else if (kind == CK_BYZ || kind == CK_BYZ_SF || kind == CK_BYZ_NS) {  // :544-564, 588-603, 617-634
     const int toSend = d.cg->byzToSend;
-    cReevaluate(d, c, n);  // reevaluateH (:529-542)
+    cReevaluate(d, c, n, tc);  // reevaluateH (:529-542)
+    if (tc.hit) return;
     int head = d.cHead[n];
     while (d.cbHeight[head] >= toSend) head = d.cbParent[head];
     const int h = (tick - d.cByzDelay) / CASPER_SLOT;
@@ -398,7 +425,7 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
       }
     }
     c.sync();
-    int nb = cBuildBlock(d, c, n, head, toSend);
+    int nb = cBuildBlock(d, c, n, head, toSend, item);
     int base = descAlloc(d, c, n, 2);
     if (c.lane() == 0 && base >= 0 && nb >= 0) {
       d.cg->byzH = h;
@@ -408,7 +435,7 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
       d.cg->byzSkipped += skipped;
       d.cHead[n] = nb;
       d.cg->byzToSend = toSend + d.cBpCount;
-      cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
+      cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime, tc.used);
       cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
     }
     slots = 2;
@@ -416,7 +443,8 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
   } else if (kind == CK_BYZ_WF) {
     const int toSend = d.cg->byzToSend;
     if (d.cHead[n] == 0 && toSend == 1) {  // kick off the system (:658-663)
-      cReevaluate(d, c, n);
+      cReevaluate(d, c, n, tc);
+      if (tc.hit) return;
       int head = d.cHead[n];
       while (d.cbHeight[head] >= toSend) head = d.cbParent[head];
       int h = (tick - d.cByzDelay) / CASPER_SLOT;
@@ -425,13 +453,13 @@ WTG_HD void cPeriodic(const Dev& d, C& c, int n, int item, int& slots, int& draw
         return;
       }
       c.sync();
-      int nb = cBuildBlock(d, c, n, head, h);
+      int nb = cBuildBlock(d, c, n, head, h, item);
       int base = descAlloc(d, c, n, 2);
       if (c.lane() == 0 && base >= 0 && nb >= 0) {
         d.cg->byzH = h;
         d.cHead[n] = nb;
         d.cg->byzToSend = toSend + d.cBpCount;
-        cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime);
+        cWriteSendAll(d, base, n, item, 0, CM_BLOCK, (u64)(uint32_t)nb, tick + d.cBlockTime, tc.used);
         cWriteInsert(d, base + 1, n, item, 1, EV_PERIODIC, 0, 0, tick + period);
       }
       slots = 2;
@@ -453,7 +481,7 @@ template <class C>
 WTG_HD void cBuildTask(const Dev& d, C& c, int n, u64 pl, int item, int& slots, int& draws) {
   const int tick = d.ctl->tick;
   int b = (int)(uint32_t)pl, th = (int)(pl >> 32);
-  int nb = cBuildBlock(d, c, n, b, th);
+  int nb = cBuildBlock(d, c, n, b, th, item);
   int base = descAlloc(d, c, n, 1);
   if (c.lane() == 0 && base >= 0 && nb >= 0) {
     d.cHead[n] = nb;
@@ -464,26 +492,200 @@ WTG_HD void cBuildTask(const Dev& d, C& c, int n, u64 pl, int item, int& slots, 
   c.sync();
 }
 
+// Block.id is a global counter (Block.java:10, 49): two blocks created in the same millisecond get their ids in the order of
+// the events that created them.  The parallel handler pass hands the ids out in arbitrary order; this pass (one coop, only when
+// more than one block was created) gives the new blocks the ids of the processing order: permutes the new rows of the block
+// table and patches what refers to them — the creator's head and the SendBlock descriptors of the pass.
+constexpr int CASPER_MAX_NEW = 8;
 template <class C>
-WTG_HD void casperDeliver(const Dev& d, C& c, int n, uint32_t evKind, uint32_t meta, u64 pl, int item, int& slots, int& draws) {
+WTG_HD void casperRenumber(const Dev& d, C& c) {
+  const int k = d.cg->createdThisTick;
+  if (k <= 1) return;
+  if (k > CASPER_MAX_NEW) {
+    setError(d, ERR_UNSUPPORTED, 4);
+    return;
+  }
+  const int first = d.cg->nBlocks - k;
+  int newId[CASPER_MAX_NEW];
+  bool same = true;
+  for (int i = 0; i < k; ++i) {
+    int r = 0;
+    for (int j = 0; j < k; ++j)
+      if (d.cbItem[first + j] < d.cbItem[first + i]) ++r;
+    newId[i] = first + r;
+    same = same && r == i;
+  }
+  if (same) return;
+#if !defined(__CUDA_ARCH__) && defined(WTG_DEBUG_RENUMBER)
+  fprintf(stderr, "renumber non-identity k=%d tick=%d\n", k, d.ctl->tick);
+#endif
+  const int W = d.cAttWords;
+  // rows -> scratch (in the new order), then back
+  for (int i = 0; i < k; ++i) {
+    const int dst = newId[i] - first;
+    for (int w = c.lane(); w < W; w += C::LANES) d.cbTmp[(size_t)dst * W + w] = d.cbIncluded[(size_t)(first + i) * W + w];
+    if (c.lane() == 0) {
+      int* t = d.cbTmpRow + dst * 5;
+      t[0] = d.cbHeight[first + i];
+      t[1] = d.cbParent[first + i];
+      t[2] = d.cbProducer[first + i];
+      t[3] = d.cbTime[first + i];
+      t[4] = d.cbItem[first + i];
+    }
+  }
+  c.sync();
+  for (int i = 0; i < k; ++i) {
+    for (int w = c.lane(); w < W; w += C::LANES) d.cbIncluded[(size_t)(first + i) * W + w] = d.cbTmp[(size_t)i * W + w];
+    if (c.lane() == 0) {
+      const int* t = d.cbTmpRow + i * 5;
+      d.cbHeight[first + i] = t[0];
+      d.cbParent[first + i] = t[1];
+      d.cbProducer[first + i] = t[2];
+      d.cbTime[first + i] = t[3];
+      d.cbItem[first + i] = t[4];
+    }
+  }
+  c.sync();
+  if (c.lane() == 0)
+    for (int i = 0; i < k; ++i) {  // the creator adopted its block as head (createAndSendBlock :430-436, ByzBlockProducer* :561, 686)
+      const int n = d.cbProducer[newId[i]];
+      if (d.cHead[n] == first + i) d.cHead[n] = newId[i];
+    }
+  // head patches of two creators cannot collide: every creator made exactly one of the new blocks and its head is that block
+  const int per = d.descCap / ARENA_STRIPES;
+  for (int st = 0; st < ARENA_STRIPES; ++st) {
+    int cnt = d.ctl->descCnt[st];
+    if (cnt > per) cnt = per;
+    for (int j = c.lane(); j < cnt; j += C::LANES) {
+      Desc& ds = d.desc[st * per + j];
+      if (ds.dkind == DK_SEND_ALL && ds.meta == CM_BLOCK) {
+        int b = (int)(uint32_t)ds.pl;
+        if (b >= first && b < first + k) ds.pl = (u64)(uint32_t)newId[b - first];
+      }
+    }
+  }
+  c.sync();
+}
+
+// one event of node n; false: a fork-choice tie was hit in the parallel pass — nothing was written, the node is suspended
+template <class C>
+WTG_HD bool casperEvent(const Dev& d, C& c, int n, uint32_t evKind, uint32_t meta, u64 pl, int item, int& slots, int& draws, CTie& tc) {
   if (evKind == EV_MSG || evKind == EV_MULTI) {
+    if (meta == CM_ATT) {
+      if (c.lane() == 0) cOnAttestation(d, n, (int)(uint32_t)pl);
+      c.sync();
+    } else {
+      cOnBlock(d, c, n, (int)(uint32_t)pl, item, slots, draws, tc);
+      if (tc.hit) return false;
+    }
     if (c.lane() == 0) {
       d.msgReceived[n] += 1;
       d.bytesReceived[n] += 1;  // Message.size() default (messages/Message.java:27-29)
       statAdd(d, n, ST_DELIVERIES, 1ULL);
     }
-    if (meta == CM_ATT) {
-      if (c.lane() == 0) cOnAttestation(d, n, (int)(uint32_t)pl);
-      c.sync();
-    } else {
-      cOnBlock(d, c, n, (int)(uint32_t)pl, item, slots, draws);
-    }
   } else if (evKind == EV_PERIODIC) {
+    cPeriodic(d, c, n, item, slots, draws, tc);
+    if (tc.hit) return false;
     if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
-    cPeriodic(d, c, n, item, slots, draws);
   } else {
     if (c.lane() == 0) statAdd(d, n, ST_TASKS, 1ULL);
     cBuildTask(d, c, n, pl, item, slots, draws);
+  }
+  draws += tc.used;
+  return true;
+}
+template <class C>
+WTG_HD void casperDeliver(const Dev& d, C& c, int n, uint32_t evKind, uint32_t meta, u64 pl, int item, int& slots, int& draws) {
+  if (d.cRandomTies && d.cTieItem[n] >= 0) return;  // suspended earlier in this pass: the tie pass runs the node's later events
+  CTie tc;
+  tc.resolve = 0;
+  tc.base = 0;
+  tc.used = 0;
+  tc.hit = false;
+  if (casperEvent(d, c, n, evKind, meta, pl, item, slots, draws, tc)) return;
+  slots = 0;
+  draws = 0;
+  if (c.lane() == 0) {  // suspend the node at this event
+    d.cTieItem[n] = item;
+    d.cTieCnt[n] = d.inboxFill[n];
+    d.cTieList[WTG_ATOMIC_ADD(&d.ctl->tieCnt, 1)] = n;
+  }
+  c.sync();
+}
+// The tie pass (one coop, after the parallel handler pass): repeatedly take the suspended node whose suspended event comes
+// first in processing order — every earlier event of the pass is complete, so the number of draws before it is exact — run
+// that event with its ties drawn, then the node's later events (a later tie suspends it again, further down the order).
+template <class C>
+WTG_HD void casperResolveTies(const Dev& d, C& c) {
+  Ctl& ctl = *d.ctl;
+  const Ev* bucket = d.buckets + (size_t)(ctl.tick & (d.ring - 1)) * (size_t)d.bcap;
+  for (;;) {
+    const int ns = ctl.tieCnt;
+    int bestItem = 0x7fffffff;
+    for (int i = c.lane(); i < ns; i += C::LANES) {
+      int it = d.cTieItem[d.cTieList[i]];
+      if (it >= 0 && it < bestItem) bestItem = it;
+    }
+    bestItem = c.minv(bestItem);
+    if (bestItem == 0x7fffffff) break;
+    int n = -1;
+    for (int i = c.lane(); i < ns; i += C::LANES)
+      if (d.cTieItem[d.cTieList[i]] == bestItem) n = d.cTieList[i];
+    n = c.maxv(n);
+    int sum = 0;  // draws of every event processed before bestItem
+    for (int it = c.lane(); it < bestItem; it += C::LANES) sum += d.evDraws[it];
+    const u64 base = (u64)(uint32_t)c.sum(sum);
+    const int cnt = d.cTieCnt[n];
+    const u64* in = d.inbox + d.inboxOff[n];
+    c.sync();
+    if (c.lane() == 0) d.cTieItem[n] = -1;
+    c.sync();
+    int lastItem = bestItem - 1;
+    bool first = true;
+    for (;;) {  // the node's events from the suspended one on, in processing order
+      int nxt = 0x7fffffff;
+      u64 w = 0;
+      for (int i = 0; i < cnt; ++i) {  // inboxes are tiny
+        int it = inboxItem(in[i]);
+        if (it > lastItem && it < nxt) {
+          nxt = it;
+          w = in[i];
+        }
+      }
+      if (nxt == 0x7fffffff) break;
+      lastItem = nxt;
+      const Ev ev = bucket[inboxEntry(w)];
+      uint32_t meta = ev.meta;
+      u64 pl = ev.pl;
+      if (ev.kind == EV_MULTI) {
+        const MultiRec& rc = d.rec[ev.aux];
+        meta = rc.meta;
+        pl = rc.pl;
+      }
+      int slots = 0, draws = 0;
+      const bool isTask = ev.kind == EV_TASK || ev.kind == EV_PERIODIC;
+      const uint32_t envFrom = isTask ? (uint32_t)n : (ev.kind == EV_MULTI ? d.rec[ev.aux].from : ev.from);
+      bool done = true;
+      if (!d.ndown[n] && d.npart[envFrom] == d.npart[n]) {  // Network.java:606 (as in deliver())
+        CTie tc;
+        tc.resolve = first ? 1 : 0;
+        tc.base = base;
+        tc.used = 0;
+        tc.hit = false;
+        done = casperEvent(d, c, n, ev.kind, meta, pl, nxt, slots, draws, tc);
+      }
+      if (!done) {  // a later event of the node ties as well: its draw index depends on the events in between
+        if (c.lane() == 0) d.cTieItem[n] = nxt;
+        c.sync();
+        break;
+      }
+      if (c.lane() == 0) {
+        d.evSlots[nxt] = slots;
+        d.evDraws[nxt] = draws;
+      }
+      c.sync();
+      first = false;
+    }
   }
 }
 
@@ -677,7 +879,7 @@ template <class C>
 WTG_HD void emitAll(const Dev& d, C& c, int di, int* tmp, int* hist) {
   const Desc ds = d.desc[di];
   const int g = d.slotBase[ds.item] + (int)ds.sub;
-  const u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub);
+  const u64 drawIdx = (u64)(d.drawBase[ds.item] + (int)ds.sub) + (u64)ds.to;  // ds.to: fork-choice ties the handler drew first
   emitAllCore(d, c, ds.from, ds.meta, ds.pl, ds.target, g, drawIdx, -1, tmp, hist);
 }
 // node-sharded: publish this shard's j-th sendAll of the pass (global creation / draw index) into every shard's list ...
@@ -689,7 +891,7 @@ WTG_HD void xPublishAll(const Dev& d, int j) {
   a.pl = ds.pl;
   a.sendTime = ds.target;
   a.g = d.slotBase[ds.item] + (int)ds.sub + (int)d.xoffS[ds.item - d.nLoc];
-  a.draw = (u64)(d.drawBase[ds.item] + (int)ds.sub) + (u64)d.xoffD[ds.item - d.nLoc];
+  a.draw = (u64)(d.drawBase[ds.item] + (int)ds.sub) + (u64)ds.to + (u64)d.xoffD[ds.item - d.nLoc];
   for (int q = 0; q < d.G; ++q) d.peer[q].all[(size_t)d.rank * d.xAllCap + j] = a;
 }
 WTG_HD void xPublishAllCount(const Dev& d) {
@@ -860,6 +1062,7 @@ WTG_HD void tickBeginFfwd(const Dev& d, C& c) {
     ctl.allCnt = 0;
     ctl.shufReject = 0;
     if (d.cg) d.cg->createdThisTick = 0;
+    ctl.tieCnt = 0;
     if (d.G > 1) {
       ctl.xseq += 1;
       ctl.nEvGlobal = 0;

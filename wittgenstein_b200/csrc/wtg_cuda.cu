@@ -264,6 +264,16 @@ __device__ __forceinline__ void b_node_tasks(const Dev& d, const int VB, const i
 }
 // three blocks per SM = 80 registers: measured best (profiles/README.md, round 2: 64 / 80 / 128 registers -> 258 / 251 / 382 ms)
 __global__ void __launch_bounds__(256, 3) k_node_tasks(Dev d) { b_node_tasks(d, blockIdx.x, gridDim.x); }
+// CasperIMD, after the parallel handler pass (one warp; both are rare): nodes that hit a fork-choice tie run in processing
+// order with their exact draw index (randomOnTies), and several blocks created in one millisecond get their ids in
+// processing order
+__device__ __forceinline__ void b_casper_fixups(const Dev& d, const int VB, const int VG) {
+  if (d.ctl->error || VB != 0 || threadIdx.x >= 32) return;
+  CoopWarp c;
+  if (d.cRandomTies && d.ctl->tieCnt > 0) casperResolveTies(d, c);
+  if (d.G == 1 && d.cg->createdThisTick > 1) casperRenumber(d, c);
+}
+__global__ void k_casper_fixups(Dev d) { b_casper_fixups(d, blockIdx.x, gridDim.x); }
 // ---- pair scans ---------------------------------------------------------------------------
 __device__ __forceinline__ Pair pairAdd(Pair x, Pair y) {
   Pair r;
@@ -1046,6 +1056,10 @@ class CudaBackend : public Backend {
       profBegin(7);
     k_node_msgs<<<(d.nLoc + 255) / 256, 256, 0, st>>>(d);
     k_node_tasks<<<ARENA_STRIPES * 19, 256, NODE_TMA_SMEM, st>>>(d);
+    if (d.proto == PROTO_CASPER) {
+      k_casper_fixups<<<1, 32, 0, st>>>(d);
+      launches += 1;
+    }
     profEnd();
       launches += 6;
     }

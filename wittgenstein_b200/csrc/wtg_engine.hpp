@@ -1181,6 +1181,15 @@ class Engine {
       d.cg = dalloc<CasperG>(1);
     }
     be->upload(d.cg, &g, sizeof(g));
+    {  // randomOnTies: nodes suspended at a fork-choice tie (wtg_casper.cuh, casperResolveTies)
+      std::vector<int> none((size_t)N, -1);
+      d.cTieItem = dupload(none);
+      d.cTieCnt = dalloc<int>(N);
+      d.cTieList = dalloc<int>(N);
+      d.cbItem = dalloc<int>(d.cMaxBlocks);
+      d.cbTmp = dalloc<unsigned long long>((size_t)CASPER_MAX_NEW * d.cAttWords);
+      d.cbTmpRow = dalloc<int>(CASPER_MAX_NEW * 5);
+    }
     // sendAll machinery: records recycled over recSlots slots of N destinations
     d.allCap = N + 64;
     if (sharded()) d.allCap = d.xAllCap;

@@ -1531,6 +1531,11 @@ WTG_HD void sfHandle(const Dev& d, int n, uint32_t from, uint32_t type, u64 pl, 
   }
 }
 
+// inbox word of a node: (scan item << 32) | index of the bucket entry
+WTG_HD u64 inboxMake(int item, int entry) { return ((u64)(uint32_t)item << 32) | (u64)(uint32_t)entry; }
+WTG_HD int inboxItem(u64 w) { return (int)(w >> 32); }
+WTG_HD int inboxEntry(u64 w) { return (int)(w & 0xFFFFFFFFULL); }
+
 }  // namespace wtg
 #include "wtg_handel.cuh"
 #include "wtg_casper.cuh"
@@ -1646,9 +1651,6 @@ WTG_HD void deliver(const Dev& d, C& c, int n, const Ev& ev, uint32_t from, uint
 // node work item: process this tick's inbox of node n in reference order
 // inbox word: (item << 32) | (entry index << 8 ... see below)
 // ------------------------------------------------------------------------------------------
-WTG_HD u64 inboxMake(int item, int entry) { return ((u64)(uint32_t)item << 32) | (u64)(uint32_t)entry; }
-WTG_HD int inboxItem(u64 w) { return (int)(w >> 32); }
-WTG_HD int inboxEntry(u64 w) { return (int)(w & 0xFFFFFFFFULL); }
 
 // filter 0: every item in reference order (generic).  filter 1: messages only; filter 2: tasks only — used by the
 // CUDA handler kernel for GSF / PingPong, where a message delivery (onNewSig: queue, individual-seen row, receive
@@ -2182,7 +2184,7 @@ WTG_HD void tickEnd(const Dev& d, int mode) {
   }
   if (mode != 2 && mode != 3) d.bucketCount[c.tick & (d.ring - 1)] = 0;  // 3: host-injected sends at the current time
   for (int t = 0; t < ARENA_STRIPES; ++t) c.freeCnt[t] = 0;
-  if (d.proto == PROTO_CASPER && d.cg->createdThisTick > 1) setError(d, ERR_UNSUPPORTED, 4);
+  if (d.proto == PROTO_CASPER && d.G > 1 && d.cg->createdThisTick > 1) setError(d, ERR_UNSUPPORTED, 4);  // unsharded: casperRenumber
   if (d.G > 1 && d.allCap > 0 && mode != 3) c.allSeq = (int)(((unsigned)c.allSeq + (unsigned)xAllTotal(d)) & 0x3fffffffu);  // record slots of the next pass
   if (d.proto == PROTO_GSF && (c.tick & 15) == 0)
     for (int l = INLINE_MAX_LEVEL + 1; l < d.L; ++l) {

@@ -236,6 +236,7 @@ struct Ctl {  // device-resident control block (one per engine)
   int stageTop[MAX_SHARDS];      // words staged for shard q in this pass
   int xRecTop[MAX_SHARDS];       // records / destinations allocated in this shard's sub-arena of shard q
   int xRecDestTop[MAX_SHARDS];
+  int tieCnt;                    // CasperIMD randomOnTies: nodes suspended at a fork-choice tie in this pass
   int allSeq;                    // sendAll envelopes created so far over all shards: the next record slot (replicated records)
   int xNext, xAfter;             // global results of the begin exchange of this pass
   int poolMinFree[MAX_LEVELS];                 // low-water mark of free slots per level (sampled at tick end)
@@ -385,6 +386,12 @@ struct Dev {
   unsigned long long* cbIncluded;  // [cMaxBlocks][cAttWords] attestations newly included by the block
   int* attHead;     // [cMaxAtts] block index the attestation votes for
   int* attHeight;   // [cMaxAtts] slot of the vote
+  int* cbItem;      // [cMaxBlocks] scan item of the event that created the block (ids follow the processing order)
+  unsigned long long* cbTmp;  // [8][cAttWords] scratch of the renumbering pass
+  int* cbTmpRow;    // [8][5]
+  int* cTieItem;    // [N] randomOnTies: scan item of the event the node is suspended at (-1: not suspended)
+  int* cTieCnt;     // [N] ... and the size of its inbox in that pass
+  int* cTieList;    // [N] suspended nodes of the pass
   // ---- Handel ----
   int hLevelWait, hFastPath, hExtraCycle, hByzSuicide, hWinInit, hWinMin, hWinMax;
   unsigned long long* hLastAgg;   // [N][W64] lastAggVerified (all levels of a node in one row)
