@@ -4,8 +4,16 @@
 // on a machine without a GPU.  It is NOT part of the product: the package never loads it, and it
 // exports wtgemu_* symbols only.  Scans and the multisplit are plain sequential loops here; the
 // CUDA kernels that implement them are validated on the GPU by tests/ -m gpu.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../wittgenstein_b200/csrc/wtg_engine.hpp"
@@ -16,10 +24,84 @@ class HostBackend : public Backend {
  public:
   long long launches = 0;
   void* alloc(size_t bytes) override { return std::calloc(1, bytes); }
-  void release(void* p) override { std::free(p); }
+  void release(void* p) override {
+    if (shm.count(p))
+      releaseShared(p);
+    else
+      std::free(p);
+  }
   void upload(void* dst, const void* src, size_t bytes) override { std::memcpy(dst, src, bytes); }
   void download(void* dst, const void* src, size_t bytes) override { std::memcpy(dst, src, bytes); }
   void sync() override {}
+
+  // Exchange regions of node-sharded runs live in POSIX shared memory, so that the multi-process form of the sharded engine
+  // (one shard per process, handles exchanged through torch.distributed: DistributedGSFSignature / DistributedCasperIMD) can
+  // be driven over gloo on a machine without a GPU — the host counterpart of cudaIpcGetMemHandle / cudaIpcOpenMemHandle.
+  struct Shm {
+    std::string name;
+    size_t bytes;
+    bool owner;
+  };
+  std::map<void*, Shm> shm;
+  void* allocShared(size_t bytes) override {
+    static std::atomic<int> counter{0};
+    char name[64];
+    std::snprintf(name, sizeof(name), "/wtgemu_%d_%d", (int)getpid(), counter.fetch_add(1));
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) throw std::runtime_error("shm_open failed");
+    if (ftruncate(fd, (off_t)bytes) != 0) {
+      close(fd);
+      shm_unlink(name);
+      throw std::runtime_error("ftruncate failed");
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);  // zero-filled
+    close(fd);
+    if (p == MAP_FAILED) {
+      shm_unlink(name);
+      throw std::runtime_error("mmap failed");
+    }
+    shm[p] = Shm{name, bytes, true};
+    return p;
+  }
+  void exportShared(void* p, unsigned char* handle) override {  // [0,64) name, [64,72) pid, [72,80) address, [80,88) size
+    std::memset(handle, 0, 128);
+    auto it = shm.find(p);
+    if (it == shm.end()) throw std::runtime_error("not a shared region");
+    std::memcpy(handle, it->second.name.c_str(), it->second.name.size() + 1);
+    long long pid = (long long)getpid();
+    std::memcpy(handle + 64, &pid, sizeof(pid));
+    std::memcpy(handle + 72, &p, sizeof(p));
+    unsigned long long sz = it->second.bytes;
+    std::memcpy(handle + 80, &sz, sizeof(sz));
+  }
+  void* importShared(const unsigned char* handle) override {
+    long long pid;
+    std::memcpy(&pid, handle + 64, sizeof(pid));
+    if (pid == (long long)getpid()) {  // a shard of this process: same address space
+      void* p;
+      std::memcpy(&p, handle + 72, sizeof(p));
+      return p;
+    }
+    unsigned long long sz;
+    std::memcpy(&sz, handle + 80, sizeof(sz));
+    int fd = shm_open(reinterpret_cast<const char*>(handle), O_RDWR, 0600);
+    if (fd < 0) throw std::runtime_error("shm_open of a peer's region failed");
+    void* p = mmap(nullptr, (size_t)sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) throw std::runtime_error("mmap of a peer's region failed");
+    shm[p] = Shm{std::string(reinterpret_cast<const char*>(handle)), (size_t)sz, false};
+    return p;
+  }
+  void releaseShared(void* p) {
+    auto it = shm.find(p);
+    if (it == shm.end()) return;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    shm.erase(it);
+  }
+  ~HostBackend() override {
+    while (!shm.empty()) releaseShared(shm.begin()->first);
+  }
 
   void pairScan(const Dev& d, int which) {
     int M = scanCount(d, which);

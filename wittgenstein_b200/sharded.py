@@ -190,9 +190,9 @@ class DistributedCasperIMD:
     """This process's shard of a CasperIMD network spread over the ranks of a torch.distributed group (one GPU each): the
     handles of the exchange regions travel once through `torch.distributed`; the data path is peer stores between kernels."""
 
-    def __init__(self, params, dist, rank, world, device, tunables=None):
+    def __init__(self, params, dist, rank, world, device, tunables=None, _api=None):
         self.params, self.dist, self.rank, self.world = params, dist, rank, world
-        self.local = CasperIMD(params, None, tunables, shard=(rank, world), device=device)
+        self.local = CasperIMD(params, _api, tunables, shard=(rank, world), device=device)
 
     def network(self):
         return self.local.network()
@@ -221,9 +221,9 @@ class DistributedCasperIMD:
 class DistributedGSFSignature:
     """This process's shard of a GSFSignature network spread over the ranks of a torch.distributed group (one GPU each)."""
 
-    def __init__(self, params, dist, rank, world, device, tunables=None):
+    def __init__(self, params, dist, rank, world, device, tunables=None, _api=None):
         self.params, self.dist, self.rank, self.world = params, dist, rank, world
-        self.local = GSFSignature(params, None, tunables, shard=(rank, world), device=device)
+        self.local = GSFSignature(params, _api, tunables, shard=(rank, world), device=device)
 
     def network(self):
         return self.local.network()
@@ -244,6 +244,7 @@ class DistributedGSFSignature:
         """some live node of some shard is still below the threshold"""
         import torch
 
-        t = torch.tensor([1 if self.local.continue_if() else 0], dtype=torch.int32, device=f"cuda:{self.local.network().device}")
+        dev = f"cuda:{self.local.network().device}" if self.dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([1 if self.local.continue_if() else 0], dtype=torch.int32, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return bool(t.item())
