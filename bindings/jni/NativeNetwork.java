@@ -62,6 +62,12 @@ public final class NativeNetwork implements AutoCloseable {
 
   public native int msgsSizeAt(int t);
 
+  /**
+   * network.msgs.peekMessages() (Network.java:279-286): one row of {from, to, sentAt, arrivingAt, kind, msgType} per
+   * pending arrival, sorted by arrival time, flattened (6 ints per row) — the data of EnvelopeInfo (EnvelopeInfo.java:8-14).
+   */
+  public native int[] peekMessages(int maxRows);
+
   public native void stopNode(int id);
 
   public native void startNode(int id);

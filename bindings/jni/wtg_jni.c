@@ -76,6 +76,25 @@ JNIEXPORT jboolean JNICALL NN(runMs)(JNIEnv* e, jobject o, jint ms) { return che
 JNIEXPORT jint JNICALL NN(time)(JNIEnv* e, jobject o) { return wtg_time(H(e, o)); }
 JNIEXPORT jint JNICALL NN(msgsSize)(JNIEnv* e, jobject o) { return check(e, wtg_msgs_size(H(e, o))); }
 JNIEXPORT jint JNICALL NN(msgsSizeAt)(JNIEnv* e, jobject o, jint t) { return check(e, wtg_msgs_size_at(H(e, o), t)); }
+JNIEXPORT jintArray JNICALL NN(peekMessages)(JNIEnv* e, jobject o, jint maxRows) {
+  wtg_net* n = H(e, o);
+  if (maxRows < 0) maxRows = 0;
+  int* col = (int*)malloc(sizeof(int) * 6 * (size_t)(maxRows > 0 ? maxRows : 1));
+  jintArray out = 0;
+  int total = check(e, wtg_peek_messages(n, col, col + maxRows, col + 2 * (size_t)maxRows, col + 3 * (size_t)maxRows,
+                                         col + 4 * (size_t)maxRows, col + 5 * (size_t)maxRows, maxRows));
+  if (total >= 0) {
+    int rows = total < maxRows ? total : maxRows;
+    int* flat = (int*)malloc(sizeof(int) * 6 * (size_t)(rows > 0 ? rows : 1));
+    for (int i = 0; i < rows; ++i)
+      for (int k = 0; k < 6; ++k) flat[6 * i + k] = col[(size_t)k * (size_t)maxRows + (size_t)i];
+    out = (*e)->NewIntArray(e, 6 * rows);
+    (*e)->SetIntArrayRegion(e, out, 0, 6 * rows, (const jint*)flat);
+    free(flat);
+  }
+  free(col);
+  return out;
+}
 JNIEXPORT void JNICALL NN(stopNode)(JNIEnv* e, jobject o, jint id) { check(e, wtg_stop_node(H(e, o), id)); }
 JNIEXPORT void JNICALL NN(startNode)(JNIEnv* e, jobject o, jint id) { check(e, wtg_start_node(H(e, o), id)); }
 JNIEXPORT void JNICALL NN(partition)(JNIEnv* e, jobject o, jfloat part) { check(e, wtg_partition(H(e, o), part)); }
