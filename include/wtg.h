@@ -114,8 +114,8 @@ int wtg_casper_init_byz(wtg_net* net, int kind, int byz_delay);
 
 /* network.send(msg, from, to) / send(msg, from, dests) / sendAll(msg, from) called by the host between two runMs windows —
  * Network.java:341-366: one rd.nextInt() per call, send time = time + 1.  `type` / `payload` name a message of the running
- * protocol: PingPong 1 = Ping, 2 = Pong (payload unused); CasperIMD 2 = SendBlock(block id).  At most 16 destinations per
- * wtg_send; wtg_send_all needs the sendAll path (CasperIMD).  Other protocols' messages carry device-resident payloads and are
+ * protocol: PingPong 1 = Ping, 2 = Pong (payload unused); CasperIMD 2 = SendBlock(block id).  Any number of
+ * destinations per wtg_send; wtg_send_all needs the sendAll path (CasperIMD).  Other protocols' messages carry device-resident payloads and are
  * not offered. */
 int wtg_send(wtg_net* net, int type, unsigned long long payload, int from, const int* to, int n);
 int wtg_send_all(wtg_net* net, int type, unsigned long long payload, int from);

@@ -65,3 +65,25 @@ def test_rest_workflow_on_device():
         assert client.post("/w/network/init/" + p, json=prm).status_code == 200, p
         assert client.post("/w/network/runMs/50").status_code == 200, p
         assert client.get("/w/network/messages").status_code == 200, p
+
+
+def test_pingpong_caller_sends_to_many_destinations():
+    """network.send(msg, from, dests) with 300 / 40 destinations (more than any handler uses), also with delaysBetweenMessage"""
+    from wittgenstein_b200 import PingPong, PingPongParameters
+
+    p = PingPong(PingPongParameters(400, None, None))
+    o = OraclePingPong(400, None, None)
+    p.init(); o.init()
+    p.network().run_ms(300); o.run_ms(300)
+    for i in (5, 77, 399):
+        p.network().stop_node(i); o.stop_node(i)
+    d1 = [(7 * k + 3) % 400 for k in range(300)]
+    p.network().send(1, 2, d1); o.send(1, 2, d1)
+    d2 = list(range(399, 359, -1))
+    p.network().send(1, 9, d2, send_time=p.network().time + 10, delay_between=3)
+    o.send(1, 9, d2, send_time=o.time + 10, delay_between=3)
+    same_rows(p.network(), o, "after the caller's sends")
+    for _ in range(12):
+        assert p.network().run_ms(50) == o.run_ms(50)
+        assert (p.pongs() == o.pongs()).all() and (p.network().counters() == o.counters()).all()
+    assert p.network().rng_state() == o.rng_state() and p.network().msgs_size() == o.msgs_size() == 0

@@ -109,3 +109,26 @@ def test_casper(api):
         bad = compare_casper(p, o, f"t={o.time}")
         assert not bad, bad
     assert not compare_casper(p, o, "end", atts=True)
+
+
+def test_pingpong_caller_sends_to_many_destinations(api):
+    """network.send(msg, from, dests) with more destinations than any handler uses (Network.java:352-362): 300 and 40 destinations,
+    with and without delaysBetweenMessage, stopped nodes among them"""
+    from wittgenstein_b200 import PingPong, PingPongParameters
+
+    p = PingPong(PingPongParameters(400, None, None), _api=api)
+    o = OraclePingPong(400, None, None)
+    p.init(); o.init()
+    p.network().run_ms(300); o.run_ms(300)
+    for i in (5, 77, 399):
+        p.network().stop_node(i); o.stop_node(i)
+    d1 = [(7 * k + 3) % 400 for k in range(300)]
+    p.network().send(1, 2, d1); o.send(1, 2, d1)
+    d2 = list(range(399, 359, -1))
+    p.network().send(1, 9, d2, send_time=p.network().time + 10, delay_between=3)
+    o.send(1, 9, d2, send_time=o.time + 10, delay_between=3)
+    assert p.network().msgs_size() == o.msgs_size()
+    for _ in range(12):
+        assert p.network().run_ms(50) == o.run_ms(50)
+        assert (p.pongs() == o.pongs()).all() and (p.network().counters() == o.counters()).all()
+    assert p.network().rng_state() == o.rng_state() and p.network().msgs_size() == o.msgs_size() == 0

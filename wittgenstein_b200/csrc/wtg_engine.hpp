@@ -1319,7 +1319,6 @@ class Engine {
         ds.nDest = 1;
         fan = 1;
       } else {
-        if ((int)hs.to.size() > MAX_ACC) throw std::invalid_argument("at most 16 destinations per send (or none: sendAll)");
         ds.dkind = DK_SEND_MULTI;
         ds.to = (uint32_t)scratch.size();
         ds.nDest = (uint32_t)hs.to.size();
@@ -1327,13 +1326,15 @@ class Engine {
           if (t < 0 || t >= d.N) throw std::invalid_argument("The to node is not in the network");
           scratch.push_back((uint32_t)t);
         }
+        if ((int)hs.to.size() > MAX_ACC) scratch.insert(scratch.end(), hs.to.size(), 0u);  // room for the arrivals (emitBigMulti)
         fan = (int)hs.to.size();
       }
       descs[(size_t)i] = ds;
       sent[(size_t)hs.from] += fan;
       bytes[(size_t)hs.from] += (long long)fan * msgSizeOf(hs.meta);
     }
-    if ((int)scratch.size() > d.destScratchCap / ARENA_STRIPES || (int)allList.size() > d.allCap) throw std::runtime_error("too many destinations in one call");
+    if ((int)scratch.size() > d.destScratchCap || (int)allList.size() > d.allCap)  // no handler runs in this pass: the whole scratch is the caller's
+      throw std::runtime_error("too many destinations in one call");
     // control block of a "tick" at the current time with no bucket events, n items of one descriptor and one draw each
     c.tick = time;
     c.condMode = 0;

@@ -1961,6 +1961,69 @@ WTG_HD void dispatchScatterCoop(const Dev& d, C& c, int i) {
 // ------------------------------------------------------------------------------------------
 // emit: turn one descriptor into a new envelope (seed -> latency -> arrival), in creation order
 // ------------------------------------------------------------------------------------------
+// A multi-destination send with more destinations than MAX_ACC (only the caller issues those: network.send(msg, from, dests),
+// Network.java:352-362): the arrivals live next to the destination list in destScratch ([nDest] ids, then [nDest] arrivals) and
+// are sorted there (createMessageArrivals :449-467, stable); the envelope choice is the same (:435-446).  Unsharded only.
+WTG_HD void emitBigMulti(const Dev& d, const Desc& ds, int g, int32_t seed, int sendTime, int step, Ev ev) {
+  const Ctl& ctl = *d.ctl;
+  const int m = (int)ds.nDest, from = (int)ds.from;
+  uint32_t* list = d.destScratch + ds.to;
+  int* arr = reinterpret_cast<int*>(d.destScratch + ds.to + m);
+  int cnt = 0;
+  for (int i = 0; i < m; ++i) {
+    int to = (int)list[i];
+    if (d.npart[from] == d.npart[to] && !d.ndown[from] && !d.ndown[to]) {
+      int nt = latency(d, from, to, pseudoRandom(to, seed));
+      if (nt < d.msgDiscardTime) {
+        int a = sendTime + i * step + nt;
+        int j = cnt++;
+        while (j > 0 && arr[j - 1] > a) {
+          arr[j] = arr[j - 1];
+          list[j] = list[j - 1];
+          --j;
+        }
+        arr[j] = a;
+        list[j] = (uint32_t)to;
+      }
+    }
+  }
+  int target = -1;
+  if (cnt == 1) {
+    ev.to = list[0];
+    target = arr[0];
+  } else if (cnt > 1) {
+    int ri = WTG_ATOMIC_ADD(&d.ctl->recTop, 1);
+    int off = WTG_ATOMIC_ADD(&d.ctl->recDestTop, cnt);
+    if (ri >= d.recCap || off + cnt > d.recDestCap) {
+      setError(d, ERR_REC_OVERFLOW, ri);
+    } else {
+      MultiRec rc;
+      rc.from = ds.from;
+      rc.meta = ds.meta;
+      rc.pl = ds.pl;
+      rc.n = (uint32_t)cnt;
+      rc.cur = 0;
+      rc.off = (uint32_t)off;
+      rc.pad = (uint32_t)sendTime + 1u;
+      d.rec[ri] = rc;
+      for (int i = 0; i < cnt; ++i) {
+        d.recDest[off + i] = list[i];
+        d.recArrival[off + i] = arr[i];
+      }
+      ev.kind = EV_MULTI;
+      ev.to = list[0];
+      ev.aux = (uint32_t)ri;
+      target = arr[0];
+    }
+  }
+  if (target >= 0 && cnt > 0 && arr[cnt - 1] - ctl.tick >= d.ring) {  // a record's arrivals must all lie inside the ring
+    setError(d, ERR_FAR_FUTURE, arr[cnt - 1]);
+    target = -1;
+  }
+  d.newEv[g] = ev;
+  d.newTarget[g] = target;
+}
+
 WTG_HD void emitDesc(const Dev& d, int di) {
   const Ctl& ctl = *d.ctl;
   const Desc& ds = d.desc[di];
@@ -2017,6 +2080,13 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     ev.pad = (uint32_t)sendTime + 1u;
     const int delay = (int)(ds.aux >> DESC_DELAY_SHIFT);
     const int step = delay > 0 ? delay + 1 : 0;  // sendTime += delaysBetweenMessage + 1 after every destination (:455-459)
+    if (ds.dkind == DK_SEND_MULTI && (int)ds.nDest > MAX_ACC) {
+      if (shard)
+        setError(d, ERR_UNSUPPORTED, 8);
+      else
+        emitBigMulti(d, ds, g, seed, sendTime, step, ev);
+      return;
+    }
     if (ds.dkind == DK_SEND_SINGLE) {
       int to = (int)ds.to;
       // createMessageArrival :478-484

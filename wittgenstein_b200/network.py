@@ -104,7 +104,7 @@ class Network:
 
     # ---- sends issued by the caller (Network.java:341-366) ----
     def send(self, msg_type, from_id, to, payload=0, send_time=None, delay_between=0):
-        """network.send(msg, from, to) / send(msg, from, dests): `to` is a node id or a list of at most 16 ids.  With
+        """network.send(msg, from, to) / send(msg, from, dests): `to` is a node id or a list of ids.  With
         `send_time` (> time): send(msg, sendTime, from, to) / send(msg, sendTime, from, dests, delaysBetweenMessage)."""
         dests = np.asarray([to] if np.isscalar(to) else list(to), np.int32)
         if send_time is None:
