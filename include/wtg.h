@@ -137,7 +137,8 @@ int wtg_msgs_size_at(wtg_net* net, int t);
  * multi-destination envelope is a row — sorted by arrival time.  from/to: node ids; sent_at: Envelope.sendTime (-1 when the
  * engine did not record it: tasks registered by init()); kind: 0 message, 2 Task, 3 PeriodicTask; msg_type: the protocol's
  * message type code (GSF/Handel: payload kind and level).  Returns the number of pending arrivals; at most `cap` rows are
- * written (any output pointer may be NULL).  On a node-sharded network: the arrivals at this shard's nodes. */
+ * written (any output pointer may be NULL).  On a node-sharded network every pending
+ * arrival is reported by exactly one shard (single-destination envelopes by the destination's shard). */
 int wtg_peek_messages(wtg_net* net, int* from, int* to, int* sent_at, int* arriving_at, int* kind, int* msg_type, int cap);
 
 /* node.stop() / node.start() — Node.java:120-127 */

@@ -529,6 +529,9 @@ double wo_casper_run_timed(void* h, int ms, int step) {  // wall seconds of `ms`
 int wo_casper_time(void* h) { return static_cast<CasperIMD*>(h)->network.time; }
 int wo_casper_node_count(void* h) { return static_cast<int>(static_cast<CasperIMD*>(h)->network.allNodes.size()); }
 int64_t wo_casper_msgs_live(void* h) { return static_cast<CasperIMD*>(h)->network.msgs.live; }
+int wo_casper_peek_messages(void* h, int32_t* from, int32_t* to, int32_t* sentAt, int32_t* arrivingAt, int32_t* isTask, int cap) {
+  return peekRows(static_cast<CasperIMD*>(h)->network, from, to, sentAt, arrivingAt, isTask, cap);
+}
 int wo_casper_msgs_size_at(void* h, int t) { return static_cast<CasperIMD*>(h)->network.msgs.sizeAt(t); }
 uint64_t wo_casper_rng_state(void* h) { return static_cast<CasperIMD*>(h)->network.rd.seed; }
 int64_t wo_casper_deliveries(void* h) { return static_cast<CasperIMD*>(h)->network.statDeliveries; }

@@ -54,3 +54,32 @@ def test_gsf_rows(api):
         same_rows(p.network(), o, f"t={o.time}")  # messages, accelerated multi-sends, update tasks, periodic re-arms
     t, rows = p.network().peek_messages(cap=5)
     assert t > 5 and len(rows["from"]) == 5
+
+
+def test_rows_of_node_sharded_networks(api):
+    """every pending arrival of a node-sharded network is reported by exactly one shard: GSFSignature (records copied to the
+    shards of the next group) and CasperIMD (replicated sendAll records, far-future calendar)"""
+    from tests.oracle_lib import OracleCasper
+    from wittgenstein_b200 import CasperParemeters, GSFSignatureParameters
+    from wittgenstein_b200.sharded import ShardedCasperIMD, ShardedGSFSignature
+
+    prm = GSFSignatureParameters(128, 0.8, 4, 50, 20, 10, 0.1, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency")
+    p = ShardedGSFSignature(prm, 4, _api=api)
+    o = OracleGSF(128, prm.threshold, 4, 50, 20, 10, prm.nodes_down, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency")
+    p.init(); o.init()
+    p.network().msgs_size_rows = lambda: p.network().peek_messages(cap=0)[0]
+    for _ in range(25):
+        p.network().run_ms(9); o.run_ms(9)
+        same_rows(p.network(), o, f"gsf t={o.time}")
+    p.close()
+    args = (2, False, 3, 6, 1000, 1, None, None)
+    c = ShardedCasperIMD(CasperParemeters(*args), 4, _api=api, tunables={"casper_votes": 12})
+    oc = OracleCasper(*args)
+    c.init(9000); oc.init(9000)
+    c.network().msgs_size_rows = lambda: c.network().peek_messages(cap=0)[0]
+    same_rows(c.network(), oc, "casper after init")
+    for k in range(60):
+        step = 4000 if k % 3 else 37  # stop in the middle of the arrivals of a vote / a block as well
+        c.network().run_ms(step); oc.run_ms(step)
+        same_rows(c.network(), oc, f"casper t={oc.time}")
+    c.close()

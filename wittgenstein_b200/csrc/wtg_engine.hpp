@@ -1495,12 +1495,42 @@ class Engine {
     std::vector<Ev> evs;
     std::vector<uint32_t> rd;
     std::vector<int> ra;
+    // node-sharded sendAll protocols: the records are replicated and a shard holds a bucket entry only while it owns a
+    // destination of the envelope's next group, so the pending arrivals at this shard's nodes are read from the records
+    // themselves (a slot is live while its last arrival lies ahead; arrivals up to `time` have been delivered)
+    const bool replicated = sharded() && d.allCap > 0;
+    if (replicated) {
+      std::vector<MultiRec> recs((size_t)d.recSlots);
+      be->download(recs.data(), d.rec, recs.size() * sizeof(MultiRec));
+      for (const MultiRec& rc : recs) {
+        if (rc.n == 0) continue;
+        int last = 0;
+        be->download(&last, d.recArrival + rc.off + rc.n - 1, sizeof(int));
+        if (last <= time) continue;
+        rd.resize(rc.n);
+        ra.resize(rc.n);
+        be->download(rd.data(), d.recDest + rc.off, sizeof(uint32_t) * rc.n);
+        be->download(ra.data(), d.recArrival + rc.off, sizeof(int) * rc.n);
+        for (uint32_t i = 0; i < rc.n; ++i) {
+          if (ra[i] <= time || ownerOf(d, (int)rd[i]) != d.rank) continue;
+          ++total;
+          if ((long long)out.size() < cap) out.push_back(PeekRow{(int)rc.from, (int)rd[i], (int)rc.pad - 1, ra[i], (int)EV_MSG, rc.meta});
+        }
+      }
+    }
     auto addOne = [&](const Ev& e, int arrival) {
+      if (e.kind == EV_MULTI && replicated) return;
       if (e.kind == EV_MULTI) {
         MultiRec rc;
         be->download(&rc, d.rec + e.aux, sizeof(MultiRec));
         const int m = (int)rc.n - (int)rc.cur;
         if (m <= 0) return;
+        if (sharded()) {  // the envelope has an entry (and a copy of the record) on every shard that owns a destination of its
+                          // next group: the shard of the group's first destination reports all remaining destinations
+          uint32_t first = 0;
+          be->download(&first, d.recDest + rc.off + rc.cur, sizeof(uint32_t));
+          if (ownerOf(d, (int)first) != d.rank) return;
+        }
         total += m;
         long long room = cap - (long long)out.size();
         int take = (int)std::max<long long>(0, std::min<long long>(room, m));
@@ -1509,13 +1539,8 @@ class Engine {
           ra.resize((size_t)take);
           be->download(rd.data(), d.recDest + rc.off + rc.cur, sizeof(uint32_t) * (size_t)take);
           be->download(ra.data(), d.recArrival + rc.off + rc.cur, sizeof(int) * (size_t)take);
-          for (int i = 0; i < take; ++i) {
-            if (sharded() && ownerOf(d, (int)rd[(size_t)i]) != d.rank) {  // the owner's shard reports this destination
-              --total;
-              continue;
-            }
+          for (int i = 0; i < take; ++i)
             out.push_back(PeekRow{(int)rc.from, (int)rd[(size_t)i], (int)rc.pad - 1, ra[(size_t)i], (int)EV_MSG, rc.meta});
-          }
         }
       } else {
         total += 1;

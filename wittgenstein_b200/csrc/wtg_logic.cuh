@@ -2053,7 +2053,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
     }
     if (shard && ds.evKind == EV_MULTI) {  // re-push of a multi-destination envelope: its next arrivals may lie on other shards
       const MultiRec& rc = d.rec[ds.aux];
-      xPlaceMulti(d, g, rc.from, rc.meta, rc.pl, (int)rc.n, (int)rc.cur, d.recDest + rc.off, d.recArrival + rc.off, (int)ds.aux);
+      xPlaceMulti(d, g, rc.from, rc.meta, rc.pl, (int)rc.n, (int)rc.cur, d.recDest + rc.off, d.recArrival + rc.off, (int)ds.aux, rc.pad);
       return;
     }
   } else {
@@ -2124,7 +2124,7 @@ WTG_HD void emitDesc(const Dev& d, int di) {
           setError(d, ERR_FAR_FUTURE, arr[cnt - 1]);
           return;
         }
-        xPlaceMulti(d, g, ds.from, ds.meta, ds.pl, cnt, 0, dst, arr, -1);
+        xPlaceMulti(d, g, ds.from, ds.meta, ds.pl, cnt, 0, dst, arr, -1, (uint32_t)sendTime + 1u);
         return;
       } else if (cnt > 1) {
         ev.aux = 0;

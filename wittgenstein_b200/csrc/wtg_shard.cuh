@@ -219,7 +219,7 @@ WTG_HD void xStoreEnvelope(const Dev& d, int q, int g, const Ev& ev, int target)
   d.peer[q].newTarget[g] = target;
 }
 // copy of a multi-destination record into shard q's sub-arena of this shard; returns the record index on q or -1
-WTG_HD int xCopyRecord(const Dev& d, int q, uint32_t from, uint32_t meta, u64 pl, int n, int cur, const uint32_t* dst, const int* arr) {
+WTG_HD int xCopyRecord(const Dev& d, int q, uint32_t from, uint32_t meta, u64 pl, int n, int cur, const uint32_t* dst, const int* arr, uint32_t pad) {
   int ri = WTG_ATOMIC_ADD(&d.ctl->xRecTop[q], 1);
   int off = WTG_ATOMIC_ADD(&d.ctl->xRecDestTop[q], n);
   if (ri >= d.xRecCap || off + n > d.xRecDestCap) {
@@ -235,7 +235,7 @@ WTG_HD int xCopyRecord(const Dev& d, int q, uint32_t from, uint32_t meta, u64 pl
   rc.n = (uint32_t)n;
   rc.cur = (uint32_t)cur;
   rc.off = (uint32_t)off;
-  rc.pad = 0;
+  rc.pad = pad;  // Envelope.sendTime + 1 (peekMessages)
   d.peer[q].rec[ri] = rc;
   for (int i = 0; i < n; ++i) {
     d.peer[q].recDest[off + i] = dst[i];
@@ -246,7 +246,7 @@ WTG_HD int xCopyRecord(const Dev& d, int q, uint32_t from, uint32_t meta, u64 pl
 // A multi-destination envelope whose next arrivals (indices [j0, up) of the sorted list share one arrival) lie on several
 // shards gets one bucket entry on every shard that owns one of them, all with the same creation index; each entry
 // references a record copy on its shard.  `localRec` >= 0: this shard already holds the record (re-push).
-WTG_HD void xPlaceMulti(const Dev& d, int g, uint32_t from, uint32_t meta, u64 pl, int n, int j0, const uint32_t* dst, const int* arr, int localRec) {
+WTG_HD void xPlaceMulti(const Dev& d, int g, uint32_t from, uint32_t meta, u64 pl, int n, int j0, const uint32_t* dst, const int* arr, int localRec, uint32_t pad) {
   int up = j0;
   while (up < n && arr[up] == arr[j0]) ++up;
   uint32_t done = 0;
@@ -254,7 +254,7 @@ WTG_HD void xPlaceMulti(const Dev& d, int g, uint32_t from, uint32_t meta, u64 p
     int q = ownerOf(d, (int)dst[j]);
     if (done & (1u << q)) continue;
     done |= 1u << q;
-    int ri = (q == d.rank && localRec >= 0) ? localRec : xCopyRecord(d, q, from, meta, pl, n, j0, dst, arr);
+    int ri = (q == d.rank && localRec >= 0) ? localRec : xCopyRecord(d, q, from, meta, pl, n, j0, dst, arr, pad);
     if (ri < 0) return;
     Ev ev;
     ev.kind = EV_MULTI;
@@ -263,7 +263,7 @@ WTG_HD void xPlaceMulti(const Dev& d, int g, uint32_t from, uint32_t meta, u64 p
     ev.meta = 0;
     ev.pl = 0;
     ev.aux = (uint32_t)ri;
-    ev.pad = 0;
+    ev.pad = pad;
     xStoreEnvelope(d, q, g, ev, arr[j0]);
   }
 }

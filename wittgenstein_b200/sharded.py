@@ -53,6 +53,15 @@ class _ShardedNetwork:
     def counters(self):
         return np.concatenate(self._each(lambda s: s.network().counters()), axis=1)
 
+    def peek_messages(self, cap=1 << 16):
+        """network.msgs.peekMessages(): every pending arrival is reported by exactly one shard; merged and sorted like the
+        unsharded read-back (arrivingAt, from, to, sentAt)"""
+        parts = self._each(lambda s: s.network().peek_messages(cap))
+        total = sum(p[0] for p in parts)
+        rows = {k: np.concatenate([p[1][k] for p in parts]) for k in parts[0][1]}
+        order = np.lexsort((rows["sent_at"], rows["to"], rows["from"], rows["arriving_at"]))
+        return total, {k: v[order] for k, v in rows.items()}
+
     def attrs(self):
         return self._o.shards[0].network().attrs()
 
