@@ -81,3 +81,19 @@ def test_gsf_wide_peer_ids_host_build():
             p.network().run_ms(10); o.run_ms(10)
             bad = parity.compare_gsf(p, o, f"t={o.time}", full=(i % 8 == 0))
             assert not bad, bad
+
+
+def test_gsf_config5_shape_8_shards_wide_peer_ids():
+    """BASELINE config #5's shape (8 shards, 32-bit absolute peer ids as from 262 144 nodes on) at 2 048 nodes: 256 nodes per shard,
+    the top three levels cross shards"""
+    prm = GSFSignatureParameters(2048, 0.8, 4, 50, 20, 10, 0.1, AWS_NB, AWS_NL)
+    p = ShardedGSFSignature(prm, 8, _api=emu_lib.api(), tunables={"peer_bits_32": 1})
+    o = OracleGSF(2048, prm.threshold, 4, 50, 20, 10, prm.nodes_down, AWS_NB, AWS_NL)
+    p.init(); o.init()
+    assert p.network().stats()["peer_bits"] == 32
+    assert not parity.compare_init(p, o)
+    for i in range(45):
+        assert p.network().run_ms(10) == o.run_ms(10)
+        bad = parity.compare_gsf(p, o, f"t={o.time}", full=(i % 9 == 8))
+        assert not bad, bad
+    p.close()
