@@ -88,33 +88,3 @@ def test_pingpong_caller_sends_to_many_destinations():
         assert (p.pongs() == o.pongs()).all() and (p.network().counters() == o.counters()).all()
     assert p.network().rng_state() == o.rng_state() and p.network().msgs_size() == o.msgs_size() == 0
 
-
-def test_peek_messages_of_node_sharded_networks():
-    """every pending arrival of a node-sharded network is reported by exactly one shard (GSFSignature: record copies; CasperIMD:
-    replicated sendAll records); not run on a GPU before the round's last bench session — host-build twin:
-    tests/test_peek_messages_emu.py::test_rows_of_node_sharded_networks"""
-    import torch
-
-    from tests.oracle_lib import OracleCasper
-    from wittgenstein_b200 import CasperParemeters, GSFSignatureParameters
-    from wittgenstein_b200.sharded import ShardedCasperIMD, ShardedGSFSignature
-
-    ndev = max(1, torch.cuda.device_count())
-    devs = [r % ndev for r in range(4)]
-    prm = GSFSignatureParameters(128, 0.8, 4, 50, 20, 10, 0.1, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency")
-    p = ShardedGSFSignature(prm, 4, devices=devs)
-    o = OracleGSF(128, prm.threshold, 4, 50, 20, 10, prm.nodes_down, "AWS_SPEED=GAUSSIAN_TOR=0.33", "AwsRegionNetworkLatency")
-    p.init(); o.init()
-    for _ in range(25):
-        p.network().run_ms(9); o.run_ms(9)
-        same_rows(p.network(), o, f"gsf t={o.time}")
-    p.close()
-    args = (2, False, 3, 6, 1000, 1, None, None)
-    c = ShardedCasperIMD(CasperParemeters(*args), 4, devices=devs, tunables={"casper_votes": 12})
-    oc = OracleCasper(*args)
-    c.init(9000); oc.init(9000)
-    for k in range(60):
-        step = 4000 if k % 3 else 37
-        c.network().run_ms(step); oc.run_ms(step)
-        same_rows(c.network(), oc, f"casper t={oc.time}")
-    c.close()
